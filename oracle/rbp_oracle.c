@@ -345,9 +345,16 @@ static void env_alloc(env_t *e, int n, const int *first) {
 static void env_free(env_t *e) { free(e->first); free(e->off); free(e->v); }
 #define ENV(e, r, c) ((e)->v[(e)->off[r] + (size_t)((c) - (e)->first[r])])
 
-static int env_chol(env_t *e) {
+/* Pivots that elimination has driven below PIVOT_REL of their original diagonal belong to rows that are
+ * numerically dependent on earlier ones (an equality among variables that active inequality rows already pin:
+ * LICQ fails there and the multiplier is not unique).  They are replaced by a huge value, which zeroes that
+ * component of the solve (the "Cholesky-infinity" device of barrier codes); the primal solution is unaffected. */
+#define PIVOT_REL 1e-13
+#define PIVOT_BIG 1e128
+static int env_chol(env_t *e, int safeguard) {
     for (int r = 0; r < e->n; r++) {
         int fr = e->first[r];
+        double orig = ENV(e, r, r);
         for (int c = fr; c <= r; c++) {
             int fc = e->first[c], t0 = fr > fc ? fr : fc;
             double s = ENV(e, r, c);
@@ -355,7 +362,9 @@ static int env_chol(env_t *e) {
             for (int t = 0; t < c - t0; t++) s -= lr[t] * lc[t];
             if (c < r) ENV(e, r, c) = s / ENV(e, c, c);
             else {
-                if (!(s > 0)) return -1;
+                if (!(s == s)) return -1;
+                if (safeguard) { if (!(s > PIVOT_REL * orig) || !(s > 0)) s = PIVOT_BIG; }
+                else if (!(s > 0)) return -1;
                 ENV(e, r, r) = sqrt(s);
             }
         }
@@ -483,7 +492,7 @@ static int kkt_factor(kkt_t *K, const double *w) {
             }
         }
     }
-    if (env_chol(H)) return -1;
+    if (env_chol(H, 0)) return -1;
     if (ne == 0) return 0;
     /* Y columns */
     for (int c = 0; c < ne; c++) { K->ylo[c] = nv; K->yhi[c] = -1; }
@@ -522,7 +531,7 @@ static int kkt_factor(kkt_t *K, const double *w) {
             for (int t = lo; t <= hi; t++) s += yr[t] * yc[t];
             ENV(&K->S, r, c) = s;
         }
-    if (env_chol(&K->S)) return -2;
+    if (env_chol(&K->S, 1)) return -2;
     return 0;
 }
 
@@ -561,6 +570,56 @@ static double inf_norm(const double *v, int n) {
     return m;
 }
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Presolve (what CPLEX's presolve does to this model before the barrier sees it): singleton equality
+ * rows fix their column -- here the start rows fix control points 0..2 of the first segment and the
+ * goal rows fix 3..5 of the last one (rows 0-5 of Aeq_base are triangular in them, RP L380-L387) --
+ * and inequality rows all of whose columns are fixed are checked against their right-hand side
+ * (feasibility tolerance 1e-6, CPLEX's default) and dropped.  Without this a start or goal lying on a
+ * face of its SFC box, which the corridor generator produces routinely, leaves the QP without a strict
+ * interior.  dead[r] = 1 for dropped rows.  Returns 0, or ORACLE_INFEASIBLE.
+ * ---------------------------------------------------------------------------------------------- */
+#define PRESOLVE_FEAS_TOL 1e-6
+static int presolve_dead_rows(const oracle_qp *q, unsigned char *dead, int *n_live) {
+    int nv = q->nv, ne = q->ne, mi = q->mi, rc = 0;
+    unsigned char *fixed = (unsigned char *)calloc(nv + 1, 1), *used = (unsigned char *)calloc(ne + 1, 1);
+    double *xf = (double *)calloc(nv + 1, sizeof(double));
+    int progress = 1;
+    while (progress) {
+        progress = 0;
+        for (int r = 0; r < ne; r++) {
+            if (used[r]) continue;
+            int nfree = 0, col = -1;
+            double rhs = q->b[r], a = 0;
+            for (int t = q->a_ptr[r]; t < q->a_ptr[r + 1]; t++) {
+                int c = q->a_idx[t];
+                if (fixed[c]) rhs -= q->a_val[t] * xf[c];
+                else { nfree++; col = c; a = q->a_val[t]; }
+            }
+            if (nfree == 1 && a != 0) {
+                fixed[col] = 1; xf[col] = rhs / a; used[r] = 1; progress = 1;
+            }
+        }
+    }
+    int live = 0;
+    for (int r = 0; r < mi; r++) {
+        int all = q->g_ptr[r + 1] > q->g_ptr[r];
+        double gx = 0;
+        for (int t = q->g_ptr[r]; t < q->g_ptr[r + 1]; t++) {
+            int c = q->g_idx[t];
+            if (!fixed[c]) { all = 0; break; }
+            gx += q->g_val[t] * xf[c];
+        }
+        dead[r] = (unsigned char)all;
+        if (all) { if (gx - q->h[r] > PRESOLVE_FEAS_TOL) rc = ORACLE_INFEASIBLE; }
+        else live++;
+    }
+    *n_live = live;
+    free(fixed); free(used); free(xf);
+    return rc;
+}
+
 int oracle_solve_qp(const oracle_qp *q, const oracle_solver_opts *opts, double *x, double *obj_out,
                     int *iters_out, double *res_out) {
     int nv = q->nv, ne = q->ne, mi = q->mi;
@@ -579,20 +638,26 @@ int oracle_solve_qp(const oracle_qp *q, const oracle_solver_opts *opts, double *
     double *dsa = (double *)malloc(sizeof(double) * (mi + 1)), *dza = (double *)malloc(sizeof(double) * (mi + 1));
     double *gx = (double *)malloc(sizeof(double) * (mi + 1)), *px = (double *)malloc(sizeof(double) * nv);
     int status = ORACLE_NOT_CONVERGED, it = 0;
-    double bn = inf_norm(q->b, ne), hn = inf_norm(q->h, mi), gap = 0, obj = 0;
+    unsigned char *dead = (unsigned char *)calloc(mi + 1, 1);
+    int n_live = mi;
+    double bn = inf_norm(q->b, ne), hn = 0, gap = 0, obj = 0;
+    if (presolve_dead_rows(q, dead, &n_live)) { status = ORACLE_INFEASIBLE; goto done; }
+    for (int r = 0; r < mi; r++) if (!dead[r] && fabs(q->h[r]) > hn) hn = fabs(q->h[r]);
 
     /* initial point (standard least-squares start): W = I */
     for (int r = 0; r < mi; r++) K.w[r] = 1.0;
     if (kkt_factor(&K, K.w)) { status = ORACLE_NOT_CONVERGED; goto done; }
     for (int i = 0; i < nv; i++) r1[i] = 0;
-    csr_mulTv_add(mi, q->g_ptr, q->g_idx, q->g_val, q->h, r1);
+    for (int r = 0; r < mi; r++) tt[r] = dead[r] ? 0.0 : q->h[r];
+    csr_mulTv_add(mi, q->g_ptr, q->g_idx, q->g_val, tt, r1);
     kkt_solve(&K, r1, q->b, x, y);
     csr_mulv(mi, q->g_ptr, q->g_idx, q->g_val, x, gx);
     {
         double ap = -1e300, ad = -1e300;
         for (int r = 0; r < mi; r++) { z[r] = gx[r] - q->h[r]; s[r] = -z[r]; }
-        for (int r = 0; r < mi; r++) { if (-s[r] > ap) ap = -s[r]; if (-z[r] > ad) ad = -z[r]; }
+        for (int r = 0; r < mi; r++) { if (dead[r]) continue; if (-s[r] > ap) ap = -s[r]; if (-z[r] > ad) ad = -z[r]; }
         for (int r = 0; r < mi; r++) {
+            if (dead[r]) { s[r] = 1.0; z[r] = 0.0; continue; }  /* dropped row: no multiplier, unit weight in H */
             if (ap >= 0) s[r] += 1.0 + ap;
             if (ad >= 0) z[r] += 1.0 + ad;
         }
@@ -608,8 +673,11 @@ int oracle_solve_qp(const oracle_qp *q, const oracle_solver_opts *opts, double *
         for (int r = 0; r < ne; r++) rp[r] -= q->b[r];
         csr_mulv(mi, q->g_ptr, q->g_idx, q->g_val, x, gx);
         double mu = 0;
-        for (int r = 0; r < mi; r++) { rg[r] = gx[r] + s[r] - q->h[r]; mu += s[r] * z[r]; }
-        mu /= (mi > 0 ? mi : 1);
+        for (int r = 0; r < mi; r++) {
+            if (dead[r]) { rg[r] = 0; continue; }
+            rg[r] = gx[r] + s[r] - q->h[r]; mu += s[r] * z[r];
+        }
+        mu /= (n_live > 0 ? n_live : 1);
         obj = 0;
         for (int i = 0; i < nv; i++) obj += 0.5 * x[i] * px[i];
         gap = mu;
@@ -625,7 +693,7 @@ int oracle_solve_qp(const oracle_qp *q, const oracle_solver_opts *opts, double *
         /* primal infeasibility certificate: z>=0, G'z + A'y ~ 0, h'z + b'y < 0 */
         {
             double hz = 0;
-            for (int r = 0; r < mi; r++) hz += q->h[r] * z[r];
+            for (int r = 0; r < mi; r++) if (!dead[r]) hz += q->h[r] * z[r];
             for (int r = 0; r < ne; r++) hz += q->b[r] * y[r];
             if (hz < 0) {
                 for (int i = 0; i < nv; i++) r1[i] = 0;
@@ -634,10 +702,10 @@ int oracle_solve_qp(const oracle_qp *q, const oracle_solver_opts *opts, double *
                 if (inf_norm(r1, nv) / (-hz) < 1e-8) { status = ORACLE_INFEASIBLE; break; }
             }
         }
-        for (int r = 0; r < mi; r++) K.w[r] = z[r] / s[r];
+        for (int r = 0; r < mi; r++) K.w[r] = dead[r] ? 1.0 : z[r] / s[r];
         if (kkt_factor(&K, K.w)) { status = ORACLE_NOT_CONVERGED; break; }
         /* affine direction: rc = s.z  =>  t = (z.rg - rc)/s = w.rg - z */
-        for (int r = 0; r < mi; r++) tt[r] = K.w[r] * rg[r] - z[r];
+        for (int r = 0; r < mi; r++) tt[r] = dead[r] ? 0.0 : K.w[r] * rg[r] - z[r];
         for (int i = 0; i < nv; i++) r1[i] = -rd[i];
         for (int r = 0; r < mi; r++) tt[r] = -tt[r];
         csr_mulTv_add(mi, q->g_ptr, q->g_idx, q->g_val, tt, r1);
@@ -646,19 +714,20 @@ int oracle_solve_qp(const oracle_qp *q, const oracle_solver_opts *opts, double *
         csr_mulv(mi, q->g_ptr, q->g_idx, q->g_val, dx, gx);
         double aa = 1.0;
         for (int r = 0; r < mi; r++) {
+            if (dead[r]) { dsa[r] = 0; dza[r] = 0; continue; }
             dsa[r] = -rg[r] - gx[r];
             dza[r] = -z[r] - K.w[r] * dsa[r];
             if (dsa[r] < 0) { double a = -s[r] / dsa[r]; if (a < aa) aa = a; }
             if (dza[r] < 0) { double a = -z[r] / dza[r]; if (a < aa) aa = a; }
         }
         double mua = 0;
-        for (int r = 0; r < mi; r++) mua += (s[r] + aa * dsa[r]) * (z[r] + aa * dza[r]);
-        mua /= (mi > 0 ? mi : 1);
+        for (int r = 0; r < mi; r++) if (!dead[r]) mua += (s[r] + aa * dsa[r]) * (z[r] + aa * dza[r]);
+        mua /= (n_live > 0 ? n_live : 1);
         double sigma = (mu > 0) ? pow(mua / mu, 3.0) : 0;
         /* corrector: rc = s.z + dsa.dza - sigma mu */
         for (int r = 0; r < mi; r++) {
             double rc = s[r] * z[r] + dsa[r] * dza[r] - sigma * mu;
-            tt[r] = -(z[r] * rg[r] - rc) / s[r];
+            tt[r] = dead[r] ? 0.0 : -(z[r] * rg[r] - rc) / s[r];
         }
         for (int i = 0; i < nv; i++) r1[i] = -rd[i];
         csr_mulTv_add(mi, q->g_ptr, q->g_idx, q->g_val, tt, r1);
@@ -666,6 +735,7 @@ int oracle_solve_qp(const oracle_qp *q, const oracle_solver_opts *opts, double *
         csr_mulv(mi, q->g_ptr, q->g_idx, q->g_val, dx, gx);
         double am = 1e300;
         for (int r = 0; r < mi; r++) {
+            if (dead[r]) { ds[r] = 0; dz[r] = 0; continue; }
             double rc = s[r] * z[r] + dsa[r] * dza[r] - sigma * mu;
             ds[r] = -rg[r] - gx[r];
             dz[r] = (-rc - z[r] * ds[r]) / s[r];
@@ -681,6 +751,7 @@ done:
     if (obj_out) *obj_out = obj;
     if (iters_out) *iters_out = it;
     kkt_free(&K);
+    free(dead);
     free(y); free(s); free(z); free(rd); free(rp); free(rg); free(r1); free(r2); free(tt);
     free(dx); free(dy); free(ds); free(dz); free(dsa); free(dza); free(gx); free(px);
     return status;

@@ -1,0 +1,384 @@
+// rbpe_api.cu -- host side of the C ABI in include/rbpe.h: device memory, H2D/D2H, kernel launches, timing.
+// One handle = one device + one stream.  No CPU fallback: without a usable CUDA device every call fails.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/rbpe.h"
+#include "rbpe_kernels.cuh"
+
+using namespace rbpe;
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T *as() const { return (T *)p; }
+};
+
+char g_create_error[512] = "";
+
+}  // namespace
+
+struct rbpe_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int max_iter = 100;
+    double tol_gap = 1e-10, tol_res = 1e-9;
+    size_t smem_budget = 0, smem_optin = 0;
+    int sm_count = 0;
+    char err[512] = "";
+    // resident problem
+    bool resident = false;
+    int count = 0, N = 0, M = 0, sequential = 0, bs = 1, nbatch = 0, iteration = 1, nrec = 1, sweep = 0;
+    DevBuf T, start, goal, radius, sfc_offs, sfc_base, sfc_box, sfc_t, rsfc_n, rsfc_t, init_traj;
+    DevBuf segbox, reln, segmat, ctrl, frozen, coef, qp_obj, qp_iters, qp_status, qp_res, status, scratch;
+    rbpe_timing timing;
+    std::vector<int> host_status;
+};
+
+static int fail(rbpe_handle *h, int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(h ? h->err : g_create_error, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(h, RBPE_CUDA_ERROR, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" int rbpe_set_batch(int N, int sequential, int batch_size, int batch_iter, int *ebs, int *ebi) {
+    // RBPPlanner::setBatch, rbp_planner.hpp L849-L872
+    if (batch_size <= 0) batch_size = 1;
+    int bmax = (N + batch_size - 1) / batch_size;
+    if (sequential) {
+        if (batch_iter < 0 || batch_iter > bmax) batch_iter = bmax;
+    } else {
+        batch_size = N;
+        batch_iter = 1;
+    }
+    if (ebs) *ebs = batch_size;
+    if (ebi) *ebi = batch_iter;
+    return bmax;
+}
+
+extern "C" int rbpe_create(const rbpe_config *cfg, rbpe_handle **out) {
+    if (!out) return RBPE_BAD_ARG;
+    *out = nullptr;
+    rbpe_handle *h = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, RBPE_CUDA_ERROR, "no CUDA device (%s); this engine has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    int dev = cfg ? cfg->device : 0;
+    if (dev < 0 || dev >= ndev) return fail(nullptr, RBPE_BAD_ARG, "device %d out of range (%d devices)", dev, ndev);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, dev)) != cudaSuccess)
+        return fail(nullptr, RBPE_CUDA_ERROR, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, RBPE_CUDA_ERROR, "device %d is sm_%d%d; this library holds sm_100a code only", dev, prop.major,
+                    prop.minor);
+    h = new rbpe_handle();
+    h->device = dev;
+    h->sm_count = prop.multiProcessorCount;
+    h->smem_optin = prop.sharedMemPerBlockOptin;
+    if (cfg) {
+        if (cfg->max_iter > 0) h->max_iter = cfg->max_iter;
+        if (cfg->tol_gap > 0) h->tol_gap = cfg->tol_gap;
+        if (cfg->tol_res > 0) h->tol_res = cfg->tol_res;
+        h->smem_budget = cfg->smem_budget;
+    }
+    if (h->smem_budget == 0) h->smem_budget = 100 * 1024;
+    if (h->smem_budget > h->smem_optin) h->smem_budget = h->smem_optin;
+    memset(&h->timing, 0, sizeof(h->timing));
+    if ((e = cudaSetDevice(dev)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        fail(nullptr, RBPE_CUDA_ERROR, "stream creation: %s", cudaGetErrorString(e));
+        delete h;
+        return RBPE_CUDA_ERROR;
+    }
+    for (int i = 0; i < 7; i++) cudaEventCreate(&h->ev[i]);
+    cudaFuncSetAttribute(pdip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
+    *out = h;
+    return RBPE_OK;
+}
+
+extern "C" void rbpe_destroy(rbpe_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    DevBuf *all[] = {&h->T, &h->start, &h->goal, &h->radius, &h->sfc_offs, &h->sfc_base, &h->sfc_box, &h->sfc_t,
+                     &h->rsfc_n, &h->rsfc_t, &h->init_traj, &h->segbox, &h->reln, &h->segmat, &h->ctrl, &h->frozen,
+                     &h->coef, &h->qp_obj, &h->qp_iters, &h->qp_status, &h->qp_res, &h->status, &h->scratch};
+    for (DevBuf *b : all) b->release();
+    for (int i = 0; i < 7; i++)
+        if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" const char *rbpe_last_error(const rbpe_handle *h) { return h ? h->err : g_create_error; }
+
+static int up(rbpe_handle *h, DevBuf &b, const void *src, size_t bytes) {
+    if (bytes == 0) return RBPE_OK;
+    CU(b.reserve(bytes));
+    CU(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    return RBPE_OK;
+}
+
+extern "C" int rbpe_upload(rbpe_handle *h, const rbpe_problem *p, int count) {
+    if (!h) return RBPE_BAD_ARG;
+    if (!p || count <= 0 || p->N <= 0 || p->M <= 0 || p->M > MAX_M || p->batch_size <= 0 || p->iteration < 0)
+        return fail(h, RBPE_BAD_ARG, "bad problem shape (N=%d M=%d batch_size=%d count=%d)", p ? p->N : -1, p ? p->M : -1,
+                    p ? p->batch_size : -1, count);
+    if (!p->T || !p->start || !p->goal || !p->radius || !p->sfc_offs || !p->sfc_base || !p->sfc_box || !p->sfc_t ||
+        (p->N > 1 && (!p->rsfc_n || !p->rsfc_t)) || (p->sequential && !p->init_traj))
+        return fail(h, RBPE_BAD_ARG, "null input array");
+    CU(cudaSetDevice(h->device));
+    h->resident = false;
+    const int N = p->N, M = p->M;
+    const size_t P = (size_t)N * (N - 1) / 2, per = (size_t)N * 18 * M;
+    h->count = count; h->N = N; h->M = M; h->sequential = p->sequential ? 1 : 0; h->iteration = p->iteration;
+    rbpe_set_batch(N, h->sequential, p->batch_size, p->batch_iter, &h->bs, &h->nbatch);
+    h->nrec = h->iteration * h->nbatch;
+    if (h->nrec < 1) h->nrec = 1;
+    h->sweep = 0;
+    const size_t nbox = (size_t)p->sfc_base[count];
+
+    CU(cudaEventRecord(h->ev[0], h->stream));
+    int rc;
+    if ((rc = up(h, h->T, p->T, (size_t)count * (M + 1) * 8))) return rc;
+    if ((rc = up(h, h->start, p->start, (size_t)count * N * 9 * 8))) return rc;
+    if ((rc = up(h, h->goal, p->goal, (size_t)count * N * 9 * 8))) return rc;
+    if ((rc = up(h, h->radius, p->radius, (size_t)count * N * 8))) return rc;
+    if ((rc = up(h, h->sfc_offs, p->sfc_offs, (size_t)count * (N + 1) * 4))) return rc;
+    if ((rc = up(h, h->sfc_base, p->sfc_base, (size_t)(count + 1) * 4))) return rc;
+    if ((rc = up(h, h->sfc_box, p->sfc_box, nbox * 6 * 8))) return rc;
+    if ((rc = up(h, h->sfc_t, p->sfc_t, nbox * 8))) return rc;
+    if ((rc = up(h, h->rsfc_n, p->rsfc_n, (size_t)count * P * M * 3 * 4))) return rc;
+    if ((rc = up(h, h->rsfc_t, p->rsfc_t, (size_t)count * P * M * 8))) return rc;
+    if (p->sequential && (rc = up(h, h->init_traj, p->init_traj, (size_t)count * N * (M + 1) * 3 * 4))) return rc;
+    CU(cudaEventRecord(h->ev[1], h->stream));
+
+    CU(h->segbox.reserve((size_t)count * N * M * 6 * 8));
+    CU(h->reln.reserve((size_t)count * (P ? P : 1) * M * 3 * 4));
+    CU(h->segmat.reserve((size_t)count * M * SEGMAT * 8));
+    CU(h->ctrl.reserve(count * per * 8));
+    CU(h->frozen.reserve(count * per * 8));
+    CU(h->coef.reserve(count * per * 8));
+    CU(h->qp_obj.reserve((size_t)count * h->nrec * 8));
+    CU(h->qp_iters.reserve((size_t)count * h->nrec * 4));
+    CU(h->qp_status.reserve((size_t)count * h->nrec * 4));
+    CU(h->qp_res.reserve((size_t)count * h->nrec * 32));
+    CU(h->status.reserve((size_t)count * 4));
+    CU(cudaMemsetAsync(h->status.p, 0, (size_t)count * 4, h->stream));
+    CU(cudaMemsetAsync(h->qp_obj.p, 0, (size_t)count * h->nrec * 8, h->stream));
+    CU(cudaMemsetAsync(h->qp_iters.p, 0, (size_t)count * h->nrec * 4, h->stream));
+    CU(cudaMemsetAsync(h->qp_status.p, 0, (size_t)count * h->nrec * 4, h->stream));
+    CU(cudaMemsetAsync(h->qp_res.p, 0, (size_t)count * h->nrec * 32, h->stream));
+
+    AssembleArgs A;
+    A.count = count; A.N = N; A.M = M; A.sequential = h->sequential;
+    A.T = h->T.as<double>(); A.sfc_offs = h->sfc_offs.as<int>(); A.sfc_base = h->sfc_base.as<int>();
+    A.sfc_box = h->sfc_box.as<double>(); A.sfc_t = h->sfc_t.as<double>();
+    A.rsfc_n = h->rsfc_n.as<float>(); A.rsfc_t = h->rsfc_t.as<double>(); A.init_traj = h->init_traj.as<float>();
+    A.segbox = h->segbox.as<double>(); A.reln = h->reln.as<float>(); A.ctrl = h->ctrl.as<double>();
+    A.segmat = h->segmat.as<double>(); A.status = h->status.as<int>();
+    const long per_mission = (long)N + (long)P * M + (long)per + M;
+    long total = per_mission * count;
+    int blocks = (int)((total + 255) / 256);
+    int cap = h->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    assemble_kernel<<<blocks, 256, 0, h->stream>>>(A);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(h->ev[2], h->stream));
+    h->timing.kernel_launches = 1;
+    h->resident = true;
+    return RBPE_OK;
+}
+
+static size_t smem_for(const rbpe_handle *h, size_t scratch_d) {
+    size_t need = scratch_d * 8 + 1024;
+    size_t s = need < h->smem_budget ? need : h->smem_budget;
+    return (s + 15) & ~(size_t)15;
+}
+
+static int launch_convert(rbpe_handle *h) {
+    ConvertArgs C;
+    C.count = h->count; C.N = h->N; C.M = h->M;
+    C.ctrl = h->ctrl.as<double>(); C.segmat = h->segmat.as<double>(); C.coef = h->coef.as<double>();
+    long total = (long)h->count * h->N * 18 * h->M;
+    int blocks = (int)((total + 255) / 256), cap = h->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    convert_kernel<<<blocks, 256, 0, h->stream>>>(C);
+    CU(cudaGetLastError());
+    h->timing.kernel_launches++;
+    return RBPE_OK;
+}
+
+static int fill_solve_args(rbpe_handle *h, SolveArgs &S, int mode, int grid) {
+    S.count = h->count; S.N = h->N; S.M = h->M; S.bs = h->bs; S.nbatch = h->nbatch; S.iteration = h->iteration;
+    S.sequential = h->sequential; S.mode = mode; S.batch_begin = 0; S.batch_end = h->nbatch; S.rec_offset = 0;
+    S.max_iter = h->max_iter; S.tol_gap = h->tol_gap; S.tol_res = h->tol_res;
+    S.start = h->start.as<double>(); S.goal = h->goal.as<double>(); S.radius = h->radius.as<double>();
+    S.segbox = h->segbox.as<double>(); S.reln = h->reln.as<float>(); S.segmat = h->segmat.as<double>();
+    S.ctrl = h->ctrl.as<double>(); S.ctrl_frozen = h->frozen.as<double>();
+    S.qp_obj = h->qp_obj.as<double>(); S.qp_iters = h->qp_iters.as<int>(); S.qp_status = h->qp_status.as<int>();
+    S.qp_res = h->qp_res.as<double>(); S.nrec = h->nrec; S.status = h->status.as<int>();
+    S.scratch_stride = scratch_doubles(h->N, h->M, h->bs);
+    S.smem_bytes = (unsigned)smem_for(h, S.scratch_stride);
+    CU(h->scratch.reserve(S.scratch_stride * 8 * (size_t)grid));
+    S.scratch = h->scratch.as<double>();
+    return RBPE_OK;
+}
+
+extern "C" int rbpe_run(rbpe_handle *h, int mode) {
+    if (!h) return RBPE_BAD_ARG;
+    if (!h->resident) return fail(h, RBPE_BAD_ARG, "rbpe_run: nothing uploaded");
+    CU(cudaSetDevice(h->device));
+    CU(cudaEventRecord(h->ev[3], h->stream));
+    int rc;
+    if (h->nbatch > 0 && h->iteration > 0) {
+        SolveArgs S;
+        if (mode == RBPE_MODE_GAUSS_SEIDEL) {
+            if ((rc = fill_solve_args(h, S, 0, h->count))) return rc;
+            pdip_kernel<<<h->count, CTA_THREADS, S.smem_bytes, h->stream>>>(S);
+            CU(cudaGetLastError());
+            h->timing.kernel_launches++;
+        } else {
+            int grid = h->count * h->nbatch;
+            if ((rc = fill_solve_args(h, S, 1, grid))) return rc;
+            for (int it = 0; it < h->iteration; it++) {
+                CU(cudaMemcpyAsync(h->frozen.p, h->ctrl.p, (size_t)h->count * h->N * 18 * h->M * 8, cudaMemcpyDeviceToDevice,
+                                   h->stream));
+                S.rec_offset = it * h->nbatch;
+                pdip_kernel<<<grid, CTA_THREADS, S.smem_bytes, h->stream>>>(S);
+                CU(cudaGetLastError());
+                h->timing.kernel_launches++;
+            }
+        }
+    }
+    if ((rc = launch_convert(h))) return rc;
+    CU(cudaEventRecord(h->ev[4], h->stream));
+    return RBPE_OK;
+}
+
+extern "C" int rbpe_run_jacobi_range(rbpe_handle *h, int b0, int b1) {
+    if (!h) return RBPE_BAD_ARG;
+    if (!h->resident) return fail(h, RBPE_BAD_ARG, "rbpe_run_jacobi_range: nothing uploaded");
+    if (b0 < 0 || b1 > h->nbatch || b0 > b1) return fail(h, RBPE_BAD_ARG, "batch range [%d,%d) outside [0,%d)", b0, b1, h->nbatch);
+    CU(cudaSetDevice(h->device));
+    CU(cudaEventRecord(h->ev[3], h->stream));
+    int rc;
+    CU(cudaMemcpyAsync(h->frozen.p, h->ctrl.p, (size_t)h->count * h->N * 18 * h->M * 8, cudaMemcpyDeviceToDevice, h->stream));
+    if (b1 > b0) {
+        SolveArgs S;
+        int grid = h->count * (b1 - b0);
+        if ((rc = fill_solve_args(h, S, 1, grid))) return rc;
+        S.batch_begin = b0; S.batch_end = b1;
+        S.rec_offset = (h->iteration > 0 ? h->sweep % h->iteration : 0) * h->nbatch;
+        pdip_kernel<<<grid, CTA_THREADS, S.smem_bytes, h->stream>>>(S);
+        CU(cudaGetLastError());
+        h->timing.kernel_launches++;
+    }
+    h->sweep++;
+    if ((rc = launch_convert(h))) return rc;
+    CU(cudaEventRecord(h->ev[4], h->stream));
+    return RBPE_OK;
+}
+
+extern "C" int rbpe_download(rbpe_handle *h, rbpe_result *r) {
+    if (!h || !r) return RBPE_BAD_ARG;
+    if (!h->resident) return fail(h, RBPE_BAD_ARG, "rbpe_download: nothing uploaded");
+    CU(cudaSetDevice(h->device));
+    const size_t per = (size_t)h->N * 18 * h->M * 8, c = h->count;
+    const size_t nr = (size_t)h->iteration * h->nbatch;
+    CU(cudaEventRecord(h->ev[6], h->stream));
+    if (r->coef) CU(cudaMemcpyAsync(r->coef, h->coef.p, c * per, cudaMemcpyDeviceToHost, h->stream));
+    if (r->ctrl) CU(cudaMemcpyAsync(r->ctrl, h->ctrl.p, c * per, cudaMemcpyDeviceToHost, h->stream));
+    if (nr) {
+        if (r->qp_obj) CU(cudaMemcpyAsync(r->qp_obj, h->qp_obj.p, c * nr * 8, cudaMemcpyDeviceToHost, h->stream));
+        if (r->qp_iters) CU(cudaMemcpyAsync(r->qp_iters, h->qp_iters.p, c * nr * 4, cudaMemcpyDeviceToHost, h->stream));
+        if (r->qp_status) CU(cudaMemcpyAsync(r->qp_status, h->qp_status.p, c * nr * 4, cudaMemcpyDeviceToHost, h->stream));
+        if (r->qp_res) CU(cudaMemcpyAsync(r->qp_res, h->qp_res.p, c * nr * 32, cudaMemcpyDeviceToHost, h->stream));
+    }
+    h->host_status.resize(c);
+    CU(cudaMemcpyAsync(h->host_status.data(), h->status.p, c * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaEventRecord(h->ev[5], h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    int rc = RBPE_OK;
+    for (size_t i = 0; i < c; i++) {
+        if (r->status) r->status[i] = h->host_status[i];
+        if (rc == RBPE_OK && h->host_status[i] != RBPE_OK) rc = h->host_status[i];
+    }
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]) == cudaSuccess) h->timing.h2d_ms = ms;
+    if (cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]) == cudaSuccess) h->timing.assemble_ms = ms;
+    if (cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]) == cudaSuccess) h->timing.solve_ms = ms;
+    if (cudaEventElapsedTime(&ms, h->ev[6], h->ev[5]) == cudaSuccess) h->timing.d2h_ms = ms;
+    if (cudaEventElapsedTime(&ms, h->ev[0], h->ev[5]) == cudaSuccess) h->timing.total_ms = ms;
+    cudaGetLastError();
+    if (rc != RBPE_OK) snprintf(h->err, sizeof(h->err), "a mission ended with status %d (1 infeasible, 2 not converged, 3 bad input)", rc);
+    return rc;
+}
+
+extern "C" int rbpe_solve_many(rbpe_handle *h, const rbpe_problem *p, int count, int mode, rbpe_result *r) {
+    int rc = rbpe_upload(h, p, count);
+    if (rc) return rc;
+    if ((rc = rbpe_run(h, mode))) return rc;
+    return rbpe_download(h, r);
+}
+
+extern "C" int rbpe_solve(rbpe_handle *h, const rbpe_problem *p, rbpe_result *r) {
+    int base[2] = {0, 0};
+    if (!h) return RBPE_BAD_ARG;
+    if (!p || p->N <= 0 || !p->sfc_offs) return fail(h, RBPE_BAD_ARG, "bad problem");
+    rbpe_problem q = *p;
+    if (!q.sfc_base) {  // single mission: CSR offsets already absolute
+        base[1] = p->sfc_offs[p->N];
+        q.sfc_base = base;
+    }
+    return rbpe_solve_many(h, &q, 1, RBPE_MODE_GAUSS_SEIDEL, r);
+}
+
+extern "C" double *rbpe_device_ctrl(rbpe_handle *h) { return h ? h->ctrl.as<double>() : nullptr; }
+extern "C" double *rbpe_device_coef(rbpe_handle *h) { return h ? h->coef.as<double>() : nullptr; }
+extern "C" void *rbpe_stream(rbpe_handle *h) { return h ? (void *)h->stream : nullptr; }
+extern "C" int rbpe_sync(rbpe_handle *h) {
+    if (!h) return RBPE_BAD_ARG;
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    return RBPE_OK;
+}
+extern "C" int rbpe_last_timing(const rbpe_handle *h, rbpe_timing *t) {
+    if (!h || !t) return RBPE_BAD_ARG;
+    *t = h->timing;
+    return RBPE_OK;
+}

@@ -1,0 +1,997 @@
+// rbpe_kernels.cuh -- sm_100a kernels of the batched RBP trajectory-QP engine.
+//
+//   assemble_kernel  (k1)  constraint assembly: per-segment SFC box, per pair/segment RSFC normal, initial
+//                          control points, equality / cost / conversion constants
+//                          (rbp_planner.hpp build_Q_base..build_dummy, L327-L549)
+//   pdip_kernel      (k2)  one CTA per mission (Gauss-Seidel chain over its batches, L140-L201) or per
+//                          (mission, batch) (Jacobi): builds the batch QP of populatebyrow (L551-L688)
+//                          implicitly -- rows are never materialised as a matrix -- and solves it with a
+//                          Mehrotra predictor-corrector interior-point method in FP64:
+//                          H = 2Q + G'WG is block diagonal over segments (blocks of 18b), the Schur complement
+//                          S = A H^-1 A' is block tridiagonal over knots (blocks of 9b).
+//   convert_kernel   (k3)  Bernstein control points -> monomial coefficients (L167-L196, timeMatrix L695-L700)
+//
+// The same source compiles under tests/cpu_emu (a fiber emulator of the CUDA execution model used to debug the
+// kernel logic where no GPU exists); that harness is test infrastructure only and is never loaded by the product.
+#pragma once
+#include "rbpe_types.h"
+
+#ifndef RBPE_EMU
+#include <cuda_runtime.h>
+#define RBPE_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
+#include <math.h>
+
+namespace rbpe {
+
+// ------------------------------------------------------------------------------------------------------------
+// constants (build_Q_base, L327-L347): Q_base = 60^2 D3' G2 D3 (jerk Gram matrix in the quintic Bernstein basis),
+// basis[i][j] = coefficient of t^(5-j) in B_i^5(t).  Both are integer matrices; derived, not copied.
+// ------------------------------------------------------------------------------------------------------------
+__host__ __device__ inline double binom_d(int n, int k) {
+    double r = 1;
+    for (int i = 1; i <= k; i++) r = r * (n - k + i) / i;
+    return r;
+}
+__host__ __device__ inline double q_base_entry(int a, int b) {
+    // third forward difference rows r: (-1, 3, -3, 1) at columns r..r+3
+    double s = 0;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            int ca = a - i, cb = b - j;
+            if (ca < 0 || ca > 3 || cb < 0 || cb > 3) continue;
+            const double st[4] = {-1, 3, -3, 1};
+            double g2 = binom_d(2, i) * binom_d(2, j) / (5.0 * binom_d(4, i + j));
+            s += st[ca] * g2 * st[cb];
+        }
+    return rint(3600.0 * s);
+}
+__host__ __device__ inline double basis_entry(int i, int j) {  // coefficient of t^(5-j) in B_i^5
+    int pw = 5 - j, l = pw - i;
+    if (l < 0 || l > 5 - i) return 0.0;
+    return binom_d(5, i) * binom_d(5 - i, l) * ((l & 1) ? -1.0 : 1.0);
+}
+// i-th forward difference stencil at tau=0 / backward at tau=1 (A_0.row(i), A_T.row(i), L362-L374)
+__host__ __device__ inline double diff0_entry(int i, int c) {
+    if (c > i) return 0.0;
+    return binom_d(i, c) * (((i - c) & 1) ? -1.0 : 1.0);
+}
+__host__ __device__ inline double diffT_entry(int i, int c) {
+    int cc = c - (5 - i);
+    if (cc < 0 || cc > i) return 0.0;
+    return binom_d(i, cc) * (((i - cc) & 1) ? -1.0 : 1.0);
+}
+
+__host__ __device__ inline long pair_index(int N, int qi, int qj) {  // lexicographic qi<qj (`iter`, L477-L503)
+    return (long)qi * N - (long)qi * (qi + 1) / 2 + (qj - qi - 1);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// per-QP scratch size (doubles) for a batch of bs agents; must match Layout below
+// ------------------------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t al2(size_t nd) { return (nd + 1) & ~(size_t)1; }
+__host__ __device__ inline size_t scratch_doubles(int N, int M, int bs) {
+    size_t n = 18 * (size_t)bs, kb = 9 * (size_t)bs, nv = n * M, ne = kb * (M + 1);
+    size_t NE = (size_t)(N - bs > 0 ? N - bs : 0), rext = (size_t)bs * M * 6 * NE;
+    if (bs > 0 && N % bs) {  // the last, smaller batch sees more frozen agents
+        size_t nl = (size_t)(N % bs), rl = nl * M * 6 * (N - nl);
+        if (rl > rext) rext = rl;
+    }
+    size_t rint_ = (size_t)bs * (bs - 1) / 2 * 6 * M;
+    size_t t = 0;
+    t += 14 * al2(nv) + 5 * al2(ne);
+    t += al2((M + 1) * kb * kb) + al2(M * kb * kb);
+    t += 2 * al2(M * n * n);
+    t += 3 * al2(rext) + 3 * al2((rext + 1) / 2);
+    t += 3 * al2(rint_) + 3 * al2((rint_ + 1) / 2);
+    t += 64 + 36;
+    return t;
+}
+
+#ifdef __CUDACC__
+#define RBPE_DEV __device__ __forceinline__
+#else
+#define RBPE_DEV inline
+#endif
+
+#if defined(__CUDACC__) || defined(RBPE_EMU)
+
+// ------------------------------------------------------------------------------------------------------------
+// k1: assembly
+// ------------------------------------------------------------------------------------------------------------
+__global__ void assemble_kernel(AssembleArgs A) {
+    const int N = A.N, M = A.M;
+    const long P = (long)N * (N - 1) / 2;
+    const long per_box = N, per_rel = P * M, per_dummy = (long)N * 3 * 6 * M, per_seg = M;
+    const long per_mission = per_box + per_rel + per_dummy + per_seg;
+    const long total = per_mission * A.count;
+    for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
+        int c = (int)(g / per_mission);
+        long w = g - (long)c * per_mission;
+        const double *T = A.T + (size_t)c * (M + 1);
+        if (w < per_box) {
+            // build_dlq box part (L443-L474): first box whose end time >= T[m+1]; bi is monotone over m
+            int qi = (int)w;
+            const int *offs = A.sfc_offs + (size_t)c * (N + 1);
+            int base = A.sfc_base[c] + offs[qi], nb = offs[qi + 1] - offs[qi], bi = 0;
+            for (int m = 0; m < M; m++) {
+                while (bi < nb && A.sfc_t[base + bi] < T[m + 1]) bi++;
+                int b = bi;
+                if (b >= nb) { A.status[c] = ST_BAD_ARG; b = nb - 1; }
+                double *o = A.segbox + (((size_t)c * N + qi) * M + m) * 6;
+                for (int k = 0; k < 6; k++) o[k] = (b >= 0) ? A.sfc_box[(size_t)(base + b) * 6 + k] : 0.0;
+            }
+            continue;
+        }
+        w -= per_box;
+        if (w < per_rel) {
+            // build_dlq RSFC part (L476-L504): ri restarts from 0 for every segment
+            long it = w / M;
+            int m = (int)(w - it * M), ri = 0;
+            const double *rt = A.rsfc_t + ((size_t)c * P + it) * M;
+            while (ri < M && rt[ri] < T[m + 1]) ri++;
+            if (ri >= M) { A.status[c] = ST_BAD_ARG; ri = M - 1; }
+            const float *src = A.rsfc_n + (((size_t)c * P + it) * M + ri) * 3;
+            float *dst = A.reln + (((size_t)c * P + it) * M + m) * 3;
+            dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+            continue;
+        }
+        w -= per_rel;
+        if (w < per_dummy) {
+            // build_dummy (L513-L549): control points 0..2 = pi_m, 3..5 = pi_{m+1}; float32 promoted to double
+            int j = (int)(w % (6 * M));
+            long r = w / (6 * M);
+            int k = (int)(r % 3), qi = (int)(r / 3);
+            double v = 0.0;
+            if (A.sequential) {
+                int m = j / 6, i = j % 6, idx = m + ((i < 3) ? 0 : 1);
+                v = (double)A.init_traj[(((size_t)c * N + qi) * (M + 1) + idx) * 3 + k];
+            }
+            A.ctrl[(size_t)c * per_dummy + w] = v;
+            continue;
+        }
+        w -= per_dummy;
+        {
+            // per-segment constants: build_Aeq_base (L353-L405), build_Q_p (L349-L351), timeMatrix (L695-L700)
+            int m = (int)w;
+            double dt = T[m + 1] - T[m];
+            double *o = A.segmat + ((size_t)c * M + m) * SEGMAT;
+            double nn = 1;
+            for (int d = 0; d < 3; d++) {
+                double sc = pow(dt, (double)-d) * nn;
+                for (int i = 0; i < 6; i++) {
+                    o[SEGMAT_AL + d * 6 + i] = (m == 0 ? sc : -sc) * diff0_entry(d, i);
+                    o[SEGMAT_AR + d * 6 + i] = sc * diffT_entry(d, i);
+                }
+                nn = nn * (5 - d);
+            }
+            o[SEGMAT_QS] = pow(dt, -5.0);
+            for (int j = 0; j < 6; j++) o[SEGMAT_TP + j] = pow(1.0 / dt, (double)(5 - j));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// k3: conversion (L167-L196): c_j = sum_i ctrl_i * (basis[i][j] * (1/dt)^(5-j)), highest power first
+// ------------------------------------------------------------------------------------------------------------
+__global__ void convert_kernel(ConvertArgs A) {
+    const long per = (long)A.N * 3 * 6 * A.M, total = per * A.count;
+    for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
+        int c = (int)(g / per);
+        long w = g - (long)c * per;
+        int j = (int)(w % 6), m = (int)((w / 6) % A.M);
+        const double *src = A.ctrl + (size_t)c * per + (w - j);
+        const double *tp = A.segmat + ((size_t)c * A.M + m) * SEGMAT + SEGMAT_TP;
+        double s = 0;
+        for (int i = 0; i < 6; i++) s += src[i] * (basis_entry(i, j) * tp[j]);
+        A.coef[(size_t)c * per + w] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// k2: PDIP
+// ------------------------------------------------------------------------------------------------------------
+struct CtaTeam {
+    RBPE_DEV int rank() const { return threadIdx.x; }
+    RBPE_DEV int size() const { return blockDim.x; }
+    RBPE_DEV void sync() const { __syncthreads(); }
+};
+struct WarpTeam {
+    RBPE_DEV int rank() const { return threadIdx.x & 31; }
+    RBPE_DEV int size() const { return 32; }
+    RBPE_DEV void sync() const { __syncwarp(); }
+};
+
+// In-place lower Cholesky of a row-major n x n matrix (only the lower triangle is read or written).
+// Right-looking with deferred scaling: one team barrier per column.  Returns false on a non-positive pivot.
+template <class TM>
+RBPE_DEV bool chol_lower(TM tm, int n, double *A, int ld) {
+    bool ok = true;
+    for (int j = 0; j < n; j++) {
+        tm.sync();
+        double d = A[(size_t)j * ld + j];
+        if (!(d > 0)) { ok = false; d = 1.0; }
+        double inv = 1.0 / d;
+        int w = n - j - 1;
+        for (int idx = tm.rank(); idx < w * w; idx += tm.size()) {
+            int i = j + 1 + idx / w, k = j + 1 + idx % w;
+            if (k <= i) A[(size_t)i * ld + k] -= A[(size_t)i * ld + j] * A[(size_t)k * ld + j] * inv;
+        }
+    }
+    tm.sync();
+    for (int idx = tm.rank(); idx < n * n; idx += tm.size()) {
+        int i = idx / n, j = idx % n;
+        if (j < i) {
+            double d = A[(size_t)j * ld + j];
+            A[(size_t)i * ld + j] *= (d > 0) ? 1.0 / sqrt(d) : 0.0;
+        }
+    }
+    tm.sync();
+    for (int j = tm.rank(); j < n; j += tm.size()) {
+        double d = A[(size_t)j * ld + j];
+        A[(size_t)j * ld + j] = (d > 0) ? sqrt(d) : 1.0;
+    }
+    tm.sync();
+    return ok;
+}
+
+// u <- L^-1 u
+template <class TM>
+RBPE_DEV void fwd_vec(TM tm, int n, const double *L, int ld, double *u) {
+    for (int j = 0; j < n; j++) {
+        tm.sync();
+        double uj = u[j] / L[(size_t)j * ld + j];
+        for (int i = j + 1 + tm.rank(); i < n; i += tm.size()) u[i] -= L[(size_t)i * ld + j] * uj;
+    }
+    tm.sync();
+    for (int j = tm.rank(); j < n; j += tm.size()) u[j] /= L[(size_t)j * ld + j];
+    tm.sync();
+}
+// u <- L^-T u
+template <class TM>
+RBPE_DEV void bwd_vec(TM tm, int n, const double *L, int ld, double *u) {
+    for (int j = n - 1; j >= 0; j--) {
+        tm.sync();
+        double uj = u[j] / L[(size_t)j * ld + j];
+        for (int i = tm.rank(); i < j; i += tm.size()) u[i] -= L[(size_t)j * ld + i] * uj;
+    }
+    tm.sync();
+    for (int j = tm.rank(); j < n; j += tm.size()) u[j] /= L[(size_t)j * ld + j];
+    tm.sync();
+}
+// B (n x nc, row-major, ld = ldb) <- L^-1 B ; one thread per column, no barriers inside
+template <class TM>
+RBPE_DEV void trsm_cols(TM tm, int n, const double *L, int ld, int nc, double *B, int ldb, const int *first_row) {
+    for (int c = tm.rank(); c < nc; c += tm.size()) {
+        int r0 = first_row ? first_row[c] : 0;
+        for (int r = r0; r < n; r++) {
+            double v = B[(size_t)r * ldb + c];
+            const double *Lr = L + (size_t)r * ld;
+            for (int t = r0; t < r; t++) v -= Lr[t] * B[(size_t)t * ldb + c];
+            B[(size_t)r * ldb + c] = v / Lr[r];
+        }
+    }
+    tm.sync();
+}
+
+struct QP {
+    int N, M, nb, q0, NE, n, kb, nv, ne, nrext, nrint, mi;
+    int c;  // mission
+    const double *start, *goal, *radius, *segbox, *segmat;
+    const float *reln;
+    const double *ctrl_src;
+    // vectors (nv)
+    double *x, *dxa, *dx, *rd, *r1, *px, *ub, *lbn, *sub, *zub, *slb, *zlb, *vA, *vB;
+    // vectors (ne)
+    double *y, *dy, *rp, *r2, *beq;
+    double *Sd, *So, *H, *Y;
+    double *he, *se, *ze;
+    float *nex, *ney, *nez;
+    double *hi, *si, *zi;
+    float *nix, *niy, *niz;
+    double *red;  // 64 doubles
+    double *QB;   // 36 doubles: Q_base
+};
+
+struct Arena {
+    unsigned char *sm;
+    size_t sm_left;
+    double *gl;
+    RBPE_DEV double *take(size_t nd) {
+        nd = al2(nd);
+        size_t bytes = nd * 8;
+        if (bytes <= sm_left) {
+            double *p = (double *)sm;
+            sm += bytes;
+            sm_left -= bytes;
+            return p;
+        }
+        double *p = gl;
+        gl += nd;
+        return p;
+    }
+};
+
+RBPE_DEV void layout(QP &q, unsigned char *smem, size_t smem_bytes, double *gscratch) {
+    Arena a;
+    a.sm = smem;
+    a.sm_left = smem_bytes;
+    a.gl = gscratch;
+    q.red = a.take(64);
+    q.QB = a.take(36);
+    double **vv[14] = {&q.x, &q.dxa, &q.dx, &q.rd, &q.r1, &q.px, &q.ub, &q.lbn, &q.sub, &q.zub, &q.slb, &q.zlb, &q.vA, &q.vB};
+    for (int i = 0; i < 14; i++) *vv[i] = a.take(q.nv);
+    double **ee[5] = {&q.y, &q.dy, &q.rp, &q.r2, &q.beq};
+    for (int i = 0; i < 5; i++) *ee[i] = a.take(q.ne);
+    q.Sd = a.take((size_t)(q.M + 1) * q.kb * q.kb);
+    q.So = a.take((size_t)q.M * q.kb * q.kb);
+    q.H = a.take((size_t)q.M * q.n * q.n);
+    q.Y = a.take((size_t)q.M * q.n * q.n);
+    q.he = a.take(q.nrext); q.se = a.take(q.nrext); q.ze = a.take(q.nrext);
+    q.nex = (float *)a.take(((size_t)q.nrext + 1) / 2);
+    q.ney = (float *)a.take(((size_t)q.nrext + 1) / 2);
+    q.nez = (float *)a.take(((size_t)q.nrext + 1) / 2);
+    q.hi = a.take(q.nrint); q.si = a.take(q.nrint); q.zi = a.take(q.nrint);
+    q.nix = (float *)a.take(((size_t)q.nrint + 1) / 2);
+    q.niy = (float *)a.take(((size_t)q.nrint + 1) / 2);
+    q.niz = (float *)a.take(((size_t)q.nrint + 1) / 2);
+}
+
+template <class T>
+RBPE_DEV T shfl_down_t(T v, int o) { return __shfl_down_sync(0xffffffffu, v, o); }
+
+// CTA-wide reduction of (sum, sum, max, min); every thread returns the same values (fixed summation order).
+RBPE_DEV void block_reduce4(double &s1, double &s2, double &mx, double &mn, double *red) {
+    for (int o = 16; o > 0; o >>= 1) {
+        s1 += shfl_down_t(s1, o);
+        s2 += shfl_down_t(s2, o);
+        mx = fmax(mx, shfl_down_t(mx, o));
+        mn = fmin(mn, shfl_down_t(mn, o));
+    }
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (l == 0) { red[w * 4 + 0] = s1; red[w * 4 + 1] = s2; red[w * 4 + 2] = mx; red[w * 4 + 3] = mn; }
+    __syncthreads();
+    s1 = 0; s2 = 0; mx = -1e300; mn = 1e300;
+    for (int i = 0; i < nw; i++) {
+        s1 += red[i * 4 + 0]; s2 += red[i * 4 + 1];
+        mx = fmax(mx, red[i * 4 + 2]); mn = fmin(mn, red[i * 4 + 3]);
+    }
+}
+
+enum { P_INIT = 0, P_START, P_SHIFT, P_RES, P_AFF, P_MUA, P_COR, P_STEP, P_UPD };
+
+struct Acc {  // lane-local reductions of a row pass
+    double s1, s2, mx, mn;
+};
+
+// One inequality row.  in: h, s, z, gx = g.x, ga = g.dx_aff, gd = g.dx.  sa/sb: pass scalars.
+// out: cA, cB (coefficients of g in the two G' products), w (weight of g g' in H); s, z may be rewritten.
+template <int MODE>
+RBPE_DEV void row_eval(double h, double &s, double &z, double gx, double ga, double gd, double sa, double sb,
+                       bool owner, double &cA, double &cB, double &w, Acc &acc) {
+    cA = 0; cB = 0; w = 0;
+    if (MODE == P_INIT) { w = 1.0; cA = h; return; }
+    if (MODE == P_START) {  // z = Gx - h, s = -z (least-squares start)
+        z = gx - h; s = -z;
+        if (owner) { acc.mx = fmax(acc.mx, -s); acc.s1 = fmax(acc.s1, -z); }  // s1 doubles as a second max here
+        return;
+    }
+    if (MODE == P_SHIFT) { s += sa; z += sb; return; }
+    double rg = gx + s - h;
+    w = z / s;
+    if (MODE == P_RES) {
+        cA = z;
+        cB = -(w * rg - z);
+        if (owner) { acc.s1 += s * z; acc.s2 += h * z; acc.mx = fmax(acc.mx, fabs(rg)); }
+        return;
+    }
+    double dsa = -rg - ga, dza = -z - w * dsa;
+    if (MODE == P_AFF) {
+        if (dsa < 0) acc.mn = fmin(acc.mn, -s / dsa);
+        if (dza < 0) acc.mn = fmin(acc.mn, -z / dza);
+        return;
+    }
+    if (MODE == P_MUA) {
+        if (owner) acc.s1 += (s + sa * dsa) * (z + sa * dza);
+        return;
+    }
+    double rc = s * z + dsa * dza - sa;  // sa = sigma * mu
+    if (MODE == P_COR) { cA = -(z * rg - rc) / s; return; }
+    double ds = -rg - gd, dz = (-rc - z * ds) / s;
+    if (MODE == P_STEP) {
+        if (ds < 0) acc.mn = fmin(acc.mn, -s / ds);
+        if (dz < 0) acc.mn = fmin(acc.mn, -z / dz);
+        return;
+    }
+    if (MODE == P_UPD) { s += sb * ds; z += sb * dz; }  // sb = step length
+}
+
+// All inequality rows touching control point (m, a, i) of the batch, executed by one warp.
+template <int MODE>
+RBPE_DEV void cp_task(const QP &q, int m, int a, int i, double sa, double sb, Acc &acc) {
+    constexpr bool WR = (MODE == P_START || MODE == P_SHIFT || MODE == P_UPD);
+    constexpr bool VEC = (MODE == P_INIT || MODE == P_RES || MODE == P_COR);
+    constexpr bool MAT = (MODE == P_INIT || MODE == P_RES);
+    const int lane = threadIdx.x & 31;
+    const int base = m * q.n, v0 = base + a * 18 + i;
+    double x0 = q.x[v0], x1 = q.x[v0 + 6], x2 = q.x[v0 + 12];
+    double a0 = q.dxa[v0], a1 = q.dxa[v0 + 6], a2 = q.dxa[v0 + 12];
+    double d0 = q.dx[v0], d1 = q.dx[v0 + 6], d2 = q.dx[v0 + 12];
+    double vA0 = 0, vA1 = 0, vA2 = 0, vB0 = 0, vB1 = 0, vB2 = 0;
+    double Dxx = 0, Dxy = 0, Dxz = 0, Dyy = 0, Dyz = 0, Dzz = 0;
+    // rows against agents outside the batch (L643-L668)
+    {
+        const size_t rb = ((size_t)(a * q.M + m) * 6 + i) * q.NE;
+        for (int e = lane; e < q.NE; e += 32) {
+            size_t r = rb + e;
+            double n0 = q.nex[r], n1 = q.ney[r], n2 = q.nez[r];
+            double h = q.he[r], s = q.se[r], z = q.ze[r], cA, cB, w;
+            row_eval<MODE>(h, s, z, n0 * x0 + n1 * x1 + n2 * x2, n0 * a0 + n1 * a1 + n2 * a2,
+                           n0 * d0 + n1 * d1 + n2 * d2, sa, sb, true, cA, cB, w, acc);
+            if (WR) { q.se[r] = s; q.ze[r] = z; }
+            if (VEC) { vA0 += cA * n0; vA1 += cA * n1; vA2 += cA * n2; vB0 += cB * n0; vB1 += cB * n1; vB2 += cB * n2; }
+            if (MAT) {
+                Dxx += w * n0 * n0; Dxy += w * n0 * n1; Dxz += w * n0 * n2;
+                Dyy += w * n1 * n1; Dyz += w * n1 * n2; Dzz += w * n2 * n2;
+            }
+        }
+    }
+    // rows between two agents of the batch (L669-L680); evaluated from both ends, owned by the lower index
+    for (int o = lane; o < q.nb; o += 32) {
+        if (o == a) continue;
+        int lo = a < o ? a : o, hi = a < o ? o : a;
+        size_t r = ((size_t)lo * q.nb - (size_t)lo * (lo + 1) / 2 + (hi - lo - 1)) * 6 * q.M + m * 6 + i;
+        double sg = (a == lo) ? 1.0 : -1.0;
+        double n0 = sg * q.nix[r], n1 = sg * q.niy[r], n2 = sg * q.niz[r];
+        int vo = base + o * 18 + i;
+        double gx = n0 * (x0 - q.x[vo]) + n1 * (x1 - q.x[vo + 6]) + n2 * (x2 - q.x[vo + 12]);
+        double ga = n0 * (a0 - q.dxa[vo]) + n1 * (a1 - q.dxa[vo + 6]) + n2 * (a2 - q.dxa[vo + 12]);
+        double gd = n0 * (d0 - q.dx[vo]) + n1 * (d1 - q.dx[vo + 6]) + n2 * (d2 - q.dx[vo + 12]);
+        double h = q.hi[r], s = q.si[r], z = q.zi[r], cA, cB, w;
+        bool own = (a == lo);
+        row_eval<MODE>(h, s, z, gx, ga, gd, sa, sb, own, cA, cB, w, acc);
+        if (WR && own) { q.si[r] = s; q.zi[r] = z; }
+        if (VEC) { vA0 += cA * n0; vA1 += cA * n1; vA2 += cA * n2; vB0 += cB * n0; vB1 += cB * n1; vB2 += cB * n2; }
+        if (MAT) {
+            Dxx += w * n0 * n0; Dxy += w * n0 * n1; Dxz += w * n0 * n2;
+            Dyy += w * n1 * n1; Dyz += w * n1 * n2; Dzz += w * n2 * n2;
+            if (own) {  // off-diagonal block H[(hi,k,i),(lo,k',i)] = -w n_k n_k'
+                double *Hm = q.H + (size_t)m * q.n * q.n;
+                double nn[3] = {n0, n1, n2};
+                for (int k = 0; k < 3; k++)
+                    for (int kk = 0; kk < 3; kk++)
+                        Hm[(size_t)(hi * 18 + k * 6 + i) * q.n + (lo * 18 + kk * 6 + i)] = -w * nn[k] * nn[kk];
+            }
+        }
+    }
+    // box rows (L626-L635): x <= ub, -x <= -lb
+    if (lane < 3) {
+        int v = v0 + 6 * lane;
+        double xk = lane == 0 ? x0 : (lane == 1 ? x1 : x2);
+        double ak = lane == 0 ? a0 : (lane == 1 ? a1 : a2);
+        double dk = lane == 0 ? d0 : (lane == 1 ? d1 : d2);
+        double cA, cB, w, s, z, tA = 0, tB = 0, tw = 0;
+        s = q.sub[v]; z = q.zub[v];
+        row_eval<MODE>(q.ub[v], s, z, xk, ak, dk, sa, sb, true, cA, cB, w, acc);
+        if (WR) { q.sub[v] = s; q.zub[v] = z; }
+        tA += cA; tB += cB; tw += w;
+        s = q.slb[v]; z = q.zlb[v];
+        row_eval<MODE>(q.lbn[v], s, z, -xk, -ak, -dk, sa, sb, true, cA, cB, w, acc);
+        if (WR) { q.slb[v] = s; q.zlb[v] = z; }
+        tA -= cA; tB -= cB; tw += w;
+        if (lane == 0) { vA0 += tA; vB0 += tB; Dxx += tw; }
+        if (lane == 1) { vA1 += tA; vB1 += tB; Dyy += tw; }
+        if (lane == 2) { vA2 += tA; vB2 += tB; Dzz += tw; }
+    }
+    if (VEC) {
+        for (int o = 16; o > 0; o >>= 1) {
+            vA0 += shfl_down_t(vA0, o); vA1 += shfl_down_t(vA1, o); vA2 += shfl_down_t(vA2, o);
+            if (MODE == P_RES) { vB0 += shfl_down_t(vB0, o); vB1 += shfl_down_t(vB1, o); vB2 += shfl_down_t(vB2, o); }
+        }
+        if (lane == 0) {
+            q.vA[v0] = vA0; q.vA[v0 + 6] = vA1; q.vA[v0 + 12] = vA2;
+            if (MODE == P_RES) { q.vB[v0] = vB0; q.vB[v0 + 6] = vB1; q.vB[v0 + 12] = vB2; }
+        }
+    }
+    if (MAT) {
+        for (int o = 16; o > 0; o >>= 1) {
+            Dxx += shfl_down_t(Dxx, o); Dxy += shfl_down_t(Dxy, o); Dxz += shfl_down_t(Dxz, o);
+            Dyy += shfl_down_t(Dyy, o); Dyz += shfl_down_t(Dyz, o); Dzz += shfl_down_t(Dzz, o);
+        }
+        if (lane == 0) {
+            double *Hm = q.H + (size_t)m * q.n * q.n;
+            int r0 = a * 18 + i, r1 = r0 + 6, r2 = r0 + 12;
+            Hm[(size_t)r0 * q.n + r0] += Dxx;
+            Hm[(size_t)r1 * q.n + r0] += Dxy; Hm[(size_t)r1 * q.n + r1] += Dyy;
+            Hm[(size_t)r2 * q.n + r0] += Dxz; Hm[(size_t)r2 * q.n + r1] += Dyz; Hm[(size_t)r2 * q.n + r2] += Dzz;
+        }
+    }
+}
+
+// H <- 2 Q (lower triangle), zero elsewhere in the lower triangle
+RBPE_DEV void init_H(const QP &q) {
+    const size_t nn = (size_t)q.n * q.n;
+    for (size_t idx = threadIdx.x; idx < nn * q.M; idx += blockDim.x) {
+        int m = (int)(idx / nn);
+        int r = (int)((idx - m * nn) / q.n), c = (int)((idx - m * nn) % q.n);
+        double v = 0;
+        if (c <= r && r / 6 == c / 6) v = 2.0 * q.QB[(r % 6) * 6 + c % 6] * q.segmat[m * SEGMAT + SEGMAT_QS];
+        q.H[idx] = v;
+    }
+}
+
+template <int MODE>
+RBPE_DEV void row_pass(const QP &q, double sa, double sb, Acc &out) {
+    Acc acc;
+    acc.s1 = (MODE == P_START) ? -1e300 : 0.0;
+    acc.s2 = 0; acc.mx = -1e300; acc.mn = 1e300;
+    if (MODE == P_INIT || MODE == P_RES) { init_H(q); __syncthreads(); }
+    const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5, ntask = q.M * q.nb * 6;
+    for (int t = warp; t < ntask; t += nw) {
+        int i = t % 6, a = (t / 6) % q.nb, m = t / (6 * q.nb);
+        cp_task<MODE>(q, m, a, i, sa, sb, acc);
+    }
+    if (MODE == P_START) {  // two max reductions: mx and s1
+        double m2 = acc.s1, z0 = 0, mn = 1e300, s1 = 0;
+        block_reduce4(s1, z0, acc.mx, mn, q.red);
+        double mx2 = m2; s1 = 0; z0 = 0; mn = 1e300;
+        block_reduce4(s1, z0, mx2, mn, q.red);
+        out.mx = acc.mx; out.s1 = mx2; out.s2 = 0; out.mn = 0;
+        return;
+    }
+    block_reduce4(acc.s1, acc.s2, acc.mx, acc.mn, q.red);
+    out = acc;
+}
+
+// ---- linear algebra on the reduced KKT system ----------------------------------------------------------------
+// factor: H_m = L_m L_m' ; Y_m = L_m^-1 A_m' ; S = Y'Y (block tridiagonal) ; S = Ls Ls'
+template <class TM>
+RBPE_DEV bool factor_seg(TM tm, const QP &q, int m) {
+    double *Hm = q.H + (size_t)m * q.n * q.n, *Ym = q.Y + (size_t)m * q.n * q.n;
+    const double *sm = q.segmat + m * SEGMAT;
+    const int n = q.n, kb = q.kb;
+    // Y_m = A_m' : rows = variables (a,k,i), columns = (side, (a,k), d)
+    for (int idx = tm.rank(); idx < n * n; idx += tm.size()) {
+        int r = idx / n, c = idx % n, side = c / kb, cc = c % kb;
+        double v = 0;
+        if (cc / 3 == r / 6) v = sm[(side ? SEGMAT_AR : SEGMAT_AL) + (cc % 3) * 6 + (r % 6)];
+        Ym[idx] = v;
+    }
+    bool ok = chol_lower(tm, n, Hm, n);
+    trsm_cols(tm, n, Hm, n, n, Ym, n, (const int *)0);
+    return ok;
+}
+
+RBPE_DEV void build_S(const QP &q) {
+    const int n = q.n, kb = q.kb, M = q.M;
+    const int kk = kb * kb;
+    for (int idx = threadIdx.x; idx < (2 * M + 1) * kk; idx += blockDim.x) {
+        int blk = idx / kk, r = (idx % kk) / kb, c = idx % kb;
+        if (blk <= M) {  // diagonal block of knot t = blk (lower triangle)
+            int t = blk;
+            double s = 0;
+            if (c <= r) {
+                if (t > 0) {
+                    const double *Y = q.Y + (size_t)(t - 1) * n * n + kb;
+                    for (int k = 0; k < n; k++) s += Y[(size_t)k * n + r] * Y[(size_t)k * n + c];
+                }
+                if (t < M) {
+                    const double *Y = q.Y + (size_t)t * n * n;
+                    for (int k = 0; k < n; k++) s += Y[(size_t)k * n + r] * Y[(size_t)k * n + c];
+                }
+            }
+            q.Sd[(size_t)t * kk + r * kb + c] = s;
+        } else {  // block (t+1, t): rows = right columns of segment t, cols = left columns of segment t
+            int t = blk - M - 1;
+            const double *Y = q.Y + (size_t)t * n * n;
+            double s = 0;
+            for (int k = 0; k < n; k++) s += Y[(size_t)k * n + kb + r] * Y[(size_t)k * n + c];
+            q.So[(size_t)t * kk + r * kb + c] = s;
+        }
+    }
+}
+
+template <class TM>
+RBPE_DEV bool factor_S(TM tm, const QP &q) {
+    const int kb = q.kb, M = q.M, kk = kb * kb;
+    bool ok = true;
+    for (int t = 0; t <= M; t++) {
+        double *D = q.Sd + (size_t)t * kk;
+        if (t > 0) {
+            const double *Lo = q.So + (size_t)(t - 1) * kk;
+            for (int idx = tm.rank(); idx < kk; idx += tm.size()) {
+                int r = idx / kb, c = idx % kb;
+                if (c <= r) {
+                    double s = 0;
+                    for (int k = 0; k < kb; k++) s += Lo[r * kb + k] * Lo[c * kb + k];
+                    D[idx] -= s;
+                }
+            }
+        }
+        ok = chol_lower(tm, kb, D, kb) && ok;
+        if (t < M) {  // Lo_t = So_t D^-T : row-wise forward substitution, one thread per row
+            double *O = q.So + (size_t)t * kk;
+            for (int r = tm.rank(); r < kb; r += tm.size()) {
+                for (int c = 0; c < kb; c++) {
+                    double v = O[r * kb + c];
+                    for (int k = 0; k < c; k++) v -= O[r * kb + k] * D[c * kb + k];
+                    O[r * kb + c] = v / D[c * kb + c];
+                }
+            }
+            tm.sync();
+        }
+    }
+    return ok;
+}
+
+template <class TM>
+RBPE_DEV void solve_S(TM tm, const QP &q, double *g) {
+    const int kb = q.kb, M = q.M, kk = kb * kb;
+    for (int t = 0; t <= M; t++) {
+        if (t > 0) {
+            const double *Lo = q.So + (size_t)(t - 1) * kk;
+            for (int r = tm.rank(); r < kb; r += tm.size()) {
+                double s = 0;
+                for (int k = 0; k < kb; k++) s += Lo[r * kb + k] * g[(t - 1) * kb + k];
+                g[t * kb + r] -= s;
+            }
+        }
+        fwd_vec(tm, kb, q.Sd + (size_t)t * kk, kb, g + t * kb);
+    }
+    for (int t = M; t >= 0; t--) {
+        if (t < M) {
+            const double *Lo = q.So + (size_t)t * kk;
+            for (int c = tm.rank(); c < kb; c += tm.size()) {
+                double s = 0;
+                for (int k = 0; k < kb; k++) s += Lo[k * kb + c] * g[(t + 1) * kb + k];
+                g[t * kb + c] -= s;
+            }
+        }
+        bwd_vec(tm, kb, q.Sd + (size_t)t * kk, kb, g + t * kb);
+    }
+}
+
+RBPE_DEV bool kkt_factor(const QP &q) {
+    const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    bool ok = true;
+    __syncthreads();
+    if (q.n <= 72) {
+        for (int m = warp; m < q.M; m += nw) ok = factor_seg(WarpTeam(), q, m) && ok;
+    } else {
+        for (int m = 0; m < q.M; m++) ok = factor_seg(CtaTeam(), q, m) && ok;
+    }
+    __syncthreads();
+    build_S(q);
+    __syncthreads();
+    if (q.kb <= 36) {
+        if (warp == 0) ok = factor_S(WarpTeam(), q) && ok;
+    } else {
+        ok = factor_S(CtaTeam(), q) && ok;
+    }
+    // combine the verdict over the CTA
+    double s1 = ok ? 0.0 : 1.0, s2 = 0, mx = -1e300, mn = 1e300;
+    block_reduce4(s1, s2, mx, mn, q.red);
+    return s1 == 0.0;
+}
+
+// solve  H dx + A' dy = r1 ; A dx = r2.  u (nv) holds r1 on entry and dx on exit; g (ne) holds r2 on entry, dy on exit.
+RBPE_DEV void kkt_solve(const QP &q, double *u, double *g) {
+    const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5, n = q.n, kb = q.kb, M = q.M;
+    __syncthreads();
+    if (n <= 72) {
+        for (int m = warp; m < M; m += nw) fwd_vec(WarpTeam(), n, q.H + (size_t)m * n * n, n, u + m * n);
+    } else {
+        for (int m = 0; m < M; m++) fwd_vec(CtaTeam(), n, q.H + (size_t)m * n * n, n, u + m * n);
+    }
+    __syncthreads();
+    // g_t = YR_{t-1}' u_{t-1} + YL_t' u_t - r2_t
+    for (int e = threadIdx.x; e < q.ne; e += blockDim.x) {
+        int t = e / kb, c = e % kb;
+        double s = 0;
+        if (t > 0) {
+            const double *Y = q.Y + (size_t)(t - 1) * n * n + kb + c, *uu = u + (t - 1) * n;
+            for (int k = 0; k < n; k++) s += Y[(size_t)k * n] * uu[k];
+        }
+        if (t < M) {
+            const double *Y = q.Y + (size_t)t * n * n + c, *uu = u + t * n;
+            for (int k = 0; k < n; k++) s += Y[(size_t)k * n] * uu[k];
+        }
+        g[e] = s - g[e];
+    }
+    __syncthreads();
+    if (kb <= 36) {
+        if (warp == 0) solve_S(WarpTeam(), q, g);
+    } else {
+        solve_S(CtaTeam(), q, g);
+    }
+    __syncthreads();
+    // u -= Y dy
+    for (int v = threadIdx.x; v < q.nv; v += blockDim.x) {
+        int m = v / n, r = v % n;
+        const double *Yr = q.Y + (size_t)m * n * n + (size_t)r * n, *gl = g + m * kb;
+        double s = 0;
+        for (int c = 0; c < 2 * kb; c++) s += Yr[c] * gl[c];  // left knot m then right knot m+1 are contiguous in g
+        u[v] -= s;
+    }
+    __syncthreads();
+    if (n <= 72) {
+        for (int m = warp; m < M; m += nw) bwd_vec(WarpTeam(), n, q.H + (size_t)m * n * n, n, u + m * n);
+    } else {
+        for (int m = 0; m < M; m++) bwd_vec(CtaTeam(), n, q.H + (size_t)m * n * n, n, u + m * n);
+    }
+    __syncthreads();
+}
+
+// px = P x = 2 Q x ; returns nothing (reductions done by the caller)
+RBPE_DEV void apply_P(const QP &q, const double *x, double *px) {
+    for (int v = threadIdx.x; v < q.nv; v += blockDim.x) {
+        int m = v / q.n, i = v % 6, b6 = v - i;
+        double s = 0;
+        for (int j = 0; j < 6; j++) s += q.QB[i * 6 + j] * x[b6 + j];
+        px[v] = 2.0 * q.segmat[m * SEGMAT + SEGMAT_QS] * s;
+    }
+}
+// out[v] += (A'y)[v]
+RBPE_DEV double At_y(const QP &q, const double *y, int v) {
+    int m = v / q.n, r = v % q.n, ak = r / 6, i = r % 6;
+    const double *sm = q.segmat + m * SEGMAT;
+    const double *yl = y + m * q.kb + ak * 3, *yr = yl + q.kb;
+    double s = 0;
+    for (int d = 0; d < 3; d++) s += sm[SEGMAT_AL + d * 6 + i] * yl[d] + sm[SEGMAT_AR + d * 6 + i] * yr[d];
+    return s;
+}
+// (A x)[e]
+RBPE_DEV double A_x(const QP &q, const double *x, int e) {
+    int t = e / q.kb, cc = e % q.kb, ak = cc / 3, d = cc % 3;
+    double s = 0;
+    if (t < q.M) {
+        const double *sm = q.segmat + t * SEGMAT + SEGMAT_AL + d * 6, *xx = x + t * q.n + ak * 6;
+        for (int i = 0; i < 6; i++) s += sm[i] * xx[i];
+    }
+    if (t > 0) {
+        const double *sm = q.segmat + (t - 1) * SEGMAT + SEGMAT_AR + d * 6, *xx = x + (t - 1) * q.n + ak * 6;
+        for (int i = 0; i < 6; i++) s += sm[i] * xx[i];
+    }
+    return s;
+}
+
+// rows of populatebyrow for the batch starting at agent q0 (h, normals; s = z = 1 until the start point is known)
+RBPE_DEV void setup_rows(const QP &q) {
+    const int M = q.M, N = q.N;
+    // box bounds per variable (L626-L635) and equality right-hand sides (build_deq L408-L432)
+    for (int v = threadIdx.x; v < q.nv; v += blockDim.x) {
+        int m = v / q.n, r = v % q.n, a = r / 18, k = (r % 18) / 6;
+        const double *box = q.segbox + ((size_t)(q.q0 + a) * M + m) * 6;
+        q.ub[v] = box[3 + k];
+        q.lbn[v] = -box[k];
+        q.sub[v] = 1; q.zub[v] = 1; q.slb[v] = 1; q.zlb[v] = 1;
+        q.x[v] = 0; q.dxa[v] = 0; q.dx[v] = 0;
+    }
+    for (int e = threadIdx.x; e < q.ne; e += blockDim.x) {
+        int t = e / q.kb, cc = e % q.kb, a = cc / 9, k = (cc % 9) / 3, d = cc % 3;
+        double v = 0;
+        if (t == 0) v = q.start[(size_t)(q.q0 + a) * 9 + k + 3 * d];
+        if (t == M) v = q.goal[(size_t)(q.q0 + a) * 9 + k + 3 * d];
+        q.beq[e] = v;
+        q.y[e] = 0;
+    }
+    // RSFC rows against frozen agents: g = sg*n on x_a,  h = sg*n.dummy_other - (r_a + r_other)
+    for (int r = threadIdx.x; r < q.nrext; r += blockDim.x) {
+        int e = r % q.NE, rest = r / q.NE, i = rest % 6, m = (rest / 6) % M, a = rest / (6 * M);
+        int qa = q.q0 + a, qo = (e < q.q0) ? e : e + q.nb;
+        double sg = (qa < qo) ? 1.0 : -1.0;
+        long it = (qa < qo) ? pair_index(N, qa, qo) : pair_index(N, qo, qa);
+        const float *nf = q.reln + ((size_t)it * M + m) * 3;
+        float f0 = nf[0], f1 = nf[1], f2 = nf[2];
+        const double *co = q.ctrl_src + (size_t)qo * 18 * M + m * 6 + i;
+        double h = -(q.radius[qa] + q.radius[qo]);
+        h += sg * ((double)f0 * co[0]);
+        h += sg * ((double)f1 * co[6 * M]);
+        h += sg * ((double)f2 * co[12 * M]);
+        if (sg < 0) { f0 = -f0; f1 = -f1; f2 = -f2; }
+        q.nex[r] = f0; q.ney[r] = f1; q.nez[r] = f2;
+        q.he[r] = h; q.se[r] = 1; q.ze[r] = 1;
+    }
+    // RSFC rows between two batch agents lo<hi: n.x_lo - n.x_hi <= -(r_lo + r_hi)
+    for (int r = threadIdx.x; r < q.nrint; r += blockDim.x) {
+        int j = r % (6 * M), pp = r / (6 * M), m = j / 6;
+        int lo = 0, rem = pp;
+        while (rem >= q.nb - 1 - lo) { rem -= q.nb - 1 - lo; lo++; }
+        int hi = lo + 1 + rem;
+        long it = pair_index(N, q.q0 + lo, q.q0 + hi);
+        const float *nf = q.reln + ((size_t)it * M + m) * 3;
+        q.nix[r] = nf[0]; q.niy[r] = nf[1]; q.niz[r] = nf[2];
+        q.hi[r] = -(q.radius[q.q0 + lo] + q.radius[q.q0 + hi]);
+        q.si[r] = 1; q.zi[r] = 1;
+    }
+}
+
+// Solves the QP described by q. Returns status; x holds the solution.
+RBPE_DEV int pdip_solve(const QP &q, int max_iter, double tol_gap, double tol_res, double *obj_out, int *it_out,
+                        double *res_out) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    Acc acc;
+    setup_rows(q);
+    __syncthreads();
+    // |b|, |h| norms for the relative tolerances
+    double bn, hn;
+    {
+        double s1 = 0, s2 = 0, mx = -1e300, mn = 1e300, mh = 0;
+        for (int e = tid; e < q.ne; e += nt) mx = fmax(mx, fabs(q.beq[e]));
+        for (int v = tid; v < q.nv; v += nt) mh = fmax(mh, fmax(fabs(q.ub[v]), fabs(q.lbn[v])));
+        for (int r = tid; r < q.nrext; r += nt) mh = fmax(mh, fabs(q.he[r]));
+        for (int r = tid; r < q.nrint; r += nt) mh = fmax(mh, fabs(q.hi[r]));
+        mx = fmax(mx, 0.0);
+        block_reduce4(s1, s2, mx, mn, q.red);
+        bn = mx;
+        s1 = 0; s2 = 0; mn = 1e300;
+        block_reduce4(s1, s2, mh, mn, q.red);
+        hn = mh;
+    }
+    int status = ST_NOT_CONVERGED, it = 0;
+    double obj = 0, gap = 0, nrp = 0, nrd = 0, nrg = 0;
+
+    // ---- initial point: W = I, [H A'; A 0][x; y] = [G'h; b] ----
+    row_pass<P_INIT>(q, 0, 0, acc);
+    __syncthreads();
+    bool fok = kkt_factor(q);
+    if (fok) {
+        for (int v = tid; v < q.nv; v += nt) q.r1[v] = q.vA[v];
+        for (int e = tid; e < q.ne; e += nt) q.r2[e] = q.beq[e];
+        kkt_solve(q, q.r1, q.r2);
+        for (int v = tid; v < q.nv; v += nt) q.x[v] = q.r1[v];
+        for (int e = tid; e < q.ne; e += nt) q.y[e] = q.r2[e];
+        __syncthreads();
+        row_pass<P_START>(q, 0, 0, acc);  // acc.mx = max(-s), acc.s1 = max(-z)
+        double ap = acc.mx, ad = acc.s1;
+        __syncthreads();
+        row_pass<P_SHIFT>(q, ap >= 0 ? 1.0 + ap : 0.0, ad >= 0 ? 1.0 + ad : 0.0, acc);
+        __syncthreads();
+    }
+
+    for (it = 0; fok && it < max_iter; it++) {
+        // ---- residuals ----
+        apply_P(q, q.x, q.px);
+        __syncthreads();
+        row_pass<P_RES>(q, 0, 0, acc);  // vA = G'z, vB = G't_aff, H assembled; s1 = s'z, s2 = h'z, mx = |rg|
+        __syncthreads();
+        double mu = acc.s1 / (q.mi > 0 ? q.mi : 1), hz = acc.s2;
+        nrg = fmax(acc.mx, 0.0);
+        double s1 = 0, s2 = 0, mx = 0, mn = 1e300, mpx = 0, mcert = 0, mrp = 0;
+        for (int v = tid; v < q.nv; v += nt) {
+            double aty = At_y(q, q.y, v), pxv = q.px[v];
+            double rdv = pxv + aty + q.vA[v];
+            q.rd[v] = rdv;
+            s1 += 0.5 * q.x[v] * pxv;
+            mx = fmax(mx, fabs(rdv));
+            mpx = fmax(mpx, fabs(pxv));
+            mcert = fmax(mcert, fabs(aty + q.vA[v]));
+        }
+        for (int e = tid; e < q.ne; e += nt) {
+            double r = A_x(q, q.x, e) - q.beq[e];
+            q.rp[e] = r;
+            mrp = fmax(mrp, fabs(r));
+            s2 += q.beq[e] * q.y[e];
+        }
+        block_reduce4(s1, s2, mx, mn, q.red);
+        obj = s1; hz += s2; nrd = mx;
+        {
+            double t1 = 0, t2 = 0, m2 = mpx, n2 = 1e300;
+            block_reduce4(t1, t2, m2, n2, q.red);
+            mpx = m2;
+            t1 = 0; t2 = 0; m2 = mcert; n2 = 1e300;
+            block_reduce4(t1, t2, m2, n2, q.red);
+            mcert = m2;
+            t1 = 0; t2 = 0; m2 = mrp; n2 = 1e300;
+            block_reduce4(t1, t2, m2, n2, q.red);
+            nrp = m2;
+        }
+        gap = mu;
+        if (!(mu == mu) || !(nrd == nrd)) { status = ST_NOT_CONVERGED; break; }
+        if (gap <= tol_gap * fmax(1.0, fabs(obj)) && nrp <= tol_res * (1 + bn) && nrg <= tol_res * (1 + hn) &&
+            nrd <= tol_res * (1.0 + mpx)) {
+            status = ST_OK;
+            break;
+        }
+        if (hz < 0 && mcert / (-hz) < 1e-8) { status = ST_INFEASIBLE; break; }  // Farkas certificate
+        // ---- factor with W = z/s (H was assembled by the residual pass) ----
+        if (!kkt_factor(q)) { status = ST_NOT_CONVERGED; break; }
+        // ---- affine direction ----
+        for (int v = tid; v < q.nv; v += nt) q.dxa[v] = -q.rd[v] + q.vB[v];
+        for (int e = tid; e < q.ne; e += nt) q.r2[e] = -q.rp[e];
+        kkt_solve(q, q.dxa, q.r2);
+        row_pass<P_AFF>(q, 0, 0, acc);
+        double aa = fmin(1.0, acc.mn);
+        __syncthreads();
+        row_pass<P_MUA>(q, aa, 0, acc);
+        double mua = acc.s1 / (q.mi > 0 ? q.mi : 1);
+        double sigma = (mu > 0) ? (mua / mu) * (mua / mu) * (mua / mu) : 0.0;
+        __syncthreads();
+        // ---- corrector ----
+        row_pass<P_COR>(q, sigma * mu, 0, acc);
+        __syncthreads();
+        for (int v = tid; v < q.nv; v += nt) q.dx[v] = -q.rd[v] + q.vA[v];
+        for (int e = tid; e < q.ne; e += nt) q.dy[e] = -q.rp[e];
+        kkt_solve(q, q.dx, q.dy);
+        row_pass<P_STEP>(q, sigma * mu, 0, acc);
+        double al = fmin(1.0, 0.99 * acc.mn);
+        __syncthreads();
+        row_pass<P_UPD>(q, sigma * mu, al, acc);
+        __syncthreads();
+        for (int v = tid; v < q.nv; v += nt) q.x[v] += al * q.dx[v];
+        for (int e = tid; e < q.ne; e += nt) q.y[e] += al * q.dy[e];
+        __syncthreads();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        *obj_out = obj;
+        *it_out = it;
+        res_out[0] = gap; res_out[1] = nrp; res_out[2] = nrd; res_out[3] = nrg;
+    }
+    return status;
+}
+
+__global__ void __launch_bounds__(CTA_THREADS) pdip_kernel(SolveArgs S) {
+    RBPE_DYN_SMEM(smem);
+    const int N = S.N, M = S.M;
+    int c, l_begin, l_end;
+    if (S.mode == 0) {
+        c = blockIdx.x; l_begin = 0; l_end = S.nbatch;
+    } else {
+        int per = S.batch_end - S.batch_begin;
+        c = blockIdx.x / per;
+        l_begin = S.batch_begin + blockIdx.x % per;
+        l_end = l_begin + 1;
+    }
+    if (c >= S.count) return;
+    if (S.status[c] != ST_OK && S.mode == 0) return;
+    const long P = (long)N * (N - 1) / 2;
+    QP q;
+    q.N = N; q.M = M; q.c = c;
+    q.start = S.start + (size_t)c * N * 9;
+    q.goal = S.goal + (size_t)c * N * 9;
+    q.radius = S.radius + (size_t)c * N;
+    q.segbox = S.segbox + (size_t)c * N * M * 6;
+    q.segmat = S.segmat + (size_t)c * M * SEGMAT;
+    q.reln = S.reln + (size_t)c * P * M * 3;
+    double *ctrl = S.ctrl + (size_t)c * N * 18 * M;
+    q.ctrl_src = (S.mode == 0) ? ctrl : S.ctrl_frozen + (size_t)c * N * 18 * M;
+    double *gs = S.scratch + (size_t)blockIdx.x * S.scratch_stride;
+    const int iters = (S.mode == 0) ? S.iteration : 1;
+    for (int iter = 0; iter < iters; iter++)
+        for (int l = l_begin; l < l_end; l++) {
+            q.q0 = l * S.bs;
+            q.nb = (q.q0 + S.bs <= N) ? S.bs : N - q.q0;
+            if (q.nb <= 0) continue;
+            q.NE = S.sequential ? N - q.nb : 0;
+            q.n = 18 * q.nb; q.kb = 9 * q.nb; q.nv = q.n * M; q.ne = q.kb * (M + 1);
+            q.nrext = q.nb * M * 6 * q.NE;
+            q.nrint = q.nb * (q.nb - 1) / 2 * 6 * M;
+            q.mi = 2 * q.nv + q.nrext + q.nrint;
+            layout(q, smem, S.smem_bytes, gs);
+            if (threadIdx.x < 36) q.QB[threadIdx.x] = q_base_entry(threadIdx.x / 6, threadIdx.x % 6);
+            __syncthreads();
+            int rec = (S.mode == 0 ? iter * S.nbatch : S.rec_offset) + l;
+            int st = pdip_solve(q, S.max_iter, S.tol_gap, S.tol_res, S.qp_obj + (size_t)c * S.nrec + rec,
+                                S.qp_iters + (size_t)c * S.nrec + rec, S.qp_res + ((size_t)c * S.nrec + rec) * 4);
+            if (threadIdx.x == 0) {
+                S.qp_status[(size_t)c * S.nrec + rec] = st;
+                if (st != ST_OK && S.status[c] == ST_OK) S.status[c] = st;
+            }
+            if (st != ST_OK) {
+                if (S.mode == 0) return;  // RBPPlanner::update() aborts on the first failed batch (L158-L161)
+                continue;
+            }
+            // dummy <- vals for the agents of the batch (L182-L184)
+            for (int v = threadIdx.x; v < q.nv; v += blockDim.x) {
+                int m = v / q.n, r = v % q.n, a = r / 18, k = (r % 18) / 6, i = r % 6;
+                ctrl[(size_t)(q.q0 + a) * 18 * M + (size_t)k * 6 * M + m * 6 + i] = q.x[v];
+            }
+            __syncthreads();
+        }
+}
+
+#endif  // __CUDACC__ || RBPE_EMU
+}  // namespace rbpe

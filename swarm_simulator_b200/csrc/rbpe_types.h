@@ -1,0 +1,75 @@
+// rbpe_types.h -- launch descriptors shared by the host API (rbpe_api.cu) and the kernels.
+#pragma once
+#include <stddef.h>
+
+namespace rbpe {
+
+constexpr int NCP = 6;            // n+1 control points per segment (n = 5 only: rbp_planner.hpp L328, L361)
+constexpr int CTA_THREADS = 256;  // PDIP kernel block size
+constexpr int MAX_M = 64;
+
+// status codes == include/rbpe.h
+enum { ST_OK = 0, ST_INFEASIBLE = 1, ST_NOT_CONVERGED = 2, ST_BAD_ARG = 3 };
+
+// Raw mission inputs on the device (what rbpe_problem points to, after H2D) + what the assembly kernel makes of them.
+struct AssembleArgs {
+    int count, N, M, sequential;
+    const double *T;         // [count][M+1]
+    const int *sfc_offs;     // [count][N+1]
+    const int *sfc_base;     // [count+1]
+    const double *sfc_box;   // [nbox][6]
+    const double *sfc_t;     // [nbox]
+    const float *rsfc_n;     // [count][P][M][3]
+    const double *rsfc_t;    // [count][P][M]
+    const float *init_traj;  // [count][N][M+1][3]
+    // outputs
+    double *segbox;          // [count][N][M][6]   box chosen for every segment (build_dlq box part, L443-L474)
+    float *reln;             // [count][P][M][3]   normal chosen for every pair/segment (build_dlq RSFC part, L476-L504)
+    double *ctrl;            // [count][N][3][6M]  `dummy` (build_dummy L513-L549), zeros when !sequential
+    double *segmat;          // [count][M][SEGMAT] per-segment constants, see SEGMAT_* below
+    int *status;             // [count] ST_BAD_ARG when an SFC / RSFC look-up runs off the end (UB in the reference)
+};
+
+// per-segment constant block: AL[3][6], AR[3][6], qscale, tpow[6]
+constexpr int SEGMAT_AL = 0;      // left-knot equality coefficients of this segment  (build_Aeq_base L353-L405)
+constexpr int SEGMAT_AR = 18;     // right-knot equality coefficients
+constexpr int SEGMAT_QS = 36;     // dt^(-2 phi + 1) (build_Q_p L349-L351)
+constexpr int SEGMAT_TP = 37;     // (1/dt)^(5-j), j = 0..5 (timeMatrix L695-L700)
+constexpr int SEGMAT = 44;
+
+struct SolveArgs {
+    int count, N, M;
+    int bs;             // effective batch size (agents per QP)
+    int nbatch;         // effective batch_iter (QPs per outer iteration)
+    int iteration;
+    int sequential;
+    int mode;           // 0 Gauss-Seidel chain inside one CTA per mission, 1 Jacobi (one CTA per (mission, batch))
+    int batch_begin, batch_end;  // Jacobi: range of batches solved by this launch
+    int rec_offset;     // Jacobi: record slot offset (outer iteration * nbatch)
+    int max_iter;
+    double tol_gap, tol_res;
+    const double *start, *goal, *radius;  // [count][N][9], [count][N][9], [count][N]
+    const double *segbox;   // [count][N][M][6]
+    const float *reln;      // [count][P][M][3]
+    const double *segmat;   // [count][M][SEGMAT]
+    double *ctrl;           // [count][N][3][6M] control-point table, updated in place by solved batches
+    const double *ctrl_frozen;  // Jacobi: table the RSFC rows are built from (copy of ctrl before the sweep)
+    double *qp_obj;         // [count][nrec]
+    int *qp_iters;          // [count][nrec]
+    int *qp_status;         // [count][nrec]
+    double *qp_res;         // [count][nrec][4]
+    int nrec;
+    int *status;            // [count] mission status (assembly may already have set BAD_ARG)
+    double *scratch;        // per-CTA global scratch
+    size_t scratch_stride;  // doubles per CTA
+    unsigned smem_bytes;    // dynamic shared memory given to the kernel
+};
+
+struct ConvertArgs {
+    int count, N, M;
+    const double *ctrl;     // [count][N][3][6M]
+    const double *segmat;
+    double *coef;           // [count][N][3][6M]
+};
+
+}  // namespace rbpe

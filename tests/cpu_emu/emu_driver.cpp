@@ -1,0 +1,96 @@
+// emu_driver.cpp -- TEST INFRASTRUCTURE ONLY.  Runs the product kernels (rbpe_kernels.cuh) under the fiber emulator
+// of cuda_emu.h on host memory, with the same launch sequence as rbpe_api.cu, so that kernel logic can be debugged
+// against the oracle without a GPU.  Not linked into, loaded by, or a fallback of the product library.
+#include <stdio.h>
+#include <stdint.h>
+
+#include "cuda_emu.h"
+#define RBPE_EMU 1
+#include "../../swarm_simulator_b200/csrc/rbpe_kernels.cuh"
+#include "../../include/rbpe.h"
+
+using namespace rbpe;
+
+extern "C" int emu_solve_many(const rbpe_problem *p, int count, int mode, rbpe_result *r, size_t smem_bytes,
+                              int max_iter, double tol_gap, double tol_res, int threads) {
+    const int N = p->N, M = p->M;
+    int bs, nbatch;
+    rbpe_set_batch(N, p->sequential, p->batch_size, p->batch_iter, &bs, &nbatch);
+    const long P = (long)N * (N - 1) / 2;
+    const size_t per = (size_t)N * 18 * M;
+    std::vector<double> segbox((size_t)count * N * M * 6), segmat((size_t)count * M * SEGMAT), ctrl(count * per),
+        coef(count * per), frozen(count * per);
+    std::vector<float> reln((size_t)count * (P > 0 ? P : 1) * M * 3);
+    std::vector<int> status(count, 0);
+    AssembleArgs A;
+    A.count = count; A.N = N; A.M = M; A.sequential = p->sequential;
+    A.T = p->T; A.sfc_offs = p->sfc_offs; A.sfc_base = p->sfc_base; A.sfc_box = p->sfc_box; A.sfc_t = p->sfc_t;
+    A.rsfc_n = p->rsfc_n; A.rsfc_t = p->rsfc_t; A.init_traj = p->init_traj;
+    A.segbox = segbox.data(); A.reln = reln.data(); A.ctrl = ctrl.data(); A.segmat = segmat.data();
+    A.status = status.data();
+    emu::launch([&] { assemble_kernel(A); }, 4, 64, 0);
+
+    int nrec = p->iteration * nbatch;
+    if (nrec < 1) nrec = 1;
+    std::vector<double> obj((size_t)count * nrec, 0.0), res((size_t)count * nrec * 4, 0.0);
+    std::vector<int> its((size_t)count * nrec, 0), qst((size_t)count * nrec, 0);
+    SolveArgs S;
+    S.count = count; S.N = N; S.M = M; S.bs = bs; S.nbatch = nbatch; S.iteration = p->iteration;
+    S.sequential = p->sequential; S.mode = mode; S.batch_begin = 0; S.batch_end = nbatch; S.rec_offset = 0;
+    S.max_iter = max_iter > 0 ? max_iter : 100;
+    S.tol_gap = tol_gap > 0 ? tol_gap : 1e-10;
+    S.tol_res = tol_res > 0 ? tol_res : 1e-9;
+    S.start = p->start; S.goal = p->goal; S.radius = p->radius;
+    S.segbox = segbox.data(); S.reln = reln.data(); S.segmat = segmat.data();
+    S.ctrl = ctrl.data(); S.ctrl_frozen = frozen.data();
+    S.qp_obj = obj.data(); S.qp_iters = its.data(); S.qp_status = qst.data(); S.qp_res = res.data();
+    S.nrec = nrec; S.status = status.data();
+    S.scratch_stride = scratch_doubles(N, M, bs);
+    S.smem_bytes = (unsigned)smem_bytes;
+    if (nbatch > 0) {
+        if (mode == 0) {
+            std::vector<double> scratch(S.scratch_stride * count);
+            S.scratch = scratch.data();
+            emu::launch([&] { pdip_kernel(S); }, count, threads, smem_bytes);
+        } else {
+            std::vector<double> scratch(S.scratch_stride * count * nbatch);
+            S.scratch = scratch.data();
+            for (int it = 0; it < p->iteration; it++) {
+                frozen = ctrl;
+                S.rec_offset = it * nbatch;
+                emu::launch([&] { pdip_kernel(S); }, count * nbatch, threads, smem_bytes);
+            }
+        }
+    }
+    ConvertArgs C;
+    C.count = count; C.N = N; C.M = M; C.ctrl = ctrl.data(); C.segmat = segmat.data(); C.coef = coef.data();
+    emu::launch([&] { convert_kernel(C); }, 4, 64, 0);
+
+    memcpy(r->coef, coef.data(), coef.size() * 8);
+    if (r->ctrl) memcpy(r->ctrl, ctrl.data(), ctrl.size() * 8);
+    if (r->qp_obj) memcpy(r->qp_obj, obj.data(), (size_t)count * p->iteration * nbatch * 8);
+    if (r->qp_iters) memcpy(r->qp_iters, its.data(), (size_t)count * p->iteration * nbatch * 4);
+    if (r->qp_status) memcpy(r->qp_status, qst.data(), (size_t)count * p->iteration * nbatch * 4);
+    if (r->qp_res) memcpy(r->qp_res, res.data(), (size_t)count * p->iteration * nbatch * 32);
+    int rc = 0;
+    for (int c = 0; c < count; c++) {
+        if (r->status) r->status[c] = status[c];
+        if (!rc && status[c]) rc = status[c];
+    }
+    return rc;
+}
+
+// same definition as the product's (rbpe_api.cu); restated here because the emulator links nothing of it
+extern "C" int rbpe_set_batch(int N, int sequential, int batch_size, int batch_iter, int *ebs, int *ebi) {
+    if (batch_size <= 0) batch_size = 1;
+    int bmax = (N + batch_size - 1) / batch_size;
+    if (sequential) {
+        if (batch_iter < 0 || batch_iter > bmax) batch_iter = bmax;
+    } else {
+        batch_size = N;
+        batch_iter = 1;
+    }
+    *ebs = batch_size;
+    *ebi = batch_iter;
+    return bmax;
+}

@@ -1,0 +1,38 @@
+"""TEST INFRASTRUCTURE: runs the product kernels under tests/cpu_emu (fiber emulator, no GPU). Never used by the product."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from swarm_simulator_b200 import engine as E
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_EMU_DIR = os.path.join(_HERE, "cpu_emu")
+_EMU_LIB = os.path.join(_EMU_DIR, "librbpe_emu.so")
+_SRCS = [os.path.join(_EMU_DIR, "emu_driver.cpp"), os.path.join(_EMU_DIR, "cuda_emu.h"),
+         os.path.join(_HERE, "..", "swarm_simulator_b200", "csrc", "rbpe_kernels.cuh"),
+         os.path.join(_HERE, "..", "swarm_simulator_b200", "csrc", "rbpe_types.h")]
+
+
+def build():
+    if (not os.path.exists(_EMU_LIB)) or os.path.getmtime(_EMU_LIB) < max(os.path.getmtime(s) for s in _SRCS):
+        subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-Wno-unused", "-o", _EMU_LIB,
+                               _SRCS[0]])
+    return _EMU_LIB
+
+
+_lib = None
+
+
+def emu_solve_many(prob, mode=0, smem_bytes=48 * 1024, max_iter=0, tol_gap=0.0, tol_res=0.0, threads=256):
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.emu_solve_many.argtypes = [C.POINTER(E.RbpeProblem), C.c_int, C.c_int, C.POINTER(E.RbpeResult),
+                                        C.c_size_t, C.c_int, C.c_double, C.c_double, C.c_int]
+        _lib.emu_solve_many.restype = C.c_int
+    r = E.Result(prob)
+    r.rc = _lib.emu_solve_many(C.byref(prob.c), prob.count, mode, C.byref(r.c), smem_bytes, max_iter, tol_gap,
+                               tol_res, threads)
+    return r
