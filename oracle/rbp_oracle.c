@@ -329,85 +329,66 @@ oracle_qp *oracle_populate(const oracle_problem *p, const double *dummy, int l) 
 }
 
 /* ------------------------------------------------------------------------------------------------
- * Envelope (skyline) Cholesky: row r stores columns first[r]..r contiguously.
+ * Newton systems by the null-space method over the C2 knot states.
+ *
+ * The equality rows (build_Aeq_base, RP L353-L405) say: the (pos, vel, acc) of segment m-1 at tau=1 equals
+ * that of segment m at tau=0, and the first / last knot equal the start / goal state.  Per segment and
+ * (agent, axis) the 6x6 matrix E_m = [rows of the left knot ; rows of the right knot] restricted to the
+ * segment's 6 control points is invertible (quintic Hermite interpolation), so with the knot states
+ * sigma = (s_1 .. s_{M-1}) as free variables  x = x_p + Z sigma  parametrises {x : A x = b} exactly, and
+ *     H dx + A' dy = r1, A dx = 0   <=>   (Z' H Z) dsigma = Z' r1,  dx = Z dsigma.
+ * Z'HZ is symmetric positive definite (Q is positive definite on null(A)) and block tridiagonal over knots
+ * (blocks of 9b).  Same Newton direction as the KKT system, without ever inverting H = 2Q + G'WG, which is
+ * numerically singular near convergence (Q has rank 3 per 6x6 block and inactive rows' weights vanish).
+ * This plays the role of CPLEX's own presolve / free-variable handling; E_m^-1 is obtained numerically from A.
  * ---------------------------------------------------------------------------------------------- */
-typedef struct { int n; int *first; size_t *off; double *v; } env_t;
-
-static void env_alloc(env_t *e, int n, const int *first) {
-    e->n = n;
-    e->first = (int *)malloc(sizeof(int) * n);
-    e->off = (size_t *)malloc(sizeof(size_t) * (n + 1));
-    size_t t = 0;
-    for (int r = 0; r < n; r++) { e->first[r] = first[r]; e->off[r] = t; t += (size_t)(r - first[r] + 1); }
-    e->off[n] = t;
-    e->v = (double *)malloc(sizeof(double) * (t ? t : 1));
-}
-static void env_free(env_t *e) { free(e->first); free(e->off); free(e->v); }
-#define ENV(e, r, c) ((e)->v[(e)->off[r] + (size_t)((c) - (e)->first[r])])
-
-/* Pivots that elimination has driven below PIVOT_REL of their original diagonal belong to rows that are
- * numerically dependent on earlier ones (an equality among variables that active inequality rows already pin:
- * LICQ fails there and the multiplier is not unique).  They are replaced by a huge value, which zeroes that
- * component of the solve (the "Cholesky-infinity" device of barrier codes); the primal solution is unaffected. */
-#define PIVOT_REL 1e-13
-#define PIVOT_BIG 1e128
-static int env_chol(env_t *e, int safeguard) {
-    for (int r = 0; r < e->n; r++) {
-        int fr = e->first[r];
-        double orig = ENV(e, r, r);
-        for (int c = fr; c <= r; c++) {
-            int fc = e->first[c], t0 = fr > fc ? fr : fc;
-            double s = ENV(e, r, c);
-            const double *lr = &ENV(e, r, t0), *lc = &ENV(e, c, t0);
-            for (int t = 0; t < c - t0; t++) s -= lr[t] * lc[t];
-            if (c < r) ENV(e, r, c) = s / ENV(e, c, c);
-            else {
-                if (!(s == s)) return -1;
-                if (safeguard) { if (!(s > PIVOT_REL * orig) || !(s > 0)) s = PIVOT_BIG; }
-                else if (!(s > 0)) return -1;
-                ENV(e, r, r) = sqrt(s);
-            }
+static int chol_dense(int n, double *A, int ld) { /* lower triangle, in place */
+    for (int j = 0; j < n; j++) {
+        double d = A[j * ld + j];
+        for (int t = 0; t < j; t++) d -= A[j * ld + t] * A[j * ld + t];
+        if (!(d > 0)) return -1;
+        d = sqrt(d);
+        A[j * ld + j] = d;
+        for (int i = j + 1; i < n; i++) {
+            double v = A[i * ld + j];
+            for (int t = 0; t < j; t++) v -= A[i * ld + t] * A[j * ld + t];
+            A[i * ld + j] = v / d;
         }
     }
     return 0;
 }
-/* forward solve in place; v nonzero only in [*lo, *hi]; tracks the range (sparse right-hand sides) */
-static void env_fwd(const env_t *e, double *v, int *lo, int *hi) {
-    int l0 = *lo, last = *hi;
-    for (int r = l0; r < e->n; r++) {
-        int fr = e->first[r];
-        if (r > *hi && fr > last) { v[r] = 0; continue; }
-        int t0 = fr > l0 ? fr : l0;
-        double s = v[r];
-        for (int t = t0; t < r; t++) s -= ENV(e, r, t) * v[t];
-        v[r] = s / ENV(e, r, r);
-        if (v[r] != 0) last = r;
+static int inv6(const double *E, double *Ei) { /* Gauss-Jordan with partial pivoting */
+    double a[6][12];
+    for (int i = 0; i < 6; i++)
+        for (int j = 0; j < 6; j++) { a[i][j] = E[i * 6 + j]; a[i][6 + j] = (i == j); }
+    for (int c = 0; c < 6; c++) {
+        int pv = c;
+        for (int r = c + 1; r < 6; r++) if (fabs(a[r][c]) > fabs(a[pv][c])) pv = r;
+        if (a[pv][c] == 0) return -1;
+        if (pv != c) for (int j = 0; j < 12; j++) { double t = a[c][j]; a[c][j] = a[pv][j]; a[pv][j] = t; }
+        double d = a[c][c];
+        for (int j = 0; j < 12; j++) a[c][j] /= d;
+        for (int r = 0; r < 6; r++) if (r != c) {
+            double f = a[r][c];
+            if (f != 0) for (int j = 0; j < 12; j++) a[r][j] -= f * a[c][j];
+        }
     }
-    *hi = last;
-}
-static void env_bwd(const env_t *e, double *v) {
-    for (int r = e->n - 1; r >= 0; r--) {
-        double x = v[r] / ENV(e, r, r);
-        v[r] = x;
-        if (x != 0)
-            for (int c = e->first[r]; c < r; c++) v[c] -= ENV(e, r, c) * x;
-    }
+    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) Ei[i * 6 + j] = a[i][6 + j];
+    return 0;
 }
 
-/* ------------------------------------------------------------------------------------------------
- * Mehrotra predictor-corrector on  min 1/2 x'Px  s.t. Ax=b, Gx+s=h, s>=0   with P = Q+Q'.
- * Normal equations: H = P + G'WG (block diagonal over segments in perm_x order), S = A H^-1 A'
- * (block tridiagonal over knots in perm_y order); both factored with the envelope Cholesky.
- * ---------------------------------------------------------------------------------------------- */
 typedef struct {
     const oracle_qp *q;
-    int nv, ne, mi;
-    env_t H, S;
-    int *px, *py;            /* perms */
-    double *Y; int *ylo, *yhi; /* Y = L^-1 A' (column c = eq row in perm order), dense nv per column */
-    double *w;               /* z/s */
-    double *t1, *t2, *t3;    /* scratch nv, nv, ne */
-} kkt_t;
+    int nv, ne, mi, M, nb, n, kb, nr;
+    int *seg, *loc;       /* per variable: segment, local index (agent*3+axis)*6 + i */
+    int *rseg;            /* per inequality row: segment of its variables */
+    double *Zc;           /* [nv][6]: x_v = xp_v + sum_d Zc[v][d] s_m[ak][d] + Zc[v][3+d] s_{m+1}[ak][d] */
+    double *xp;           /* [nv] particular solution (sigma = 0) */
+    double *Hs;           /* [M][n*n] H per segment, full symmetric */
+    double *Wd, *Wo;      /* reduced Hessian: [(M-1)][kb*kb] diagonal, [(M-2)][kb*kb] blocks (t+1,t) */
+    double *T, *Wm;       /* scratch n*2kb, 2kb*2kb */
+    double *w;
+} nsp_t;
 
 static void csr_mulv(int m, const int *ptr, const int *idx, const double *val, const double *x, double *y) {
     for (int r = 0; r < m; r++) {
@@ -431,137 +412,221 @@ static void p_mulv(const oracle_qp *q, const double *x, double *y) { /* y = (Q+Q
     }
 }
 
-static int kkt_init(kkt_t *K, const oracle_qp *q) {
+static void nsp_free(nsp_t *K) {
+    free(K->seg); free(K->loc); free(K->rseg); free(K->Zc); free(K->xp); free(K->Hs); free(K->Wd); free(K->Wo);
+    free(K->T); free(K->Wm); free(K->w);
+}
+
+/* returns 0, or ORACLE_BAD_ARG when the equality structure is not the knot structure described above */
+static int nsp_init(nsp_t *K, const oracle_qp *q) {
     memset(K, 0, sizeof(*K));
     K->q = q; K->nv = q->nv; K->ne = q->ne; K->mi = q->mi;
     int nv = q->nv, ne = q->ne;
-    K->px = q->perm_x; K->py = q->perm_y;
-    int *first = (int *)malloc(sizeof(int) * nv);
-    for (int i = 0; i < nv; i++) first[i] = i;
-    for (int t = 0; t < q->qnnz; t++) {
-        int a = K->px[q->qi[t]], b = K->px[q->qj[t]];
-        if (a < b) { int s = a; a = b; b = s; }
-        if (b < first[a]) first[a] = b;
-    }
-    for (int r = 0; r < q->mi; r++) {
-        int mn = nv;
-        for (int t = q->g_ptr[r]; t < q->g_ptr[r + 1]; t++) { int a = K->px[q->g_idx[t]]; if (a < mn) mn = a; }
-        for (int t = q->g_ptr[r]; t < q->g_ptr[r + 1]; t++) { int a = K->px[q->g_idx[t]]; if (mn < first[a]) first[a] = mn; }
-    }
-    /* an envelope must be monotone enough for fill: first[r] <= min over c in [first[r], r] handled by
-     * the algorithm itself (entries outside a row's envelope are structurally zero and stay zero). */
-    env_alloc(&K->H, nv, first);
-    free(first);
-    K->Y = (double *)malloc(sizeof(double) * (size_t)nv * (ne ? ne : 1));
-    K->ylo = (int *)malloc(sizeof(int) * (ne + 1));
-    K->yhi = (int *)malloc(sizeof(int) * (ne + 1));
-    K->w = (double *)malloc(sizeof(double) * (q->mi + 1));
-    K->t1 = (double *)malloc(sizeof(double) * nv);
-    K->t2 = (double *)malloc(sizeof(double) * nv);
-    K->t3 = (double *)malloc(sizeof(double) * (ne + 1));
-    K->S.n = 0;
-    return 0;
-}
-static void kkt_free(kkt_t *K) {
-    env_free(&K->H);
-    if (K->S.n) env_free(&K->S);
-    free(K->Y); free(K->ylo); free(K->yhi); free(K->w); free(K->t1); free(K->t2); free(K->t3);
-}
-
-/* factor with weights w (mi) */
-static int kkt_factor(kkt_t *K, const double *w) {
-    const oracle_qp *q = K->q;
-    int nv = K->nv, ne = K->ne;
-    env_t *H = &K->H;
-    memset(H->v, 0, sizeof(double) * H->off[nv]);
-    for (int t = 0; t < q->qnnz; t++) { /* P = Q + Q' */
-        int a = K->px[q->qi[t]], b = K->px[q->qj[t]];
-        if (a >= b) ENV(H, a, b) += q->qv[t]; else ENV(H, b, a) += q->qv[t];
-        if (a == b) ENV(H, a, a) += q->qv[t];
-    }
-    /* note: for a != b the pair (i,j),(j,i) both appear in the triplets, each adds Q_ij to the lower entry:
-     * total 2 Q_ij = P_ij. For a == b the single triplet adds Q_ii twice = P_ii. */
-    for (int r = 0; r < q->mi; r++) {
-        double wr = w[r];
-        for (int t = q->g_ptr[r]; t < q->g_ptr[r + 1]; t++) {
-            int a = K->px[q->g_idx[t]];
-            double va = wr * q->g_val[t];
-            for (int u = q->g_ptr[r]; u < q->g_ptr[r + 1]; u++) {
-                int b = K->px[q->g_idx[u]];
-                if (b <= a) ENV(H, a, b) += va * q->g_val[u];
+    /* nv = 18 nb M, ne = 9 nb (M+1) */
+    if (nv <= 0 || nv % 18 || ne % 9) return ORACLE_BAD_ARG;
+    int a18 = nv / 18, a9 = ne / 9; /* nb*M, nb*(M+1) */
+    int nb = a9 - a18;
+    if (nb <= 0 || a18 % nb) return ORACLE_BAD_ARG;
+    int M = a18 / nb, n = 18 * nb, kb = 9 * nb;
+    K->M = M; K->nb = nb; K->n = n; K->kb = kb; K->nr = kb * (M - 1);
+    K->seg = (int *)malloc(sizeof(int) * nv); K->loc = (int *)malloc(sizeof(int) * nv);
+    int *varof = (int *)malloc(sizeof(int) * nv), *rowof = (int *)malloc(sizeof(int) * ne);
+    for (int v = 0; v < nv; v++) { int p = q->perm_x[v]; K->seg[v] = p / n; K->loc[v] = p % n; varof[p] = v; }
+    for (int r = 0; r < ne; r++) rowof[q->perm_y[r]] = r;
+    K->Zc = (double *)calloc((size_t)nv * 6, sizeof(double));
+    K->xp = (double *)calloc(nv, sizeof(double));
+    int rc = 0;
+    for (int m = 0; m < M && !rc; m++)
+        for (int ak = 0; ak < 3 * nb && !rc; ak++) {
+            double E[36] = {0}, Ei[36], rhs[6];
+            for (int side = 0; side < 2; side++)
+                for (int d = 0; d < 3; d++) {
+                    int r = rowof[(m + side) * kb + ak * 3 + d];
+                    for (int t = q->a_ptr[r]; t < q->a_ptr[r + 1]; t++) {
+                        int c = q->a_idx[t], p = q->perm_x[c];
+                        if (p / n == m) {
+                            if ((p % n) / 6 != ak) rc = ORACLE_BAD_ARG;
+                            else E[(side * 3 + d) * 6 + p % 6] = q->a_val[t];
+                        } else if (p / n != m + (side ? 1 : -1)) rc = ORACLE_BAD_ARG;
+                    }
+                    /* the knot's right-hand side belongs to the side that closes it: the first knot to
+                     * segment 0, every other knot to the segment on its left */
+                    rhs[side * 3 + d] = (side == 1 || m == 0) ? q->b[r] : 0.0;
+                }
+            if (rc || inv6(E, Ei)) { rc = ORACLE_BAD_ARG; break; }
+            for (int i = 0; i < 6; i++) {
+                int v = varof[m * n + ak * 6 + i];
+                double xpv = 0;
+                for (int j = 0; j < 6; j++) xpv += Ei[i * 6 + j] * rhs[j];
+                K->xp[v] = xpv;
+                for (int d = 0; d < 3; d++) {
+                    /* interior knot t: s_t := (rows of knot t on segment t-1) x_{t-1} - b_t  = -(rows on segment t) x_t */
+                    K->Zc[(size_t)v * 6 + d] = (m > 0) ? -Ei[i * 6 + d] : 0.0;
+                    K->Zc[(size_t)v * 6 + 3 + d] = (m < M - 1) ? Ei[i * 6 + 3 + d] : 0.0;
+                }
             }
         }
-    }
-    if (env_chol(H, 0)) return -1;
-    if (ne == 0) return 0;
-    /* Y columns */
-    for (int c = 0; c < ne; c++) { K->ylo[c] = nv; K->yhi[c] = -1; }
-    memset(K->Y, 0, sizeof(double) * (size_t)nv * ne);
-    for (int r = 0; r < ne; r++) {
-        int c = K->py[r];
-        double *y = K->Y + (size_t)c * nv;
-        for (int t = q->a_ptr[r]; t < q->a_ptr[r + 1]; t++) {
-            int a = K->px[q->a_idx[t]];
-            y[a] = q->a_val[t];
-            if (a < K->ylo[c]) K->ylo[c] = a;
-            if (a > K->yhi[c]) K->yhi[c] = a;
+    free(varof); free(rowof);
+    if (rc) return rc;
+    K->rseg = (int *)malloc(sizeof(int) * (q->mi + 1));
+    for (int r = 0; r < q->mi; r++) {
+        int sg = -1;
+        for (int t = q->g_ptr[r]; t < q->g_ptr[r + 1]; t++) {
+            int s2 = K->seg[q->g_idx[t]];
+            if (sg < 0) sg = s2; else if (sg != s2) return ORACLE_BAD_ARG;
         }
+        K->rseg[r] = sg;
     }
-    for (int c = 0; c < ne; c++)
-        if (K->yhi[c] >= 0) env_fwd(H, K->Y + (size_t)c * nv, &K->ylo[c], &K->yhi[c]);
-    /* S = Y'Y with envelope from range intersections */
-    int *first = (int *)malloc(sizeof(int) * ne);
-    for (int r = 0; r < ne; r++) {
-        first[r] = r;
-        for (int c = 0; c < r; c++) {
-            int lo = K->ylo[r] > K->ylo[c] ? K->ylo[r] : K->ylo[c];
-            int hi = K->yhi[r] < K->yhi[c] ? K->yhi[r] : K->yhi[c];
-            if (lo <= hi) { first[r] = c; break; }
-        }
-    }
-    if (K->S.n) env_free(&K->S);
-    env_alloc(&K->S, ne, first);
-    free(first);
-    for (int r = 0; r < ne; r++)
-        for (int c = K->S.first[r]; c <= r; c++) {
-            int lo = K->ylo[r] > K->ylo[c] ? K->ylo[r] : K->ylo[c];
-            int hi = K->yhi[r] < K->yhi[c] ? K->yhi[r] : K->yhi[c];
-            double s = 0;
-            const double *yr = K->Y + (size_t)r * nv, *yc = K->Y + (size_t)c * nv;
-            for (int t = lo; t <= hi; t++) s += yr[t] * yc[t];
-            ENV(&K->S, r, c) = s;
-        }
-    if (env_chol(&K->S, 1)) return -2;
+    K->Hs = (double *)malloc(sizeof(double) * (size_t)M * n * n);
+    K->Wd = (double *)malloc(sizeof(double) * (size_t)(M > 1 ? M - 1 : 1) * kb * kb);
+    K->Wo = (double *)malloc(sizeof(double) * (size_t)(M > 2 ? M - 2 : 1) * kb * kb);
+    K->T = (double *)malloc(sizeof(double) * (size_t)n * 2 * kb);
+    K->Wm = (double *)malloc(sizeof(double) * (size_t)4 * kb * kb);
+    K->w = (double *)malloc(sizeof(double) * (q->mi + 1));
     return 0;
 }
 
-/* solve  H dx + A' dy = r1 ; A dx = r2   (r1 in original variable order, r2 in original row order) */
-static void kkt_solve(kkt_t *K, const double *r1, const double *r2, double *dx, double *dy) {
-    int nv = K->nv, ne = K->ne;
-    double *u = K->t1, *g = K->t3;
-    for (int i = 0; i < nv; i++) u[K->px[i]] = r1[i];
-    int lo = 0, hi = nv - 1;
-    env_fwd(&K->H, u, &lo, &hi);
-    if (ne) {
-        for (int r = 0; r < ne; r++) {
-            int c = K->py[r];
-            const double *y = K->Y + (size_t)c * nv;
-            double s = 0;
-            for (int t = K->ylo[c]; t <= K->yhi[c]; t++) s += y[t] * u[t];
-            g[c] = s - r2[r];
-        }
-        lo = 0; hi = ne - 1;
-        env_fwd(&K->S, g, &lo, &hi);
-        env_bwd(&K->S, g);
-        for (int r = 0; r < ne; r++) dy[r] = g[K->py[r]];
-        for (int c = 0; c < ne; c++) {
-            const double *y = K->Y + (size_t)c * nv;
-            double gc = g[c];
-            for (int t = K->ylo[c]; t <= K->yhi[c]; t++) u[t] -= y[t] * gc;
+/* out[nr] = Z' g */
+static void nsp_Zt(const nsp_t *K, const double *g, double *out) {
+    for (int i = 0; i < K->nr; i++) out[i] = 0;
+    for (int v = 0; v < K->nv; v++) {
+        int m = K->seg[v], ak = K->loc[v] / 6;
+        const double *z = K->Zc + (size_t)v * 6;
+        if (m > 0) for (int d = 0; d < 3; d++) out[(m - 1) * K->kb + ak * 3 + d] += z[d] * g[v];
+        if (m < K->M - 1) for (int d = 0; d < 3; d++) out[m * K->kb + ak * 3 + d] += z[3 + d] * g[v];
+    }
+}
+/* out[nv] = Z sigma */
+static void nsp_Z(const nsp_t *K, const double *sg, double *out) {
+    for (int v = 0; v < K->nv; v++) {
+        int m = K->seg[v], ak = K->loc[v] / 6;
+        const double *z = K->Zc + (size_t)v * 6;
+        double s = 0;
+        if (m > 0) for (int d = 0; d < 3; d++) s += z[d] * sg[(m - 1) * K->kb + ak * 3 + d];
+        if (m < K->M - 1) for (int d = 0; d < 3; d++) s += z[3 + d] * sg[m * K->kb + ak * 3 + d];
+        out[v] = s;
+    }
+}
+
+/* reduced Hessian Z'(P + G'WG)Z and its block tridiagonal Cholesky */
+static int nsp_factor(nsp_t *K, const double *w) {
+    const oracle_qp *q = K->q;
+    int M = K->M, n = K->n, kb = K->kb, k2 = 2 * kb;
+    if (M < 2) return 0;
+    memset(K->Hs, 0, sizeof(double) * (size_t)M * n * n);
+    for (int t = 0; t < q->qnnz; t++) { /* P = Q + Q' */
+        int a = q->qi[t], b = q->qj[t];
+        double *Hm = K->Hs + (size_t)K->seg[a] * n * n;
+        Hm[K->loc[a] * n + K->loc[b]] += q->qv[t];
+        Hm[K->loc[b] * n + K->loc[a]] += q->qv[t];
+    }
+    for (int r = 0; r < q->mi; r++) {
+        double wr = w[r];
+        if (wr == 0 || K->rseg[r] < 0) continue;
+        double *Hm = K->Hs + (size_t)K->rseg[r] * n * n;
+        for (int t = q->g_ptr[r]; t < q->g_ptr[r + 1]; t++) {
+            double va = wr * q->g_val[t];
+            int la = K->loc[q->g_idx[t]];
+            for (int u = q->g_ptr[r]; u < q->g_ptr[r + 1]; u++) Hm[la * n + K->loc[q->g_idx[u]]] += va * q->g_val[u];
         }
     }
-    env_bwd(&K->H, u);
-    for (int i = 0; i < nv; i++) dx[i] = u[K->px[i]];
+    memset(K->Wd, 0, sizeof(double) * (size_t)(M - 1) * kb * kb);
+    if (M > 2) memset(K->Wo, 0, sizeof(double) * (size_t)(M - 2) * kb * kb);
+    /* Zc of the variable at local index l of segment m: need a map (m, l) -> v; loc/seg give the inverse, so
+     * gather the per-segment Z coefficients into a dense [n][6] table first */
+    double *zt = (double *)malloc(sizeof(double) * (size_t)M * n * 6);
+    for (int v = 0; v < K->nv; v++) memcpy(zt + ((size_t)K->seg[v] * n + K->loc[v]) * 6, K->Zc + (size_t)v * 6, 48);
+    for (int m = 0; m < M; m++) {
+        const double *Hm = K->Hs + (size_t)m * n * n, *zm = zt + (size_t)m * n * 6;
+        /* T[r][(side,ak,d)] = sum_i Hm[r][(ak,i)] z[(ak,i)][side*3+d] */
+        for (int r = 0; r < n; r++)
+            for (int side = 0; side < 2; side++)
+                for (int ak = 0; ak < 3 * K->nb; ak++)
+                    for (int d = 0; d < 3; d++) {
+                        double s = 0;
+                        for (int i = 0; i < 6; i++) s += Hm[r * n + ak * 6 + i] * zm[(ak * 6 + i) * 6 + side * 3 + d];
+                        K->T[(size_t)r * k2 + side * kb + ak * 3 + d] = s;
+                    }
+        for (int side = 0; side < 2; side++)
+            for (int ak = 0; ak < 3 * K->nb; ak++)
+                for (int d = 0; d < 3; d++) {
+                    int row = side * kb + ak * 3 + d;
+                    for (int c = 0; c < k2; c++) {
+                        double s = 0;
+                        for (int i = 0; i < 6; i++) s += zm[(ak * 6 + i) * 6 + side * 3 + d] * K->T[(size_t)(ak * 6 + i) * k2 + c];
+                        K->Wm[(size_t)row * k2 + c] = s;
+                    }
+                }
+        for (int r = 0; r < kb; r++)
+            for (int c = 0; c < kb; c++) {
+                if (m > 0) K->Wd[(size_t)(m - 1) * kb * kb + r * kb + c] += K->Wm[(size_t)r * k2 + c];                  /* LL -> knot m */
+                if (m < M - 1) K->Wd[(size_t)m * kb * kb + r * kb + c] += K->Wm[(size_t)(kb + r) * k2 + kb + c];         /* RR -> knot m+1 */
+                if (m > 0 && m < M - 1) K->Wo[(size_t)(m - 1) * kb * kb + r * kb + c] = K->Wm[(size_t)(kb + r) * k2 + c]; /* RL */
+            }
+    }
+    free(zt);
+    /* block tridiagonal Cholesky: D_t <- chol(D_t - O_{t-1} O_{t-1}'), O_t <- O_t D_t^-T */
+    for (int t = 0; t < M - 1; t++) {
+        double *D = K->Wd + (size_t)t * kb * kb;
+        if (t > 0) {
+            const double *O = K->Wo + (size_t)(t - 1) * kb * kb;
+            for (int r = 0; r < kb; r++)
+                for (int c = 0; c <= r; c++) {
+                    double s = 0;
+                    for (int k = 0; k < kb; k++) s += O[r * kb + k] * O[c * kb + k];
+                    D[r * kb + c] -= s;
+                }
+        }
+        if (chol_dense(kb, D, kb)) return -1;
+        if (t < M - 2) {
+            double *O = K->Wo + (size_t)t * kb * kb;
+            for (int r = 0; r < kb; r++)
+                for (int c = 0; c < kb; c++) {
+                    double v = O[r * kb + c];
+                    for (int k = 0; k < c; k++) v -= O[r * kb + k] * D[c * kb + k];
+                    O[r * kb + c] = v / D[c * kb + c];
+                }
+        }
+    }
+    return 0;
+}
+/* g (nr) <- (Z'HZ)^-1 g */
+static void nsp_solve(const nsp_t *K, double *g) {
+    int M = K->M, kb = K->kb;
+    for (int t = 0; t < M - 1; t++) {
+        const double *D = K->Wd + (size_t)t * kb * kb;
+        double *gt = g + t * kb;
+        if (t > 0) {
+            const double *O = K->Wo + (size_t)(t - 1) * kb * kb;
+            for (int r = 0; r < kb; r++) {
+                double s = 0;
+                for (int k = 0; k < kb; k++) s += O[r * kb + k] * g[(t - 1) * kb + k];
+                gt[r] -= s;
+            }
+        }
+        for (int r = 0; r < kb; r++) {
+            double v = gt[r];
+            for (int k = 0; k < r; k++) v -= D[r * kb + k] * gt[k];
+            gt[r] = v / D[r * kb + r];
+        }
+    }
+    for (int t = M - 2; t >= 0; t--) {
+        const double *D = K->Wd + (size_t)t * kb * kb;
+        double *gt = g + t * kb;
+        if (t < M - 2) {
+            const double *O = K->Wo + (size_t)t * kb * kb;
+            for (int c = 0; c < kb; c++) {
+                double s = 0;
+                for (int k = 0; k < kb; k++) s += O[k * kb + c] * g[(t + 1) * kb + k];
+                gt[c] -= s;
+            }
+        }
+        for (int r = kb - 1; r >= 0; r--) {
+            double v = gt[r];
+            for (int k = r + 1; k < kb; k++) v -= D[k * kb + r] * gt[k];
+            gt[r] = v / D[r * kb + r];
+        }
+    }
 }
 
 static double inf_norm(const double *v, int n) {
@@ -570,190 +635,187 @@ static double inf_norm(const double *v, int n) {
     return m;
 }
 
-
-/* ------------------------------------------------------------------------------------------------
- * Presolve (what CPLEX's presolve does to this model before the barrier sees it): singleton equality
- * rows fix their column -- here the start rows fix control points 0..2 of the first segment and the
- * goal rows fix 3..5 of the last one (rows 0-5 of Aeq_base are triangular in them, RP L380-L387) --
- * and inequality rows all of whose columns are fixed are checked against their right-hand side
- * (feasibility tolerance 1e-6, CPLEX's default) and dropped.  Without this a start or goal lying on a
- * face of its SFC box, which the corridor generator produces routinely, leaves the QP without a strict
- * interior.  dead[r] = 1 for dropped rows.  Returns 0, or ORACLE_INFEASIBLE.
- * ---------------------------------------------------------------------------------------------- */
+/* Rows all of whose variables are fixed by the start / goal equalities (control points 0..2 of the first and
+ * 3..5 of the last segment: their Z rows vanish) are constant: checked against their right-hand side with
+ * CPLEX's default feasibility tolerance 1e-6 and dropped, as a presolve would.  A start or goal lying on a face
+ * of its SFC box, which the corridor generator produces routinely, would otherwise leave no strict interior. */
 #define PRESOLVE_FEAS_TOL 1e-6
-static int presolve_dead_rows(const oracle_qp *q, unsigned char *dead, int *n_live) {
-    int nv = q->nv, ne = q->ne, mi = q->mi, rc = 0;
-    unsigned char *fixed = (unsigned char *)calloc(nv + 1, 1), *used = (unsigned char *)calloc(ne + 1, 1);
-    double *xf = (double *)calloc(nv + 1, sizeof(double));
-    int progress = 1;
-    while (progress) {
-        progress = 0;
-        for (int r = 0; r < ne; r++) {
-            if (used[r]) continue;
-            int nfree = 0, col = -1;
-            double rhs = q->b[r], a = 0;
-            for (int t = q->a_ptr[r]; t < q->a_ptr[r + 1]; t++) {
-                int c = q->a_idx[t];
-                if (fixed[c]) rhs -= q->a_val[t] * xf[c];
-                else { nfree++; col = c; a = q->a_val[t]; }
-            }
-            if (nfree == 1 && a != 0) {
-                fixed[col] = 1; xf[col] = rhs / a; used[r] = 1; progress = 1;
-            }
-        }
-    }
-    int live = 0;
-    for (int r = 0; r < mi; r++) {
+static int presolve_dead_rows(const nsp_t *K, unsigned char *dead, int *n_live) {
+    const oracle_qp *q = K->q;
+    int rc = 0, live = 0;
+    for (int r = 0; r < q->mi; r++) {
         int all = q->g_ptr[r + 1] > q->g_ptr[r];
         double gx = 0;
-        for (int t = q->g_ptr[r]; t < q->g_ptr[r + 1]; t++) {
+        for (int t = q->g_ptr[r]; t < q->g_ptr[r + 1] && all; t++) {
             int c = q->g_idx[t];
-            if (!fixed[c]) { all = 0; break; }
-            gx += q->g_val[t] * xf[c];
+            for (int d = 0; d < 6; d++) if (K->Zc[(size_t)c * 6 + d] != 0) { all = 0; break; }
+            gx += q->g_val[t] * K->xp[c];
         }
         dead[r] = (unsigned char)all;
         if (all) { if (gx - q->h[r] > PRESOLVE_FEAS_TOL) rc = ORACLE_INFEASIBLE; }
         else live++;
     }
     *n_live = live;
-    free(fixed); free(used); free(xf);
     return rc;
 }
 
+/* Mehrotra predictor-corrector on  min x'Qx  s.t. Ax=b, Gx+s=h, s>=0  (P = Q+Q'). */
 int oracle_solve_qp(const oracle_qp *q, const oracle_solver_opts *opts, double *x, double *obj_out,
                     int *iters_out, double *res_out) {
     int nv = q->nv, ne = q->ne, mi = q->mi;
     int max_iter = (opts && opts->max_iter > 0) ? opts->max_iter : 100;
     double tol_gap = (opts && opts->tol_gap > 0) ? opts->tol_gap : 1e-10;
     double tol_res = (opts && opts->tol_res > 0) ? opts->tol_res : 1e-9;
-    kkt_t K;
-    kkt_init(&K, q);
-    double *y = (double *)calloc(ne + 1, sizeof(double)), *s = (double *)malloc(sizeof(double) * (mi + 1));
-    double *z = (double *)malloc(sizeof(double) * (mi + 1));
-    double *rd = (double *)malloc(sizeof(double) * nv), *rp = (double *)malloc(sizeof(double) * (ne + 1));
-    double *rg = (double *)malloc(sizeof(double) * (mi + 1)), *r1 = (double *)malloc(sizeof(double) * nv);
-    double *r2 = (double *)malloc(sizeof(double) * (ne + 1)), *tt = (double *)malloc(sizeof(double) * (mi + 1));
-    double *dx = (double *)malloc(sizeof(double) * nv), *dy = (double *)malloc(sizeof(double) * (ne + 1));
-    double *ds = (double *)malloc(sizeof(double) * (mi + 1)), *dz = (double *)malloc(sizeof(double) * (mi + 1));
-    double *dsa = (double *)malloc(sizeof(double) * (mi + 1)), *dza = (double *)malloc(sizeof(double) * (mi + 1));
+    nsp_t K;
+    int status = ORACLE_NOT_CONVERGED, it = 0, n_live = mi;
+    double gap = 0, obj = 0, nrd = 0, nrg = 0, hn = 0;
+    if (nsp_init(&K, q)) {
+        nsp_free(&K);
+        if (obj_out) *obj_out = 0;
+        if (iters_out) *iters_out = 0;
+        return ORACLE_BAD_ARG;
+    }
+    int nr = K.nr;
+    double *s = (double *)malloc(sizeof(double) * (mi + 1)), *z = (double *)malloc(sizeof(double) * (mi + 1));
+    double *rd = (double *)malloc(sizeof(double) * nv), *rg = (double *)malloc(sizeof(double) * (mi + 1));
+    double *r1 = (double *)malloc(sizeof(double) * nv), *tt = (double *)malloc(sizeof(double) * (mi + 1));
+    double *dx = (double *)malloc(sizeof(double) * nv), *dxa = (double *)malloc(sizeof(double) * nv);
     double *gx = (double *)malloc(sizeof(double) * (mi + 1)), *px = (double *)malloc(sizeof(double) * nv);
-    int status = ORACLE_NOT_CONVERGED, it = 0;
+    double *gxa = (double *)malloc(sizeof(double) * (mi + 1)), *hs = (double *)malloc(sizeof(double) * (mi + 1));
+    double *sg = (double *)malloc(sizeof(double) * (nr + 1)), *ax = (double *)malloc(sizeof(double) * (ne + 1));
     unsigned char *dead = (unsigned char *)calloc(mi + 1, 1);
-    int n_live = mi;
-    double bn = inf_norm(q->b, ne), hn = 0, gap = 0, obj = 0;
-    if (presolve_dead_rows(q, dead, &n_live)) { status = ORACLE_INFEASIBLE; goto done; }
+    if (presolve_dead_rows(&K, dead, &n_live)) { status = ORACLE_INFEASIBLE; goto done; }
     for (int r = 0; r < mi; r++) if (!dead[r] && fabs(q->h[r]) > hn) hn = fabs(q->h[r]);
+    for (int i = 0; i < nv; i++) x[i] = K.xp[i];
+    if (nr == 0) { /* a single segment: start and goal fix everything */
+        p_mulv(q, x, px);
+        for (int i = 0; i < nv; i++) obj += 0.5 * x[i] * px[i];
+        status = ORACLE_OK;
+        goto done;
+    }
+    /* reduced right-hand side h - G x_p (used by the infeasibility certificate) */
+    csr_mulv(mi, q->g_ptr, q->g_idx, q->g_val, K.xp, hs);
+    for (int r = 0; r < mi; r++) hs[r] = q->h[r] - hs[r];
 
-    /* initial point (standard least-squares start): W = I */
-    for (int r = 0; r < mi; r++) K.w[r] = 1.0;
-    if (kkt_factor(&K, K.w)) { status = ORACLE_NOT_CONVERGED; goto done; }
-    for (int i = 0; i < nv; i++) r1[i] = 0;
-    for (int r = 0; r < mi; r++) tt[r] = dead[r] ? 0.0 : q->h[r];
+    /* initial point (least-squares start, W = I): min 1/2 x'(P+G'G)x - (G'h)'x  s.t. Ax = b */
+    for (int r = 0; r < mi; r++) K.w[r] = dead[r] ? 0.0 : 1.0;
+    if (nsp_factor(&K, K.w)) goto done;
+    p_mulv(q, x, px);
+    for (int i = 0; i < nv; i++) r1[i] = -px[i];
+    for (int r = 0; r < mi; r++) tt[r] = dead[r] ? 0.0 : hs[r];
     csr_mulTv_add(mi, q->g_ptr, q->g_idx, q->g_val, tt, r1);
-    kkt_solve(&K, r1, q->b, x, y);
+    nsp_Zt(&K, r1, sg);
+    nsp_solve(&K, sg);
+    nsp_Z(&K, sg, dx);
+    for (int i = 0; i < nv; i++) x[i] += dx[i];
     csr_mulv(mi, q->g_ptr, q->g_idx, q->g_val, x, gx);
     {
         double ap = -1e300, ad = -1e300;
         for (int r = 0; r < mi; r++) { z[r] = gx[r] - q->h[r]; s[r] = -z[r]; }
         for (int r = 0; r < mi; r++) { if (dead[r]) continue; if (-s[r] > ap) ap = -s[r]; if (-z[r] > ad) ad = -z[r]; }
         for (int r = 0; r < mi; r++) {
-            if (dead[r]) { s[r] = 1.0; z[r] = 0.0; continue; }  /* dropped row: no multiplier, unit weight in H */
+            if (dead[r]) { s[r] = 1.0; z[r] = 0.0; continue; }
             if (ap >= 0) s[r] += 1.0 + ap;
             if (ad >= 0) z[r] += 1.0 + ad;
         }
     }
 
     for (it = 0; it < max_iter; it++) {
-        /* residuals */
         p_mulv(q, x, px);
         for (int i = 0; i < nv; i++) rd[i] = px[i];
-        csr_mulTv_add(ne, q->a_ptr, q->a_idx, q->a_val, y, rd);
-        csr_mulTv_add(mi, q->g_ptr, q->g_idx, q->g_val, z, rd);
-        csr_mulv(ne, q->a_ptr, q->a_idx, q->a_val, x, rp);
-        for (int r = 0; r < ne; r++) rp[r] -= q->b[r];
+        csr_mulTv_add(mi, q->g_ptr, q->g_idx, q->g_val, z, rd);   /* rd = Px + G'z; its part in range(A') is the multiplier */
         csr_mulv(mi, q->g_ptr, q->g_idx, q->g_val, x, gx);
-        double mu = 0;
+        double mu = 0, hz = 0;
         for (int r = 0; r < mi; r++) {
             if (dead[r]) { rg[r] = 0; continue; }
-            rg[r] = gx[r] + s[r] - q->h[r]; mu += s[r] * z[r];
+            rg[r] = gx[r] + s[r] - q->h[r]; mu += s[r] * z[r]; hz += hs[r] * z[r];
         }
         mu /= (n_live > 0 ? n_live : 1);
         obj = 0;
         for (int i = 0; i < nv; i++) obj += 0.5 * x[i] * px[i];
         gap = mu;
-        double nrp = inf_norm(rp, ne), nrg = inf_norm(rg, mi), nrd = inf_norm(rd, nv);
+        nsp_Zt(&K, rd, sg);
+        nrd = inf_norm(sg, nr);
+        nrg = inf_norm(rg, mi);
         double dscale = 1.0 + inf_norm(px, nv);
-        if (res_out) { res_out[0] = gap; res_out[1] = nrp; res_out[2] = nrd; res_out[3] = nrg; }
         if (!(mu == mu) || !(nrd == nrd)) { status = ORACLE_NOT_CONVERGED; break; }
-        if (gap <= tol_gap * fmax(1.0, fabs(obj)) && nrp <= tol_res * (1 + bn) && nrg <= tol_res * (1 + hn) &&
-            nrd <= tol_res * dscale) {
+        if (gap <= tol_gap * fmax(1.0, fabs(obj)) && nrg <= tol_res * (1 + hn) && nrd <= tol_res * dscale) {
             status = ORACLE_OK;
             break;
         }
-        /* primal infeasibility certificate: z>=0, G'z + A'y ~ 0, h'z + b'y < 0 */
-        {
-            double hz = 0;
-            for (int r = 0; r < mi; r++) if (!dead[r]) hz += q->h[r] * z[r];
-            for (int r = 0; r < ne; r++) hz += q->b[r] * y[r];
-            if (hz < 0) {
-                for (int i = 0; i < nv; i++) r1[i] = 0;
-                csr_mulTv_add(ne, q->a_ptr, q->a_idx, q->a_val, y, r1);
-                csr_mulTv_add(mi, q->g_ptr, q->g_idx, q->g_val, z, r1);
-                if (inf_norm(r1, nv) / (-hz) < 1e-8) { status = ORACLE_INFEASIBLE; break; }
-            }
+        /* infeasibility certificate of the reduced problem {G Z sigma <= h - G x_p}: z >= 0, (GZ)'z ~ 0, (h - G x_p)'z < 0 */
+        if (hz < 0) {
+            for (int i = 0; i < nv; i++) r1[i] = 0;
+            csr_mulTv_add(mi, q->g_ptr, q->g_idx, q->g_val, z, r1);
+            nsp_Zt(&K, r1, sg);
+            if (inf_norm(sg, nr) / (-hz) < 1e-8) { status = ORACLE_INFEASIBLE; break; }
         }
-        for (int r = 0; r < mi; r++) K.w[r] = dead[r] ? 1.0 : z[r] / s[r];
-        if (kkt_factor(&K, K.w)) { status = ORACLE_NOT_CONVERGED; break; }
-        /* affine direction: rc = s.z  =>  t = (z.rg - rc)/s = w.rg - z */
-        for (int r = 0; r < mi; r++) tt[r] = dead[r] ? 0.0 : K.w[r] * rg[r] - z[r];
+        for (int r = 0; r < mi; r++) K.w[r] = dead[r] ? 0.0 : z[r] / s[r];
+        if (nsp_factor(&K, K.w)) { status = ORACLE_NOT_CONVERGED; break; }
+        /* affine direction: rc = s.z  =>  G' coefficient -(w rg - z) */
+        for (int r = 0; r < mi; r++) tt[r] = dead[r] ? 0.0 : -(K.w[r] * rg[r] - z[r]);
         for (int i = 0; i < nv; i++) r1[i] = -rd[i];
-        for (int r = 0; r < mi; r++) tt[r] = -tt[r];
         csr_mulTv_add(mi, q->g_ptr, q->g_idx, q->g_val, tt, r1);
-        for (int r = 0; r < ne; r++) r2[r] = -rp[r];
-        kkt_solve(&K, r1, r2, dx, dy);
-        csr_mulv(mi, q->g_ptr, q->g_idx, q->g_val, dx, gx);
+        nsp_Zt(&K, r1, sg);
+        nsp_solve(&K, sg);
+        nsp_Z(&K, sg, dxa);
+        csr_mulv(mi, q->g_ptr, q->g_idx, q->g_val, dxa, gxa);
         double aa = 1.0;
         for (int r = 0; r < mi; r++) {
-            if (dead[r]) { dsa[r] = 0; dza[r] = 0; continue; }
-            dsa[r] = -rg[r] - gx[r];
-            dza[r] = -z[r] - K.w[r] * dsa[r];
-            if (dsa[r] < 0) { double a = -s[r] / dsa[r]; if (a < aa) aa = a; }
-            if (dza[r] < 0) { double a = -z[r] / dza[r]; if (a < aa) aa = a; }
+            if (dead[r]) continue;
+            double dsa = -rg[r] - gxa[r], dza = -z[r] - K.w[r] * dsa;
+            if (dsa < 0) { double a = -s[r] / dsa; if (a < aa) aa = a; }
+            if (dza < 0) { double a = -z[r] / dza; if (a < aa) aa = a; }
         }
         double mua = 0;
-        for (int r = 0; r < mi; r++) if (!dead[r]) mua += (s[r] + aa * dsa[r]) * (z[r] + aa * dza[r]);
+        for (int r = 0; r < mi; r++) {
+            if (dead[r]) continue;
+            double dsa = -rg[r] - gxa[r], dza = -z[r] - K.w[r] * dsa;
+            mua += (s[r] + aa * dsa) * (z[r] + aa * dza);
+        }
         mua /= (n_live > 0 ? n_live : 1);
-        double sigma = (mu > 0) ? pow(mua / mu, 3.0) : 0;
+        double sigma = (mu > 0) ? (mua / mu) * (mua / mu) * (mua / mu) : 0;
         /* corrector: rc = s.z + dsa.dza - sigma mu */
         for (int r = 0; r < mi; r++) {
-            double rc = s[r] * z[r] + dsa[r] * dza[r] - sigma * mu;
-            tt[r] = dead[r] ? 0.0 : -(z[r] * rg[r] - rc) / s[r];
+            if (dead[r]) { tt[r] = 0; continue; }
+            double dsa = -rg[r] - gxa[r], dza = -z[r] - K.w[r] * dsa;
+            double rc = s[r] * z[r] + dsa * dza - sigma * mu;
+            tt[r] = -(z[r] * rg[r] - rc) / s[r];
         }
         for (int i = 0; i < nv; i++) r1[i] = -rd[i];
         csr_mulTv_add(mi, q->g_ptr, q->g_idx, q->g_val, tt, r1);
-        kkt_solve(&K, r1, r2, dx, dy);
+        nsp_Zt(&K, r1, sg);
+        nsp_solve(&K, sg);
+        nsp_Z(&K, sg, dx);
         csr_mulv(mi, q->g_ptr, q->g_idx, q->g_val, dx, gx);
         double am = 1e300;
         for (int r = 0; r < mi; r++) {
-            if (dead[r]) { ds[r] = 0; dz[r] = 0; continue; }
-            double rc = s[r] * z[r] + dsa[r] * dza[r] - sigma * mu;
-            ds[r] = -rg[r] - gx[r];
-            dz[r] = (-rc - z[r] * ds[r]) / s[r];
-            if (ds[r] < 0) { double a = -s[r] / ds[r]; if (a < am) am = a; }
-            if (dz[r] < 0) { double a = -z[r] / dz[r]; if (a < am) am = a; }
+            if (dead[r]) { tt[r] = 0; rg[r] = 0; continue; }
+            double dsa = -rg[r] - gxa[r], dza = -z[r] - K.w[r] * dsa;
+            double rc = s[r] * z[r] + dsa * dza - sigma * mu;
+            double ds = -rg[r] - gx[r], dz = (-rc - z[r] * ds) / s[r];
+            tt[r] = ds; rg[r] = dz; /* reuse as ds, dz */
+            if (ds < 0) { double a = -s[r] / ds; if (a < am) am = a; }
+            if (dz < 0) { double a = -z[r] / dz; if (a < am) am = a; }
         }
         double al = fmin(1.0, 0.99 * am);
         for (int i = 0; i < nv; i++) x[i] += al * dx[i];
-        for (int r = 0; r < ne; r++) y[r] += al * dy[r];
-        for (int r = 0; r < mi; r++) { s[r] += al * ds[r]; z[r] += al * dz[r]; }
+        for (int r = 0; r < mi; r++) { if (dead[r]) continue; s[r] += al * tt[r]; z[r] += al * rg[r]; }
     }
 done:
+    if (res_out) {
+        double nrp = 0;
+        if (ne > 0 && status != ORACLE_BAD_ARG) {
+            csr_mulv(ne, q->a_ptr, q->a_idx, q->a_val, x, ax);
+            for (int r = 0; r < ne; r++) { double a = fabs(ax[r] - q->b[r]); if (a > nrp) nrp = a; }
+        }
+        res_out[0] = gap; res_out[1] = nrp; res_out[2] = nrd; res_out[3] = nrg;
+    }
     if (obj_out) *obj_out = obj;
     if (iters_out) *iters_out = it;
-    kkt_free(&K);
-    free(dead);
-    free(y); free(s); free(z); free(rd); free(rp); free(rg); free(r1); free(r2); free(tt);
-    free(dx); free(dy); free(ds); free(dz); free(dsa); free(dza); free(gx); free(px);
+    nsp_free(&K);
+    free(s); free(z); free(rd); free(rg); free(r1); free(tt); free(dx); free(dxa); free(gx); free(px);
+    free(gxa); free(hs); free(sg); free(ax); free(dead);
     return status;
 }
 
