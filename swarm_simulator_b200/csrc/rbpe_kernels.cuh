@@ -6,9 +6,10 @@
 //   pdip_kernel      (k2)  one CTA per mission (Gauss-Seidel chain over its batches, L140-L201) or per
 //                          (mission, batch) (Jacobi): builds the batch QP of populatebyrow (L551-L688)
 //                          implicitly -- rows are never materialised as a matrix -- and solves it with a
-//                          Mehrotra predictor-corrector interior-point method in FP64:
-//                          H = 2Q + G'WG is block diagonal over segments (blocks of 18b), the Schur complement
-//                          S = A H^-1 A' is block tridiagonal over knots (blocks of 9b).
+//                          Mehrotra predictor-corrector interior-point method in FP64.  Newton systems use the
+//                          null-space method over the C2 knot states (pos, vel, acc at every interior knot):
+//                          x = x_p + Z sigma parametrises {Ax = b} exactly (quintic Hermite <-> Bernstein), and
+//                          Z'(2Q + G'WG)Z is SPD and block tridiagonal over knots (blocks of 9b).
 //   convert_kernel   (k3)  Bernstein control points -> monomial coefficients (L167-L196, timeMatrix L695-L700)
 //
 // The same source compiles under tests/cpu_emu (a fiber emulator of the CUDA execution model used to debug the
@@ -63,6 +64,15 @@ __host__ __device__ inline double diffT_entry(int i, int c) {
     return binom_d(i, cc) * (((i - cc) & 1) ? -1.0 : 1.0);
 }
 
+// 3x3 inverse by cofactors (row-major)
+__host__ __device__ inline void inv3(const double *a, double *o) {
+    double c00 = a[4] * a[8] - a[5] * a[7], c01 = a[5] * a[6] - a[3] * a[8], c02 = a[3] * a[7] - a[4] * a[6];
+    double det = a[0] * c00 + a[1] * c01 + a[2] * c02, id = 1.0 / det;
+    o[0] = c00 * id; o[1] = (a[2] * a[7] - a[1] * a[8]) * id; o[2] = (a[1] * a[5] - a[2] * a[4]) * id;
+    o[3] = c01 * id; o[4] = (a[0] * a[8] - a[2] * a[6]) * id; o[5] = (a[2] * a[3] - a[0] * a[5]) * id;
+    o[6] = c02 * id; o[7] = (a[1] * a[6] - a[0] * a[7]) * id; o[8] = (a[0] * a[4] - a[1] * a[3]) * id;
+}
+
 __host__ __device__ inline long pair_index(int N, int qi, int qj) {  // lexicographic qi<qj (`iter`, L477-L503)
     return (long)qi * N - (long)qi * (qi + 1) / 2 + (qj - qi - 1);
 }
@@ -72,20 +82,19 @@ __host__ __device__ inline long pair_index(int N, int qi, int qj) {  // lexicogr
 // ------------------------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t al2(size_t nd) { return (nd + 1) & ~(size_t)1; }
 __host__ __device__ inline size_t scratch_doubles(int N, int M, int bs) {
-    size_t n = 18 * (size_t)bs, kb = 9 * (size_t)bs, nv = n * M, ne = kb * (M + 1);
+    size_t n = 18 * (size_t)bs, kb = 9 * (size_t)bs, nv = n * M, nr = kb * (size_t)(M > 1 ? M - 1 : 0);
     size_t NE = (size_t)(N - bs > 0 ? N - bs : 0), rext = (size_t)bs * M * 6 * NE;
     if (bs > 0 && N % bs) {  // the last, smaller batch sees more frozen agents
         size_t nl = (size_t)(N % bs), rl = nl * M * 6 * (N - nl);
         if (rl > rext) rext = rl;
     }
     size_t rint_ = (size_t)bs * (bs - 1) / 2 * 6 * M;
-    size_t t = 0;
-    t += 14 * al2(nv) + 5 * al2(ne);
-    t += al2((M + 1) * kb * kb) + al2(M * kb * kb);
-    t += 2 * al2(M * n * n);
+    size_t t = 64 + 36;
+    t += 12 * al2(nv) + 2 * al2(nr);
+    t += al2((size_t)M * bs * 36) + al2(rint_ * 6);                  // Dcp, Dint
+    t += al2((size_t)(M > 1 ? M - 1 : 1) * kb * kb) + al2((size_t)(M > 2 ? M - 2 : 1) * kb * kb);
     t += 3 * al2(rext) + 3 * al2((rext + 1) / 2);
     t += 3 * al2(rint_) + 3 * al2((rint_ + 1) / 2);
-    t += 64 + 36;
     return t;
 }
 
@@ -168,6 +177,26 @@ __global__ void assemble_kernel(AssembleArgs A) {
             }
             o[SEGMAT_QS] = pow(dt, -5.0);
             for (int j = 0; j < 6; j++) o[SEGMAT_TP + j] = pow(1.0 / dt, (double)(5 - j));
+            // Hermite <-> Bernstein: control points 0..2 = CL * (pos, vel, acc at the left knot), 3..5 = CR * (right knot)
+            double EL[9], ER[9];
+            for (int d = 0; d < 3; d++)
+                for (int i = 0; i < 3; i++) {
+                    double v = o[SEGMAT_AL + d * 6 + i];
+                    EL[d * 3 + i] = (m == 0) ? v : -v;     // interior knots carry the minus sign of the continuity row
+                    ER[d * 3 + i] = o[SEGMAT_AR + d * 6 + 3 + i];
+                }
+            inv3(EL, o + SEGMAT_CL);
+            inv3(ER, o + SEGMAT_CR);
+            // reduced cost Hessian of the segment over (left state, right state): C' (2 dt^-5 Q) C
+            for (int r = 0; r < 6; r++)
+                for (int cc = 0; cc < 6; cc++) {
+                    const double *Cr = o + (r < 3 ? SEGMAT_CL : SEGMAT_CR), *Cc = o + (cc < 3 ? SEGMAT_CL : SEGMAT_CR);
+                    double sum = 0;
+                    for (int i = 0; i < 3; i++)
+                        for (int ii = 0; ii < 3; ii++)
+                            sum += Cr[i * 3 + r % 3] * q_base_entry((r < 3 ? 0 : 3) + i, (cc < 3 ? 0 : 3) + ii) * Cc[ii * 3 + cc % 3];
+                    o[SEGMAT_RQ + r * 6 + cc] = 2.0 * o[SEGMAT_QS] * sum;
+                }
         }
     }
 }
@@ -276,16 +305,18 @@ RBPE_DEV void trsm_cols(TM tm, int n, const double *L, int ld, int nc, double *B
 }
 
 struct QP {
-    int N, M, nb, q0, NE, n, kb, nv, ne, nrext, nrint, mi;
+    int N, M, nb, q0, NE, n, kb, nv, nr, nrext, nrint, mi;
     int c;  // mission
     const double *start, *goal, *radius, *segbox, *segmat;
     const float *reln;
     const double *ctrl_src;
-    // vectors (nv)
-    double *x, *dxa, *dx, *rd, *r1, *px, *ub, *lbn, *sub, *zub, *slb, *zlb, *vA, *vB;
-    // vectors (ne)
-    double *y, *dy, *rp, *r2, *beq;
-    double *Sd, *So, *H, *Y;
+    // x-space vectors (nv), segment-major: v = m*18nb + (a*3+k)*6 + i
+    double *x, *dxa, *dx, *rdx, *ub, *lbn, *sub, *zub, *slb, *zlb, *vA, *vB;
+    // knot-space vectors (nr): r = (t-1)*9nb + (a*3+k)*3 + d, t = 1..M-1
+    double *sg, *sg2;
+    double *Wd, *Wo;     // reduced Hessian Z'HZ: (M-1) diagonal blocks, (M-2) blocks (t+1,t), each 9nb x 9nb
+    double *Dcp;         // [M*nb*6][6]  sum_rows w g g' restricted to one control point (3x3 symmetric over axes)
+    double *Dint;        // [nrint][6]   -w n n' of a row between two batch agents
     double *he, *se, *ze;
     float *nex, *ney, *nez;
     double *hi, *si, *zi;
@@ -320,14 +351,14 @@ RBPE_DEV void layout(QP &q, unsigned char *smem, size_t smem_bytes, double *gscr
     a.gl = gscratch;
     q.red = a.take(64);
     q.QB = a.take(36);
-    double **vv[14] = {&q.x, &q.dxa, &q.dx, &q.rd, &q.r1, &q.px, &q.ub, &q.lbn, &q.sub, &q.zub, &q.slb, &q.zlb, &q.vA, &q.vB};
-    for (int i = 0; i < 14; i++) *vv[i] = a.take(q.nv);
-    double **ee[5] = {&q.y, &q.dy, &q.rp, &q.r2, &q.beq};
-    for (int i = 0; i < 5; i++) *ee[i] = a.take(q.ne);
-    q.Sd = a.take((size_t)(q.M + 1) * q.kb * q.kb);
-    q.So = a.take((size_t)q.M * q.kb * q.kb);
-    q.H = a.take((size_t)q.M * q.n * q.n);
-    q.Y = a.take((size_t)q.M * q.n * q.n);
+    double **vv[12] = {&q.x, &q.dxa, &q.dx, &q.rdx, &q.ub, &q.lbn, &q.sub, &q.zub, &q.slb, &q.zlb, &q.vA, &q.vB};
+    for (int i = 0; i < 12; i++) *vv[i] = a.take(q.nv);
+    q.sg = a.take(q.nr);
+    q.sg2 = a.take(q.nr);
+    q.Dcp = a.take((size_t)q.M * q.nb * 36);
+    q.Dint = a.take((size_t)q.nrint * 6);
+    q.Wd = a.take((size_t)(q.M > 1 ? q.M - 1 : 1) * q.kb * q.kb);
+    q.Wo = a.take((size_t)(q.M > 2 ? q.M - 2 : 1) * q.kb * q.kb);
     q.he = a.take(q.nrext); q.se = a.take(q.nrext); q.ze = a.take(q.nrext);
     q.nex = (float *)a.take(((size_t)q.nrext + 1) / 2);
     q.ney = (float *)a.take(((size_t)q.nrext + 1) / 2);
@@ -360,7 +391,7 @@ RBPE_DEV void block_reduce4(double &s1, double &s2, double &mx, double &mn, doub
     }
 }
 
-enum { P_INIT = 0, P_START, P_SHIFT, P_RES, P_AFF, P_MUA, P_COR, P_STEP, P_UPD };
+enum { P_INIT = 0, P_START, P_SHIFT, P_RES, P_AFF, P_MUA, P_COR, P_STEP, P_UPD, P_DEAD };
 
 struct Acc {  // lane-local reductions of a row pass
     double s1, s2, mx, mn;
@@ -372,7 +403,8 @@ template <int MODE>
 RBPE_DEV void row_eval(double h, double &s, double &z, double gx, double ga, double gd, double sa, double sb,
                        bool owner, double &cA, double &cB, double &w, Acc &acc) {
     cA = 0; cB = 0; w = 0;
-    if (MODE == P_INIT) { w = 1.0; cA = h; return; }
+    if (MODE == P_DEAD) { acc.mx = fmax(acc.mx, gx - h); return; }   // constant row: violation of its right-hand side
+    if (MODE == P_INIT) { w = 1.0; cA = h - gx; return; }
     if (MODE == P_START) {  // z = Gx - h, s = -z (least-squares start)
         z = gx - h; s = -z;
         if (owner) { acc.mx = fmax(acc.mx, -s); acc.s1 = fmax(acc.s1, -z); }  // s1 doubles as a second max here
@@ -407,6 +439,9 @@ RBPE_DEV void row_eval(double h, double &s, double &z, double gx, double ga, dou
     }
     if (MODE == P_UPD) { s += sb * ds; z += sb * dz; }  // sb = step length
 }
+
+// Control points fixed by the start / goal equalities: 0..2 of the first segment, 3..5 of the last one.
+RBPE_DEV bool cp_dead(const QP &q, int m, int i) { return (m == 0 && i < 3) || (m == q.M - 1 && i >= 3); }
 
 // All inequality rows touching control point (m, a, i) of the batch, executed by one warp.
 template <int MODE>
@@ -457,12 +492,10 @@ RBPE_DEV void cp_task(const QP &q, int m, int a, int i, double sa, double sb, Ac
         if (MAT) {
             Dxx += w * n0 * n0; Dxy += w * n0 * n1; Dxz += w * n0 * n2;
             Dyy += w * n1 * n1; Dyz += w * n1 * n2; Dzz += w * n2 * n2;
-            if (own) {  // off-diagonal block H[(hi,k,i),(lo,k',i)] = -w n_k n_k'
-                double *Hm = q.H + (size_t)m * q.n * q.n;
-                double nn[3] = {n0, n1, n2};
-                for (int k = 0; k < 3; k++)
-                    for (int kk = 0; kk < 3; kk++)
-                        Hm[(size_t)(hi * 18 + k * 6 + i) * q.n + (lo * 18 + kk * 6 + i)] = -w * nn[k] * nn[kk];
+            if (own) {  // coupling block between the two agents at this control point: -w n n'
+                double *D = q.Dint + r * 6;
+                D[0] = -w * n0 * n0; D[1] = -w * n0 * n1; D[2] = -w * n0 * n2;
+                D[3] = -w * n1 * n1; D[4] = -w * n1 * n2; D[5] = -w * n2 * n2;
             }
         }
     }
@@ -501,24 +534,9 @@ RBPE_DEV void cp_task(const QP &q, int m, int a, int i, double sa, double sb, Ac
             Dyy += shfl_down_t(Dyy, o); Dyz += shfl_down_t(Dyz, o); Dzz += shfl_down_t(Dzz, o);
         }
         if (lane == 0) {
-            double *Hm = q.H + (size_t)m * q.n * q.n;
-            int r0 = a * 18 + i, r1 = r0 + 6, r2 = r0 + 12;
-            Hm[(size_t)r0 * q.n + r0] += Dxx;
-            Hm[(size_t)r1 * q.n + r0] += Dxy; Hm[(size_t)r1 * q.n + r1] += Dyy;
-            Hm[(size_t)r2 * q.n + r0] += Dxz; Hm[(size_t)r2 * q.n + r1] += Dyz; Hm[(size_t)r2 * q.n + r2] += Dzz;
+            double *D = q.Dcp + ((size_t)(m * q.nb + a) * 6 + i) * 6;
+            D[0] = Dxx; D[1] = Dxy; D[2] = Dxz; D[3] = Dyy; D[4] = Dyz; D[5] = Dzz;
         }
-    }
-}
-
-// H <- 2 Q (lower triangle), zero elsewhere in the lower triangle
-RBPE_DEV void init_H(const QP &q) {
-    const size_t nn = (size_t)q.n * q.n;
-    for (size_t idx = threadIdx.x; idx < nn * q.M; idx += blockDim.x) {
-        int m = (int)(idx / nn);
-        int r = (int)((idx - m * nn) / q.n), c = (int)((idx - m * nn) % q.n);
-        double v = 0;
-        if (c <= r && r / 6 == c / 6) v = 2.0 * q.QB[(r % 6) * 6 + c % 6] * q.segmat[m * SEGMAT + SEGMAT_QS];
-        q.H[idx] = v;
     }
 }
 
@@ -527,10 +545,10 @@ RBPE_DEV void row_pass(const QP &q, double sa, double sb, Acc &out) {
     Acc acc;
     acc.s1 = (MODE == P_START) ? -1e300 : 0.0;
     acc.s2 = 0; acc.mx = -1e300; acc.mn = 1e300;
-    if (MODE == P_INIT || MODE == P_RES) { init_H(q); __syncthreads(); }
     const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5, ntask = q.M * q.nb * 6;
     for (int t = warp; t < ntask; t += nw) {
         int i = t % 6, a = (t / 6) % q.nb, m = t / (6 * q.nb);
+        if (cp_dead(q, m, i) != (MODE == P_DEAD)) continue;   // live passes skip fixed control points and vice versa
         cp_task<MODE>(q, m, a, i, sa, sb, acc);
     }
     if (MODE == P_START) {  // two max reductions: mx and s1
@@ -545,62 +563,83 @@ RBPE_DEV void row_pass(const QP &q, double sa, double sb, Acc &out) {
     out = acc;
 }
 
-// ---- linear algebra on the reduced KKT system ----------------------------------------------------------------
-// factor: H_m = L_m L_m' ; Y_m = L_m^-1 A_m' ; S = Y'Y (block tridiagonal) ; S = Ls Ls'
-template <class TM>
-RBPE_DEV bool factor_seg(TM tm, const QP &q, int m) {
-    double *Hm = q.H + (size_t)m * q.n * q.n, *Ym = q.Y + (size_t)m * q.n * q.n;
-    const double *sm = q.segmat + m * SEGMAT;
-    const int n = q.n, kb = q.kb;
-    // Y_m = A_m' : rows = variables (a,k,i), columns = (side, (a,k), d)
-    for (int idx = tm.rank(); idx < n * n; idx += tm.size()) {
-        int r = idx / n, c = idx % n, side = c / kb, cc = c % kb;
-        double v = 0;
-        if (cc / 3 == r / 6) v = sm[(side ? SEGMAT_AR : SEGMAT_AL) + (cc % 3) * 6 + (r % 6)];
-        Ym[idx] = v;
-    }
-    bool ok = chol_lower(tm, n, Hm, n);
-    trsm_cols(tm, n, Hm, n, n, Ym, n, (const int *)0);
-    return ok;
+// ---- knot space ------------------------------------------------------------------------------------------------
+RBPE_DEV int sym6(int k, int kk) {  // index of (k,kk) in (xx, xy, xz, yy, yz, zz)
+    int lo = k < kk ? k : kk, hi = k < kk ? kk : k;
+    return lo == 0 ? hi : (lo == 1 ? 2 + hi : 5);
 }
-
-RBPE_DEV void build_S(const QP &q) {
-    const int n = q.n, kb = q.kb, M = q.M;
-    const int kk = kb * kb;
-    for (int idx = threadIdx.x; idx < (2 * M + 1) * kk; idx += blockDim.x) {
-        int blk = idx / kk, r = (idx % kk) / kb, c = idx % kb;
-        if (blk <= M) {  // diagonal block of knot t = blk (lower triangle)
-            int t = blk;
-            double s = 0;
-            if (c <= r) {
-                if (t > 0) {
-                    const double *Y = q.Y + (size_t)(t - 1) * n * n + kb;
-                    for (int k = 0; k < n; k++) s += Y[(size_t)k * n + r] * Y[(size_t)k * n + c];
-                }
-                if (t < M) {
-                    const double *Y = q.Y + (size_t)t * n * n;
-                    for (int k = 0; k < n; k++) s += Y[(size_t)k * n + r] * Y[(size_t)k * n + c];
-                }
+// out (nr) = Z' vec (nv)
+RBPE_DEV void Zt_apply(const QP &q, const double *vec, double *out) {
+    for (int r = threadIdx.x; r < q.nr; r += blockDim.x) {
+        int t = r / q.kb + 1, cc = r % q.kb, ak = cc / 3, d = cc % 3;
+        const double *CR = q.segmat + (t - 1) * SEGMAT + SEGMAT_CR, *CL = q.segmat + t * SEGMAT + SEGMAT_CL;
+        const double *vl = vec + (t - 1) * q.n + ak * 6 + 3, *vr = vec + t * q.n + ak * 6;
+        double s = 0;
+        for (int j = 0; j < 3; j++) s += CR[j * 3 + d] * vl[j] + CL[j * 3 + d] * vr[j];
+        out[r] = s;
+    }
+}
+// out (nv) = Z sg (nr)
+RBPE_DEV void Z_apply(const QP &q, const double *sg, double *out) {
+    for (int v = threadIdx.x; v < q.nv; v += blockDim.x) {
+        int m = v / q.n, r = v % q.n, ak = r / 6, i = r % 6;
+        double s = 0;
+        if (i < 3) {
+            if (m > 0) {
+                const double *C = q.segmat + m * SEGMAT + SEGMAT_CL + i * 3, *g = sg + (m - 1) * q.kb + ak * 3;
+                s = C[0] * g[0] + C[1] * g[1] + C[2] * g[2];
             }
-            q.Sd[(size_t)t * kk + r * kb + c] = s;
-        } else {  // block (t+1, t): rows = right columns of segment t, cols = left columns of segment t
-            int t = blk - M - 1;
-            const double *Y = q.Y + (size_t)t * n * n;
-            double s = 0;
-            for (int k = 0; k < n; k++) s += Y[(size_t)k * n + kb + r] * Y[(size_t)k * n + c];
-            q.So[(size_t)t * kk + r * kb + c] = s;
+        } else if (m < q.M - 1) {
+            const double *C = q.segmat + m * SEGMAT + SEGMAT_CR + (i - 3) * 3, *g = sg + m * q.kb + ak * 3;
+            s = C[0] * g[0] + C[1] * g[1] + C[2] * g[2];
         }
+        out[v] = s;
     }
 }
 
+// reduced Hessian Z'(2Q + G'WG)Z from the per-control-point blocks left by the last P_INIT / P_RES pass
+RBPE_DEV void build_W(const QP &q) {
+    const int kb = q.kb, kk = kb * kb, M = q.M;
+    for (int idx = threadIdx.x; idx < (M - 1) * kk; idx += blockDim.x) {
+        int t = idx / kk + 1, r = (idx % kk) / kb, c = idx % kb;
+        double s = 0;
+        if (c <= r) {
+            int a = r / 9, k = (r % 9) / 3, d = r % 3, a2 = c / 9, k2 = (c % 9) / 3, d2 = c % 3;
+            const double *CR = q.segmat + (t - 1) * SEGMAT + SEGMAT_CR, *CL = q.segmat + t * SEGMAT + SEGMAT_CL;
+            int e = sym6(k, k2);
+            if (a == a2) {
+                const double *Dl = q.Dcp + ((size_t)((t - 1) * q.nb + a) * 6 + 3) * 6 + e;
+                const double *Dr = q.Dcp + ((size_t)(t * q.nb + a) * 6) * 6 + e;
+                for (int j = 0; j < 3; j++) s += CR[j * 3 + d] * CR[j * 3 + d2] * Dl[j * 6] + CL[j * 3 + d] * CL[j * 3 + d2] * Dr[j * 6];
+                if (k == k2)
+                    s += q.segmat[(t - 1) * SEGMAT + SEGMAT_RQ + (3 + d) * 6 + 3 + d2] + q.segmat[t * SEGMAT + SEGMAT_RQ + d * 6 + d2];
+            } else {  // a > a2: rows between the two batch agents
+                size_t pp = (size_t)a2 * q.nb - (size_t)a2 * (a2 + 1) / 2 + (a - a2 - 1);
+                const double *Dl = q.Dint + (pp * 6 * M + (t - 1) * 6 + 3) * 6 + e;
+                const double *Dr = q.Dint + (pp * 6 * M + t * 6) * 6 + e;
+                for (int j = 0; j < 3; j++) s += CR[j * 3 + d] * CR[j * 3 + d2] * Dl[j * 6] + CL[j * 3 + d] * CL[j * 3 + d2] * Dr[j * 6];
+            }
+        }
+        q.Wd[idx] = s;
+    }
+    // blocks (t+1, t), t = 1..M-2: only the cost couples neighbouring knots, per (agent, axis)
+    for (int idx = threadIdx.x; idx < (M - 2) * kk; idx += blockDim.x) {
+        int t = idx / kk + 1, r = (idx % kk) / kb, c = idx % kb;
+        double s = 0;
+        if (r / 3 == c / 3) s = q.segmat[t * SEGMAT + SEGMAT_RQ + (3 + r % 3) * 6 + c % 3];
+        q.Wo[idx] = s;
+    }
+}
+
+// block tridiagonal Cholesky of nblk diagonal blocks D (kb x kb, lower) and nblk-1 blocks O = (t+1, t)
 template <class TM>
-RBPE_DEV bool factor_S(TM tm, const QP &q) {
-    const int kb = q.kb, M = q.M, kk = kb * kb;
+RBPE_DEV bool factor_bt(TM tm, int nblk, int kb, double *Dall, double *Oall) {
+    const int kk = kb * kb;
     bool ok = true;
-    for (int t = 0; t <= M; t++) {
-        double *D = q.Sd + (size_t)t * kk;
+    for (int t = 0; t < nblk; t++) {
+        double *D = Dall + (size_t)t * kk;
         if (t > 0) {
-            const double *Lo = q.So + (size_t)(t - 1) * kk;
+            const double *Lo = Oall + (size_t)(t - 1) * kk;
             for (int idx = tm.rank(); idx < kk; idx += tm.size()) {
                 int r = idx / kb, c = idx % kb;
                 if (c <= r) {
@@ -611,8 +650,8 @@ RBPE_DEV bool factor_S(TM tm, const QP &q) {
             }
         }
         ok = chol_lower(tm, kb, D, kb) && ok;
-        if (t < M) {  // Lo_t = So_t D^-T : row-wise forward substitution, one thread per row
-            double *O = q.So + (size_t)t * kk;
+        if (t < nblk - 1) {  // O_t <- O_t D^-T : row-wise forward substitution, one thread per row
+            double *O = Oall + (size_t)t * kk;
             for (int r = tm.rank(); r < kb; r += tm.size()) {
                 for (int c = 0; c < kb; c++) {
                     double v = O[r * kb + c];
@@ -627,155 +666,82 @@ RBPE_DEV bool factor_S(TM tm, const QP &q) {
 }
 
 template <class TM>
-RBPE_DEV void solve_S(TM tm, const QP &q, double *g) {
-    const int kb = q.kb, M = q.M, kk = kb * kb;
-    for (int t = 0; t <= M; t++) {
+RBPE_DEV void solve_bt(TM tm, int nblk, int kb, const double *Dall, const double *Oall, double *g) {
+    const int kk = kb * kb;
+    for (int t = 0; t < nblk; t++) {
         if (t > 0) {
-            const double *Lo = q.So + (size_t)(t - 1) * kk;
+            const double *Lo = Oall + (size_t)(t - 1) * kk;
             for (int r = tm.rank(); r < kb; r += tm.size()) {
                 double s = 0;
                 for (int k = 0; k < kb; k++) s += Lo[r * kb + k] * g[(t - 1) * kb + k];
                 g[t * kb + r] -= s;
             }
         }
-        fwd_vec(tm, kb, q.Sd + (size_t)t * kk, kb, g + t * kb);
+        fwd_vec(tm, kb, Dall + (size_t)t * kk, kb, g + t * kb);
     }
-    for (int t = M; t >= 0; t--) {
-        if (t < M) {
-            const double *Lo = q.So + (size_t)t * kk;
+    for (int t = nblk - 1; t >= 0; t--) {
+        if (t < nblk - 1) {
+            const double *Lo = Oall + (size_t)t * kk;
             for (int c = tm.rank(); c < kb; c += tm.size()) {
                 double s = 0;
                 for (int k = 0; k < kb; k++) s += Lo[k * kb + c] * g[(t + 1) * kb + k];
                 g[t * kb + c] -= s;
             }
         }
-        bwd_vec(tm, kb, q.Sd + (size_t)t * kk, kb, g + t * kb);
+        bwd_vec(tm, kb, Dall + (size_t)t * kk, kb, g + t * kb);
     }
 }
 
 RBPE_DEV bool kkt_factor(const QP &q) {
-    const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    build_W(q);
+    __syncthreads();
     bool ok = true;
-    __syncthreads();
-    if (q.n <= 72) {
-        for (int m = warp; m < q.M; m += nw) ok = factor_seg(WarpTeam(), q, m) && ok;
-    } else {
-        for (int m = 0; m < q.M; m++) ok = factor_seg(CtaTeam(), q, m) && ok;
-    }
-    __syncthreads();
-    build_S(q);
-    __syncthreads();
     if (q.kb <= 36) {
-        if (warp == 0) ok = factor_S(WarpTeam(), q) && ok;
+        if ((threadIdx.x >> 5) == 0) ok = factor_bt(WarpTeam(), q.M - 1, q.kb, q.Wd, q.Wo);
     } else {
-        ok = factor_S(CtaTeam(), q) && ok;
+        ok = factor_bt(CtaTeam(), q.M - 1, q.kb, q.Wd, q.Wo);
     }
-    // combine the verdict over the CTA
     double s1 = ok ? 0.0 : 1.0, s2 = 0, mx = -1e300, mn = 1e300;
     block_reduce4(s1, s2, mx, mn, q.red);
     return s1 == 0.0;
 }
 
-// solve  H dx + A' dy = r1 ; A dx = r2.  u (nv) holds r1 on entry and dx on exit; g (ne) holds r2 on entry, dy on exit.
-RBPE_DEV void kkt_solve(const QP &q, double *u, double *g) {
-    const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5, n = q.n, kb = q.kb, M = q.M;
+// dxout (nv) = Z (Z'HZ)^-1 Z' r   with r (nv) in x-space; uses q.sg
+RBPE_DEV void kkt_solve(const QP &q, const double *r, double *dxout) {
     __syncthreads();
-    if (n <= 72) {
-        for (int m = warp; m < M; m += nw) fwd_vec(WarpTeam(), n, q.H + (size_t)m * n * n, n, u + m * n);
+    Zt_apply(q, r, q.sg);
+    __syncthreads();
+    if (q.kb <= 36) {
+        if ((threadIdx.x >> 5) == 0) solve_bt(WarpTeam(), q.M - 1, q.kb, q.Wd, q.Wo, q.sg);
     } else {
-        for (int m = 0; m < M; m++) fwd_vec(CtaTeam(), n, q.H + (size_t)m * n * n, n, u + m * n);
+        solve_bt(CtaTeam(), q.M - 1, q.kb, q.Wd, q.Wo, q.sg);
     }
     __syncthreads();
-    // g_t = YR_{t-1}' u_{t-1} + YL_t' u_t - r2_t
-    for (int e = threadIdx.x; e < q.ne; e += blockDim.x) {
-        int t = e / kb, c = e % kb;
-        double s = 0;
-        if (t > 0) {
-            const double *Y = q.Y + (size_t)(t - 1) * n * n + kb + c, *uu = u + (t - 1) * n;
-            for (int k = 0; k < n; k++) s += Y[(size_t)k * n] * uu[k];
-        }
-        if (t < M) {
-            const double *Y = q.Y + (size_t)t * n * n + c, *uu = u + t * n;
-            for (int k = 0; k < n; k++) s += Y[(size_t)k * n] * uu[k];
-        }
-        g[e] = s - g[e];
-    }
-    __syncthreads();
-    if (kb <= 36) {
-        if (warp == 0) solve_S(WarpTeam(), q, g);
-    } else {
-        solve_S(CtaTeam(), q, g);
-    }
-    __syncthreads();
-    // u -= Y dy
-    for (int v = threadIdx.x; v < q.nv; v += blockDim.x) {
-        int m = v / n, r = v % n;
-        const double *Yr = q.Y + (size_t)m * n * n + (size_t)r * n, *gl = g + m * kb;
-        double s = 0;
-        for (int c = 0; c < 2 * kb; c++) s += Yr[c] * gl[c];  // left knot m then right knot m+1 are contiguous in g
-        u[v] -= s;
-    }
-    __syncthreads();
-    if (n <= 72) {
-        for (int m = warp; m < M; m += nw) bwd_vec(WarpTeam(), n, q.H + (size_t)m * n * n, n, u + m * n);
-    } else {
-        for (int m = 0; m < M; m++) bwd_vec(CtaTeam(), n, q.H + (size_t)m * n * n, n, u + m * n);
-    }
+    Z_apply(q, q.sg, dxout);
     __syncthreads();
 }
 
-// px = P x = 2 Q x ; returns nothing (reductions done by the caller)
-RBPE_DEV void apply_P(const QP &q, const double *x, double *px) {
-    for (int v = threadIdx.x; v < q.nv; v += blockDim.x) {
-        int m = v / q.n, i = v % 6, b6 = v - i;
-        double s = 0;
-        for (int j = 0; j < 6; j++) s += q.QB[i * 6 + j] * x[b6 + j];
-        px[v] = 2.0 * q.segmat[m * SEGMAT + SEGMAT_QS] * s;
-    }
-}
-// out[v] += (A'y)[v]
-RBPE_DEV double At_y(const QP &q, const double *y, int v) {
-    int m = v / q.n, r = v % q.n, ak = r / 6, i = r % 6;
-    const double *sm = q.segmat + m * SEGMAT;
-    const double *yl = y + m * q.kb + ak * 3, *yr = yl + q.kb;
-    double s = 0;
-    for (int d = 0; d < 3; d++) s += sm[SEGMAT_AL + d * 6 + i] * yl[d] + sm[SEGMAT_AR + d * 6 + i] * yr[d];
-    return s;
-}
-// (A x)[e]
-RBPE_DEV double A_x(const QP &q, const double *x, int e) {
-    int t = e / q.kb, cc = e % q.kb, ak = cc / 3, d = cc % 3;
-    double s = 0;
-    if (t < q.M) {
-        const double *sm = q.segmat + t * SEGMAT + SEGMAT_AL + d * 6, *xx = x + t * q.n + ak * 6;
-        for (int i = 0; i < 6; i++) s += sm[i] * xx[i];
-    }
-    if (t > 0) {
-        const double *sm = q.segmat + (t - 1) * SEGMAT + SEGMAT_AR + d * 6, *xx = x + (t - 1) * q.n + ak * 6;
-        for (int i = 0; i < 6; i++) s += sm[i] * xx[i];
-    }
-    return s;
-}
-
-// rows of populatebyrow for the batch starting at agent q0 (h, normals; s = z = 1 until the start point is known)
+// rows of populatebyrow for the batch starting at agent q0 (h, normals; s = z = 1 until the start point is known);
+// x <- particular solution x_p (fixed control points from the start / goal states, zero elsewhere)
 RBPE_DEV void setup_rows(const QP &q) {
     const int M = q.M, N = q.N;
-    // box bounds per variable (L626-L635) and equality right-hand sides (build_deq L408-L432)
     for (int v = threadIdx.x; v < q.nv; v += blockDim.x) {
-        int m = v / q.n, r = v % q.n, a = r / 18, k = (r % 18) / 6;
+        int m = v / q.n, r = v % q.n, a = r / 18, k = (r % 18) / 6, i = r % 6;
         const double *box = q.segbox + ((size_t)(q.q0 + a) * M + m) * 6;
         q.ub[v] = box[3 + k];
         q.lbn[v] = -box[k];
         q.sub[v] = 1; q.zub[v] = 1; q.slb[v] = 1; q.zlb[v] = 1;
-        q.x[v] = 0; q.dxa[v] = 0; q.dx[v] = 0;
-    }
-    for (int e = threadIdx.x; e < q.ne; e += blockDim.x) {
-        int t = e / q.kb, cc = e % q.kb, a = cc / 9, k = (cc % 9) / 3, d = cc % 3;
-        double v = 0;
-        if (t == 0) v = q.start[(size_t)(q.q0 + a) * 9 + k + 3 * d];
-        if (t == M) v = q.goal[(size_t)(q.q0 + a) * 9 + k + 3 * d];
-        q.beq[e] = v;
-        q.y[e] = 0;
+        double xp = 0;
+        if (m == 0 && i < 3) {          // build_deq rows 0..2 (L408-L432): start pos / vel / acc
+            const double *C = q.segmat + SEGMAT_CL + i * 3, *st = q.start + (size_t)(q.q0 + a) * 9 + k;
+            xp = C[0] * st[0] + C[1] * st[3] + C[2] * st[6];
+        }
+        if (m == M - 1 && i >= 3) {     // rows 3..5: goal
+            const double *C = q.segmat + (M - 1) * SEGMAT + SEGMAT_CR + (i - 3) * 3, *gl = q.goal + (size_t)(q.q0 + a) * 9 + k;
+            xp = C[0] * gl[0] + C[1] * gl[3] + C[2] * gl[6];
+        }
+        q.x[v] = xp; q.dxa[v] = 0; q.dx[v] = 0; q.vA[v] = 0; q.vB[v] = 0;
     }
     // RSFC rows against frozen agents: g = sg*n on x_a,  h = sg*n.dummy_other - (r_a + r_other)
     for (int r = threadIdx.x; r < q.nrext; r += blockDim.x) {
@@ -808,6 +774,26 @@ RBPE_DEV void setup_rows(const QP &q) {
     }
 }
 
+// rdx = 2Q x + vA (x-space); returns lane-local partial sums through the arguments
+RBPE_DEV void dual_residual(const QP &q, double &obj_part, double &mpx) {
+    for (int v = threadIdx.x; v < q.nv; v += blockDim.x) {
+        int m = v / q.n, i = v % 6, b6 = v - i;
+        double s = 0;
+        for (int j = 0; j < 6; j++) s += q.QB[i * 6 + j] * q.x[b6 + j];
+        double pxv = 2.0 * q.segmat[m * SEGMAT + SEGMAT_QS] * s;
+        q.rdx[v] = pxv + q.vA[v];
+        obj_part += 0.5 * q.x[v] * pxv;
+        mpx = fmax(mpx, fabs(pxv));
+    }
+}
+RBPE_DEV double block_max(double v, double *red) {
+    double s1 = 0, s2 = 0, mn = 1e300;
+    block_reduce4(s1, s2, v, mn, red);
+    return v;
+}
+
+constexpr double PRESOLVE_FEAS_TOL = 1e-6;  // CPLEX's default feasibility tolerance, for rows made constant by the endpoints
+
 // Solves the QP described by q. Returns status; x holds the solution.
 RBPE_DEV int pdip_solve(const QP &q, int max_iter, double tol_gap, double tol_res, double *obj_out, int *it_out,
                         double *res_out) {
@@ -815,34 +801,47 @@ RBPE_DEV int pdip_solve(const QP &q, int max_iter, double tol_gap, double tol_re
     Acc acc;
     setup_rows(q);
     __syncthreads();
-    // |b|, |h| norms for the relative tolerances
-    double bn, hn;
-    {
-        double s1 = 0, s2 = 0, mx = -1e300, mn = 1e300, mh = 0;
-        for (int e = tid; e < q.ne; e += nt) mx = fmax(mx, fabs(q.beq[e]));
-        for (int v = tid; v < q.nv; v += nt) mh = fmax(mh, fmax(fabs(q.ub[v]), fabs(q.lbn[v])));
-        for (int r = tid; r < q.nrext; r += nt) mh = fmax(mh, fabs(q.he[r]));
-        for (int r = tid; r < q.nrint; r += nt) mh = fmax(mh, fabs(q.hi[r]));
-        mx = fmax(mx, 0.0);
-        block_reduce4(s1, s2, mx, mn, q.red);
-        bn = mx;
-        s1 = 0; s2 = 0; mn = 1e300;
-        block_reduce4(s1, s2, mh, mn, q.red);
-        hn = mh;
-    }
     int status = ST_NOT_CONVERGED, it = 0;
-    double obj = 0, gap = 0, nrp = 0, nrd = 0, nrg = 0;
-
-    // ---- initial point: W = I, [H A'; A 0][x; y] = [G'h; b] ----
-    row_pass<P_INIT>(q, 0, 0, acc);
-    __syncthreads();
-    bool fok = kkt_factor(q);
-    if (fok) {
-        for (int v = tid; v < q.nv; v += nt) q.r1[v] = q.vA[v];
-        for (int e = tid; e < q.ne; e += nt) q.r2[e] = q.beq[e];
-        kkt_solve(q, q.r1, q.r2);
-        for (int v = tid; v < q.nv; v += nt) q.x[v] = q.r1[v];
-        for (int e = tid; e < q.ne; e += nt) q.y[e] = q.r2[e];
+    double obj = 0, gap = 0, nrd = 0, nrg = 0, hn = 0;
+    bool go = true;
+    // presolve: rows on fixed control points are constants; check them and leave them out
+    row_pass<P_DEAD>(q, 0, 0, acc);
+    if (acc.mx > PRESOLVE_FEAS_TOL) { status = ST_INFEASIBLE; go = false; }
+    if (go && q.nr == 0) {  // single segment: the endpoints fix everything
+        double o = 0, mpx = 0, s2 = 0, mx = 0, mn = 1e300;
+        dual_residual(q, o, mpx);
+        block_reduce4(o, s2, mx, mn, q.red);
+        obj = o;
+        status = ST_OK;
+        go = false;
+    }
+    if (go) {
+        double mh = 0;
+        for (int v = tid; v < q.nv; v += nt) {
+            int m = v / q.n, i = v % 6;
+            if (!cp_dead(q, m, i)) mh = fmax(mh, fmax(fabs(q.ub[v]), fabs(q.lbn[v])));
+        }
+        for (int r = tid; r < q.nrext; r += nt) {
+            int rest = r / q.NE, i = rest % 6, m = (rest / 6) % q.M;
+            if (!cp_dead(q, m, i)) mh = fmax(mh, fabs(q.he[r]));
+        }
+        for (int r = tid; r < q.nrint; r += nt) {
+            int j = r % (6 * q.M);
+            if (!cp_dead(q, j / 6, j % 6)) mh = fmax(mh, fabs(q.hi[r]));
+        }
+        hn = block_max(mh, q.red);
+        // ---- initial point: W = I,  min 1/2 x'(P + G'G)x - (G'h)'x  over x = x_p + Z sigma ----
+        row_pass<P_INIT>(q, 0, 0, acc);   // vA = G'(h - G x_p), Dcp/Dint with unit weights
+        __syncthreads();
+        if (!kkt_factor(q)) go = false;
+    }
+    if (go) {
+        double o = 0, mpx = 0;
+        dual_residual(q, o, mpx);          // rdx = P x_p + vA
+        __syncthreads();
+        for (int v = tid; v < q.nv; v += nt) q.rdx[v] = 2.0 * q.vA[v] - q.rdx[v];   // G'(h - G x_p) - P x_p
+        kkt_solve(q, q.rdx, q.dx);
+        for (int v = tid; v < q.nv; v += nt) { q.x[v] += q.dx[v]; q.dx[v] = 0; }
         __syncthreads();
         row_pass<P_START>(q, 0, 0, acc);  // acc.mx = max(-s), acc.s1 = max(-z)
         double ap = acc.mx, ad = acc.s1;
@@ -851,57 +850,35 @@ RBPE_DEV int pdip_solve(const QP &q, int max_iter, double tol_gap, double tol_re
         __syncthreads();
     }
 
-    for (it = 0; fok && it < max_iter; it++) {
+    for (it = 0; go && it < max_iter; it++) {
         // ---- residuals ----
-        apply_P(q, q.x, q.px);
-        __syncthreads();
-        row_pass<P_RES>(q, 0, 0, acc);  // vA = G'z, vB = G't_aff, H assembled; s1 = s'z, s2 = h'z, mx = |rg|
+        row_pass<P_RES>(q, 0, 0, acc);  // vA = G'z, vB = G't_aff, Dcp/Dint; s1 = s'z, s2 = h'z, mx = |rg|
         __syncthreads();
         double mu = acc.s1 / (q.mi > 0 ? q.mi : 1), hz = acc.s2;
         nrg = fmax(acc.mx, 0.0);
-        double s1 = 0, s2 = 0, mx = 0, mn = 1e300, mpx = 0, mcert = 0, mrp = 0;
-        for (int v = tid; v < q.nv; v += nt) {
-            double aty = At_y(q, q.y, v), pxv = q.px[v];
-            double rdv = pxv + aty + q.vA[v];
-            q.rd[v] = rdv;
-            s1 += 0.5 * q.x[v] * pxv;
-            mx = fmax(mx, fabs(rdv));
-            mpx = fmax(mpx, fabs(pxv));
-            mcert = fmax(mcert, fabs(aty + q.vA[v]));
-        }
-        for (int e = tid; e < q.ne; e += nt) {
-            double r = A_x(q, q.x, e) - q.beq[e];
-            q.rp[e] = r;
-            mrp = fmax(mrp, fabs(r));
-            s2 += q.beq[e] * q.y[e];
-        }
-        block_reduce4(s1, s2, mx, mn, q.red);
-        obj = s1; hz += s2; nrd = mx;
-        {
-            double t1 = 0, t2 = 0, m2 = mpx, n2 = 1e300;
-            block_reduce4(t1, t2, m2, n2, q.red);
-            mpx = m2;
-            t1 = 0; t2 = 0; m2 = mcert; n2 = 1e300;
-            block_reduce4(t1, t2, m2, n2, q.red);
-            mcert = m2;
-            t1 = 0; t2 = 0; m2 = mrp; n2 = 1e300;
-            block_reduce4(t1, t2, m2, n2, q.red);
-            nrp = m2;
-        }
+        double o = 0, mpx = 0, s2 = 0, mn = 1e300;
+        dual_residual(q, o, mpx);
+        block_reduce4(o, s2, mpx, mn, q.red);
+        obj = o;
+        Zt_apply(q, q.rdx, q.sg);
+        Zt_apply(q, q.vA, q.sg2);
+        __syncthreads();
+        double mr = 0, mc = 0;
+        for (int r = tid; r < q.nr; r += nt) { mr = fmax(mr, fabs(q.sg[r])); mc = fmax(mc, fabs(q.sg2[r])); }
+        nrd = block_max(mr, q.red);
+        double mcert = block_max(mc, q.red);
         gap = mu;
         if (!(mu == mu) || !(nrd == nrd)) { status = ST_NOT_CONVERGED; break; }
-        if (gap <= tol_gap * fmax(1.0, fabs(obj)) && nrp <= tol_res * (1 + bn) && nrg <= tol_res * (1 + hn) &&
-            nrd <= tol_res * (1.0 + mpx)) {
+        if (gap <= tol_gap * fmax(1.0, fabs(obj)) && nrg <= tol_res * (1 + hn) && nrd <= tol_res * (1.0 + mpx)) {
             status = ST_OK;
             break;
         }
-        if (hz < 0 && mcert / (-hz) < 1e-8) { status = ST_INFEASIBLE; break; }  // Farkas certificate
-        // ---- factor with W = z/s (H was assembled by the residual pass) ----
+        if (hz < 0 && mcert / (-hz) < 1e-8) { status = ST_INFEASIBLE; break; }  // Farkas certificate (reduced problem)
+        // ---- factor with W = z/s ----
         if (!kkt_factor(q)) { status = ST_NOT_CONVERGED; break; }
         // ---- affine direction ----
-        for (int v = tid; v < q.nv; v += nt) q.dxa[v] = -q.rd[v] + q.vB[v];
-        for (int e = tid; e < q.ne; e += nt) q.r2[e] = -q.rp[e];
-        kkt_solve(q, q.dxa, q.r2);
+        for (int v = tid; v < q.nv; v += nt) q.vB[v] = -q.rdx[v] + q.vB[v];
+        kkt_solve(q, q.vB, q.dxa);
         row_pass<P_AFF>(q, 0, 0, acc);
         double aa = fmin(1.0, acc.mn);
         __syncthreads();
@@ -912,23 +889,39 @@ RBPE_DEV int pdip_solve(const QP &q, int max_iter, double tol_gap, double tol_re
         // ---- corrector ----
         row_pass<P_COR>(q, sigma * mu, 0, acc);
         __syncthreads();
-        for (int v = tid; v < q.nv; v += nt) q.dx[v] = -q.rd[v] + q.vA[v];
-        for (int e = tid; e < q.ne; e += nt) q.dy[e] = -q.rp[e];
-        kkt_solve(q, q.dx, q.dy);
+        for (int v = tid; v < q.nv; v += nt) q.vA[v] = -q.rdx[v] + q.vA[v];
+        kkt_solve(q, q.vA, q.dx);
         row_pass<P_STEP>(q, sigma * mu, 0, acc);
         double al = fmin(1.0, 0.99 * acc.mn);
         __syncthreads();
         row_pass<P_UPD>(q, sigma * mu, al, acc);
         __syncthreads();
         for (int v = tid; v < q.nv; v += nt) q.x[v] += al * q.dx[v];
-        for (int e = tid; e < q.ne; e += nt) q.y[e] += al * q.dy[e];
         __syncthreads();
     }
     __syncthreads();
+    // |Ax - b| for the record (the parametrisation keeps it at rounding level)
+    double mrp = 0;
+    for (int e = tid; e < q.kb * (q.M + 1); e += nt) {
+        int t = e / q.kb, cc = e % q.kb, ak = cc / 3, d = cc % 3, a = ak / 3, k = ak % 3;
+        double s = 0;
+        if (t < q.M) {
+            const double *sm = q.segmat + t * SEGMAT + SEGMAT_AL + d * 6, *xx = q.x + t * q.n + ak * 6;
+            for (int i = 0; i < 6; i++) s += sm[i] * xx[i];
+        }
+        if (t > 0) {
+            const double *sm = q.segmat + (t - 1) * SEGMAT + SEGMAT_AR + d * 6, *xx = q.x + (t - 1) * q.n + ak * 6;
+            for (int i = 0; i < 6; i++) s += sm[i] * xx[i];
+        }
+        if (t == 0) s -= q.start[(size_t)(q.q0 + a) * 9 + k + 3 * d];
+        if (t == q.M) s -= q.goal[(size_t)(q.q0 + a) * 9 + k + 3 * d];
+        mrp = fmax(mrp, fabs(s));
+    }
+    mrp = block_max(mrp, q.red);
     if (tid == 0) {
         *obj_out = obj;
         *it_out = it;
-        res_out[0] = gap; res_out[1] = nrp; res_out[2] = nrd; res_out[3] = nrg;
+        res_out[0] = gap; res_out[1] = mrp; res_out[2] = nrd; res_out[3] = nrg;
     }
     return status;
 }
@@ -966,10 +959,13 @@ __global__ void __launch_bounds__(CTA_THREADS) pdip_kernel(SolveArgs S) {
             q.nb = (q.q0 + S.bs <= N) ? S.bs : N - q.q0;
             if (q.nb <= 0) continue;
             q.NE = S.sequential ? N - q.nb : 0;
-            q.n = 18 * q.nb; q.kb = 9 * q.nb; q.nv = q.n * M; q.ne = q.kb * (M + 1);
+            q.n = 18 * q.nb; q.kb = 9 * q.nb; q.nv = q.n * M; q.nr = q.kb * (M > 1 ? M - 1 : 0);
             q.nrext = q.nb * M * 6 * q.NE;
             q.nrint = q.nb * (q.nb - 1) / 2 * 6 * M;
-            q.mi = 2 * q.nv + q.nrext + q.nrint;
+            {   // live rows: every row on the 6M-6 control points per agent that the endpoints do not fix
+                int live_cp = 6 * M - 6;
+                q.mi = q.nb * live_cp * (6 + q.NE) + q.nb * (q.nb - 1) / 2 * live_cp;
+            }
             layout(q, smem, S.smem_bytes, gs);
             if (threadIdx.x < 36) q.QB[threadIdx.x] = q_base_entry(threadIdx.x / 6, threadIdx.x % 6);
             __syncthreads();

@@ -30,12 +30,15 @@ struct AssembleArgs {
     int *status;             // [count] ST_BAD_ARG when an SFC / RSFC look-up runs off the end (UB in the reference)
 };
 
-// per-segment constant block: AL[3][6], AR[3][6], qscale, tpow[6]
+// per-segment constant block: AL[3][6], AR[3][6], qscale, tpow[6], CL[3][3], CR[3][3], RQ[6][6]
 constexpr int SEGMAT_AL = 0;      // left-knot equality coefficients of this segment  (build_Aeq_base L353-L405)
 constexpr int SEGMAT_AR = 18;     // right-knot equality coefficients
 constexpr int SEGMAT_QS = 36;     // dt^(-2 phi + 1) (build_Q_p L349-L351)
 constexpr int SEGMAT_TP = 37;     // (1/dt)^(5-j), j = 0..5 (timeMatrix L695-L700)
-constexpr int SEGMAT = 44;
+constexpr int SEGMAT_CL = 44;     // control points 0..2 = CL[i][d] * (pos, vel, acc)[d] at the left knot
+constexpr int SEGMAT_CR = 53;     // control points 3..5 = CR[i-3][d] * state[d] at the right knot
+constexpr int SEGMAT_RQ = 62;     // 6x6 cost Hessian over (left state, right state): C'(2 dt^-5 Q_base)C
+constexpr int SEGMAT = 98;
 
 struct SolveArgs {
     int count, N, M;
