@@ -104,17 +104,23 @@ int rbpe_solve(rbpe_handle *h, const rbpe_problem *p, rbpe_result *r);
 
 /* ---- resident (device-side) interface: inputs stay in HBM across calls; used for kernel-only timing and
  * for the multi-GPU Jacobi mode where the caller exchanges control points between sweeps. ---- */
-int rbpe_upload(rbpe_handle *h, const rbpe_problem *p, int count);          /* H2D + assembly kernel */
-int rbpe_run(rbpe_handle *h, int mode);                                      /* PDIP kernel(s) on resident data */
-/* Jacobi sweep restricted to batches [batch_begin, batch_end) of every resident mission (agent sharding) */
+int rbpe_upload(rbpe_handle *h, const rbpe_problem *p, int count);          /* H2D of the raw inputs */
+int rbpe_assemble(rbpe_handle *h);                                           /* assembly kernel; resets `dummy` */
+int rbpe_run(rbpe_handle *h, int mode);                                      /* assembly + PDIP + conversion kernels on resident inputs */
+/* Jacobi sweep restricted to batches [batch_begin, batch_end) of every resident mission (agent sharding);
+ * needs rbpe_upload + rbpe_assemble first; does not reset the control-point table */
 int rbpe_run_jacobi_range(rbpe_handle *h, int batch_begin, int batch_end);
+int rbpe_set_ctrl(rbpe_handle *h, const double *ctrl);                       /* H2D: overwrite `dummy` [count][N][3][6M] */
 int rbpe_download(rbpe_handle *h, rbpe_result *r);                           /* D2H of results */
 /* device pointers of the resident control-point table [count][N][3][6M] (f64) and coefficient table */
 double *rbpe_device_ctrl(rbpe_handle *h);
 double *rbpe_device_coef(rbpe_handle *h);
 void *rbpe_stream(rbpe_handle *h);                                           /* cudaStream_t */
 int rbpe_sync(rbpe_handle *h);
-int rbpe_last_timing(const rbpe_handle *h, rbpe_timing *t);
+int rbpe_last_timing(const rbpe_handle *h, rbpe_timing *t);                  /* kernel_launches = total since creation */
+/* CUDA-event stopwatch on the engine's stream: start synchronises first; stop returns the elapsed milliseconds */
+int rbpe_timer_start(rbpe_handle *h);
+int rbpe_timer_stop(rbpe_handle *h, float *ms);
 
 #ifdef __cplusplus
 }

@@ -50,7 +50,9 @@ struct rbpe_handle {
     int sm_count = 0;
     char err[512] = "";
     // resident problem
-    bool resident = false;
+    bool resident = false, assembled = false;
+    long launches = 0;
+    cudaEvent_t tev[2] = {nullptr, nullptr};
     int count = 0, N = 0, M = 0, sequential = 0, bs = 1, nbatch = 0, iteration = 1, nrec = 1, sweep = 0;
     DevBuf T, start, goal, radius, sfc_offs, sfc_base, sfc_box, sfc_t, rsfc_n, rsfc_t, init_traj;
     DevBuf segbox, reln, segmat, ctrl, frozen, coef, qp_obj, qp_iters, qp_status, qp_res, status, scratch;
@@ -124,6 +126,8 @@ extern "C" int rbpe_create(const rbpe_config *cfg, rbpe_handle **out) {
         return RBPE_CUDA_ERROR;
     }
     for (int i = 0; i < 7; i++) cudaEventCreate(&h->ev[i]);
+    cudaEventCreate(&h->tev[0]);
+    cudaEventCreate(&h->tev[1]);
     cudaFuncSetAttribute(pdip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
     *out = h;
     return RBPE_OK;
@@ -139,6 +143,8 @@ extern "C" void rbpe_destroy(rbpe_handle *h) {
     for (DevBuf *b : all) b->release();
     for (int i = 0; i < 7; i++)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    for (int i = 0; i < 2; i++)
+        if (h->tev[i]) cudaEventDestroy(h->tev[i]);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -168,7 +174,6 @@ extern "C" int rbpe_upload(rbpe_handle *h, const rbpe_problem *p, int count) {
     rbpe_set_batch(N, h->sequential, p->batch_size, p->batch_iter, &h->bs, &h->nbatch);
     h->nrec = h->iteration * h->nbatch;
     if (h->nrec < 1) h->nrec = 1;
-    h->sweep = 0;
     const size_t nbox = (size_t)p->sfc_base[count];
 
     CU(cudaEventRecord(h->ev[0], h->stream));
@@ -186,6 +191,19 @@ extern "C" int rbpe_upload(rbpe_handle *h, const rbpe_problem *p, int count) {
     if (p->sequential && (rc = up(h, h->init_traj, p->init_traj, (size_t)count * N * (M + 1) * 3 * 4))) return rc;
     CU(cudaEventRecord(h->ev[1], h->stream));
 
+    h->resident = true;
+    h->assembled = false;
+    return RBPE_OK;
+}
+
+// k1 on the resident raw inputs: (re)builds segbox / reln / segmat and resets the control-point table to `dummy`
+extern "C" int rbpe_assemble(rbpe_handle *h) {
+    if (!h) return RBPE_BAD_ARG;
+    if (!h->resident) return fail(h, RBPE_BAD_ARG, "rbpe_assemble: nothing uploaded");
+    CU(cudaSetDevice(h->device));
+    const int N = h->N, M = h->M, count = h->count;
+    const size_t P = (size_t)N * (N - 1) / 2, per = (size_t)N * 18 * M;
+    CU(cudaEventRecord(h->ev[1], h->stream));
     CU(h->segbox.reserve((size_t)count * N * M * 6 * 8));
     CU(h->reln.reserve((size_t)count * (P ? P : 1) * M * 3 * 4));
     CU(h->segmat.reserve((size_t)count * M * SEGMAT * 8));
@@ -219,8 +237,9 @@ extern "C" int rbpe_upload(rbpe_handle *h, const rbpe_problem *p, int count) {
     assemble_kernel<<<blocks, 256, 0, h->stream>>>(A);
     CU(cudaGetLastError());
     CU(cudaEventRecord(h->ev[2], h->stream));
-    h->timing.kernel_launches = 1;
-    h->resident = true;
+    h->launches++;
+    h->sweep = 0;
+    h->assembled = true;
     return RBPE_OK;
 }
 
@@ -239,7 +258,7 @@ static int launch_convert(rbpe_handle *h) {
     if (blocks > cap) blocks = cap;
     convert_kernel<<<blocks, 256, 0, h->stream>>>(C);
     CU(cudaGetLastError());
-    h->timing.kernel_launches++;
+    h->launches++;
     return RBPE_OK;
 }
 
@@ -262,16 +281,16 @@ static int fill_solve_args(rbpe_handle *h, SolveArgs &S, int mode, int grid) {
 extern "C" int rbpe_run(rbpe_handle *h, int mode) {
     if (!h) return RBPE_BAD_ARG;
     if (!h->resident) return fail(h, RBPE_BAD_ARG, "rbpe_run: nothing uploaded");
-    CU(cudaSetDevice(h->device));
-    CU(cudaEventRecord(h->ev[3], h->stream));
     int rc;
+    if ((rc = rbpe_assemble(h))) return rc;   // k1 is part of the hot path; it also resets `dummy`, so runs are repeatable
+    CU(cudaEventRecord(h->ev[3], h->stream));
     if (h->nbatch > 0 && h->iteration > 0) {
         SolveArgs S;
         if (mode == RBPE_MODE_GAUSS_SEIDEL) {
             if ((rc = fill_solve_args(h, S, 0, h->count))) return rc;
             pdip_kernel<<<h->count, CTA_THREADS, S.smem_bytes, h->stream>>>(S);
             CU(cudaGetLastError());
-            h->timing.kernel_launches++;
+            h->launches++;
         } else {
             int grid = h->count * h->nbatch;
             if ((rc = fill_solve_args(h, S, 1, grid))) return rc;
@@ -281,7 +300,7 @@ extern "C" int rbpe_run(rbpe_handle *h, int mode) {
                 S.rec_offset = it * h->nbatch;
                 pdip_kernel<<<grid, CTA_THREADS, S.smem_bytes, h->stream>>>(S);
                 CU(cudaGetLastError());
-                h->timing.kernel_launches++;
+                h->launches++;
             }
         }
     }
@@ -292,7 +311,7 @@ extern "C" int rbpe_run(rbpe_handle *h, int mode) {
 
 extern "C" int rbpe_run_jacobi_range(rbpe_handle *h, int b0, int b1) {
     if (!h) return RBPE_BAD_ARG;
-    if (!h->resident) return fail(h, RBPE_BAD_ARG, "rbpe_run_jacobi_range: nothing uploaded");
+    if (!h->resident || !h->assembled) return fail(h, RBPE_BAD_ARG, "rbpe_run_jacobi_range: call rbpe_upload and rbpe_assemble first");
     if (b0 < 0 || b1 > h->nbatch || b0 > b1) return fail(h, RBPE_BAD_ARG, "batch range [%d,%d) outside [0,%d)", b0, b1, h->nbatch);
     CU(cudaSetDevice(h->device));
     CU(cudaEventRecord(h->ev[3], h->stream));
@@ -306,7 +325,7 @@ extern "C" int rbpe_run_jacobi_range(rbpe_handle *h, int b0, int b1) {
         S.rec_offset = (h->iteration > 0 ? h->sweep % h->iteration : 0) * h->nbatch;
         pdip_kernel<<<grid, CTA_THREADS, S.smem_bytes, h->stream>>>(S);
         CU(cudaGetLastError());
-        h->timing.kernel_launches++;
+        h->launches++;
     }
     h->sweep++;
     if ((rc = launch_convert(h))) return rc;
@@ -342,6 +361,7 @@ extern "C" int rbpe_download(rbpe_handle *h, rbpe_result *r) {
     if (cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]) == cudaSuccess) h->timing.h2d_ms = ms;
     if (cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]) == cudaSuccess) h->timing.assemble_ms = ms;
     if (cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]) == cudaSuccess) h->timing.solve_ms = ms;
+    else h->timing.solve_ms = 0;
     if (cudaEventElapsedTime(&ms, h->ev[6], h->ev[5]) == cudaSuccess) h->timing.d2h_ms = ms;
     if (cudaEventElapsedTime(&ms, h->ev[0], h->ev[5]) == cudaSuccess) h->timing.total_ms = ms;
     cudaGetLastError();
@@ -368,6 +388,15 @@ extern "C" int rbpe_solve(rbpe_handle *h, const rbpe_problem *p, rbpe_result *r)
     return rbpe_solve_many(h, &q, 1, RBPE_MODE_GAUSS_SEIDEL, r);
 }
 
+// overwrite the resident control-point table (`dummy`) from host memory: [count][N][3][6M]
+extern "C" int rbpe_set_ctrl(rbpe_handle *h, const double *ctrl) {
+    if (!h || !ctrl) return RBPE_BAD_ARG;
+    if (!h->resident || !h->assembled) return fail(h, RBPE_BAD_ARG, "rbpe_set_ctrl: call rbpe_upload and rbpe_assemble first");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpyAsync(h->ctrl.p, ctrl, (size_t)h->count * h->N * 18 * h->M * 8, cudaMemcpyHostToDevice, h->stream));
+    return RBPE_OK;
+}
+
 extern "C" double *rbpe_device_ctrl(rbpe_handle *h) { return h ? h->ctrl.as<double>() : nullptr; }
 extern "C" double *rbpe_device_coef(rbpe_handle *h) { return h ? h->coef.as<double>() : nullptr; }
 extern "C" void *rbpe_stream(rbpe_handle *h) { return h ? (void *)h->stream : nullptr; }
@@ -380,5 +409,22 @@ extern "C" int rbpe_sync(rbpe_handle *h) {
 extern "C" int rbpe_last_timing(const rbpe_handle *h, rbpe_timing *t) {
     if (!h || !t) return RBPE_BAD_ARG;
     *t = h->timing;
+    t->kernel_launches = (int)h->launches;
+    return RBPE_OK;
+}
+// CUDA-event stopwatch on the engine's stream (the stream every kernel and copy of this handle is issued on)
+extern "C" int rbpe_timer_start(rbpe_handle *h) {
+    if (!h) return RBPE_BAD_ARG;
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaEventRecord(h->tev[0], h->stream));
+    return RBPE_OK;
+}
+extern "C" int rbpe_timer_stop(rbpe_handle *h, float *ms) {
+    if (!h || !ms) return RBPE_BAD_ARG;
+    CU(cudaSetDevice(h->device));
+    CU(cudaEventRecord(h->tev[1], h->stream));
+    CU(cudaEventSynchronize(h->tev[1]));
+    CU(cudaEventElapsedTime(ms, h->tev[0], h->tev[1]));
     return RBPE_OK;
 }

@@ -42,8 +42,8 @@ class RbpeTiming(C.Structure):
 
 
 EXPORTS = ["rbpe_create", "rbpe_destroy", "rbpe_last_error", "rbpe_set_batch", "rbpe_solve_many", "rbpe_solve",
-           "rbpe_upload", "rbpe_run", "rbpe_run_jacobi_range", "rbpe_download", "rbpe_device_ctrl",
-           "rbpe_device_coef", "rbpe_stream", "rbpe_sync", "rbpe_last_timing"]
+           "rbpe_upload", "rbpe_assemble", "rbpe_run", "rbpe_run_jacobi_range", "rbpe_set_ctrl", "rbpe_download", "rbpe_device_ctrl",
+           "rbpe_device_coef", "rbpe_stream", "rbpe_sync", "rbpe_last_timing", "rbpe_timer_start", "rbpe_timer_stop"]
 
 _lib = None
 
@@ -72,10 +72,18 @@ def load_library(path=None):
     L.rbpe_solve.restype = C.c_int
     L.rbpe_upload.argtypes = [C.c_void_p, C.POINTER(RbpeProblem), C.c_int]
     L.rbpe_upload.restype = C.c_int
+    L.rbpe_assemble.argtypes = [C.c_void_p]
+    L.rbpe_assemble.restype = C.c_int
+    L.rbpe_timer_start.argtypes = [C.c_void_p]
+    L.rbpe_timer_start.restype = C.c_int
+    L.rbpe_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    L.rbpe_timer_stop.restype = C.c_int
     L.rbpe_run.argtypes = [C.c_void_p, C.c_int]
     L.rbpe_run.restype = C.c_int
     L.rbpe_run_jacobi_range.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.rbpe_run_jacobi_range.restype = C.c_int
+    L.rbpe_set_ctrl.argtypes = [C.c_void_p, _dp]
+    L.rbpe_set_ctrl.restype = C.c_int
     L.rbpe_download.argtypes = [C.c_void_p, C.POINTER(RbpeResult)]
     L.rbpe_download.restype = C.c_int
     L.rbpe_device_ctrl.argtypes = [C.c_void_p]
@@ -195,6 +203,21 @@ class Engine:
         if rc != OK:
             raise RuntimeError("rbpe_upload failed (%d): %s" % (rc, self.last_error()))
 
+    def assemble(self):
+        rc = self.lib.rbpe_assemble(self.h)
+        if rc != OK:
+            raise RuntimeError("rbpe_assemble failed (%d): %s" % (rc, self.last_error()))
+
+    def timer_start(self):
+        if self.lib.rbpe_timer_start(self.h) != OK:
+            raise RuntimeError(self.last_error())
+
+    def timer_stop(self):
+        ms = C.c_float()
+        if self.lib.rbpe_timer_stop(self.h, C.byref(ms)) != OK:
+            raise RuntimeError(self.last_error())
+        return ms.value
+
     def run(self, mode=MODE_GAUSS_SEIDEL):
         rc = self.lib.rbpe_run(self.h, mode)
         if rc == CUDA_ERROR or rc == BAD_ARG:
@@ -206,6 +229,13 @@ class Engine:
         if rc == CUDA_ERROR or rc == BAD_ARG:
             raise RuntimeError("rbpe_run_jacobi_range failed (%d): %s" % (rc, self.last_error()))
         return rc
+
+    def set_ctrl(self, ctrl):
+        c = np.ascontiguousarray(ctrl, np.float64)
+        rc = self.lib.rbpe_set_ctrl(self.h, c.ctypes.data_as(_dp))
+        if rc != OK:
+            raise RuntimeError("rbpe_set_ctrl failed (%d): %s" % (rc, self.last_error()))
+        self.sync()
 
     def download(self, prob, result=None):
         r = result or Result(prob)

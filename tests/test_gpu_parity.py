@@ -1,0 +1,201 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI (librbpe.so), against the CPU oracle on identical
+bytes, against the reference's frozen CPLEX artefacts (tests/golden), and through size-independent properties.
+
+Tolerances.  Interior-point iterates of oracle and kernel agree to rounding (same algorithm, FP64), so control points
+are compared at 1e-8 absolute -- far inside the north-star's 1e-4 relative on coefficients.  Boolean outcomes
+(status feasible / infeasible, iteration counts, SFC / RSFC satisfaction) must be identical.
+"""
+import numpy as np
+import pytest
+
+import fixture_lp as F
+import oracle
+import oracle_util
+from swarm_simulator_b200 import engine as E, synth
+
+pytestmark = pytest.mark.gpu
+CTRL_TOL = 1e-8
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import __graft_entry__ as G
+    G.build()
+    e = E.Engine(device=0)
+    yield e
+    e.close()
+
+
+def _check_against_oracle(eng, missions, seq, bs, batch_iter=-1, iteration=1):
+    prob = E.PackedProblem(synth.pack(missions), sequential=seq, batch_size=bs, batch_iter=batch_iter, iteration=iteration)
+    r = eng.solve_many(prob)
+    for c, m in enumerate(missions):
+        ro = oracle_util.oracle_problem(m, sequential=seq, batch_size=bs, batch_iter=batch_iter, iteration=iteration).update()
+        assert r.status[c] == ro["status"] == 0
+        n = r.nrec
+        assert np.array_equal(r.qp_status[c][:n], ro["batch_status"][:n])
+        assert np.array_equal(r.qp_iters[c][:n], ro["batch_iters"][:n])            # same algorithm, same iterates
+        assert np.abs(r.ctrl[c] - ro["ctrl"]).max() < CTRL_TOL
+        scale = max(1.0, np.abs(ro["coef"]).max())
+        assert np.abs(r.coef[c] - ro["coef"]).max() < 1e-8 * scale
+        assert np.allclose(r.qp_obj[c][:n], ro["batch_obj"][:n], rtol=1e-8, atol=1e-9)
+    return prob, r
+
+
+def _properties(m, ctrl, tol=1e-6):
+    """Invariants of a solved mission: endpoints, C2 continuity, control points inside their SFC box, RSFC rows."""
+    N, M = m["N"], m["M"]
+    c = ctrl.reshape(N, 3, M, 6)
+    dt = np.diff(m["T"])
+    assert np.abs(c[:, :, 0, 0] - m["start"][:, :3]).max() < 1e-9
+    assert np.abs(c[:, :, -1, 5] - m["goal"][:, :3]).max() < 1e-9
+    for mm in range(M - 1):
+        l, r_ = c[:, :, mm], c[:, :, mm + 1]
+        assert np.abs(l[..., 5] - r_[..., 0]).max() < 1e-9
+        assert np.abs((l[..., 5] - l[..., 4]) / dt[mm] - (r_[..., 1] - r_[..., 0]) / dt[mm + 1]).max() < 1e-8
+        assert np.abs((l[..., 5] - 2 * l[..., 4] + l[..., 3]) / dt[mm] ** 2
+                      - (r_[..., 2] - 2 * r_[..., 1] + r_[..., 0]) / dt[mm + 1] ** 2).max() < 1e-7
+    for qi, (boxes, tend) in enumerate(m["sfc"]):
+        bi = 0
+        for mm in range(M):
+            while tend[bi] < m["T"][mm + 1]:
+                bi += 1
+            assert np.all(c[qi, :, mm, :] >= boxes[bi][:3, None] - tol) and np.all(c[qi, :, mm, :] <= boxes[bi][3:, None] + tol)
+    qi, qj = np.triu_indices(N, 1)
+    rel = c[qj] - c[qi]                                          # [P, 3, M, 6]
+    lhs = np.einsum("pmk,pkmi->pmi", m["rsfc_n"].astype(np.float64), rel)
+    rr = (m["radius"][qi] + m["radius"][qj])[:, None, None]
+    return float((lhs - rr).min())
+
+
+def test_config1_4_agents_empty_joint(eng):
+    """BASELINE configs[0]: 4 agents, empty map, 3 segments, one joint batch (plan/sequential=false)."""
+    ms = [synth.synth_mission(4, 3, 0.0, 1000 + i) for i in range(3)]
+    _, r = _check_against_oracle(eng, ms, False, 4)
+    for c, m in enumerate(ms):
+        assert _properties(m, r.ctrl[c]) > -1e-6
+
+
+def test_config2_16_agents_joint_and_batched(eng):
+    """BASELINE configs[1]: 16 agents, forest 0.2, 5 segments: one joint QP (b=16) and the launch default b=4."""
+    ms = [synth.synth_mission(16, 5, 0.2, 2000 + i) for i in range(2)]
+    _, r = _check_against_oracle(eng, ms, False, 16)
+    for c, m in enumerate(ms):
+        assert _properties(m, r.ctrl[c]) > -1e-6
+    _check_against_oracle(eng, ms, True, 4)
+
+
+def test_config3_64_agents_sequential(eng):
+    """BASELINE configs[2] (the bench workload): 64 agents, forest, 5 segments, per-agent QPs in sequential order."""
+    ms = [synth.synth_mission(64, 5, 0.2, 3000 + i) for i in range(2)]
+    _, r = _check_against_oracle(eng, ms, True, 1)
+    for c, m in enumerate(ms):
+        assert _properties(m, r.ctrl[c]) > -1e-6
+    _check_against_oracle(eng, ms[:1], True, 4)
+
+
+def test_batching_edge_cases(eng):
+    """ragged last batch, truncated schedule (batch_iter < ceil(N/b): coefficients of unsolved agents come from `dummy`,
+    rbp_planner.hpp L185-L190), batch_iter = 0 (publish the initial trajectory, L119-L138), two outer iterations,
+    one agent (no RSFC rows at all)."""
+    ms = [synth.synth_mission(7, 4, 0.2, 500)]
+    _check_against_oracle(eng, ms, True, 3)
+    _check_against_oracle(eng, ms, True, 3, batch_iter=2)
+    _check_against_oracle(eng, ms, True, 3, batch_iter=0)
+    _check_against_oracle(eng, ms, True, 2, iteration=2)
+    _check_against_oracle(eng, [synth.synth_mission(1, 3, 0.2, 9)], True, 1)
+    _check_against_oracle(eng, [synth.synth_mission(1, 3, 0.2, 9)], False, 1)
+
+
+def test_infeasible_mission_is_reported_identically(eng):
+    """`!cplex.solve()` -> update() returns false (L158-L161). Shrink one agent's corridor so that no trajectory exists."""
+    m = synth.synth_mission(6, 4, 0.2, 31)
+    boxes, tend = m["sfc"][2]
+    boxes = boxes.copy()
+    boxes[:, 3] = boxes[:, 0] + 1e-3                     # 1 mm wide in x, away from the goal
+    boxes[:, 0] -= 5.0
+    boxes[:, 3] -= 5.0
+    m2 = dict(m)
+    m2["sfc"] = list(m["sfc"])
+    m2["sfc"][2] = (boxes, tend)
+    prob = E.PackedProblem(synth.pack([m, m2]), sequential=True, batch_size=2)
+    r = eng.solve_many(prob)
+    ro = oracle_util.oracle_problem(m2, sequential=True, batch_size=2).update()
+    assert ro["status"] == oracle.INFEASIBLE
+    assert r.status[0] == E.OK and r.status[1] == E.INFEASIBLE and r.rc == E.INFEASIBLE
+    assert np.array_equal(r.qp_status[1][:2], ro["batch_status"][:2])
+
+
+def test_bad_corridor_lookup_is_bad_arg(eng):
+    """An SFC whose last box ends before the last segment makes the reference index past the end (UB); here: BAD_ARG."""
+    m = synth.synth_mission(4, 4, 0.0, 5)
+    m2 = dict(m)
+    m2["sfc"] = [(b, t * 0.5) for b, t in m["sfc"]]
+    r = eng.solve_many(E.PackedProblem(synth.pack([m2]), sequential=True, batch_size=1))
+    assert r.status[0] == E.BAD_ARG
+
+
+def test_jacobi_sweep_matches_per_batch_oracle_solves(eng):
+    """Jacobi mode: every batch of a sweep is solved against the table frozen before the sweep (per-QP parity)."""
+    m = synth.synth_mission(8, 5, 0.2, 77)
+    prob = E.PackedProblem(synth.pack([m]), sequential=True, batch_size=2)
+    r = eng.solve_many(prob, mode=E.MODE_JACOBI)
+    assert r.rc == E.OK
+    op = oracle_util.oracle_problem(m, sequential=True, batch_size=2)
+    dummy = op.dummy()
+    for l in range(4):
+        x = op.populate(dummy, l).solve()
+        assert x["status"] == 0 and x["iters"] == r.qp_iters[0][l]
+        ctrl = x["x"].reshape(3, 2, 30)                                   # [k][bi][6M]
+        got = r.ctrl[0][2 * l:2 * l + 2]                                  # [bi][k][6M]
+        assert np.abs(got - ctrl.transpose(1, 0, 2)).max() < CTRL_TOL
+
+
+def test_fixture_batch15_matches_cplex_csv(eng, golden):
+    """The reference's only frozen CPLEX run: log/QPmodel.lp (batch 15 of a 64-agent, 36-segment mission) and
+    log/coef61..64.csv.  The engine assembles batch 15 from the recovered inputs with agents 0..59 frozen at CPLEX's own
+    solution, solves it on the GPU, and must land within 1e-4 of CPLEX's answer (the north-star's tolerance; the CSVs
+    carry 6 significant digits)."""
+    rec = F.recover_inputs(golden["lp"], golden["csv"], golden["mission"])
+    ms = golden["mission"]
+    T = np.arange(F.M + 1, dtype=float)
+    offs, boxes, tend = F.sfc_from_seg_box(rec["seg_box"], T)
+    P = F.N * (F.N - 1) // 2
+    packed = dict(N=F.N, M=F.M, count=1, T=T[None], start=ms["start"][None], goal=ms["goal"][None],
+                  radius=ms["radius"][None], sfc_offs=offs[None], sfc_base=np.array([0, len(tend)], np.int32),
+                  sfc_box=boxes, sfc_t=tend, rsfc_n=rec["rsfc_n"][None], rsfc_t=np.tile(T[1:], (P, 1))[None],
+                  init_traj=np.zeros((1, F.N, F.M + 1, 3), np.float32))
+    prob = E.PackedProblem(packed, sequential=True, batch_size=4)
+    eng.upload(prob)
+    eng.assemble()
+    dummy = np.nan_to_num(rec["dummy"].reshape(F.N, 6 * F.M, 3).transpose(0, 2, 1), nan=0.0)   # [N][3][6M]
+    eng.set_ctrl(dummy[None])
+    eng.run_jacobi_range(15, 16)
+    r = eng.download(prob)
+    assert r.status[0] == E.OK
+    assert abs(r.qp_obj[0][15] - 0.0971578) < 2e-7                        # CPLEX-convention objective
+    ctrl = r.ctrl[0][F.B0:F.B0 + F.NB].reshape(F.NB, 3, F.M, 6).transpose(0, 2, 1, 3)   # [NB, M, 3, 6]
+    cref = F.csv_ctrl(golden["csv"]["coef"][F.B0:F.B0 + F.NB])
+    assert np.abs(ctrl - cref).max() < 1e-4 * max(1.0, np.abs(cref).max())
+    coef = r.coef[0][F.B0:F.B0 + F.NB].reshape(F.NB, 3, F.M, 6).transpose(0, 2, 1, 3)[..., ::-1]  # lowest power first
+    ref = golden["csv"]["coef"][F.B0:F.B0 + F.NB]
+    num = np.linalg.norm((coef - ref).reshape(F.NB, F.M, -1), axis=-1)
+    den = np.linalg.norm(ref.reshape(F.NB, F.M, -1), axis=-1)
+    assert (num / den).max() < 1e-4
+    # and the same QP through the oracle agrees with the GPU far below that
+    qp = oracle.QP(**F.lp_qp_arrays(golden["lp"]))
+    xo = qp.solve()
+    co = np.transpose(xo["x"].reshape(3, F.NB, F.M, 6), (1, 2, 0, 3))
+    assert np.abs(ctrl - co).max() < 1e-6
+
+
+def test_many_missions_in_one_call(eng):
+    """A batch of independent missions in one call equals the same missions solved one by one (no cross-talk)."""
+    ms = [synth.synth_mission(8, 5, 0.2, 600 + i) for i in range(5)]
+    prob = E.PackedProblem(synth.pack(ms * 60), sequential=True, batch_size=1)      # 300 CTAs: more than one wave
+    r = eng.solve_many(prob)
+    assert r.rc == E.OK
+    for c in range(5, 300):
+        assert np.array_equal(r.ctrl[c], r.ctrl[c % 5])                             # deterministic, bit for bit
+    single = eng.solve_many(E.PackedProblem(synth.pack(ms[:1]), sequential=True, batch_size=1))
+    assert np.array_equal(single.ctrl[0], r.ctrl[0])
