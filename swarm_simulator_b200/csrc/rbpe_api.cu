@@ -47,6 +47,7 @@ struct rbpe_handle {
     int max_iter = 100;
     double tol_gap = 1e-10, tol_res = 1e-9;
     size_t smem_budget = 0, smem_optin = 0;
+    int threads = 128;
     int sm_count = 0;
     char err[512] = "";
     // resident problem
@@ -116,8 +117,10 @@ extern "C" int rbpe_create(const rbpe_config *cfg, rbpe_handle **out) {
         if (cfg->tol_gap > 0) h->tol_gap = cfg->tol_gap;
         if (cfg->tol_res > 0) h->tol_res = cfg->tol_res;
         h->smem_budget = cfg->smem_budget;
+        int th = cfg->reserved[0];   // CTA size of the PDIP kernel (tuning knob): 32..256, multiple of 32
+        if (th >= 32 && th <= CTA_THREADS && th % 32 == 0) h->threads = th;
     }
-    if (h->smem_budget == 0) h->smem_budget = 100 * 1024;
+    if (h->smem_budget == 0) h->smem_budget = 48 * 1024;
     if (h->smem_budget > h->smem_optin) h->smem_budget = h->smem_optin;
     memset(&h->timing, 0, sizeof(h->timing));
     if ((e = cudaSetDevice(dev)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
@@ -288,7 +291,7 @@ extern "C" int rbpe_run(rbpe_handle *h, int mode) {
         SolveArgs S;
         if (mode == RBPE_MODE_GAUSS_SEIDEL) {
             if ((rc = fill_solve_args(h, S, 0, h->count))) return rc;
-            pdip_kernel<<<h->count, CTA_THREADS, S.smem_bytes, h->stream>>>(S);
+            pdip_kernel<<<h->count, h->threads, S.smem_bytes, h->stream>>>(S);
             CU(cudaGetLastError());
             h->launches++;
         } else {
@@ -298,7 +301,7 @@ extern "C" int rbpe_run(rbpe_handle *h, int mode) {
                 CU(cudaMemcpyAsync(h->frozen.p, h->ctrl.p, (size_t)h->count * h->N * 18 * h->M * 8, cudaMemcpyDeviceToDevice,
                                    h->stream));
                 S.rec_offset = it * h->nbatch;
-                pdip_kernel<<<grid, CTA_THREADS, S.smem_bytes, h->stream>>>(S);
+                pdip_kernel<<<grid, h->threads, S.smem_bytes, h->stream>>>(S);
                 CU(cudaGetLastError());
                 h->launches++;
             }
@@ -323,7 +326,7 @@ extern "C" int rbpe_run_jacobi_range(rbpe_handle *h, int b0, int b1) {
         if ((rc = fill_solve_args(h, S, 1, grid))) return rc;
         S.batch_begin = b0; S.batch_end = b1;
         S.rec_offset = (h->iteration > 0 ? h->sweep % h->iteration : 0) * h->nbatch;
-        pdip_kernel<<<grid, CTA_THREADS, S.smem_bytes, h->stream>>>(S);
+        pdip_kernel<<<grid, h->threads, S.smem_bytes, h->stream>>>(S);
         CU(cudaGetLastError());
         h->launches++;
     }

@@ -90,11 +90,11 @@ __host__ __device__ inline size_t scratch_doubles(int N, int M, int bs) {
     }
     size_t rint_ = (size_t)bs * (bs - 1) / 2 * 6 * M;
     size_t t = 64 + 36;
-    t += 12 * al2(nv) + 2 * al2(nr);
+    t += 12 * al2(nv) + 3 * al2(nr);
     t += al2((size_t)M * bs * 36) + al2(rint_ * 6);                  // Dcp, Dint
     t += al2((size_t)(M > 1 ? M - 1 : 1) * kb * kb) + al2((size_t)(M > 2 ? M - 2 : 1) * kb * kb);
     t += 3 * al2(rext) + 3 * al2((rext + 1) / 2);
-    t += 3 * al2(rint_) + 3 * al2((rint_ + 1) / 2);
+    t += 5 * al2(rint_) + 3 * al2((rint_ + 1) / 2);
     return t;
 }
 
@@ -314,12 +314,14 @@ struct QP {
     double *x, *dxa, *dx, *rdx, *ub, *lbn, *sub, *zub, *slb, *zlb, *vA, *vB;
     // knot-space vectors (nr): r = (t-1)*9nb + (a*3+k)*3 + d, t = 1..M-1
     double *sg, *sg2;
+    double *dinv;        // [nr] reciprocal Cholesky diagonal (one-agent batches)
     double *Wd, *Wo;     // reduced Hessian Z'HZ: (M-1) diagonal blocks, (M-2) blocks (t+1,t), each 9nb x 9nb
     double *Dcp;         // [M*nb*6][6]  sum_rows w g g' restricted to one control point (3x3 symmetric over axes)
     double *Dint;        // [nrint][6]   -w n n' of a row between two batch agents
     double *he, *se, *ze;
     float *nex, *ney, *nez;
     double *hi, *si, *zi;
+    double *si_w, *zi_w;  // write side of the (s, z) pair of rows between two batch agents during the fused residual pass
     float *nix, *niy, *niz;
     double *red;  // 64 doubles
     double *QB;   // 36 doubles: Q_base
@@ -355,6 +357,7 @@ RBPE_DEV void layout(QP &q, unsigned char *smem, size_t smem_bytes, double *gscr
     for (int i = 0; i < 12; i++) *vv[i] = a.take(q.nv);
     q.sg = a.take(q.nr);
     q.sg2 = a.take(q.nr);
+    q.dinv = a.take(q.nr);
     q.Dcp = a.take((size_t)q.M * q.nb * 36);
     q.Dint = a.take((size_t)q.nrint * 6);
     q.Wd = a.take((size_t)(q.M > 1 ? q.M - 1 : 1) * q.kb * q.kb);
@@ -364,6 +367,7 @@ RBPE_DEV void layout(QP &q, unsigned char *smem, size_t smem_bytes, double *gscr
     q.ney = (float *)a.take(((size_t)q.nrext + 1) / 2);
     q.nez = (float *)a.take(((size_t)q.nrext + 1) / 2);
     q.hi = a.take(q.nrint); q.si = a.take(q.nrint); q.zi = a.take(q.nrint);
+    q.si_w = a.take(q.nrint); q.zi_w = a.take(q.nrint);
     q.nix = (float *)a.take(((size_t)q.nrint + 1) / 2);
     q.niy = (float *)a.take(((size_t)q.nrint + 1) / 2);
     q.niz = (float *)a.take(((size_t)q.nrint + 1) / 2);
@@ -372,29 +376,33 @@ RBPE_DEV void layout(QP &q, unsigned char *smem, size_t smem_bytes, double *gscr
 template <class T>
 RBPE_DEV T shfl_down_t(T v, int o) { return __shfl_down_sync(0xffffffffu, v, o); }
 
-// CTA-wide reduction of (sum, sum, max, min); every thread returns the same values (fixed summation order).
-RBPE_DEV void block_reduce4(double &s1, double &s2, double &mx, double &mn, double *red) {
+// CTA-wide reduction of v = (sum, sum, max, max, max, min); every thread returns the same values (fixed order).
+RBPE_DEV void block_reduce6(double *v, double *red) {
     for (int o = 16; o > 0; o >>= 1) {
-        s1 += shfl_down_t(s1, o);
-        s2 += shfl_down_t(s2, o);
-        mx = fmax(mx, shfl_down_t(mx, o));
-        mn = fmin(mn, shfl_down_t(mn, o));
+        v[0] += shfl_down_t(v[0], o);
+        v[1] += shfl_down_t(v[1], o);
+        v[2] = fmax(v[2], shfl_down_t(v[2], o));
+        v[3] = fmax(v[3], shfl_down_t(v[3], o));
+        v[4] = fmax(v[4], shfl_down_t(v[4], o));
+        v[5] = fmin(v[5], shfl_down_t(v[5], o));
     }
     int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
     __syncthreads();
-    if (l == 0) { red[w * 4 + 0] = s1; red[w * 4 + 1] = s2; red[w * 4 + 2] = mx; red[w * 4 + 3] = mn; }
+    if (l == 0)
+        for (int i = 0; i < 6; i++) red[w * 6 + i] = v[i];
     __syncthreads();
-    s1 = 0; s2 = 0; mx = -1e300; mn = 1e300;
+    v[0] = 0; v[1] = 0; v[2] = -1e300; v[3] = -1e300; v[4] = -1e300; v[5] = 1e300;
     for (int i = 0; i < nw; i++) {
-        s1 += red[i * 4 + 0]; s2 += red[i * 4 + 1];
-        mx = fmax(mx, red[i * 4 + 2]); mn = fmin(mn, red[i * 4 + 3]);
+        v[0] += red[i * 6 + 0]; v[1] += red[i * 6 + 1];
+        v[2] = fmax(v[2], red[i * 6 + 2]); v[3] = fmax(v[3], red[i * 6 + 3]); v[4] = fmax(v[4], red[i * 6 + 4]);
+        v[5] = fmin(v[5], red[i * 6 + 5]);
     }
 }
 
-enum { P_INIT = 0, P_START, P_SHIFT, P_RES, P_AFF, P_MUA, P_COR, P_STEP, P_UPD, P_DEAD };
+enum { P_INIT = 0, P_START, P_SHIFT, P_RES, P_AFF, P_COR, P_STEP, P_DEAD };
 
 struct Acc {  // lane-local reductions of a row pass
-    double s1, s2, mx, mn;
+    double s1, s2, mx, mx2, mn;
 };
 
 // One inequality row.  in: h, s, z, gx = g.x, ga = g.dx_aff, gd = g.dx.  sa/sb: pass scalars.
@@ -407,10 +415,20 @@ RBPE_DEV void row_eval(double h, double &s, double &z, double gx, double ga, dou
     if (MODE == P_INIT) { w = 1.0; cA = h - gx; return; }
     if (MODE == P_START) {  // z = Gx - h, s = -z (least-squares start)
         z = gx - h; s = -z;
-        if (owner) { acc.mx = fmax(acc.mx, -s); acc.s1 = fmax(acc.s1, -z); }  // s1 doubles as a second max here
+        if (owner) { acc.mx = fmax(acc.mx, -s); acc.mx2 = fmax(acc.mx2, -z); }
         return;
     }
     if (MODE == P_SHIFT) { s += sa; z += sb; return; }
+    if (MODE == P_RES && sb != 0.0) {
+        // pending step of the previous iteration (sa = its sigma*mu, sb = its step length), fused into this pass:
+        // s += al ds, z += al dz with ds, dz recomputed from the old point; then the residual at the new point
+        double rgo = gx + s - h, wo = z / s;
+        double dsa = -rgo - ga, dza = -z - wo * dsa;
+        double rc = s * z + dsa * dza - sa;
+        double ds = -rgo - gd, dz = (-rc - z * ds) / s;
+        s += sb * ds; z += sb * dz;
+        gx += sb * gd;
+    }
     double rg = gx + s - h;
     w = z / s;
     if (MODE == P_RES) {
@@ -423,10 +441,8 @@ RBPE_DEV void row_eval(double h, double &s, double &z, double gx, double ga, dou
     if (MODE == P_AFF) {
         if (dsa < 0) acc.mn = fmin(acc.mn, -s / dsa);
         if (dza < 0) acc.mn = fmin(acc.mn, -z / dza);
-        return;
-    }
-    if (MODE == P_MUA) {
-        if (owner) acc.s1 += (s + sa * dsa) * (z + sa * dza);
+        // sum (s + a dsa)(z + a dza) = s'z + a * s1 + a^2 * s2 for whatever step a comes out of the ratio test
+        if (owner) { acc.s1 += s * dza + z * dsa; acc.s2 += dsa * dza; }
         return;
     }
     double rc = s * z + dsa * dza - sa;  // sa = sigma * mu
@@ -435,9 +451,7 @@ RBPE_DEV void row_eval(double h, double &s, double &z, double gx, double ga, dou
     if (MODE == P_STEP) {
         if (ds < 0) acc.mn = fmin(acc.mn, -s / ds);
         if (dz < 0) acc.mn = fmin(acc.mn, -z / dz);
-        return;
     }
-    if (MODE == P_UPD) { s += sb * ds; z += sb * dz; }  // sb = step length
 }
 
 // Control points fixed by the start / goal equalities: 0..2 of the first segment, 3..5 of the last one.
@@ -446,7 +460,7 @@ RBPE_DEV bool cp_dead(const QP &q, int m, int i) { return (m == 0 && i < 3) || (
 // All inequality rows touching control point (m, a, i) of the batch, executed by one warp.
 template <int MODE>
 RBPE_DEV void cp_task(const QP &q, int m, int a, int i, double sa, double sb, Acc &acc) {
-    constexpr bool WR = (MODE == P_START || MODE == P_SHIFT || MODE == P_UPD);
+    constexpr bool WR = (MODE == P_START || MODE == P_SHIFT || MODE == P_RES);
     constexpr bool VEC = (MODE == P_INIT || MODE == P_RES || MODE == P_COR);
     constexpr bool MAT = (MODE == P_INIT || MODE == P_RES);
     const int lane = threadIdx.x & 31;
@@ -487,7 +501,12 @@ RBPE_DEV void cp_task(const QP &q, int m, int a, int i, double sa, double sb, Ac
         double h = q.hi[r], s = q.si[r], z = q.zi[r], cA, cB, w;
         bool own = (a == lo);
         row_eval<MODE>(h, s, z, gx, ga, gd, sa, sb, own, cA, cB, w, acc);
-        if (WR && own) { q.si[r] = s; q.zi[r] = z; }
+        if (WR && own) {
+            // such a row is evaluated from both of its control points; in the residual pass, which also advances
+            // (s, z), the owner writes to the other half of a double buffer so that the partner still reads the old pair
+            if (MODE == P_RES) { q.si_w[r] = s; q.zi_w[r] = z; }
+            else { q.si[r] = s; q.zi[r] = z; }
+        }
         if (VEC) { vA0 += cA * n0; vA1 += cA * n1; vA2 += cA * n2; vB0 += cB * n0; vB1 += cB * n1; vB2 += cB * n2; }
         if (MAT) {
             Dxx += w * n0 * n0; Dxy += w * n0 * n1; Dxz += w * n0 * n2;
@@ -543,24 +562,17 @@ RBPE_DEV void cp_task(const QP &q, int m, int a, int i, double sa, double sb, Ac
 template <int MODE>
 RBPE_DEV void row_pass(const QP &q, double sa, double sb, Acc &out) {
     Acc acc;
-    acc.s1 = (MODE == P_START) ? -1e300 : 0.0;
-    acc.s2 = 0; acc.mx = -1e300; acc.mn = 1e300;
+    acc.s1 = 0; acc.s2 = 0; acc.mx = -1e300; acc.mx2 = -1e300; acc.mn = 1e300;
     const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5, ntask = q.M * q.nb * 6;
     for (int t = warp; t < ntask; t += nw) {
         int i = t % 6, a = (t / 6) % q.nb, m = t / (6 * q.nb);
         if (cp_dead(q, m, i) != (MODE == P_DEAD)) continue;   // live passes skip fixed control points and vice versa
         cp_task<MODE>(q, m, a, i, sa, sb, acc);
     }
-    if (MODE == P_START) {  // two max reductions: mx and s1
-        double m2 = acc.s1, z0 = 0, mn = 1e300, s1 = 0;
-        block_reduce4(s1, z0, acc.mx, mn, q.red);
-        double mx2 = m2; s1 = 0; z0 = 0; mn = 1e300;
-        block_reduce4(s1, z0, mx2, mn, q.red);
-        out.mx = acc.mx; out.s1 = mx2; out.s2 = 0; out.mn = 0;
-        return;
-    }
-    block_reduce4(acc.s1, acc.s2, acc.mx, acc.mn, q.red);
-    out = acc;
+    if (MODE == P_SHIFT) { __syncthreads(); return; }
+    double v[6] = {acc.s1, acc.s2, acc.mx, acc.mx2, -1e300, acc.mn};
+    block_reduce6(v, q.red);
+    out.s1 = v[0]; out.s2 = v[1]; out.mx = v[2]; out.mx2 = v[3]; out.mn = v[5];
 }
 
 // ---- knot space ------------------------------------------------------------------------------------------------
@@ -692,19 +704,137 @@ RBPE_DEV void solve_bt(TM tm, int nblk, int kb, const double *Dall, const double
     }
 }
 
+// ---- one-agent batches (9x9 blocks): the whole block tridiagonal system handled by one warp out of registers -------
+// lanes 0..8 hold the rows of the diagonal block D_t, lanes 9..17 the rows of O_t = block (t+1, t).
+// On exit D holds L_tt (lower), O holds L_{t+1,t}, dinv[t*9+j] = 1 / L_tt[j][j].
+RBPE_DEV bool factor_bt9(int nblk, double *Dall, double *Oall, double *dinv) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const bool isD = lane < 9, isO = lane >= 9 && lane < 18;
+    const int row = isD ? lane : lane - 9;
+    bool ok = true;
+    for (int t = 0; t < nblk; t++) {
+        double *D = Dall + t * 81, *O = Oall + t * 81;
+        const bool hasO = t < nblk - 1;
+        double a[9];
+#pragma unroll
+        for (int c = 0; c < 9; c++) a[c] = isD ? D[row * 9 + c] : ((isO && hasO) ? O[row * 9 + c] : 0.0);
+        if (t > 0 && isD) {  // D_t -= L_{t,t-1} L_{t,t-1}'
+            const double *P = Oall + (t - 1) * 81;
+            double pr[9];
+#pragma unroll
+            for (int k = 0; k < 9; k++) pr[k] = P[row * 9 + k];
+#pragma unroll
+            for (int c = 0; c < 9; c++) {
+                double sm = 0;
+#pragma unroll
+                for (int k = 0; k < 9; k++) sm += pr[k] * P[c * 9 + k];
+                a[c] -= sm;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 9; j++) {
+            double piv = __shfl_sync(FULL, a[j], j);
+            if (!(piv > 0)) { ok = false; piv = 1.0; }
+            double inv = 1.0 / sqrt(piv);
+            a[j] *= inv;                       // column j of L_tt (rows >= j) and of L_{t+1,t}
+            if (lane == j) dinv[t * 9 + j] = inv;
+#pragma unroll
+            for (int k = j + 1; k < 9; k++) {
+                double lkj = __shfl_sync(FULL, a[j], k);
+                a[k] -= a[j] * lkj;            // only entries on or below the diagonal are meaningful for D rows
+            }
+        }
+        if (isD) {
+#pragma unroll
+            for (int c = 0; c < 9; c++) D[row * 9 + c] = (c <= row) ? a[c] : 0.0;
+        } else if (isO && hasO) {
+#pragma unroll
+            for (int c = 0; c < 9; c++) O[row * 9 + c] = a[c];
+        }
+        __syncwarp();
+    }
+    return ok;
+}
+
+RBPE_DEV void solve_bt9(int nblk, const double *Dall, const double *Oall, const double *dinv, double *g) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const bool act = lane < 9;
+    double prev = 0;
+    for (int t = 0; t < nblk; t++) {  // L w = g
+        const double *L = Dall + t * 81;
+        double gv = act ? g[t * 9 + lane] : 0.0, di = act ? dinv[t * 9 + lane] : 0.0, lrow[9];
+#pragma unroll
+        for (int c = 0; c < 9; c++) lrow[c] = act ? L[lane * 9 + c] : 0.0;
+        if (t > 0) {
+            const double *P = Oall + (t - 1) * 81;
+            double sm = 0;
+#pragma unroll
+            for (int k = 0; k < 9; k++) {
+                double gk = __shfl_sync(FULL, prev, k);
+                if (act) sm += P[lane * 9 + k] * gk;
+            }
+            gv -= sm;
+        }
+#pragma unroll
+        for (int j = 0; j < 9; j++) {
+            if (lane == j) gv *= di;
+            double gj = __shfl_sync(FULL, gv, j);
+            if (act && lane > j) gv -= lrow[j] * gj;
+        }
+        prev = gv;
+        if (act) g[t * 9 + lane] = gv;
+    }
+    double next = 0;
+    for (int t = nblk - 1; t >= 0; t--) {  // L' y = w
+        const double *L = Dall + t * 81;
+        double gv = act ? g[t * 9 + lane] : 0.0, di = act ? dinv[t * 9 + lane] : 0.0, lcol[9];
+#pragma unroll
+        for (int j = 0; j < 9; j++) lcol[j] = act ? L[j * 9 + lane] : 0.0;
+        if (t < nblk - 1) {
+            const double *P = Oall + t * 81;
+            double sm = 0;
+#pragma unroll
+            for (int k = 0; k < 9; k++) {
+                double yk = __shfl_sync(FULL, next, k);
+                if (act) sm += P[k * 9 + lane] * yk;
+            }
+            gv -= sm;
+        }
+#pragma unroll
+        for (int j = 8; j >= 0; j--) {
+            if (lane == j) gv *= di;
+            double gj = __shfl_sync(FULL, gv, j);
+            if (act && lane < j) gv -= lcol[j] * gj;
+        }
+        next = gv;
+        if (act) g[t * 9 + lane] = gv;
+    }
+    __syncwarp();
+}
+
+// factorisation verdict travels through q.red[60] (written by the factoring warp / thread 0, read after a barrier)
 RBPE_DEV bool kkt_factor(const QP &q) {
     __syncthreads();
     build_W(q);
     __syncthreads();
-    bool ok = true;
-    if (q.kb <= 36) {
-        if ((threadIdx.x >> 5) == 0) ok = factor_bt(WarpTeam(), q.M - 1, q.kb, q.Wd, q.Wo);
+    if (q.kb == 9) {
+        if ((threadIdx.x >> 5) == 0) {
+            bool ok = factor_bt9(q.M - 1, q.Wd, q.Wo, q.dinv);
+            if (threadIdx.x == 0) q.red[60] = ok ? 0.0 : 1.0;
+        }
+    } else if (q.kb <= 36) {
+        if ((threadIdx.x >> 5) == 0) {
+            bool ok = factor_bt(WarpTeam(), q.M - 1, q.kb, q.Wd, q.Wo);
+            if (threadIdx.x == 0) q.red[60] = ok ? 0.0 : 1.0;
+        }
     } else {
-        ok = factor_bt(CtaTeam(), q.M - 1, q.kb, q.Wd, q.Wo);
+        bool ok = factor_bt(CtaTeam(), q.M - 1, q.kb, q.Wd, q.Wo);
+        if (threadIdx.x == 0) q.red[60] = ok ? 0.0 : 1.0;
     }
-    double s1 = ok ? 0.0 : 1.0, s2 = 0, mx = -1e300, mn = 1e300;
-    block_reduce4(s1, s2, mx, mn, q.red);
-    return s1 == 0.0;
+    __syncthreads();
+    return q.red[60] == 0.0;
 }
 
 // dxout (nv) = Z (Z'HZ)^-1 Z' r   with r (nv) in x-space; uses q.sg
@@ -712,7 +842,9 @@ RBPE_DEV void kkt_solve(const QP &q, const double *r, double *dxout) {
     __syncthreads();
     Zt_apply(q, r, q.sg);
     __syncthreads();
-    if (q.kb <= 36) {
+    if (q.kb == 9) {
+        if ((threadIdx.x >> 5) == 0) solve_bt9(q.M - 1, q.Wd, q.Wo, q.dinv, q.sg);
+    } else if (q.kb <= 36) {
         if ((threadIdx.x >> 5) == 0) solve_bt(WarpTeam(), q.M - 1, q.kb, q.Wd, q.Wo, q.sg);
     } else {
         solve_bt(CtaTeam(), q.M - 1, q.kb, q.Wd, q.Wo, q.sg);
@@ -787,16 +919,17 @@ RBPE_DEV void dual_residual(const QP &q, double &obj_part, double &mpx) {
     }
 }
 RBPE_DEV double block_max(double v, double *red) {
-    double s1 = 0, s2 = 0, mn = 1e300;
-    block_reduce4(s1, s2, v, mn, red);
-    return v;
+    double r[6] = {0, 0, v, -1e300, -1e300, 1e300};
+    block_reduce6(r, red);
+    return r[2];
 }
 
 constexpr double PRESOLVE_FEAS_TOL = 1e-6;  // CPLEX's default feasibility tolerance, for rows made constant by the endpoints
 
 // Solves the QP described by q. Returns status; x holds the solution.
-RBPE_DEV int pdip_solve(const QP &q, int max_iter, double tol_gap, double tol_res, double *obj_out, int *it_out,
+RBPE_DEV int pdip_solve(const QP &q_in, int max_iter, double tol_gap, double tol_res, double *obj_out, int *it_out,
                         double *res_out) {
+    QP q = q_in;
     const int tid = threadIdx.x, nt = blockDim.x;
     Acc acc;
     setup_rows(q);
@@ -808,10 +941,11 @@ RBPE_DEV int pdip_solve(const QP &q, int max_iter, double tol_gap, double tol_re
     row_pass<P_DEAD>(q, 0, 0, acc);
     if (acc.mx > PRESOLVE_FEAS_TOL) { status = ST_INFEASIBLE; go = false; }
     if (go && q.nr == 0) {  // single segment: the endpoints fix everything
-        double o = 0, mpx = 0, s2 = 0, mx = 0, mn = 1e300;
+        double o = 0, mpx = 0;
         dual_residual(q, o, mpx);
-        block_reduce4(o, s2, mx, mn, q.red);
-        obj = o;
+        double r[6] = {o, 0, mpx, -1e300, -1e300, 1e300};
+        block_reduce6(r, q.red);
+        obj = r[0];
         status = ST_OK;
         go = false;
     }
@@ -832,7 +966,6 @@ RBPE_DEV int pdip_solve(const QP &q, int max_iter, double tol_gap, double tol_re
         hn = block_max(mh, q.red);
         // ---- initial point: W = I,  min 1/2 x'(P + G'G)x - (G'h)'x  over x = x_p + Z sigma ----
         row_pass<P_INIT>(q, 0, 0, acc);   // vA = G'(h - G x_p), Dcp/Dint with unit weights
-        __syncthreads();
         if (!kkt_factor(q)) go = false;
     }
     if (go) {
@@ -843,30 +976,34 @@ RBPE_DEV int pdip_solve(const QP &q, int max_iter, double tol_gap, double tol_re
         kkt_solve(q, q.rdx, q.dx);
         for (int v = tid; v < q.nv; v += nt) { q.x[v] += q.dx[v]; q.dx[v] = 0; }
         __syncthreads();
-        row_pass<P_START>(q, 0, 0, acc);  // acc.mx = max(-s), acc.s1 = max(-z)
-        double ap = acc.mx, ad = acc.s1;
-        __syncthreads();
+        row_pass<P_START>(q, 0, 0, acc);  // acc.mx = max(-s), acc.mx2 = max(-z)
+        double ap = acc.mx, ad = acc.mx2;
         row_pass<P_SHIFT>(q, ap >= 0 ? 1.0 + ap : 0.0, ad >= 0 ? 1.0 + ad : 0.0, acc);
-        __syncthreads();
     }
 
+    double sigmu = 0, al = 0;   // pending step of the previous iteration, applied inside the next residual pass
     for (it = 0; go && it < max_iter; it++) {
-        // ---- residuals ----
-        row_pass<P_RES>(q, 0, 0, acc);  // vA = G'z, vB = G't_aff, Dcp/Dint; s1 = s'z, s2 = h'z, mx = |rg|
-        __syncthreads();
+        // ---- residuals (with the previous step's s, z update fused in) ----
+        row_pass<P_RES>(q, sigmu, al, acc);  // vA = G'z, vB = G't_aff, Dcp/Dint; s1 = s'z, s2 = h'z, mx = |rg|
+        { double *t1 = q.si; q.si = q.si_w; q.si_w = t1; t1 = q.zi; q.zi = q.zi_w; q.zi_w = t1; }
+        if (al != 0.0) {
+            for (int v = tid; v < q.nv; v += nt) q.x[v] += al * q.dx[v];
+            __syncthreads();
+        }
         double mu = acc.s1 / (q.mi > 0 ? q.mi : 1), hz = acc.s2;
         nrg = fmax(acc.mx, 0.0);
-        double o = 0, mpx = 0, s2 = 0, mn = 1e300;
+        double o = 0, mpx = 0;
         dual_residual(q, o, mpx);
-        block_reduce4(o, s2, mpx, mn, q.red);
-        obj = o;
+        __syncthreads();
         Zt_apply(q, q.rdx, q.sg);
         Zt_apply(q, q.vA, q.sg2);
         __syncthreads();
         double mr = 0, mc = 0;
         for (int r = tid; r < q.nr; r += nt) { mr = fmax(mr, fabs(q.sg[r])); mc = fmax(mc, fabs(q.sg2[r])); }
-        nrd = block_max(mr, q.red);
-        double mcert = block_max(mc, q.red);
+        double rr[6] = {o, 0, mpx, mr, mc, 1e300};
+        block_reduce6(rr, q.red);
+        obj = rr[0]; mpx = rr[2]; nrd = rr[3];
+        double mcert = rr[4];
         gap = mu;
         if (!(mu == mu) || !(nrd == nrd)) { status = ST_NOT_CONVERGED; break; }
         if (gap <= tol_gap * fmax(1.0, fabs(obj)) && nrg <= tol_res * (1 + hn) && nrd <= tol_res * (1.0 + mpx)) {
@@ -879,43 +1016,35 @@ RBPE_DEV int pdip_solve(const QP &q, int max_iter, double tol_gap, double tol_re
         // ---- affine direction ----
         for (int v = tid; v < q.nv; v += nt) q.vB[v] = -q.rdx[v] + q.vB[v];
         kkt_solve(q, q.vB, q.dxa);
-        row_pass<P_AFF>(q, 0, 0, acc);
+        row_pass<P_AFF>(q, 0, 0, acc);       // mn = ratio test; s1, s2 = linear / quadratic coefficient of mu_aff(a)
         double aa = fmin(1.0, acc.mn);
-        __syncthreads();
-        row_pass<P_MUA>(q, aa, 0, acc);
-        double mua = acc.s1 / (q.mi > 0 ? q.mi : 1);
+        double mua = (mu * (q.mi > 0 ? q.mi : 1) + aa * acc.s1 + aa * aa * acc.s2) / (q.mi > 0 ? q.mi : 1);
         double sigma = (mu > 0) ? (mua / mu) * (mua / mu) * (mua / mu) : 0.0;
-        __syncthreads();
+        sigmu = sigma * mu;
         // ---- corrector ----
-        row_pass<P_COR>(q, sigma * mu, 0, acc);
-        __syncthreads();
+        row_pass<P_COR>(q, sigmu, 0, acc);
         for (int v = tid; v < q.nv; v += nt) q.vA[v] = -q.rdx[v] + q.vA[v];
         kkt_solve(q, q.vA, q.dx);
-        row_pass<P_STEP>(q, sigma * mu, 0, acc);
-        double al = fmin(1.0, 0.99 * acc.mn);
-        __syncthreads();
-        row_pass<P_UPD>(q, sigma * mu, al, acc);
-        __syncthreads();
-        for (int v = tid; v < q.nv; v += nt) q.x[v] += al * q.dx[v];
-        __syncthreads();
+        row_pass<P_STEP>(q, sigmu, 0, acc);
+        al = fmin(1.0, 0.99 * acc.mn);       // s, z, x are advanced at the top of the next iteration
     }
     __syncthreads();
     // |Ax - b| for the record (the parametrisation keeps it at rounding level)
     double mrp = 0;
     for (int e = tid; e < q.kb * (q.M + 1); e += nt) {
         int t = e / q.kb, cc = e % q.kb, ak = cc / 3, d = cc % 3, a = ak / 3, k = ak % 3;
-        double s = 0;
+        double sm = 0;
         if (t < q.M) {
-            const double *sm = q.segmat + t * SEGMAT + SEGMAT_AL + d * 6, *xx = q.x + t * q.n + ak * 6;
-            for (int i = 0; i < 6; i++) s += sm[i] * xx[i];
+            const double *sp = q.segmat + t * SEGMAT + SEGMAT_AL + d * 6, *xx = q.x + t * q.n + ak * 6;
+            for (int i = 0; i < 6; i++) sm += sp[i] * xx[i];
         }
         if (t > 0) {
-            const double *sm = q.segmat + (t - 1) * SEGMAT + SEGMAT_AR + d * 6, *xx = q.x + (t - 1) * q.n + ak * 6;
-            for (int i = 0; i < 6; i++) s += sm[i] * xx[i];
+            const double *sp = q.segmat + (t - 1) * SEGMAT + SEGMAT_AR + d * 6, *xx = q.x + (t - 1) * q.n + ak * 6;
+            for (int i = 0; i < 6; i++) sm += sp[i] * xx[i];
         }
-        if (t == 0) s -= q.start[(size_t)(q.q0 + a) * 9 + k + 3 * d];
-        if (t == q.M) s -= q.goal[(size_t)(q.q0 + a) * 9 + k + 3 * d];
-        mrp = fmax(mrp, fabs(s));
+        if (t == 0) sm -= q.start[(size_t)(q.q0 + a) * 9 + k + 3 * d];
+        if (t == q.M) sm -= q.goal[(size_t)(q.q0 + a) * 9 + k + 3 * d];
+        mrp = fmax(mrp, fabs(sm));
     }
     mrp = block_max(mrp, q.red);
     if (tid == 0) {
@@ -926,7 +1055,7 @@ RBPE_DEV int pdip_solve(const QP &q, int max_iter, double tol_gap, double tol_re
     return status;
 }
 
-__global__ void __launch_bounds__(CTA_THREADS) pdip_kernel(SolveArgs S) {
+__global__ void __launch_bounds__(CTA_THREADS, 2) pdip_kernel(SolveArgs S) {
     RBPE_DYN_SMEM(smem);
     const int N = S.N, M = S.M;
     int c, l_begin, l_end;

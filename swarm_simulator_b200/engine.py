@@ -171,9 +171,10 @@ class Result:
 class Engine:
     """One engine handle = one CUDA device + one stream (include/rbpe.h). Not thread-safe."""
 
-    def __init__(self, device=0, max_iter=0, tol_gap=0.0, tol_res=0.0, smem_budget=0):
+    def __init__(self, device=0, max_iter=0, tol_gap=0.0, tol_res=0.0, smem_budget=0, threads=0):
         self.lib = load_library()
         cfg = RbpeConfig(device, max_iter, tol_gap, tol_res, smem_budget)
+        cfg.reserved[0] = threads
         h = C.c_void_p()
         rc = self.lib.rbpe_create(C.byref(cfg), C.byref(h))
         if rc != OK:

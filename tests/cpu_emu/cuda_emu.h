@@ -19,7 +19,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
-#define __launch_bounds__(x)
+#define __launch_bounds__(...)
 #define __align__(x) alignas(x)
 
 namespace emu {
@@ -143,6 +143,20 @@ inline T __shfl_down_sync(unsigned, T v, int delta) {
     emu::barrier_wait(s.warp[w]);
     T r = v;
     if (lane + delta < 32) memcpy(&r, slot + (lane + delta) * 16, sizeof(T));
+    emu::barrier_wait(s.warp[w]);
+    return r;
+}
+
+template <class T>
+inline T __shfl_sync(unsigned, T v, int src) {
+    static_assert(sizeof(T) <= 16, "emu shuffle payload");
+    emu::State &s = emu::S();
+    int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    char *slot = (char *)&s.xch[(size_t)w * 64];
+    memcpy(slot + lane * 16, &v, sizeof(T));
+    emu::barrier_wait(s.warp[w]);
+    T r;
+    memcpy(&r, slot + (src & 31) * 16, sizeof(T));
     emu::barrier_wait(s.warp[w]);
     return r;
 }

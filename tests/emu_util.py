@@ -17,7 +17,7 @@ _SRCS = [os.path.join(_EMU_DIR, "emu_driver.cpp"), os.path.join(_EMU_DIR, "cuda_
 
 def build():
     if (not os.path.exists(_EMU_LIB)) or os.path.getmtime(_EMU_LIB) < max(os.path.getmtime(s) for s in _SRCS):
-        subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-Wno-unused", "-o", _EMU_LIB,
+        subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-Wno-unused", "-Wno-unknown-pragmas", "-o", _EMU_LIB,
                                _SRCS[0]])
     return _EMU_LIB
 

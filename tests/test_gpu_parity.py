@@ -173,7 +173,7 @@ def test_fixture_batch15_matches_cplex_csv(eng, golden):
     eng.run_jacobi_range(15, 16)
     r = eng.download(prob)
     assert r.status[0] == E.OK
-    assert abs(r.qp_obj[0][15] - 0.0971578) < 2e-7                        # CPLEX-convention objective
+    assert abs(r.qp_obj[0][15] - 0.0971578) < 5e-6   # CPLEX-convention objective; frozen agents come from 6-digit CSVs
     ctrl = r.ctrl[0][F.B0:F.B0 + F.NB].reshape(F.NB, 3, F.M, 6).transpose(0, 2, 1, 3)   # [NB, M, 3, 6]
     cref = F.csv_ctrl(golden["csv"]["coef"][F.B0:F.B0 + F.NB])
     assert np.abs(ctrl - cref).max() < 1e-4 * max(1.0, np.abs(cref).max())
