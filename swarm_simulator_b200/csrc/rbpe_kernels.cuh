@@ -24,6 +24,10 @@
 
 #include <math.h>
 
+#ifdef RBPE_EMU
+inline double rsqrt(double x) { return 1.0 / sqrt(x); }
+#endif
+
 namespace rbpe {
 
 // ------------------------------------------------------------------------------------------------------------
@@ -90,11 +94,11 @@ __host__ __device__ inline size_t scratch_doubles(int N, int M, int bs) {
     }
     size_t rint_ = (size_t)bs * (bs - 1) / 2 * 6 * M;
     size_t t = 64 + 36;
-    t += 12 * al2(nv) + 3 * al2(nr);
+    t += 14 * al2(nv) + 3 * al2(nr);
     t += al2((size_t)M * bs * 36) + al2(rint_ * 6);                  // Dcp, Dint
     t += al2((size_t)(M > 1 ? M - 1 : 1) * kb * kb) + al2((size_t)(M > 2 ? M - 2 : 1) * kb * kb);
-    t += 3 * al2(rext) + 3 * al2((rext + 1) / 2);
-    t += 5 * al2(rint_) + 3 * al2((rint_ + 1) / 2);
+    t += 4 * al2(rext) + 3 * al2((rext + 1) / 2);
+    t += 7 * al2(rint_) + 3 * al2((rint_ + 1) / 2);
     return t;
 }
 
@@ -311,17 +315,17 @@ struct QP {
     const float *reln;
     const double *ctrl_src;
     // x-space vectors (nv), segment-major: v = m*18nb + (a*3+k)*6 + i
-    double *x, *dxa, *dx, *rdx, *ub, *lbn, *sub, *zub, *slb, *zlb, *vA, *vB;
+    double *x, *dxa, *dx, *rdx, *ub, *lbn, *sub, *zub, *slb, *zlb, *vA, *vB, *tub, *tlb;
     // knot-space vectors (nr): r = (t-1)*9nb + (a*3+k)*3 + d, t = 1..M-1
     double *sg, *sg2;
     double *dinv;        // [nr] reciprocal Cholesky diagonal (one-agent batches)
     double *Wd, *Wo;     // reduced Hessian Z'HZ: (M-1) diagonal blocks, (M-2) blocks (t+1,t), each 9nb x 9nb
     double *Dcp;         // [M*nb*6][6]  sum_rows w g g' restricted to one control point (3x3 symmetric over axes)
     double *Dint;        // [nrint][6]   -w n n' of a row between two batch agents
-    double *he, *se, *ze;
+    double *he, *se, *ze, *te;   // per row: right-hand side, slack, multiplier, t = 1/(s z)  (1/s = t z, 1/z = t s)
     float *nex, *ney, *nez;
-    double *hi, *si, *zi;
-    double *si_w, *zi_w;  // write side of the (s, z) pair of rows between two batch agents during the fused residual pass
+    double *hi, *si, *zi, *ti;
+    double *si_w, *zi_w, *ti_w;  // write side of the (s, z) pair of rows between two batch agents during the fused residual pass
     float *nix, *niy, *niz;
     double *red;  // 64 doubles
     double *QB;   // 36 doubles: Q_base
@@ -353,8 +357,8 @@ RBPE_DEV void layout(QP &q, unsigned char *smem, size_t smem_bytes, double *gscr
     a.gl = gscratch;
     q.red = a.take(64);
     q.QB = a.take(36);
-    double **vv[12] = {&q.x, &q.dxa, &q.dx, &q.rdx, &q.ub, &q.lbn, &q.sub, &q.zub, &q.slb, &q.zlb, &q.vA, &q.vB};
-    for (int i = 0; i < 12; i++) *vv[i] = a.take(q.nv);
+    double **vv[14] = {&q.x, &q.dxa, &q.dx, &q.rdx, &q.ub, &q.lbn, &q.sub, &q.zub, &q.slb, &q.zlb, &q.vA, &q.vB, &q.tub, &q.tlb};
+    for (int i = 0; i < 14; i++) *vv[i] = a.take(q.nv);
     q.sg = a.take(q.nr);
     q.sg2 = a.take(q.nr);
     q.dinv = a.take(q.nr);
@@ -362,12 +366,12 @@ RBPE_DEV void layout(QP &q, unsigned char *smem, size_t smem_bytes, double *gscr
     q.Dint = a.take((size_t)q.nrint * 6);
     q.Wd = a.take((size_t)(q.M > 1 ? q.M - 1 : 1) * q.kb * q.kb);
     q.Wo = a.take((size_t)(q.M > 2 ? q.M - 2 : 1) * q.kb * q.kb);
-    q.he = a.take(q.nrext); q.se = a.take(q.nrext); q.ze = a.take(q.nrext);
+    q.he = a.take(q.nrext); q.se = a.take(q.nrext); q.ze = a.take(q.nrext); q.te = a.take(q.nrext);
     q.nex = (float *)a.take(((size_t)q.nrext + 1) / 2);
     q.ney = (float *)a.take(((size_t)q.nrext + 1) / 2);
     q.nez = (float *)a.take(((size_t)q.nrext + 1) / 2);
-    q.hi = a.take(q.nrint); q.si = a.take(q.nrint); q.zi = a.take(q.nrint);
-    q.si_w = a.take(q.nrint); q.zi_w = a.take(q.nrint);
+    q.hi = a.take(q.nrint); q.si = a.take(q.nrint); q.zi = a.take(q.nrint); q.ti = a.take(q.nrint);
+    q.si_w = a.take(q.nrint); q.zi_w = a.take(q.nrint); q.ti_w = a.take(q.nrint);
     q.nix = (float *)a.take(((size_t)q.nrint + 1) / 2);
     q.niy = (float *)a.take(((size_t)q.nrint + 1) / 2);
     q.niz = (float *)a.take(((size_t)q.nrint + 1) / 2);
@@ -376,26 +380,37 @@ RBPE_DEV void layout(QP &q, unsigned char *smem, size_t smem_bytes, double *gscr
 template <class T>
 RBPE_DEV T shfl_down_t(T v, int o) { return __shfl_down_sync(0xffffffffu, v, o); }
 
-// CTA-wide reduction of v = (sum, sum, max, max, max, min); every thread returns the same values (fixed order).
+// CTA-wide reduction of the slots of v = (sum, sum, max, max, max, min) selected by MASK; every thread returns the same
+// values (fixed order).  Unselected slots are left untouched.
+template <int MASK>
 RBPE_DEV void block_reduce6(double *v, double *red) {
     for (int o = 16; o > 0; o >>= 1) {
-        v[0] += shfl_down_t(v[0], o);
-        v[1] += shfl_down_t(v[1], o);
-        v[2] = fmax(v[2], shfl_down_t(v[2], o));
-        v[3] = fmax(v[3], shfl_down_t(v[3], o));
-        v[4] = fmax(v[4], shfl_down_t(v[4], o));
-        v[5] = fmin(v[5], shfl_down_t(v[5], o));
+        if (MASK & 1) v[0] += shfl_down_t(v[0], o);
+        if (MASK & 2) v[1] += shfl_down_t(v[1], o);
+        if (MASK & 4) v[2] = fmax(v[2], shfl_down_t(v[2], o));
+        if (MASK & 8) v[3] = fmax(v[3], shfl_down_t(v[3], o));
+        if (MASK & 16) v[4] = fmax(v[4], shfl_down_t(v[4], o));
+        if (MASK & 32) v[5] = fmin(v[5], shfl_down_t(v[5], o));
     }
     int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
     __syncthreads();
     if (l == 0)
-        for (int i = 0; i < 6; i++) red[w * 6 + i] = v[i];
+        for (int i = 0; i < 6; i++)
+            if (MASK & (1 << i)) red[w * 6 + i] = v[i];
     __syncthreads();
-    v[0] = 0; v[1] = 0; v[2] = -1e300; v[3] = -1e300; v[4] = -1e300; v[5] = 1e300;
+    if (MASK & 1) v[0] = 0;
+    if (MASK & 2) v[1] = 0;
+    if (MASK & 4) v[2] = -1e300;
+    if (MASK & 8) v[3] = -1e300;
+    if (MASK & 16) v[4] = -1e300;
+    if (MASK & 32) v[5] = 1e300;
     for (int i = 0; i < nw; i++) {
-        v[0] += red[i * 6 + 0]; v[1] += red[i * 6 + 1];
-        v[2] = fmax(v[2], red[i * 6 + 2]); v[3] = fmax(v[3], red[i * 6 + 3]); v[4] = fmax(v[4], red[i * 6 + 4]);
-        v[5] = fmin(v[5], red[i * 6 + 5]);
+        if (MASK & 1) v[0] += red[i * 6 + 0];
+        if (MASK & 2) v[1] += red[i * 6 + 1];
+        if (MASK & 4) v[2] = fmax(v[2], red[i * 6 + 2]);
+        if (MASK & 8) v[3] = fmax(v[3], red[i * 6 + 3]);
+        if (MASK & 16) v[4] = fmax(v[4], red[i * 6 + 4]);
+        if (MASK & 32) v[5] = fmin(v[5], red[i * 6 + 5]);
     }
 }
 
@@ -405,10 +420,12 @@ struct Acc {  // lane-local reductions of a row pass
     double s1, s2, mx, mx2, mn;
 };
 
-// One inequality row.  in: h, s, z, gx = g.x, ga = g.dx_aff, gd = g.dx.  sa/sb: pass scalars.
-// out: cA, cB (coefficients of g in the two G' products), w (weight of g g' in H); s, z may be rewritten.
+// One inequality row.  in: h, s, z, t = 1/(s z), gx = g.x, ga = g.dx_aff, gd = g.dx.  sa/sb: pass scalars.
+// out: cA, cB (coefficients of g in the two G' products), w (weight of g g' in H); s, z, t may be rewritten.
+// One division per row and iteration (t, after the step); 1/s = t z and 1/z = t s everywhere else.  The ratio tests
+// run in max form: step = 1 / max_r(-ds_r / s_r, -dz_r / z_r).
 template <int MODE>
-RBPE_DEV void row_eval(double h, double &s, double &z, double gx, double ga, double gd, double sa, double sb,
+RBPE_DEV void row_eval(double h, double &s, double &z, double &t, double gx, double ga, double gd, double sa, double sb,
                        bool owner, double &cA, double &cB, double &w, Acc &acc) {
     cA = 0; cB = 0; w = 0;
     if (MODE == P_DEAD) { acc.mx = fmax(acc.mx, gx - h); return; }   // constant row: violation of its right-hand side
@@ -418,40 +435,40 @@ RBPE_DEV void row_eval(double h, double &s, double &z, double gx, double ga, dou
         if (owner) { acc.mx = fmax(acc.mx, -s); acc.mx2 = fmax(acc.mx2, -z); }
         return;
     }
-    if (MODE == P_SHIFT) { s += sa; z += sb; return; }
+    if (MODE == P_SHIFT) { s += sa; z += sb; t = 1.0 / (s * z); return; }
+    double rs = t * z;
     if (MODE == P_RES && sb != 0.0) {
         // pending step of the previous iteration (sa = its sigma*mu, sb = its step length), fused into this pass:
         // s += al ds, z += al dz with ds, dz recomputed from the old point; then the residual at the new point
-        double rgo = gx + s - h, wo = z / s;
+        double rgo = gx + s - h, wo = z * rs;
         double dsa = -rgo - ga, dza = -z - wo * dsa;
         double rc = s * z + dsa * dza - sa;
-        double ds = -rgo - gd, dz = (-rc - z * ds) / s;
+        double ds = -rgo - gd, dz = (-rc - z * ds) * rs;
         s += sb * ds; z += sb * dz;
         gx += sb * gd;
+        t = 1.0 / (s * z);
+        rs = t * z;
     }
     double rg = gx + s - h;
-    w = z / s;
+    w = z * rs;
     if (MODE == P_RES) {
         cA = z;
         cB = -(w * rg - z);
         if (owner) { acc.s1 += s * z; acc.s2 += h * z; acc.mx = fmax(acc.mx, fabs(rg)); }
         return;
     }
+    double rz = t * s;
     double dsa = -rg - ga, dza = -z - w * dsa;
     if (MODE == P_AFF) {
-        if (dsa < 0) acc.mn = fmin(acc.mn, -s / dsa);
-        if (dza < 0) acc.mn = fmin(acc.mn, -z / dza);
+        acc.mx = fmax(acc.mx, fmax(-dsa * rs, -dza * rz));
         // sum (s + a dsa)(z + a dza) = s'z + a * s1 + a^2 * s2 for whatever step a comes out of the ratio test
         if (owner) { acc.s1 += s * dza + z * dsa; acc.s2 += dsa * dza; }
         return;
     }
     double rc = s * z + dsa * dza - sa;  // sa = sigma * mu
-    if (MODE == P_COR) { cA = -(z * rg - rc) / s; return; }
-    double ds = -rg - gd, dz = (-rc - z * ds) / s;
-    if (MODE == P_STEP) {
-        if (ds < 0) acc.mn = fmin(acc.mn, -s / ds);
-        if (dz < 0) acc.mn = fmin(acc.mn, -z / dz);
-    }
+    if (MODE == P_COR) { cA = -(z * rg - rc) * rs; return; }
+    double ds = -rg - gd, dz = (-rc - z * ds) * rs;
+    if (MODE == P_STEP) acc.mx = fmax(acc.mx, fmax(-ds * rs, -dz * rz));
 }
 
 // Control points fixed by the start / goal equalities: 0..2 of the first segment, 3..5 of the last one.
@@ -476,10 +493,10 @@ RBPE_DEV void cp_task(const QP &q, int m, int a, int i, double sa, double sb, Ac
         for (int e = lane; e < q.NE; e += 32) {
             size_t r = rb + e;
             double n0 = q.nex[r], n1 = q.ney[r], n2 = q.nez[r];
-            double h = q.he[r], s = q.se[r], z = q.ze[r], cA, cB, w;
-            row_eval<MODE>(h, s, z, n0 * x0 + n1 * x1 + n2 * x2, n0 * a0 + n1 * a1 + n2 * a2,
+            double h = q.he[r], s = q.se[r], z = q.ze[r], t = q.te[r], cA, cB, w;
+            row_eval<MODE>(h, s, z, t, n0 * x0 + n1 * x1 + n2 * x2, n0 * a0 + n1 * a1 + n2 * a2,
                            n0 * d0 + n1 * d1 + n2 * d2, sa, sb, true, cA, cB, w, acc);
-            if (WR) { q.se[r] = s; q.ze[r] = z; }
+            if (WR) { q.se[r] = s; q.ze[r] = z; q.te[r] = t; }
             if (VEC) { vA0 += cA * n0; vA1 += cA * n1; vA2 += cA * n2; vB0 += cB * n0; vB1 += cB * n1; vB2 += cB * n2; }
             if (MAT) {
                 Dxx += w * n0 * n0; Dxy += w * n0 * n1; Dxz += w * n0 * n2;
@@ -498,14 +515,14 @@ RBPE_DEV void cp_task(const QP &q, int m, int a, int i, double sa, double sb, Ac
         double gx = n0 * (x0 - q.x[vo]) + n1 * (x1 - q.x[vo + 6]) + n2 * (x2 - q.x[vo + 12]);
         double ga = n0 * (a0 - q.dxa[vo]) + n1 * (a1 - q.dxa[vo + 6]) + n2 * (a2 - q.dxa[vo + 12]);
         double gd = n0 * (d0 - q.dx[vo]) + n1 * (d1 - q.dx[vo + 6]) + n2 * (d2 - q.dx[vo + 12]);
-        double h = q.hi[r], s = q.si[r], z = q.zi[r], cA, cB, w;
+        double h = q.hi[r], s = q.si[r], z = q.zi[r], t = q.ti[r], cA, cB, w;
         bool own = (a == lo);
-        row_eval<MODE>(h, s, z, gx, ga, gd, sa, sb, own, cA, cB, w, acc);
+        row_eval<MODE>(h, s, z, t, gx, ga, gd, sa, sb, own, cA, cB, w, acc);
         if (WR && own) {
             // such a row is evaluated from both of its control points; in the residual pass, which also advances
             // (s, z), the owner writes to the other half of a double buffer so that the partner still reads the old pair
-            if (MODE == P_RES) { q.si_w[r] = s; q.zi_w[r] = z; }
-            else { q.si[r] = s; q.zi[r] = z; }
+            if (MODE == P_RES) { q.si_w[r] = s; q.zi_w[r] = z; q.ti_w[r] = t; }
+            else { q.si[r] = s; q.zi[r] = z; q.ti[r] = t; }
         }
         if (VEC) { vA0 += cA * n0; vA1 += cA * n1; vA2 += cA * n2; vB0 += cB * n0; vB1 += cB * n1; vB2 += cB * n2; }
         if (MAT) {
@@ -524,14 +541,14 @@ RBPE_DEV void cp_task(const QP &q, int m, int a, int i, double sa, double sb, Ac
         double xk = lane == 0 ? x0 : (lane == 1 ? x1 : x2);
         double ak = lane == 0 ? a0 : (lane == 1 ? a1 : a2);
         double dk = lane == 0 ? d0 : (lane == 1 ? d1 : d2);
-        double cA, cB, w, s, z, tA = 0, tB = 0, tw = 0;
-        s = q.sub[v]; z = q.zub[v];
-        row_eval<MODE>(q.ub[v], s, z, xk, ak, dk, sa, sb, true, cA, cB, w, acc);
-        if (WR) { q.sub[v] = s; q.zub[v] = z; }
+        double cA, cB, w, s, z, t, tA = 0, tB = 0, tw = 0;
+        s = q.sub[v]; z = q.zub[v]; t = q.tub[v];
+        row_eval<MODE>(q.ub[v], s, z, t, xk, ak, dk, sa, sb, true, cA, cB, w, acc);
+        if (WR) { q.sub[v] = s; q.zub[v] = z; q.tub[v] = t; }
         tA += cA; tB += cB; tw += w;
-        s = q.slb[v]; z = q.zlb[v];
-        row_eval<MODE>(q.lbn[v], s, z, -xk, -ak, -dk, sa, sb, true, cA, cB, w, acc);
-        if (WR) { q.slb[v] = s; q.zlb[v] = z; }
+        s = q.slb[v]; z = q.zlb[v]; t = q.tlb[v];
+        row_eval<MODE>(q.lbn[v], s, z, t, -xk, -ak, -dk, sa, sb, true, cA, cB, w, acc);
+        if (WR) { q.slb[v] = s; q.zlb[v] = z; q.tlb[v] = t; }
         tA -= cA; tB -= cB; tw += w;
         if (lane == 0) { vA0 += tA; vB0 += tB; Dxx += tw; }
         if (lane == 1) { vA1 += tA; vB1 += tB; Dyy += tw; }
@@ -562,16 +579,18 @@ RBPE_DEV void cp_task(const QP &q, int m, int a, int i, double sa, double sb, Ac
 template <int MODE>
 RBPE_DEV void row_pass(const QP &q, double sa, double sb, Acc &out) {
     Acc acc;
-    acc.s1 = 0; acc.s2 = 0; acc.mx = -1e300; acc.mx2 = -1e300; acc.mn = 1e300;
+    acc.s1 = 0; acc.s2 = 0; acc.mx = (MODE == P_AFF || MODE == P_STEP) ? 0.0 : -1e300; acc.mx2 = -1e300; acc.mn = 1e300;
     const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5, ntask = q.M * q.nb * 6;
     for (int t = warp; t < ntask; t += nw) {
-        int i = t % 6, a = (t / 6) % q.nb, m = t / (6 * q.nb);
+        int i = t % 6, ma = t / 6, a, m;
+        if (q.nb == 1) { a = 0; m = ma; } else { a = ma % q.nb; m = ma / q.nb; }
         if (cp_dead(q, m, i) != (MODE == P_DEAD)) continue;   // live passes skip fixed control points and vice versa
         cp_task<MODE>(q, m, a, i, sa, sb, acc);
     }
-    if (MODE == P_SHIFT) { __syncthreads(); return; }
+    if (MODE == P_SHIFT || MODE == P_COR || MODE == P_INIT) { __syncthreads(); return; }
     double v[6] = {acc.s1, acc.s2, acc.mx, acc.mx2, -1e300, acc.mn};
-    block_reduce6(v, q.red);
+    constexpr int MASK = (MODE == P_RES) ? (1 + 2 + 4) : (MODE == P_AFF) ? (1 + 2 + 4) : (MODE == P_START) ? (4 + 8) : 4;
+    block_reduce6<MASK>(v, q.red);
     out.s1 = v[0]; out.s2 = v[1]; out.mx = v[2]; out.mx2 = v[3]; out.mn = v[5];
 }
 
@@ -736,7 +755,7 @@ RBPE_DEV bool factor_bt9(int nblk, double *Dall, double *Oall, double *dinv) {
         for (int j = 0; j < 9; j++) {
             double piv = __shfl_sync(FULL, a[j], j);
             if (!(piv > 0)) { ok = false; piv = 1.0; }
-            double inv = 1.0 / sqrt(piv);
+            double inv = rsqrt(piv);
             a[j] *= inv;                       // column j of L_tt (rows >= j) and of L_{t+1,t}
             if (lane == j) dinv[t * 9 + j] = inv;
 #pragma unroll
@@ -863,7 +882,7 @@ RBPE_DEV void setup_rows(const QP &q) {
         const double *box = q.segbox + ((size_t)(q.q0 + a) * M + m) * 6;
         q.ub[v] = box[3 + k];
         q.lbn[v] = -box[k];
-        q.sub[v] = 1; q.zub[v] = 1; q.slb[v] = 1; q.zlb[v] = 1;
+        q.sub[v] = 1; q.zub[v] = 1; q.slb[v] = 1; q.zlb[v] = 1; q.tub[v] = 1; q.tlb[v] = 1;
         double xp = 0;
         if (m == 0 && i < 3) {          // build_deq rows 0..2 (L408-L432): start pos / vel / acc
             const double *C = q.segmat + SEGMAT_CL + i * 3, *st = q.start + (size_t)(q.q0 + a) * 9 + k;
@@ -890,7 +909,7 @@ RBPE_DEV void setup_rows(const QP &q) {
         h += sg * ((double)f2 * co[12 * M]);
         if (sg < 0) { f0 = -f0; f1 = -f1; f2 = -f2; }
         q.nex[r] = f0; q.ney[r] = f1; q.nez[r] = f2;
-        q.he[r] = h; q.se[r] = 1; q.ze[r] = 1;
+        q.he[r] = h; q.se[r] = 1; q.ze[r] = 1; q.te[r] = 1;
     }
     // RSFC rows between two batch agents lo<hi: n.x_lo - n.x_hi <= -(r_lo + r_hi)
     for (int r = threadIdx.x; r < q.nrint; r += blockDim.x) {
@@ -902,7 +921,7 @@ RBPE_DEV void setup_rows(const QP &q) {
         const float *nf = q.reln + ((size_t)it * M + m) * 3;
         q.nix[r] = nf[0]; q.niy[r] = nf[1]; q.niz[r] = nf[2];
         q.hi[r] = -(q.radius[q.q0 + lo] + q.radius[q.q0 + hi]);
-        q.si[r] = 1; q.zi[r] = 1;
+        q.si[r] = 1; q.zi[r] = 1; q.ti[r] = 1;
     }
 }
 
@@ -920,7 +939,7 @@ RBPE_DEV void dual_residual(const QP &q, double &obj_part, double &mpx) {
 }
 RBPE_DEV double block_max(double v, double *red) {
     double r[6] = {0, 0, v, -1e300, -1e300, 1e300};
-    block_reduce6(r, red);
+    block_reduce6<4>(r, red);
     return r[2];
 }
 
@@ -944,7 +963,7 @@ RBPE_DEV int pdip_solve(const QP &q_in, int max_iter, double tol_gap, double tol
         double o = 0, mpx = 0;
         dual_residual(q, o, mpx);
         double r[6] = {o, 0, mpx, -1e300, -1e300, 1e300};
-        block_reduce6(r, q.red);
+        block_reduce6<1>(r, q.red);
         obj = r[0];
         status = ST_OK;
         go = false;
@@ -985,7 +1004,7 @@ RBPE_DEV int pdip_solve(const QP &q_in, int max_iter, double tol_gap, double tol
     for (it = 0; go && it < max_iter; it++) {
         // ---- residuals (with the previous step's s, z update fused in) ----
         row_pass<P_RES>(q, sigmu, al, acc);  // vA = G'z, vB = G't_aff, Dcp/Dint; s1 = s'z, s2 = h'z, mx = |rg|
-        { double *t1 = q.si; q.si = q.si_w; q.si_w = t1; t1 = q.zi; q.zi = q.zi_w; q.zi_w = t1; }
+        { double *t1 = q.si; q.si = q.si_w; q.si_w = t1; t1 = q.zi; q.zi = q.zi_w; q.zi_w = t1; t1 = q.ti; q.ti = q.ti_w; q.ti_w = t1; }
         if (al != 0.0) {
             for (int v = tid; v < q.nv; v += nt) q.x[v] += al * q.dx[v];
             __syncthreads();
@@ -1001,7 +1020,7 @@ RBPE_DEV int pdip_solve(const QP &q_in, int max_iter, double tol_gap, double tol
         double mr = 0, mc = 0;
         for (int r = tid; r < q.nr; r += nt) { mr = fmax(mr, fabs(q.sg[r])); mc = fmax(mc, fabs(q.sg2[r])); }
         double rr[6] = {o, 0, mpx, mr, mc, 1e300};
-        block_reduce6(rr, q.red);
+        block_reduce6<1 + 4 + 8 + 16>(rr, q.red);
         obj = rr[0]; mpx = rr[2]; nrd = rr[3];
         double mcert = rr[4];
         gap = mu;
@@ -1016,8 +1035,8 @@ RBPE_DEV int pdip_solve(const QP &q_in, int max_iter, double tol_gap, double tol
         // ---- affine direction ----
         for (int v = tid; v < q.nv; v += nt) q.vB[v] = -q.rdx[v] + q.vB[v];
         kkt_solve(q, q.vB, q.dxa);
-        row_pass<P_AFF>(q, 0, 0, acc);       // mn = ratio test; s1, s2 = linear / quadratic coefficient of mu_aff(a)
-        double aa = fmin(1.0, acc.mn);
+        row_pass<P_AFF>(q, 0, 0, acc);       // mx = ratio test (max form); s1, s2 = linear / quadratic coefficient of mu_aff(a)
+        double aa = (acc.mx > 1.0) ? 1.0 / acc.mx : 1.0;
         double mua = (mu * (q.mi > 0 ? q.mi : 1) + aa * acc.s1 + aa * aa * acc.s2) / (q.mi > 0 ? q.mi : 1);
         double sigma = (mu > 0) ? (mua / mu) * (mua / mu) * (mua / mu) : 0.0;
         sigmu = sigma * mu;
@@ -1026,7 +1045,7 @@ RBPE_DEV int pdip_solve(const QP &q_in, int max_iter, double tol_gap, double tol
         for (int v = tid; v < q.nv; v += nt) q.vA[v] = -q.rdx[v] + q.vA[v];
         kkt_solve(q, q.vA, q.dx);
         row_pass<P_STEP>(q, sigmu, 0, acc);
-        al = fmin(1.0, 0.99 * acc.mn);       // s, z, x are advanced at the top of the next iteration
+        al = (0.99 < acc.mx) ? 0.99 / acc.mx : 1.0;   // min(1, 0.99 * max step); s, z, x advance at the top of the next iteration
     }
     __syncthreads();
     // |Ax - b| for the record (the parametrisation keeps it at rounding level)
