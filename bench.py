@@ -149,6 +149,8 @@ def main():
     ap.add_argument("--ref-missions", type=int, default=64, help="missions per step of the CPU arm")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--jacobi-missions", type=int, default=64, help="missions (replicated on every rank) of the Jacobi leg; 0 = skip")
+    ap.add_argument("--jacobi-sweeps", type=int, default=2)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -244,6 +246,34 @@ def main():
     value = world * nqp / (ms_step * 1e-3)
     e2e = world * nqp / (ms_e2e * 1e-3)
 
+    # ---- secondary leg: Jacobi mode (north-star's agent sharding): the SAME missions on every rank, each rank solves its
+    # range of agents of every mission against the frozen table, one NCCL all-gather of control points per sweep ----
+    jac = None
+    if args.jacobi_missions > 0:
+        from swarm_simulator_b200 import dist as D
+        jpool = make_pool(min(args.pool, 4), 0)
+        jprob = E.PackedProblem(pin(synth.pack([jpool[i % len(jpool)] for i in range(args.jacobi_missions)])),
+                                sequential=True, batch_size=1, iteration=args.jacobi_sweeps)
+        jeng = E.Engine(device=local)
+        dev = torch.device("cuda", local)
+        D.jacobi_solve(jeng, jprob, args.jacobi_sweeps, device=dev)          # warm-up (also allocates)
+        jeng.sync()
+        l0 = jeng.timing()["kernel_launches"]
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            D.jacobi_solve(jeng, jprob, args.jacobi_sweeps, device=dev)
+        jeng.sync()
+        barrier()
+        ms_j = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+        jr = jeng.download(jprob)
+        jac = {"value": args.jacobi_missions * N_AGENTS * args.jacobi_sweeps / (ms_j * 1e-3), "unit": UNIT,
+               "scaling": "strong", "missions": args.jacobi_missions, "sweeps": args.jacobi_sweeps, "ms_per_step": ms_j,
+               "collective": "1 all-gather of control points per sweep (%d B per agent)" % (18 * M_SEG * 8),
+               "includes": "H2D of inputs, assembly, %d sweeps, all-gathers" % args.jacobi_sweeps,
+               "gpu_launches": int(jeng.timing()["kernel_launches"] - l0), "failed": int((jr.status != 0).sum())}
+        jeng.close()
+
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -258,6 +288,8 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clk,
     }
+    if jac:
+        out["jacobi_mode"] = jac
     if rank == 0:
         peaks = {}
         try:

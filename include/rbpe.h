@@ -41,7 +41,7 @@ typedef struct rbpe_config {
     double tol_gap;         /* complementarity gap (<=0 -> 1e-10), relative to max(1,|obj|) */
     double tol_res;         /* relative primal/dual residual (<=0 -> 1e-9) */
     size_t smem_budget;     /* bytes of dynamic shared memory a QP may use (0 -> engine default) */
-    int reserved[6];        /* reserved[0]: CTA size of the PDIP kernel (0 -> default 256); rest must be 0 */
+    int reserved[6];        /* reserved[0]: CTA size of the PDIP kernel (0 -> default 128); rest must be 0 */
 } rbpe_config;
 
 /*

@@ -48,7 +48,7 @@ struct rbpe_handle {
     int max_iter = 100;
     double tol_gap = 1e-10, tol_res = 1e-9;
     size_t smem_budget = 0, smem_optin = 0;
-    int threads = 256;
+    int threads = 128;
     int sm_count = 0;
     char err[512] = "";
     // resident problem
@@ -124,7 +124,7 @@ extern "C" int rbpe_create(const rbpe_config *cfg, rbpe_handle **out) {
     // tuning overrides (documented in DESIGN.md): RBPE_THREADS, RBPE_SMEM_KB
     if (const char *e = getenv("RBPE_THREADS")) { int th = atoi(e); if (th >= 32 && th <= CTA_THREADS && th % 32 == 0) h->threads = th; }
     if (const char *e = getenv("RBPE_SMEM_KB")) { long kb = atol(e); if (kb > 0) h->smem_budget = (size_t)kb * 1024; }
-    if (h->smem_budget == 0) h->smem_budget = 100 * 1024;
+    if (h->smem_budget == 0) h->smem_budget = 48 * 1024;
     if (h->smem_budget > h->smem_optin) h->smem_budget = h->smem_optin;
     memset(&h->timing, 0, sizeof(h->timing));
     if ((e = cudaSetDevice(dev)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {

@@ -466,3 +466,25 @@ def pack(missions):
         rsfc_t=np.ascontiguousarray([m["rsfc_t"] for m in missions], np.float64),
         init_traj=np.ascontiguousarray([m["init_traj"] for m in missions], np.float32),
     )
+
+
+def dump_text(m, path):
+    """Text dump of one mission for swarm_simulator_b200/host/planner_cli (format documented in planner_cli.cpp)."""
+    N, M = m["N"], m["M"]
+    with open(path, "w") as f:
+        f.write("%d %d\n" % (N, M))
+        f.write(" ".join(repr(float(t)) for t in m["T"]) + "\n")
+        for qi in range(N):
+            vals = list(m["start"][qi]) + list(m["goal"][qi]) + [m["radius"][qi]] + list(m["max_vel"][qi]) + list(m["max_acc"][qi])
+            f.write(" ".join(repr(float(v)) for v in vals) + "\n")
+        for qi in range(N):
+            for j in range(M + 1):
+                f.write(" ".join(repr(float(v)) for v in m["init_traj"][qi, j]) + "\n")
+        for qi in range(N):
+            boxes, tend = m["sfc"][qi]
+            f.write("%d\n" % len(tend))
+            for b, t in zip(boxes, tend):
+                f.write(" ".join(repr(float(v)) for v in list(b) + [t]) + "\n")
+        for p in range(N * (N - 1) // 2):
+            for ri in range(M):
+                f.write(" ".join(repr(float(v)) for v in list(m["rsfc_n"][p, ri]) + [m["rsfc_t"][p, ri]]) + "\n")
