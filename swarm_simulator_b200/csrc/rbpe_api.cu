@@ -49,6 +49,7 @@ struct rbpe_handle {
     double tol_gap = 1e-10, tol_res = 1e-9;
     size_t smem_budget = 0, smem_optin = 0;
     int threads = 128;
+    int force_cta = 0;   // RBPE_KERNEL=cta: never use the warp-per-QP kernel (A/B testing)
     int sm_count = 0;
     char err[512] = "";
     // resident problem
@@ -123,6 +124,7 @@ extern "C" int rbpe_create(const rbpe_config *cfg, rbpe_handle **out) {
     }
     // tuning overrides (documented in DESIGN.md): RBPE_THREADS, RBPE_SMEM_KB
     if (const char *e = getenv("RBPE_THREADS")) { int th = atoi(e); if (th >= 32 && th <= CTA_THREADS && th % 32 == 0) h->threads = th; }
+    if (const char *e = getenv("RBPE_KERNEL")) h->force_cta = (strcmp(e, "cta") == 0);
     if (const char *e = getenv("RBPE_SMEM_KB")) { long kb = atol(e); if (kb > 0) h->smem_budget = (size_t)kb * 1024; }
     if (h->smem_budget == 0) h->smem_budget = 48 * 1024;
     if (h->smem_budget > h->smem_optin) h->smem_budget = h->smem_optin;
@@ -136,6 +138,7 @@ extern "C" int rbpe_create(const rbpe_config *cfg, rbpe_handle **out) {
     cudaEventCreate(&h->tev[0]);
     cudaEventCreate(&h->tev[1]);
     cudaFuncSetAttribute(pdip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
+    cudaFuncSetAttribute(pdip1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
     *out = h;
     return RBPE_OK;
 }
@@ -285,6 +288,44 @@ static int fill_solve_args(rbpe_handle *h, SolveArgs &S, int mode, int grid) {
     return RBPE_OK;
 }
 
+// QPs per CTA of the warp-per-QP kernel (one-agent batches); 0 = use the CTA-per-QP kernel
+static int warps_per_cta(const rbpe_handle *h) {
+    if (h->bs != 1 || h->force_cta) return 0;
+    size_t per = w1_smem_doubles(h->M) * 8;
+    size_t budget = h->smem_optin < 200 * 1024 ? h->smem_optin : 200 * 1024;
+    int w = (int)(budget / per);
+    if (w > W1_WARPS) w = W1_WARPS;
+    return w;
+}
+
+// launches k2 over `units` independent work items (missions in mode 0, (mission, batch) pairs in mode 1)
+// S must have been filled by fill_solve_args (mode, ranges, record offsets already set by the caller)
+static int launch_pdip_prepared(rbpe_handle *h, SolveArgs &S, long units) {
+    int wpc = warps_per_cta(h);
+    if (wpc > 0) {
+        long grid = (units + wpc - 1) / wpc;
+        S.scratch_stride = w1_scratch_doubles(h->N, h->M);
+        S.smem_bytes = (unsigned)(wpc * w1_smem_doubles(h->M) * 8);
+        CU(h->scratch.reserve(S.scratch_stride * 8 * (size_t)grid * wpc));
+        S.scratch = h->scratch.as<double>();
+        pdip1_kernel<<<(unsigned)grid, wpc * 32, S.smem_bytes, h->stream>>>(S);
+    } else {
+        S.scratch_stride = scratch_doubles(h->N, h->M, h->bs);
+        S.smem_bytes = (unsigned)smem_for(h, S.scratch_stride);
+        CU(h->scratch.reserve(S.scratch_stride * 8 * (size_t)units));
+        S.scratch = h->scratch.as<double>();
+        pdip_kernel<<<(unsigned)units, h->threads, S.smem_bytes, h->stream>>>(S);
+    }
+    CU(cudaGetLastError());
+    h->launches++;
+    return RBPE_OK;
+}
+static int launch_pdip(rbpe_handle *h, SolveArgs &S, int mode, long units) {
+    int rc;
+    if ((rc = fill_solve_args(h, S, mode, 1))) return rc;
+    return launch_pdip_prepared(h, S, units);
+}
+
 extern "C" int rbpe_run(rbpe_handle *h, int mode) {
     if (!h) return RBPE_BAD_ARG;
     if (!h->resident) return fail(h, RBPE_BAD_ARG, "rbpe_run: nothing uploaded");
@@ -294,20 +335,14 @@ extern "C" int rbpe_run(rbpe_handle *h, int mode) {
     if (h->nbatch > 0 && h->iteration > 0) {
         SolveArgs S;
         if (mode == RBPE_MODE_GAUSS_SEIDEL) {
-            if ((rc = fill_solve_args(h, S, 0, h->count))) return rc;
-            pdip_kernel<<<h->count, h->threads, S.smem_bytes, h->stream>>>(S);
-            CU(cudaGetLastError());
-            h->launches++;
+            if ((rc = launch_pdip(h, S, 0, h->count))) return rc;
         } else {
-            int grid = h->count * h->nbatch;
-            if ((rc = fill_solve_args(h, S, 1, grid))) return rc;
             for (int it = 0; it < h->iteration; it++) {
                 CU(cudaMemcpyAsync(h->frozen.p, h->ctrl.p, (size_t)h->count * h->N * 18 * h->M * 8, cudaMemcpyDeviceToDevice,
                                    h->stream));
+                if ((rc = fill_solve_args(h, S, 1, 1))) return rc;
                 S.rec_offset = it * h->nbatch;
-                pdip_kernel<<<grid, h->threads, S.smem_bytes, h->stream>>>(S);
-                CU(cudaGetLastError());
-                h->launches++;
+                if ((rc = launch_pdip_prepared(h, S, (long)h->count * h->nbatch))) return rc;
             }
         }
     }
@@ -326,13 +361,10 @@ extern "C" int rbpe_run_jacobi_range(rbpe_handle *h, int b0, int b1) {
     CU(cudaMemcpyAsync(h->frozen.p, h->ctrl.p, (size_t)h->count * h->N * 18 * h->M * 8, cudaMemcpyDeviceToDevice, h->stream));
     if (b1 > b0) {
         SolveArgs S;
-        int grid = h->count * (b1 - b0);
-        if ((rc = fill_solve_args(h, S, 1, grid))) return rc;
+        if ((rc = fill_solve_args(h, S, 1, 1))) return rc;
         S.batch_begin = b0; S.batch_end = b1;
         S.rec_offset = (h->iteration > 0 ? h->sweep % h->iteration : 0) * h->nbatch;
-        pdip_kernel<<<grid, h->threads, S.smem_bytes, h->stream>>>(S);
-        CU(cudaGetLastError());
-        h->launches++;
+        if ((rc = launch_pdip_prepared(h, S, (long)h->count * (b1 - b0)))) return rc;
     }
     h->sweep++;
     if ((rc = launch_convert(h))) return rc;

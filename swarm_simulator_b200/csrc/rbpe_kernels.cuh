@@ -1139,3 +1139,5 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) pdip_kernel(SolveArgs S) {
 
 #endif  // __CUDACC__ || RBPE_EMU
 }  // namespace rbpe
+
+#include "rbpe_pdip1.cuh"

@@ -1,0 +1,497 @@
+// rbpe_pdip1.cuh -- k2 for one-agent batches (plan/batch_size = 1, the per-agent QP of the north-star):
+// ONE WARP PER QP, ONE LANE PER CONTROL POINT.
+//
+// Same algorithm and row order as pdip_kernel (rbpe_kernels.cuh), different mapping:
+//   * lane <-> Bernstein control point (6M of them, 32 per "slot"); the lane walks the rows that touch its control
+//     point (N-1 RSFC rows against the frozen agents + 6 box rows) and accumulates G'(.) and the 3x3 block sum w g g'
+//     in registers -- no shuffle reductions per control point, no block barriers, no idle warps;
+//   * row state (h, s, z) lives in an L2-resident arena laid out [slot][neighbour][lane] (coalesced); 1/(s z) is
+//     recomputed where needed from MUFU.RCP + two Newton steps instead of an FP64 division or a stored reciprocal;
+//   * the 9(M-1) x 9(M-1) block tridiagonal reduced system is factored / solved by the same warp out of registers
+//     (factor_bt9 / solve_bt9).
+// A CTA holds W1_WARPS independent QPs (missions in Gauss-Seidel mode, (mission, agent) pairs in Jacobi mode).
+#pragma once
+
+namespace rbpe {
+
+constexpr int W1_WARPS = 4;
+
+__host__ __device__ inline size_t w1_smem_doubles(int M) {  // per warp
+    size_t ncp = 6 * (size_t)M, nr = 9 * (size_t)(M > 1 ? M - 1 : 0);
+    return al2(6 * 3 * ncp) + al2(6 * ncp) + al2((size_t)(M > 1 ? M - 1 : 1) * 81) + al2((size_t)(M > 2 ? M - 2 : 1) * 81) + 3 * al2(nr) + 36;
+}
+__host__ __device__ inline size_t w1_scratch_doubles(int N, int M) {  // per warp, global arena
+    size_t nslot = (6 * (size_t)M + 31) / 32, NE = (size_t)(N > 1 ? N - 1 : 0);
+    size_t rows = nslot * NE * 32, boxs = nslot * 32 * 3;
+    return 3 * rows + 8 * boxs + al2(((size_t)M * NE * 3 + 1) / 2) + 8;
+}
+
+#if defined(__CUDACC__) || defined(RBPE_EMU)
+
+RBPE_DEV double rcp_nr(double a) {  // 1/a to double rounding: float seed + two Newton steps
+#ifdef RBPE_EMU
+    double r = (double)(1.0f / (float)a);
+#else
+    double r = (double)__frcp_rn((float)a);
+#endif
+    double e = fma(-a, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-a, r, 1.0);
+    return fma(r, e, r);
+}
+
+struct W1 {
+    int N, M, NE, ncp, nslot, nr, qa, mi, sequential;
+    const double *start, *goal, *radius, *segbox, *segmat;
+    const float *reln;
+    const double *ctrl_src;
+    // shared memory (per warp); x-space index v = m*18 + k*6 + i
+    double *x, *dxa, *dx, *rdx, *vA, *vB, *Dcp, *Wd, *Wo, *sg, *sg2, *dinv, *QB;
+    // global arena (per warp)
+    double *he, *se, *ze;                                   // [slot][e][lane]
+    double *ub, *lbn, *sub, *zub, *slb, *zlb;                // [slot][k][lane]
+    float *nrm;                                             // [m][e][3], sign folded in
+};
+
+template <int MASK>
+RBPE_DEV void warp_reduce(double &s1, double &s2, double &mx, double &mx2) {
+    for (int o = 16; o > 0; o >>= 1) {
+        if (MASK & 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        if (MASK & 2) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        if (MASK & 4) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (MASK & 8) mx2 = fmax(mx2, __shfl_xor_sync(0xffffffffu, mx2, o));
+    }
+}
+
+// same row algebra as row_eval (rbpe_kernels.cuh); t = 1/(s z) computed here
+template <int MODE>
+RBPE_DEV void row_eval1(double h, double &s, double &z, double gx, double ga, double gd, double sa, double sb, double &cA,
+                        double &cB, double &w, Acc &acc) {
+    cA = 0; cB = 0; w = 0;
+    if (MODE == P_DEAD) { acc.mx = fmax(acc.mx, gx - h); return; }
+    if (MODE == P_INIT) { w = 1.0; cA = h - gx; return; }
+    if (MODE == P_START) {
+        z = gx - h; s = -z;
+        acc.mx = fmax(acc.mx, -s); acc.mx2 = fmax(acc.mx2, -z);
+        return;
+    }
+    if (MODE == P_SHIFT) { s += sa; z += sb; return; }
+    double t = rcp_nr(s * z), rs = t * z;
+    if (MODE == P_RES && sb != 0.0) {  // pending step of the previous iteration, fused into the residual pass
+        double rgo = gx + s - h, wo = z * rs;
+        double dsa = -rgo - ga, dza = -z - wo * dsa;
+        double rc = s * z + dsa * dza - sa;
+        double ds = -rgo - gd, dz = (-rc - z * ds) * rs;
+        s += sb * ds; z += sb * dz;
+        gx += sb * gd;
+        t = rcp_nr(s * z);
+        rs = t * z;
+    }
+    double rg = gx + s - h;
+    w = z * rs;
+    if (MODE == P_RES) {
+        cA = z;
+        cB = -(w * rg - z);
+        acc.s1 += s * z; acc.s2 += h * z; acc.mx = fmax(acc.mx, fabs(rg));
+        return;
+    }
+    double rz = t * s;
+    double dsa = -rg - ga, dza = -z - w * dsa;
+    if (MODE == P_AFF) {
+        acc.mx = fmax(acc.mx, fmax(-dsa * rs, -dza * rz));
+        acc.s1 += s * dza + z * dsa; acc.s2 += dsa * dza;
+        return;
+    }
+    double rc = s * z + dsa * dza - sa;
+    if (MODE == P_COR) { cA = -(z * rg - rc) * rs; return; }
+    double ds = -rg - gd, dz = (-rc - z * ds) * rs;
+    if (MODE == P_STEP) acc.mx = fmax(acc.mx, fmax(-ds * rs, -dz * rz));
+}
+
+RBPE_DEV bool w1_dead(const W1 &c, int cp) { int m = cp / 6, i = cp % 6; return (m == 0 && i < 3) || (m == c.M - 1 && i >= 3); }
+
+template <int MODE>
+RBPE_DEV void w1_pass(const W1 &c, double sa, double sb, Acc &out) {
+    constexpr bool WR = (MODE == P_START || MODE == P_SHIFT || MODE == P_RES);
+    constexpr bool VEC = (MODE == P_INIT || MODE == P_RES || MODE == P_COR);
+    constexpr bool MAT = (MODE == P_INIT || MODE == P_RES);
+    const int lane = threadIdx.x & 31;
+    Acc acc;
+    acc.s1 = 0; acc.s2 = 0; acc.mx = (MODE == P_AFF || MODE == P_STEP) ? 0.0 : -1e300; acc.mx2 = -1e300; acc.mn = 1e300;
+    for (int slot = 0; slot < c.nslot; slot++) {
+        const int cp = slot * 32 + lane;
+        const bool on = cp < c.ncp && (w1_dead(c, cp) == (MODE == P_DEAD));
+        if (!__any_sync(0xffffffffu, on)) continue;
+        const int m = on ? cp / 6 : 0, i = on ? cp % 6 : 0, v0 = m * 18 + i;
+        double x0 = 0, x1 = 0, x2 = 0, a0 = 0, a1 = 0, a2 = 0, d0 = 0, d1 = 0, d2 = 0;
+        if (on) {
+            x0 = c.x[v0]; x1 = c.x[v0 + 6]; x2 = c.x[v0 + 12];
+            if (MODE == P_RES || MODE == P_AFF || MODE == P_COR || MODE == P_STEP) { a0 = c.dxa[v0]; a1 = c.dxa[v0 + 6]; a2 = c.dxa[v0 + 12]; }
+            if (MODE == P_RES || MODE == P_STEP) { d0 = c.dx[v0]; d1 = c.dx[v0 + 6]; d2 = c.dx[v0 + 12]; }
+        }
+        double vA0 = 0, vA1 = 0, vA2 = 0, vB0 = 0, vB1 = 0, vB2 = 0;
+        double Dxx = 0, Dxy = 0, Dxz = 0, Dyy = 0, Dyz = 0, Dzz = 0;
+        if (on) {
+            const float *nm = c.nrm + (size_t)m * c.NE * 3;
+            const size_t rb = (size_t)slot * c.NE * 32 + lane;
+#pragma unroll 2
+            for (int e = 0; e < c.NE; e++) {
+                const size_t r = rb + (size_t)e * 32;
+                double n0 = nm[e * 3], n1 = nm[e * 3 + 1], n2 = nm[e * 3 + 2];
+                double h = c.he[r], s = c.se[r], z = c.ze[r], cA, cB, w;
+                row_eval1<MODE>(h, s, z, n0 * x0 + n1 * x1 + n2 * x2, n0 * a0 + n1 * a1 + n2 * a2, n0 * d0 + n1 * d1 + n2 * d2,
+                                sa, sb, cA, cB, w, acc);
+                if (WR) { c.se[r] = s; c.ze[r] = z; }
+                if (VEC) { vA0 += cA * n0; vA1 += cA * n1; vA2 += cA * n2; }
+                if (MODE == P_RES) { vB0 += cB * n0; vB1 += cB * n1; vB2 += cB * n2; }
+                if (MAT) {
+                    double w0 = w * n0, w1 = w * n1, w2 = w * n2;
+                    Dxx += w0 * n0; Dxy += w0 * n1; Dxz += w0 * n2; Dyy += w1 * n1; Dyz += w1 * n2; Dzz += w2 * n2;
+                }
+            }
+            // box rows of the three axes: x <= ub, -x <= -lb
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const size_t b = ((size_t)slot * 3 + k) * 32 + lane;
+                double xk = k == 0 ? x0 : (k == 1 ? x1 : x2), ak = k == 0 ? a0 : (k == 1 ? a1 : a2), dk = k == 0 ? d0 : (k == 1 ? d1 : d2);
+                double cA, cB, w, s, z, tA = 0, tB = 0, tw = 0;
+                s = c.sub[b]; z = c.zub[b];
+                row_eval1<MODE>(c.ub[b], s, z, xk, ak, dk, sa, sb, cA, cB, w, acc);
+                if (WR) { c.sub[b] = s; c.zub[b] = z; }
+                tA += cA; tB += cB; tw += w;
+                s = c.slb[b]; z = c.zlb[b];
+                row_eval1<MODE>(c.lbn[b], s, z, -xk, -ak, -dk, sa, sb, cA, cB, w, acc);
+                if (WR) { c.slb[b] = s; c.zlb[b] = z; }
+                tA -= cA; tB -= cB; tw += w;
+                if (k == 0) { vA0 += tA; vB0 += tB; Dxx += tw; }
+                if (k == 1) { vA1 += tA; vB1 += tB; Dyy += tw; }
+                if (k == 2) { vA2 += tA; vB2 += tB; Dzz += tw; }
+            }
+            if (VEC) { c.vA[v0] = vA0; c.vA[v0 + 6] = vA1; c.vA[v0 + 12] = vA2; }
+            if (MODE == P_RES) { c.vB[v0] = vB0; c.vB[v0 + 6] = vB1; c.vB[v0 + 12] = vB2; }
+            if (MAT) {
+                double *D = c.Dcp + (size_t)cp * 6;
+                D[0] = Dxx; D[1] = Dxy; D[2] = Dxz; D[3] = Dyy; D[4] = Dyz; D[5] = Dzz;
+            }
+        }
+    }
+    if (MODE == P_RES || MODE == P_AFF) warp_reduce<1 + 2 + 4>(acc.s1, acc.s2, acc.mx, acc.mx2);
+    if (MODE == P_START) warp_reduce<4 + 8>(acc.s1, acc.s2, acc.mx, acc.mx2);
+    if (MODE == P_STEP || MODE == P_DEAD) warp_reduce<4>(acc.s1, acc.s2, acc.mx, acc.mx2);
+    __syncwarp();
+    out = acc;
+}
+
+// out (nr) = Z' vec (x-space)
+RBPE_DEV void w1_Zt(const W1 &c, const double *vec, double *out) {
+    for (int r = threadIdx.x & 31; r < c.nr; r += 32) {
+        int t = r / 9 + 1, cc = r % 9, k = cc / 3, d = cc % 3;
+        const double *CR = c.segmat + (t - 1) * SEGMAT + SEGMAT_CR, *CL = c.segmat + t * SEGMAT + SEGMAT_CL;
+        const double *vl = vec + (t - 1) * 18 + k * 6 + 3, *vr = vec + t * 18 + k * 6;
+        double s = 0;
+        for (int j = 0; j < 3; j++) s += CR[j * 3 + d] * vl[j] + CL[j * 3 + d] * vr[j];
+        out[r] = s;
+    }
+    __syncwarp();
+}
+// out (x-space) = Z sg
+RBPE_DEV void w1_Z(const W1 &c, const double *sg, double *out) {
+    const int nv = 18 * c.M;
+    for (int v = threadIdx.x & 31; v < nv; v += 32) {
+        int m = v / 18, r = v % 18, k = r / 6, i = r % 6;
+        double s = 0;
+        if (i < 3) {
+            if (m > 0) {
+                const double *C = c.segmat + m * SEGMAT + SEGMAT_CL + i * 3, *g = sg + (m - 1) * 9 + k * 3;
+                s = C[0] * g[0] + C[1] * g[1] + C[2] * g[2];
+            }
+        } else if (m < c.M - 1) {
+            const double *C = c.segmat + m * SEGMAT + SEGMAT_CR + (i - 3) * 3, *g = sg + m * 9 + k * 3;
+            s = C[0] * g[0] + C[1] * g[1] + C[2] * g[2];
+        }
+        out[v] = s;
+    }
+    __syncwarp();
+}
+RBPE_DEV void w1_build_W(const W1 &c) {
+    const int M = c.M;
+    for (int idx = threadIdx.x & 31; idx < (M - 1) * 81; idx += 32) {
+        int t = idx / 81 + 1, r = (idx % 81) / 9, cc = idx % 9;
+        double s = 0;
+        if (cc <= r) {
+            int k = r / 3, d = r % 3, k2 = cc / 3, d2 = cc % 3;
+            const double *CR = c.segmat + (t - 1) * SEGMAT + SEGMAT_CR, *CL = c.segmat + t * SEGMAT + SEGMAT_CL;
+            int e = sym6(k, k2);
+            const double *Dl = c.Dcp + ((size_t)(t - 1) * 6 + 3) * 6 + e, *Dr = c.Dcp + ((size_t)t * 6) * 6 + e;
+            for (int j = 0; j < 3; j++) s += CR[j * 3 + d] * CR[j * 3 + d2] * Dl[j * 6] + CL[j * 3 + d] * CL[j * 3 + d2] * Dr[j * 6];
+            if (k == k2) s += c.segmat[(t - 1) * SEGMAT + SEGMAT_RQ + (3 + d) * 6 + 3 + d2] + c.segmat[t * SEGMAT + SEGMAT_RQ + d * 6 + d2];
+        }
+        c.Wd[idx] = s;
+    }
+    for (int idx = threadIdx.x & 31; idx < (M - 2) * 81; idx += 32) {
+        int t = idx / 81 + 1, r = (idx % 81) / 9, cc = idx % 9;
+        c.Wo[idx] = (r / 3 == cc / 3) ? c.segmat[t * SEGMAT + SEGMAT_RQ + (3 + r % 3) * 6 + cc % 3] : 0.0;
+    }
+    __syncwarp();
+}
+// dxout = Z (Z'HZ)^-1 Z' r
+RBPE_DEV void w1_solve(const W1 &c, const double *r, double *dxout) {
+    w1_Zt(c, r, c.sg);
+    solve_bt9(c.M - 1, c.Wd, c.Wo, c.dinv, c.sg);
+    w1_Z(c, c.sg, dxout);
+}
+// rdx = 2 Q x + vA, partial sums of the objective and max|Px|
+RBPE_DEV void w1_dual(const W1 &c, double &obj, double &mpx) {
+    const int nv = 18 * c.M;
+    for (int v = threadIdx.x & 31; v < nv; v += 32) {
+        int m = v / 18, i = v % 6, b6 = v - i;
+        double s = 0;
+        for (int j = 0; j < 6; j++) s += c.QB[i * 6 + j] * c.x[b6 + j];
+        double pxv = 2.0 * c.segmat[m * SEGMAT + SEGMAT_QS] * s;
+        c.rdx[v] = pxv + c.vA[v];
+        obj += 0.5 * c.x[v] * pxv;
+        mpx = fmax(mpx, fabs(pxv));
+    }
+    __syncwarp();
+}
+
+RBPE_DEV void w1_setup(const W1 &c) {
+    const int lane = threadIdx.x & 31, M = c.M, N = c.N, nv = 18 * M;
+    for (int v = lane; v < nv; v += 32) {
+        int m = v / 18, r = v % 18, k = r / 6, i = r % 6;
+        double xp = 0;
+        if (m == 0 && i < 3) {
+            const double *C = c.segmat + SEGMAT_CL + i * 3, *st = c.start + (size_t)c.qa * 9 + k;
+            xp = C[0] * st[0] + C[1] * st[3] + C[2] * st[6];
+        }
+        if (m == M - 1 && i >= 3) {
+            const double *C = c.segmat + (M - 1) * SEGMAT + SEGMAT_CR + (i - 3) * 3, *gl = c.goal + (size_t)c.qa * 9 + k;
+            xp = C[0] * gl[0] + C[1] * gl[3] + C[2] * gl[6];
+        }
+        c.x[v] = xp; c.dxa[v] = 0; c.dx[v] = 0; c.vA[v] = 0; c.vB[v] = 0; c.rdx[v] = 0;
+    }
+    // signed normals of the RSFC rows against every other agent: g = sg*n, sg = +1 if qa < qo
+    for (int idx = lane; idx < M * c.NE; idx += 32) {
+        int m = idx / c.NE, e = idx % c.NE, qo = (e < c.qa) ? e : e + 1;
+        long it = (c.qa < qo) ? pair_index(N, c.qa, qo) : pair_index(N, qo, c.qa);
+        const float *nf = c.reln + ((size_t)it * M + m) * 3;
+        float sg = (c.qa < qo) ? 1.f : -1.f;
+        c.nrm[idx * 3] = sg * nf[0]; c.nrm[idx * 3 + 1] = sg * nf[1]; c.nrm[idx * 3 + 2] = sg * nf[2];
+    }
+    __syncwarp();
+    for (int slot = 0; slot < c.nslot; slot++) {
+        const int cp = slot * 32 + lane;
+        if (cp >= c.ncp) continue;
+        const int m = cp / 6, i = cp % 6;
+        const double *box = c.segbox + ((size_t)c.qa * M + m) * 6;
+        for (int k = 0; k < 3; k++) {
+            const size_t b = ((size_t)slot * 3 + k) * 32 + lane;
+            c.ub[b] = box[3 + k]; c.lbn[b] = -box[k];
+            c.sub[b] = 1; c.zub[b] = 1; c.slb[b] = 1; c.zlb[b] = 1;
+        }
+        const float *nm = c.nrm + (size_t)m * c.NE * 3;
+        const size_t rb = (size_t)slot * c.NE * 32 + lane;
+        for (int e = 0; e < c.NE; e++) {
+            int qo = (e < c.qa) ? e : e + 1;
+            const double *co = c.ctrl_src + (size_t)qo * 18 * M + m * 6 + i;
+            // h = sg*n.dummy_other - (r_a + r_other), accumulated in the reference's order (L643-L668)
+            double h = -(c.radius[c.qa] + c.radius[qo]);
+            h += (double)nm[e * 3] * co[0];
+            h += (double)nm[e * 3 + 1] * co[6 * M];
+            h += (double)nm[e * 3 + 2] * co[12 * M];
+            const size_t r = rb + (size_t)e * 32;
+            c.he[r] = h; c.se[r] = 1; c.ze[r] = 1;
+        }
+    }
+    __syncwarp();
+}
+
+RBPE_DEV int w1_solve_qp(const W1 &c, int max_iter, double tol_gap, double tol_res, double *obj_out, int *it_out, double *res_out) {
+    const int lane = threadIdx.x & 31;
+    Acc acc;
+    w1_setup(c);
+    int status = ST_NOT_CONVERGED, it = 0;
+    double obj = 0, gap = 0, nrd = 0, nrg = 0, hn = 0;
+    bool go = true;
+    w1_pass<P_DEAD>(c, 0, 0, acc);
+    if (acc.mx > PRESOLVE_FEAS_TOL) { status = ST_INFEASIBLE; go = false; }
+    if (go && c.nr == 0) {
+        double o = 0, mpx = 0, d1 = 0, d2 = 0;
+        w1_dual(c, o, mpx);
+        warp_reduce<1>(o, d1, mpx, d2);
+        obj = o; status = ST_OK; go = false;
+    }
+    if (go) {
+        double mh = 0, d0 = 0, d1 = 0, d2 = 0;
+        for (int slot = 0; slot < c.nslot; slot++) {
+            const int cp = slot * 32 + lane;
+            if (cp >= c.ncp || w1_dead(c, cp)) continue;
+            for (int k = 0; k < 3; k++) {
+                const size_t b = ((size_t)slot * 3 + k) * 32 + lane;
+                mh = fmax(mh, fmax(fabs(c.ub[b]), fabs(c.lbn[b])));
+            }
+            const size_t rb = (size_t)slot * c.NE * 32 + lane;
+            for (int e = 0; e < c.NE; e++) mh = fmax(mh, fabs(c.he[rb + (size_t)e * 32]));
+        }
+        warp_reduce<4>(d0, d1, mh, d2);
+        hn = mh;
+        w1_pass<P_INIT>(c, 0, 0, acc);
+        w1_build_W(c);
+        if (!factor_bt9(c.M - 1, c.Wd, c.Wo, c.dinv)) go = false;
+    }
+    if (go) {
+        double o = 0, mpx = 0;
+        w1_dual(c, o, mpx);   // rdx = P x_p + vA
+        for (int v = lane; v < 18 * c.M; v += 32) c.rdx[v] = 2.0 * c.vA[v] - c.rdx[v];
+        __syncwarp();
+        w1_solve(c, c.rdx, c.dx);
+        for (int v = lane; v < 18 * c.M; v += 32) { c.x[v] += c.dx[v]; c.dx[v] = 0; }
+        __syncwarp();
+        w1_pass<P_START>(c, 0, 0, acc);
+        double ap = acc.mx, ad = acc.mx2;
+        w1_pass<P_SHIFT>(c, ap >= 0 ? 1.0 + ap : 0.0, ad >= 0 ? 1.0 + ad : 0.0, acc);
+    }
+    double sigmu = 0, al = 0;
+    const double mi = c.mi > 0 ? (double)c.mi : 1.0;
+    for (it = 0; go && it < max_iter; it++) {
+        w1_pass<P_RES>(c, sigmu, al, acc);
+        if (al != 0.0) {
+            for (int v = lane; v < 18 * c.M; v += 32) c.x[v] += al * c.dx[v];
+            __syncwarp();
+        }
+        double mu = acc.s1 / mi, hz = acc.s2;
+        nrg = fmax(acc.mx, 0.0);
+        double o = 0, mpx = 0;
+        w1_dual(c, o, mpx);
+        w1_Zt(c, c.rdx, c.sg);
+        w1_Zt(c, c.vA, c.sg2);
+        double mr = 0, mc = 0;
+        for (int r = lane; r < c.nr; r += 32) { mr = fmax(mr, fabs(c.sg[r])); mc = fmax(mc, fabs(c.sg2[r])); }
+        double d1 = 0;
+        warp_reduce<1 + 4 + 8>(o, d1, mpx, mr);
+        warp_reduce<4>(d1, d1, mc, d1);
+        obj = o; nrd = mr;
+        gap = mu;
+        if (!(mu == mu) || !(nrd == nrd)) { status = ST_NOT_CONVERGED; break; }
+        if (gap <= tol_gap * fmax(1.0, fabs(obj)) && nrg <= tol_res * (1 + hn) && nrd <= tol_res * (1.0 + mpx)) { status = ST_OK; break; }
+        if (hz < 0 && mc / (-hz) < 1e-8) { status = ST_INFEASIBLE; break; }
+        w1_build_W(c);
+        if (!factor_bt9(c.M - 1, c.Wd, c.Wo, c.dinv)) { status = ST_NOT_CONVERGED; break; }
+        for (int v = lane; v < 18 * c.M; v += 32) c.vB[v] = -c.rdx[v] + c.vB[v];
+        __syncwarp();
+        w1_solve(c, c.vB, c.dxa);
+        w1_pass<P_AFF>(c, 0, 0, acc);
+        double aa = (acc.mx > 1.0) ? 1.0 / acc.mx : 1.0;
+        double mua = (mu * mi + aa * acc.s1 + aa * aa * acc.s2) / mi;
+        double sigma = (mu > 0) ? (mua / mu) * (mua / mu) * (mua / mu) : 0.0;
+        sigmu = sigma * mu;
+        w1_pass<P_COR>(c, sigmu, 0, acc);
+        for (int v = lane; v < 18 * c.M; v += 32) c.vA[v] = -c.rdx[v] + c.vA[v];
+        __syncwarp();
+        w1_solve(c, c.vA, c.dx);
+        w1_pass<P_STEP>(c, sigmu, 0, acc);
+        al = (0.99 < acc.mx) ? 0.99 / acc.mx : 1.0;
+    }
+    // |Ax - b| for the record
+    double mrp = 0;
+    for (int e = lane; e < 9 * (c.M + 1); e += 32) {
+        int t = e / 9, cc = e % 9, k = cc / 3, d = cc % 3;
+        double sm = 0;
+        if (t < c.M) {
+            const double *sp = c.segmat + t * SEGMAT + SEGMAT_AL + d * 6, *xx = c.x + t * 18 + k * 6;
+            for (int i = 0; i < 6; i++) sm += sp[i] * xx[i];
+        }
+        if (t > 0) {
+            const double *sp = c.segmat + (t - 1) * SEGMAT + SEGMAT_AR + d * 6, *xx = c.x + (t - 1) * 18 + k * 6;
+            for (int i = 0; i < 6; i++) sm += sp[i] * xx[i];
+        }
+        if (t == 0) sm -= c.start[(size_t)c.qa * 9 + k + 3 * d];
+        if (t == c.M) sm -= c.goal[(size_t)c.qa * 9 + k + 3 * d];
+        mrp = fmax(mrp, fabs(sm));
+    }
+    double d0 = 0, d1 = 0, d2 = 0;
+    warp_reduce<4>(d0, d1, mrp, d2);
+    if (lane == 0) {
+        *obj_out = obj;
+        *it_out = it;
+        res_out[0] = gap; res_out[1] = mrp; res_out[2] = nrd; res_out[3] = nrg;
+    }
+    return status;
+}
+
+__global__ void __launch_bounds__(W1_WARPS * 32, 4) pdip1_kernel(SolveArgs S) {   // blockDim.x = 32 * (QPs per CTA) <= W1_WARPS * 32
+    RBPE_DYN_SMEM(smem);
+    const int N = S.N, M = S.M, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long unit = (long)blockIdx.x * (blockDim.x >> 5) + warp;   // one QP chain (mode 0) or one QP (mode 1) per warp
+    int cidx, l_begin, l_end;
+    if (S.mode == 0) {
+        cidx = (int)unit; l_begin = 0; l_end = S.nbatch;
+    } else {
+        int per = S.batch_end - S.batch_begin;
+        cidx = (int)(unit / per);
+        l_begin = S.batch_begin + (int)(unit % per);
+        l_end = l_begin + 1;
+    }
+    if (cidx >= S.count) return;   // whole warps only; no block-level barrier is used in this kernel
+    if (S.status[cidx] != ST_OK && S.mode == 0) return;
+    const long P = (long)N * (N - 1) / 2;
+    W1 c;
+    c.N = N; c.M = M; c.sequential = S.sequential;
+    c.NE = S.sequential ? N - 1 : 0;
+    c.ncp = 6 * M; c.nslot = (c.ncp + 31) / 32; c.nr = 9 * (M > 1 ? M - 1 : 0);
+    c.mi = (6 * M - 6) * (6 + c.NE);
+    c.start = S.start + (size_t)cidx * N * 9;
+    c.goal = S.goal + (size_t)cidx * N * 9;
+    c.radius = S.radius + (size_t)cidx * N;
+    c.segbox = S.segbox + (size_t)cidx * N * M * 6;
+    c.segmat = S.segmat + (size_t)cidx * M * SEGMAT;
+    c.reln = S.reln + (size_t)cidx * P * M * 3;
+    double *ctrl = S.ctrl + (size_t)cidx * N * 18 * M;
+    c.ctrl_src = (S.mode == 0) ? ctrl : S.ctrl_frozen + (size_t)cidx * N * 18 * M;
+    {   // shared memory of this warp
+        double *p = (double *)smem + (size_t)warp * w1_smem_doubles(M);
+        const size_t nv = 18 * (size_t)M;
+        c.x = p; c.dxa = p + nv; c.dx = p + 2 * nv; c.rdx = p + 3 * nv; c.vA = p + 4 * nv; c.vB = p + 5 * nv;
+        p += al2(6 * 3 * c.ncp);
+        c.Dcp = p; p += al2(6 * (size_t)c.ncp);
+        c.Wd = p; p += al2((size_t)(M > 1 ? M - 1 : 1) * 81);
+        c.Wo = p; p += al2((size_t)(M > 2 ? M - 2 : 1) * 81);
+        c.sg = p; p += al2(c.nr); c.sg2 = p; p += al2(c.nr); c.dinv = p; p += al2(c.nr);
+        c.QB = p;
+        for (int e = lane; e < 36; e += 32) c.QB[e] = q_base_entry(e / 6, e % 6);
+        __syncwarp();
+    }
+    {   // global arena of this warp
+        double *g = S.scratch + (size_t)unit * S.scratch_stride;
+        const size_t rows = (size_t)c.nslot * c.NE * 32, boxs = (size_t)c.nslot * 32 * 3;
+        c.he = g; c.se = g + rows; c.ze = g + 2 * rows; g += 3 * rows;
+        c.ub = g; c.lbn = g + boxs; c.sub = g + 2 * boxs; c.zub = g + 3 * boxs; c.slb = g + 4 * boxs; c.zlb = g + 5 * boxs;
+        g += 8 * boxs;
+        c.nrm = (float *)g;
+    }
+    const int iters = (S.mode == 0) ? S.iteration : 1;
+    for (int iter = 0; iter < iters; iter++)
+        for (int l = l_begin; l < l_end; l++) {
+            c.qa = l;   // batch l of one-agent batches = agent l
+            if (c.qa >= N) continue;
+            int rec = (S.mode == 0 ? iter * S.nbatch : S.rec_offset) + l;
+            int st = w1_solve_qp(c, S.max_iter, S.tol_gap, S.tol_res, S.qp_obj + (size_t)cidx * S.nrec + rec,
+                                 S.qp_iters + (size_t)cidx * S.nrec + rec, S.qp_res + ((size_t)cidx * S.nrec + rec) * 4);
+            if (lane == 0) {
+                S.qp_status[(size_t)cidx * S.nrec + rec] = st;
+                if (st != ST_OK) atomicCAS(&S.status[cidx], (int)ST_OK, st);
+            }
+            if (st != ST_OK) {
+                if (S.mode == 0) return;
+                continue;
+            }
+            for (int v = lane; v < 18 * M; v += 32) {   // dummy <- vals (L182-L184)
+                int m = v / 18, r = v % 18, k = r / 6, i = r % 6;
+                ctrl[(size_t)c.qa * 18 * M + (size_t)k * 6 * M + m * 6 + i] = c.x[v];
+            }
+            __syncwarp();
+        }
+}
+
+#endif
+}  // namespace rbpe

@@ -160,3 +160,18 @@ inline T __shfl_sync(unsigned, T v, int src) {
     emu::barrier_wait(s.warp[w]);
     return r;
 }
+
+template <class T>
+inline T __shfl_xor_sync(unsigned, T v, int mask) {
+    return __shfl_sync(0xffffffffu, v, (int)((threadIdx.x & 31) ^ mask));
+}
+inline int __any_sync(unsigned, int pred) {
+    int v = pred ? 1 : 0, r = 0;
+    for (int l = 0; l < 32; l++) r |= __shfl_sync(0xffffffffu, v, l);
+    return r;
+}
+inline int atomicCAS(int *addr, int cmp, int val) {
+    int old = *addr;
+    if (old == cmp) *addr = val;
+    return old;
+}

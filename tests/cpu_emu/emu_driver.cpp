@@ -47,18 +47,33 @@ extern "C" int emu_solve_many(const rbpe_problem *p, int count, int mode, rbpe_r
     S.nrec = nrec; S.status = status.data();
     S.scratch_stride = scratch_doubles(N, M, bs);
     S.smem_bytes = (unsigned)smem_bytes;
+    // same kernel selection as rbpe_api.cu: one-agent batches -> warp-per-QP kernel, else CTA-per-QP kernel
+    const bool warp_kernel = (bs == 1) && threads != 64;   // threads == 64 forces the CTA kernel (A/B in tests)
+    const int wpc = 2;
+    auto launch = [&](long units) {
+        if (warp_kernel) {
+            long grid = (units + wpc - 1) / wpc;
+            S.scratch_stride = w1_scratch_doubles(N, M);
+            S.smem_bytes = (unsigned)(wpc * w1_smem_doubles(M) * 8);
+            std::vector<double> scratch(S.scratch_stride * grid * wpc);
+            S.scratch = scratch.data();
+            emu::launch([&] { pdip1_kernel(S); }, (unsigned)grid, wpc * 32, S.smem_bytes);
+        } else {
+            S.scratch_stride = scratch_doubles(N, M, bs);
+            S.smem_bytes = (unsigned)smem_bytes;
+            std::vector<double> scratch(S.scratch_stride * units);
+            S.scratch = scratch.data();
+            emu::launch([&] { pdip_kernel(S); }, (unsigned)units, threads, smem_bytes);
+        }
+    };
     if (nbatch > 0) {
         if (mode == 0) {
-            std::vector<double> scratch(S.scratch_stride * count);
-            S.scratch = scratch.data();
-            emu::launch([&] { pdip_kernel(S); }, count, threads, smem_bytes);
+            launch(count);
         } else {
-            std::vector<double> scratch(S.scratch_stride * count * nbatch);
-            S.scratch = scratch.data();
             for (int it = 0; it < p->iteration; it++) {
                 frozen = ctrl;
                 S.rec_offset = it * nbatch;
-                emu::launch([&] { pdip_kernel(S); }, count * nbatch, threads, smem_bytes);
+                launch((long)count * nbatch);
             }
         }
     }

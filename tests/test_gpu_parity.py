@@ -94,6 +94,14 @@ def test_config3_64_agents_sequential(eng):
     _check_against_oracle(eng, ms[:1], True, 4)
 
 
+def test_config4_256_agents_dense_forest_batches_of_32(eng):
+    """BASELINE configs[3]: 256 agents, forest density 0.4, 5 segments, sequential planning with plan_batch_size = 32
+    (8 joint QPs of 2 880 variables and ~236 k inequality rows each)."""
+    m = synth.synth_mission(256, 5, 0.4, 4000)
+    _, r = _check_against_oracle(eng, [m], True, 32)
+    assert _properties(m, r.ctrl[0]) > -1e-6
+
+
 def test_batching_edge_cases(eng):
     """ragged last batch, truncated schedule (batch_iter < ceil(N/b): coefficients of unsolved agents come from `dummy`,
     rbp_planner.hpp L185-L190), batch_iter = 0 (publish the initial trajectory, L119-L138), two outer iterations,
