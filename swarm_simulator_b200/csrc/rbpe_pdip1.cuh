@@ -23,16 +23,17 @@ __host__ __device__ inline size_t w1_smem_doubles(int M) {  // per warp
 __host__ __device__ inline size_t w1_scratch_doubles(int N, int M) {  // per warp, global arena
     size_t nslot = (6 * (size_t)M + 31) / 32, NE = (size_t)(N > 1 ? N - 1 : 0);
     size_t rows = nslot * NE * 32, boxs = nslot * 32 * 3;
-    return 3 * rows + 8 * boxs + al2(((size_t)M * NE * 3 + 1) / 2) + 8;
+    return 3 * rows + 8 * boxs + al2((size_t)M * NE * 3) + 8;
 }
 
 #if defined(__CUDACC__) || defined(RBPE_EMU)
 
-RBPE_DEV double rcp_nr(double a) {  // 1/a to double rounding: float seed + two Newton steps
+RBPE_DEV double rcp_nr(double a) {  // 1/a to double rounding: 20-bit hardware seed + two Newton steps
 #ifdef RBPE_EMU
     double r = (double)(1.0f / (float)a);
 #else
-    double r = (double)__frcp_rn((float)a);
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));   // MUFU.RCP64H: ~20 bits, one XU op, no FP32<->FP64 conversions
 #endif
     double e = fma(-a, r, 1.0);
     r = fma(r, e, r);
@@ -50,7 +51,7 @@ struct W1 {
     // global arena (per warp)
     double *he, *se, *ze;                                   // [slot][e][lane]
     double *ub, *lbn, *sub, *zub, *slb, *zlb;                // [slot][k][lane]
-    float *nrm;                                             // [m][e][3], sign folded in
+    double *nrm;                                            // [m][e][3], sign folded in (FP64: no per-row F2F)
 };
 
 template <int MASK>
@@ -132,7 +133,7 @@ RBPE_DEV void w1_pass(const W1 &c, double sa, double sb, Acc &out) {
         double vA0 = 0, vA1 = 0, vA2 = 0, vB0 = 0, vB1 = 0, vB2 = 0;
         double Dxx = 0, Dxy = 0, Dxz = 0, Dyy = 0, Dyz = 0, Dzz = 0;
         if (on) {
-            const float *nm = c.nrm + (size_t)m * c.NE * 3;
+            const double *nm = c.nrm + (size_t)m * c.NE * 3;
             const size_t rb = (size_t)slot * c.NE * 32 + lane;
 #pragma unroll 2
             for (int e = 0; e < c.NE; e++) {
@@ -275,8 +276,8 @@ RBPE_DEV void w1_setup(const W1 &c) {
         int m = idx / c.NE, e = idx % c.NE, qo = (e < c.qa) ? e : e + 1;
         long it = (c.qa < qo) ? pair_index(N, c.qa, qo) : pair_index(N, qo, c.qa);
         const float *nf = c.reln + ((size_t)it * M + m) * 3;
-        float sg = (c.qa < qo) ? 1.f : -1.f;
-        c.nrm[idx * 3] = sg * nf[0]; c.nrm[idx * 3 + 1] = sg * nf[1]; c.nrm[idx * 3 + 2] = sg * nf[2];
+        double sg = (c.qa < qo) ? 1.0 : -1.0;
+        c.nrm[idx * 3] = sg * (double)nf[0]; c.nrm[idx * 3 + 1] = sg * (double)nf[1]; c.nrm[idx * 3 + 2] = sg * (double)nf[2];
     }
     __syncwarp();
     for (int slot = 0; slot < c.nslot; slot++) {
@@ -289,16 +290,16 @@ RBPE_DEV void w1_setup(const W1 &c) {
             c.ub[b] = box[3 + k]; c.lbn[b] = -box[k];
             c.sub[b] = 1; c.zub[b] = 1; c.slb[b] = 1; c.zlb[b] = 1;
         }
-        const float *nm = c.nrm + (size_t)m * c.NE * 3;
+        const double *nm = c.nrm + (size_t)m * c.NE * 3;
         const size_t rb = (size_t)slot * c.NE * 32 + lane;
         for (int e = 0; e < c.NE; e++) {
             int qo = (e < c.qa) ? e : e + 1;
             const double *co = c.ctrl_src + (size_t)qo * 18 * M + m * 6 + i;
             // h = sg*n.dummy_other - (r_a + r_other), accumulated in the reference's order (L643-L668)
             double h = -(c.radius[c.qa] + c.radius[qo]);
-            h += (double)nm[e * 3] * co[0];
-            h += (double)nm[e * 3 + 1] * co[6 * M];
-            h += (double)nm[e * 3 + 2] * co[12 * M];
+            h += nm[e * 3] * co[0];
+            h += nm[e * 3 + 1] * co[6 * M];
+            h += nm[e * 3 + 2] * co[12 * M];
             const size_t r = rb + (size_t)e * 32;
             c.he[r] = h; c.se[r] = 1; c.ze[r] = 1;
         }
@@ -467,7 +468,7 @@ __global__ void __launch_bounds__(W1_WARPS * 32, 4) pdip1_kernel(SolveArgs S) { 
         c.he = g; c.se = g + rows; c.ze = g + 2 * rows; g += 3 * rows;
         c.ub = g; c.lbn = g + boxs; c.sub = g + 2 * boxs; c.zub = g + 3 * boxs; c.slb = g + 4 * boxs; c.zlb = g + 5 * boxs;
         g += 8 * boxs;
-        c.nrm = (float *)g;
+        c.nrm = g;
     }
     const int iters = (S.mode == 0) ? S.iteration : 1;
     for (int iter = 0; iter < iters; iter++)

@@ -8,7 +8,7 @@ off2line = {}
 cur = None
 infunc = False
 for l in open(dis):
-    if l.startswith('.text.'):
+    if l.startswith(".text."):
         infunc = kname in l
         continue
     if not infunc: continue
