@@ -728,7 +728,7 @@ RBPE_DEV void solve_bt(TM tm, int nblk, int kb, const double *Dall, const double
 // ---- one-agent batches (9x9 blocks): the whole block tridiagonal system handled by one warp out of registers -------
 // lanes 0..8 hold the rows of the diagonal block D_t, lanes 9..17 the rows of O_t = block (t+1, t).
 // On exit D holds L_tt (lower), O holds L_{t+1,t}, dinv[t*9+j] = 1 / L_tt[j][j].
-RBPE_NOINLINE bool factor_bt9(int nblk, double *Dall, double *Oall, double *dinv) {
+RBPE_DEV bool factor_bt9(int nblk, double *Dall, double *Oall, double *dinv) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const bool isD = lane < 9, isO = lane >= 9 && lane < 18;
@@ -778,7 +778,7 @@ RBPE_NOINLINE bool factor_bt9(int nblk, double *Dall, double *Oall, double *dinv
     return ok;
 }
 
-RBPE_NOINLINE void solve_bt9(int nblk, const double *Dall, const double *Oall, const double *dinv, double *g) {
+RBPE_DEV void solve_bt9(int nblk, const double *Dall, const double *Oall, const double *dinv, double *g) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const bool act = lane < 9;

@@ -21,9 +21,9 @@ __host__ __device__ inline size_t w1_smem_doubles(int M) {  // per warp
     return al2(6 * 3 * ncp) + al2(6 * ncp) + al2((size_t)(M > 1 ? M - 1 : 1) * 81) + al2((size_t)(M > 2 ? M - 2 : 1) * 81) + 3 * al2(nr) + 36;
 }
 __host__ __device__ inline size_t w1_scratch_doubles(int N, int M) {  // per warp, global arena
-    size_t nslot = (6 * (size_t)M + 31) / 32, NR = (size_t)(N > 1 ? N - 1 : 0) + 6;   // + the 6 box rows of a control point
-    size_t rows = nslot * NR * 32;
-    return 3 * rows + al2((size_t)M * NR * 3) + 8;
+    size_t nslot = (6 * (size_t)M + 31) / 32, NE = (size_t)(N > 1 ? N - 1 : 0);
+    size_t rows = nslot * NE * 32, boxs = nslot * 32 * 3;
+    return 3 * rows + 8 * boxs + al2((size_t)M * NE * 3) + 8;
 }
 
 #if defined(__CUDACC__) || defined(RBPE_EMU)
@@ -42,16 +42,15 @@ RBPE_DEV double rcp_nr(double a) {  // 1/a to double rounding: 20-bit hardware s
 }
 
 struct W1 {
-    int N, M, NE, NR, ncp, nslot, nr, qa, mi, sequential;
+    int N, M, NE, ncp, nslot, nr, qa, mi, sequential;
     const double *start, *goal, *radius, *segbox, *segmat;
     const float *reln;
     const double *ctrl_src;
     // shared memory (per warp); x-space index v = m*18 + k*6 + i
     double *x, *dxa, *dx, *rdx, *vA, *vB, *Dcp, *Wd, *Wo, *sg, *sg2, *dinv, *QB;
     // global arena (per warp)
-    // rows of a control point: e < NE the RSFC rows against the other agents, e = NE + 2k + side its box rows
-    // (x_k <= ub, -x_k <= -lb) written as ordinary rows with unit normals, so that every pass is ONE loop
-    double *he, *se, *ze;                                   // [slot][e][lane], e < NR = NE + 6
+    double *he, *se, *ze;                                   // [slot][e][lane]
+    double *ub, *lbn, *sub, *zub, *slb, *zlb;                // [slot][k][lane]
     double *nrm;                                            // [m][e][3], sign folded in (FP64: no per-row F2F)
 };
 
@@ -113,7 +112,7 @@ RBPE_DEV void row_eval1(double h, double &s, double &z, double gx, double ga, do
 RBPE_DEV bool w1_dead(const W1 &c, int cp) { int m = cp / 6, i = cp % 6; return (m == 0 && i < 3) || (m == c.M - 1 && i >= 3); }
 
 template <int MODE>
-RBPE_NOINLINE void w1_pass(const W1 &c, double sa, double sb, Acc &out) {
+RBPE_DEV void w1_pass(const W1 &c, double sa, double sb, Acc &out) {
     constexpr bool WR = (MODE == P_START || MODE == P_SHIFT || MODE == P_RES);
     constexpr bool VEC = (MODE == P_INIT || MODE == P_RES || MODE == P_COR);
     constexpr bool MAT = (MODE == P_INIT || MODE == P_RES);
@@ -134,10 +133,10 @@ RBPE_NOINLINE void w1_pass(const W1 &c, double sa, double sb, Acc &out) {
         double vA0 = 0, vA1 = 0, vA2 = 0, vB0 = 0, vB1 = 0, vB2 = 0;
         double Dxx = 0, Dxy = 0, Dxz = 0, Dyy = 0, Dyz = 0, Dzz = 0;
         if (on) {
-            const double *nm = c.nrm + (size_t)m * c.NR * 3;
-            const size_t rb = (size_t)slot * c.NR * 32 + lane;
-#pragma unroll 1
-            for (int e = 0; e < c.NR; e++) {
+            const double *nm = c.nrm + (size_t)m * c.NE * 3;
+            const size_t rb = (size_t)slot * c.NE * 32 + lane;
+#pragma unroll 2
+            for (int e = 0; e < c.NE; e++) {
                 const size_t r = rb + (size_t)e * 32;
                 double n0 = nm[e * 3], n1 = nm[e * 3 + 1], n2 = nm[e * 3 + 2];
                 double h = c.he[r], s = c.se[r], z = c.ze[r], cA, cB, w;
@@ -150,6 +149,24 @@ RBPE_NOINLINE void w1_pass(const W1 &c, double sa, double sb, Acc &out) {
                     double w0 = w * n0, w1 = w * n1, w2 = w * n2;
                     Dxx += w0 * n0; Dxy += w0 * n1; Dxz += w0 * n2; Dyy += w1 * n1; Dyz += w1 * n2; Dzz += w2 * n2;
                 }
+            }
+            // box rows of the three axes: x <= ub, -x <= -lb
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const size_t b = ((size_t)slot * 3 + k) * 32 + lane;
+                double xk = k == 0 ? x0 : (k == 1 ? x1 : x2), ak = k == 0 ? a0 : (k == 1 ? a1 : a2), dk = k == 0 ? d0 : (k == 1 ? d1 : d2);
+                double cA, cB, w, s, z, tA = 0, tB = 0, tw = 0;
+                s = c.sub[b]; z = c.zub[b];
+                row_eval1<MODE>(c.ub[b], s, z, xk, ak, dk, sa, sb, cA, cB, w, acc);
+                if (WR) { c.sub[b] = s; c.zub[b] = z; }
+                tA += cA; tB += cB; tw += w;
+                s = c.slb[b]; z = c.zlb[b];
+                row_eval1<MODE>(c.lbn[b], s, z, -xk, -ak, -dk, sa, sb, cA, cB, w, acc);
+                if (WR) { c.slb[b] = s; c.zlb[b] = z; }
+                tA -= cA; tB -= cB; tw += w;
+                if (k == 0) { vA0 += tA; vB0 += tB; Dxx += tw; }
+                if (k == 1) { vA1 += tA; vB1 += tB; Dyy += tw; }
+                if (k == 2) { vA2 += tA; vB2 += tB; Dzz += tw; }
             }
             if (VEC) { c.vA[v0] = vA0; c.vA[v0 + 6] = vA1; c.vA[v0 + 12] = vA2; }
             if (MODE == P_RES) { c.vB[v0] = vB0; c.vB[v0 + 6] = vB1; c.vB[v0 + 12] = vB2; }
@@ -167,7 +184,7 @@ RBPE_NOINLINE void w1_pass(const W1 &c, double sa, double sb, Acc &out) {
 }
 
 // out (nr) = Z' vec (x-space)
-RBPE_NOINLINE void w1_Zt(const W1 &c, const double *vec, double *out) {
+RBPE_DEV void w1_Zt(const W1 &c, const double *vec, double *out) {
     for (int r = threadIdx.x & 31; r < c.nr; r += 32) {
         int t = r / 9 + 1, cc = r % 9, k = cc / 3, d = cc % 3;
         const double *CR = c.segmat + (t - 1) * SEGMAT + SEGMAT_CR, *CL = c.segmat + t * SEGMAT + SEGMAT_CL;
@@ -179,7 +196,7 @@ RBPE_NOINLINE void w1_Zt(const W1 &c, const double *vec, double *out) {
     __syncwarp();
 }
 // out (x-space) = Z sg
-RBPE_NOINLINE void w1_Z(const W1 &c, const double *sg, double *out) {
+RBPE_DEV void w1_Z(const W1 &c, const double *sg, double *out) {
     const int nv = 18 * c.M;
     for (int v = threadIdx.x & 31; v < nv; v += 32) {
         int m = v / 18, r = v % 18, k = r / 6, i = r % 6;
@@ -197,7 +214,7 @@ RBPE_NOINLINE void w1_Z(const W1 &c, const double *sg, double *out) {
     }
     __syncwarp();
 }
-RBPE_NOINLINE void w1_build_W(const W1 &c) {
+RBPE_DEV void w1_build_W(const W1 &c) {
     const int M = c.M;
     for (int idx = threadIdx.x & 31; idx < (M - 1) * 81; idx += 32) {
         int t = idx / 81 + 1, r = (idx % 81) / 9, cc = idx % 9;
@@ -219,13 +236,13 @@ RBPE_NOINLINE void w1_build_W(const W1 &c) {
     __syncwarp();
 }
 // dxout = Z (Z'HZ)^-1 Z' r
-RBPE_NOINLINE void w1_solve(const W1 &c, const double *r, double *dxout) {
+RBPE_DEV void w1_solve(const W1 &c, const double *r, double *dxout) {
     w1_Zt(c, r, c.sg);
     solve_bt9(c.M - 1, c.Wd, c.Wo, c.dinv, c.sg);
     w1_Z(c, c.sg, dxout);
 }
 // rdx = 2 Q x + vA, partial sums of the objective and max|Px|
-RBPE_NOINLINE void w1_dual(const W1 &c, double &obj, double &mpx) {
+RBPE_DEV void w1_dual(const W1 &c, double &obj, double &mpx) {
     const int nv = 18 * c.M;
     for (int v = threadIdx.x & 31; v < nv; v += 32) {
         int m = v / 18, i = v % 6, b6 = v - i;
@@ -239,7 +256,7 @@ RBPE_NOINLINE void w1_dual(const W1 &c, double &obj, double &mpx) {
     __syncwarp();
 }
 
-RBPE_NOINLINE void w1_setup(const W1 &c) {
+RBPE_DEV void w1_setup(const W1 &c) {
     const int lane = threadIdx.x & 31, M = c.M, N = c.N, nv = 18 * M;
     for (int v = lane; v < nv; v += 32) {
         int m = v / 18, r = v % 18, k = r / 6, i = r % 6;
@@ -254,23 +271,13 @@ RBPE_NOINLINE void w1_setup(const W1 &c) {
         }
         c.x[v] = xp; c.dxa[v] = 0; c.dx[v] = 0; c.vA[v] = 0; c.vB[v] = 0; c.rdx[v] = 0;
     }
-    // signed normals of the RSFC rows against every other agent (g = sg*n, sg = +1 if qa < qo), then the 6 unit
-    // normals of the box rows
-    for (int idx = lane; idx < M * c.NR; idx += 32) {
-        int m = idx / c.NR, e = idx % c.NR;
-        double n0, n1, n2;
-        if (e < c.NE) {
-            int qo = (e < c.qa) ? e : e + 1;
-            long it = (c.qa < qo) ? pair_index(N, c.qa, qo) : pair_index(N, qo, c.qa);
-            const float *nf = c.reln + ((size_t)it * M + m) * 3;
-            double sg = (c.qa < qo) ? 1.0 : -1.0;
-            n0 = sg * (double)nf[0]; n1 = sg * (double)nf[1]; n2 = sg * (double)nf[2];
-        } else {
-            int k = (e - c.NE) >> 1;
-            double sg = ((e - c.NE) & 1) ? -1.0 : 1.0;
-            n0 = k == 0 ? sg : 0.0; n1 = k == 1 ? sg : 0.0; n2 = k == 2 ? sg : 0.0;
-        }
-        c.nrm[idx * 3] = n0; c.nrm[idx * 3 + 1] = n1; c.nrm[idx * 3 + 2] = n2;
+    // signed normals of the RSFC rows against every other agent: g = sg*n, sg = +1 if qa < qo
+    for (int idx = lane; idx < M * c.NE; idx += 32) {
+        int m = idx / c.NE, e = idx % c.NE, qo = (e < c.qa) ? e : e + 1;
+        long it = (c.qa < qo) ? pair_index(N, c.qa, qo) : pair_index(N, qo, c.qa);
+        const float *nf = c.reln + ((size_t)it * M + m) * 3;
+        double sg = (c.qa < qo) ? 1.0 : -1.0;
+        c.nrm[idx * 3] = sg * (double)nf[0]; c.nrm[idx * 3 + 1] = sg * (double)nf[1]; c.nrm[idx * 3 + 2] = sg * (double)nf[2];
     }
     __syncwarp();
     for (int slot = 0; slot < c.nslot; slot++) {
@@ -278,22 +285,21 @@ RBPE_NOINLINE void w1_setup(const W1 &c) {
         if (cp >= c.ncp) continue;
         const int m = cp / 6, i = cp % 6;
         const double *box = c.segbox + ((size_t)c.qa * M + m) * 6;
-        const double *nm = c.nrm + (size_t)m * c.NR * 3;
-        const size_t rb = (size_t)slot * c.NR * 32 + lane;
-        for (int e = 0; e < c.NR; e++) {
-            double h;
-            if (e < c.NE) {
-                int qo = (e < c.qa) ? e : e + 1;
-                const double *co = c.ctrl_src + (size_t)qo * 18 * M + m * 6 + i;
-                // h = sg*n.dummy_other - (r_a + r_other), accumulated in the reference's order (L643-L668)
-                h = -(c.radius[c.qa] + c.radius[qo]);
-                h += nm[e * 3] * co[0];
-                h += nm[e * 3 + 1] * co[6 * M];
-                h += nm[e * 3 + 2] * co[12 * M];
-            } else {   // x_k <= ub ; -x_k <= -lb (L626-L635)
-                int k = (e - c.NE) >> 1;
-                h = ((e - c.NE) & 1) ? -box[k] : box[3 + k];
-            }
+        for (int k = 0; k < 3; k++) {
+            const size_t b = ((size_t)slot * 3 + k) * 32 + lane;
+            c.ub[b] = box[3 + k]; c.lbn[b] = -box[k];
+            c.sub[b] = 1; c.zub[b] = 1; c.slb[b] = 1; c.zlb[b] = 1;
+        }
+        const double *nm = c.nrm + (size_t)m * c.NE * 3;
+        const size_t rb = (size_t)slot * c.NE * 32 + lane;
+        for (int e = 0; e < c.NE; e++) {
+            int qo = (e < c.qa) ? e : e + 1;
+            const double *co = c.ctrl_src + (size_t)qo * 18 * M + m * 6 + i;
+            // h = sg*n.dummy_other - (r_a + r_other), accumulated in the reference's order (L643-L668)
+            double h = -(c.radius[c.qa] + c.radius[qo]);
+            h += nm[e * 3] * co[0];
+            h += nm[e * 3 + 1] * co[6 * M];
+            h += nm[e * 3 + 2] * co[12 * M];
             const size_t r = rb + (size_t)e * 32;
             c.he[r] = h; c.se[r] = 1; c.ze[r] = 1;
         }
@@ -321,8 +327,12 @@ RBPE_DEV int w1_solve_qp(const W1 &c, int max_iter, double tol_gap, double tol_r
         for (int slot = 0; slot < c.nslot; slot++) {
             const int cp = slot * 32 + lane;
             if (cp >= c.ncp || w1_dead(c, cp)) continue;
-            const size_t rb = (size_t)slot * c.NR * 32 + lane;
-            for (int e = 0; e < c.NR; e++) mh = fmax(mh, fabs(c.he[rb + (size_t)e * 32]));
+            for (int k = 0; k < 3; k++) {
+                const size_t b = ((size_t)slot * 3 + k) * 32 + lane;
+                mh = fmax(mh, fmax(fabs(c.ub[b]), fabs(c.lbn[b])));
+            }
+            const size_t rb = (size_t)slot * c.NE * 32 + lane;
+            for (int e = 0; e < c.NE; e++) mh = fmax(mh, fabs(c.he[rb + (size_t)e * 32]));
         }
         warp_reduce<4>(d0, d1, mh, d2);
         hn = mh;
@@ -429,7 +439,6 @@ __global__ void __launch_bounds__(W1_WARPS * 32, 4) pdip1_kernel(SolveArgs S) { 
     W1 c;
     c.N = N; c.M = M; c.sequential = S.sequential;
     c.NE = S.sequential ? N - 1 : 0;
-    c.NR = c.NE + 6;
     c.ncp = 6 * M; c.nslot = (c.ncp + 31) / 32; c.nr = 9 * (M > 1 ? M - 1 : 0);
     c.mi = (6 * M - 6) * (6 + c.NE);
     c.start = S.start + (size_t)cidx * N * 9;
@@ -455,8 +464,10 @@ __global__ void __launch_bounds__(W1_WARPS * 32, 4) pdip1_kernel(SolveArgs S) { 
     }
     {   // global arena of this warp
         double *g = S.scratch + (size_t)unit * S.scratch_stride;
-        const size_t rows = (size_t)c.nslot * c.NR * 32;
+        const size_t rows = (size_t)c.nslot * c.NE * 32, boxs = (size_t)c.nslot * 32 * 3;
         c.he = g; c.se = g + rows; c.ze = g + 2 * rows; g += 3 * rows;
+        c.ub = g; c.lbn = g + boxs; c.sub = g + 2 * boxs; c.zub = g + 3 * boxs; c.slb = g + 4 * boxs; c.zlb = g + 5 * boxs;
+        g += 8 * boxs;
         c.nrm = g;
     }
     const int iters = (S.mode == 0) ? S.iteration : 1;

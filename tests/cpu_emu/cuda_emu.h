@@ -21,6 +21,7 @@
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __align__(x) alignas(x)
+#define __restrict__ __restrict
 
 namespace emu {
 struct Idx { unsigned x, y, z; };

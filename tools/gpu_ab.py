@@ -1,0 +1,21 @@
+"""A/B of alternative builds of librbpe.so (tools only): python tools/gpu_ab.py lib1.so lib2.so ..."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+from swarm_simulator_b200 import engine as E, synth
+ms = [synth.synth_mission(64, 5, 0.2, 3000 + i) for i in range(8)]
+count = int(os.environ.get("AB_COUNT", 2368))
+packed = synth.pack([ms[i % 8] for i in range(count)])
+for lib in sys.argv[1:]:
+    E._lib = None
+    E.LIB_PATH = os.path.join(ROOT, lib)
+    eng = E.Engine()
+    prob = E.PackedProblem(packed, sequential=True, batch_size=1)
+    eng.upload(prob)
+    best = 1e9
+    for rep in range(3):
+        eng.timer_start(); eng.run(); best = min(best, eng.timer_stop())
+    r = eng.download(prob)
+    print("%-40s rc=%d kernel %.1f ms -> %.0f agent-QPs/s iters %.2f" % (lib, r.rc, best, count * 64 / best * 1e3, r.qp_iters.mean()), flush=True)
+    eng.close()
