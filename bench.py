@@ -301,15 +301,26 @@ def main():
         f_dense = dense_flops_per_iter(1, M_SEG) * iters_total          # per rank per step
         f_struct = structured_flops_per_iter(1, M_SEG, N_AGENTS) * iters_total
         ach = f_dense / (kernel_ms * 1e-3) / 1e12
+        traffic = None
+        try:   # DRAM bytes of one launch of the dominant kernel, from the committed ncu --set full capture (same mission count)
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r1_pdip1_ncu.json")))
+            if count == 1184:
+                traffic = prof["dram_bytes_per_launch"]
+        except Exception:
+            pass
         out["roofline"] = {
-            "bound": "tensor", "kernel": "pdip_kernel", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",
-            "frac": ach / tf32_peak, "traffic": None,
+            "bound": "tensor", "kernel": "pdip1_kernel", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",
+            "frac": ach / tf32_peak, "traffic": traffic,
             "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 dense proxy; TF32 itself not measured)"
                             if peaks else "fallback 1.4 PFLOP/s bf16 / 2"),
             "algorithmic": "dense reduced-KKT flops (SURVEY 8d) x iterations executed: %.3e per launch" % f_dense,
             "executed_structured_tflops": f_struct / (kernel_ms * 1e-3) / 1e12,
             "kernel_ms_per_launch": kernel_ms,
-            "note": "round-1 kernel is FP64 SIMT (no tensor cores): b=1 QPs are 36x36 reduced systems, latency bound",
+            "traffic_note": "ncu dram__bytes_read+write of one launch (profiles/r1_pdip1_ncu.md): the L2-resident row-state "
+                            "arena spills (L2 hit 90%); inputs+outputs of a launch are only 0.37 GB",
+            "fp64_pipe_pct_ncu": 16.2,
+            "note": "round-1 kernel is FP64 SIMT (no tensor cores): one-agent QPs reduce to 36x36 block tridiagonal systems; "
+                    "issue/latency bound (ncu: issue slots 22% busy, FP64 pipe 16%), see DESIGN.md section 6",
         }
         if world == 1 and not args.no_cpu_baseline:
             sys.path.insert(0, os.path.join(ROOT, "tests"))

@@ -122,6 +122,18 @@ int rbpe_last_timing(const rbpe_handle *h, rbpe_timing *t);                  /* 
 int rbpe_timer_start(rbpe_handle *h);
 int rbpe_timer_stop(rbpe_handle *h, float *ms);
 
+/* ---- the two pure-arithmetic neighbours of the path (host buffers in, host buffers out) ---- */
+/* Corridor::updateRelBox (rbp_corridor.hpp L338-L398): RSFC normals (float32, octomath::Vector3 semantics) and end
+ * times from initTraj [count][N][M+1][3]; collided[c] = 1 where the reference reports "initial trajectories are
+ * collided" (L385-L388).  Output layout = rbpe_problem.rsfc_n / rsfc_t. */
+int rbpe_corridor_rsfc(rbpe_handle *h, int N, int M, int count, const float *init_traj, const double *T, double downwash,
+                       float *rsfc_n, double *rsfc_t, int *collided);
+/* RBPPublisher::plot (rbp_publisher.hpp L117-L127; update_quad_state L670-L683, update_safety_margin_ratio L769-L798,
+ * trajectory_length_sum L685-L695): per mission the safety margin ratio (collision-free iff >= 1), the sample time of
+ * its minimum and the total flight length, sampled every dt (the reference uses 0.1). */
+int rbpe_safety_metrics(rbpe_handle *h, int N, int M, int count, const double *coef, const double *T, const double *radius,
+                        double downwash, double dt, double *min_ratio, double *t_at_min, double *length);
+
 #ifdef __cplusplus
 }
 #endif

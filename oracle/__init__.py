@@ -80,6 +80,10 @@ def lib():
         L.oracle_update_many.argtypes = [C.POINTER(CProblem), C.c_int, C.POINTER(COpts),
                                          C.POINTER(_dp), C.POINTER(_dp), _ip, C.c_int]
         L.oracle_update_many.restype = C.c_int
+        L.oracle_rsfc.argtypes = [C.c_int, C.c_int, _fp, _dp, C.c_double, _fp, _dp]
+        L.oracle_rsfc.restype = C.c_int
+        L.oracle_safety_metrics.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, C.c_double, C.c_double, _dp, _dp, _dp]
+        L.oracle_safety_metrics.restype = C.c_int
         _lib = L
     return _lib
 
@@ -270,3 +274,24 @@ def update_many(problems, nthreads=0, max_iter=0, tol_gap=0.0, tol_res=0.0):
     o = COpts(int(max_iter), float(tol_gap), float(tol_res))
     lib().oracle_update_many(arr, n, C.byref(o), cp, tp, _i(st), int(nthreads))
     return coef, ctrl, st
+
+
+def rsfc(init_traj, T, downwash):
+    """Corridor::updateRelBox restatement (float32). Returns (rsfc_n[P,M,3] f32, rsfc_t[P,M], collided)."""
+    tr = np.ascontiguousarray(init_traj, np.float32)
+    T = np.ascontiguousarray(T, np.float64)
+    N, M = tr.shape[0], tr.shape[1] - 1
+    P = N * (N - 1) // 2
+    n = np.zeros((max(P, 1), M, 3), np.float32); t = np.zeros((max(P, 1), M))
+    rc = lib().oracle_rsfc(N, M, _f(tr), _d(T), float(downwash), _f(n), _d(t))
+    return n[:P], t[:P], bool(rc)
+
+
+def safety_metrics(coef, T, radius, downwash=2.0, dt=0.1):
+    """(safety_margin_ratio, time of the minimum, total flight length, samples) for coef[N,3,6M] (highest power first)."""
+    c = np.ascontiguousarray(coef, np.float64); T = np.ascontiguousarray(T, np.float64)
+    r = np.ascontiguousarray(radius, np.float64)
+    N, M = c.shape[0], len(T) - 1
+    a, b, l = C.c_double(), C.c_double(), C.c_double()
+    nt = lib().oracle_safety_metrics(N, M, _d(c), _d(T), _d(r), float(downwash), float(dt), C.byref(a), C.byref(b), C.byref(l))
+    return a.value, b.value, l.value, nt

@@ -916,3 +916,108 @@ int oracle_update_many(const oracle_problem *ps, int count, const oracle_solver_
     }
     return bad;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Corridor::updateRelBox (rbp_corridor.hpp L338-L398): relative safe flight corridor normals.
+ * All arithmetic is octomap::point3d = octomath::Vector3 arithmetic, i.e. FLOAT32 with these semantics
+ * (octomap is not vendored under /root/reference; restated from its public header math/Vector3.h):
+ *   operator-, operator*(float), operator/=(float): component-wise float;
+ *   dot(), norm_sq(): float products and sums, returned as double; norm() = sqrt of that double;
+ *   normalize(): len = norm(); if (len > 0) *this /= (float)len.
+ * For pair (qi<qj) and segment iter=1..M: a, b = relative positions at iter-1, iter with z divided by the
+ * downwash coefficient; m = closest point of segment a-b to the origin (candidates a, b, and the foot of the
+ * perpendicular if it falls inside); normalise; divide z by downwash again.  Returns 0, or 1 if some normal
+ * is zero ("initial trajectories are collided", L385-L388).
+ * ---------------------------------------------------------------------------------------------- */
+static double v3_norm(const float *v) { float s = v[0] * v[0] + v[1] * v[1] + v[2] * v[2]; return sqrt((double)s); }
+static double v3_dot(const float *a, const float *b) { float s = a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; return (double)s; }
+static void v3_normalize(float *v) {
+    double len = v3_norm(v);
+    if (len > 0) { float f = (float)len; v[0] /= f; v[1] /= f; v[2] /= f; }
+}
+int oracle_rsfc(int N, int M, const float *init_traj /*[N][M+1][3]*/, const double *T, double downwash,
+                float *rsfc_n /*[P][M][3]*/, double *rsfc_t /*[P][M]*/) {
+    int rc = 0;
+    long it = 0;
+    for (int qi = 0; qi < N; qi++)
+        for (int qj = qi + 1; qj < N; qj++, it++)
+            for (int iter = 1; iter <= M; iter++) {
+                const float *pi0 = init_traj + ((size_t)qi * (M + 1) + iter - 1) * 3, *pj0 = init_traj + ((size_t)qj * (M + 1) + iter - 1) * 3;
+                const float *pi1 = pi0 + 3, *pj1 = pj0 + 3;
+                float a[3], b[3], m[3], n[3], c[3], ca[3], cb[3];
+                for (int k = 0; k < 3; k++) { a[k] = pj0[k] - pi0[k]; b[k] = pj1[k] - pi1[k]; }
+                a[2] = (float)((double)a[2] / downwash);      /* a.z() = a.z() / param.downwash (float / double -> float) */
+                b[2] = (float)((double)b[2] / downwash);
+                if (a[0] == b[0] && a[1] == b[1] && a[2] == b[2]) {
+                    for (int k = 0; k < 3; k++) m[k] = a[k];
+                } else {
+                    for (int k = 0; k < 3; k++) m[k] = a[k];
+                    double dist_min = v3_norm(a), dist = v3_norm(b);
+                    if (dist_min > dist) { for (int k = 0; k < 3; k++) m[k] = b[k]; dist_min = dist; }
+                    for (int k = 0; k < 3; k++) n[k] = b[k] - a[k];
+                    v3_normalize(n);
+                    float f = (float)v3_dot(a, n);            /* n * a.dot(n): the double narrows to operator*(float) */
+                    for (int k = 0; k < 3; k++) c[k] = a[k] - n[k] * f;
+                    dist = v3_norm(c);
+                    for (int k = 0; k < 3; k++) { ca[k] = c[k] - a[k]; cb[k] = c[k] - b[k]; }
+                    if (v3_dot(ca, cb) < 0 && dist_min > dist) for (int k = 0; k < 3; k++) m[k] = c[k];
+                }
+                v3_normalize(m);
+                m[2] = (float)((double)m[2] / downwash);
+                if (v3_norm(m) == 0) rc = 1;
+                float *o = rsfc_n + ((size_t)it * M + iter - 1) * 3;
+                o[0] = m[0]; o[1] = m[1]; o[2] = m[2];
+                rsfc_t[(size_t)it * M + iter - 1] = T[iter];
+            }
+    return rc;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * RBPPublisher post-hoc checks (rbp_publisher.hpp): sampling t_i = i*dt, i < floor(T_M/dt) (L47-L51); segment
+ * of a sample = last m with T[m] < t (strict), local time t - T[m] (timeMatrix L169-L183); position = sum_j
+ * coef_j tseg^j (update_quad_state L670-L683); safety_margin_ratio = min over samples and pairs of
+ * sqrt(dx^2 + dy^2 + (dz/downwash)^2) / (r_i + r_j) (L769-L798) -- collision-free iff >= 1; flight length =
+ * sum over agents of the polyline through the samples (L685-L695).
+ * Powers of tseg are formed by repeated multiplication and sums run lowest power first (the reference calls pow()
+ * and Eigen's product; bit-level agreement with that binary is unattainable, the boolean outcome is what matters).
+ * coef: [N][3][6M], highest power first per segment (the msgs_traj_coef layout).
+ * ---------------------------------------------------------------------------------------------- */
+static void eval_pos(const double *coef, int M, const double *T, double t, double *p /*[3]*/) {
+    int index = 0;
+    double tseg = 0;
+    for (int m = 0; m < M; m++) {
+        if (T[m] < t) { tseg = T[m]; index = m; } else break;
+    }
+    tseg = t - tseg;
+    for (int k = 0; k < 3; k++) {
+        const double *c = coef + (size_t)k * 6 * M + index * 6;
+        double s = 0, pw = 1;
+        for (int j = 0; j < 6; j++) { s = s + c[5 - j] * pw; pw = pw * tseg; }
+        p[k] = s;
+    }
+}
+int oracle_safety_metrics(int N, int M, const double *coef, const double *T, const double *radius, double downwash,
+                          double dt, double *min_ratio, double *t_at_min, double *length) {
+    int nt = (int)floor(T[M] / dt);
+    double best = 1e9, tbest = 0, len = 0;
+    double *pos = (double *)malloc(sizeof(double) * (size_t)N * 3 * (nt > 0 ? nt : 1));
+    for (int i = 0; i < nt; i++)
+        for (int q = 0; q < N; q++) eval_pos(coef + (size_t)q * 18 * M, M, T, i * dt, pos + ((size_t)i * N + q) * 3);
+    for (int i = 0; i < nt; i++)
+        for (int qi = 0; qi < N; qi++)
+            for (int qj = qi + 1; qj < N; qj++) {
+                const double *a = pos + ((size_t)i * N + qi) * 3, *b = pos + ((size_t)i * N + qj) * 3;
+                double dx = a[0] - b[0], dy = a[1] - b[1], dz = (a[2] - b[2]) / downwash;
+                double ratio = sqrt(dx * dx + dy * dy + dz * dz) / (radius[qi] + radius[qj]);
+                if (ratio < best) { best = ratio; tbest = i * dt; }
+            }
+    for (int q = 0; q < N; q++)
+        for (int i = 0; i + 1 < nt; i++) {
+            const double *a = pos + ((size_t)i * N + q) * 3, *b = pos + ((size_t)(i + 1) * N + q) * 3;
+            double dx = b[0] - a[0], dy = b[1] - a[1], dz = b[2] - a[2];
+            len += sqrt(dx * dx + dy * dy + dz * dz);
+        }
+    free(pos);
+    *min_ratio = best; *t_at_min = tbest; *length = len;
+    return nt;
+}

@@ -96,9 +96,12 @@ int oracle_update(const oracle_problem *p, const oracle_solver_opts *opts, doubl
 int oracle_update_many(const oracle_problem *ps, int count, const oracle_solver_opts *opts,
                        double **coef, double **ctrl, int *status, int nthreads);
 
-/* timeScale (L209-L266, L708-L847), in place on coef[N][3][6M]; returns the scale (>=1). */
-double oracle_time_scale(const oracle_problem *p, const double *max_vel /*[N][3]*/,
-                         const double *max_acc /*[N][3]*/, double *coef);
+/* Corridor::updateRelBox (rbp_corridor.hpp L338-L398) in float32 (octomath::Vector3 semantics). Returns 1 if a normal is zero. */
+int oracle_rsfc(int N, int M, const float *init_traj, const double *T, double downwash, float *rsfc_n, double *rsfc_t);
+
+/* RBPPublisher post-hoc checks (rbp_publisher.hpp L47-L51, L169-L183, L670-L695, L769-L798): returns the sample count. */
+int oracle_safety_metrics(int N, int M, const double *coef, const double *T, const double *radius, double downwash,
+                          double dt, double *min_ratio, double *t_at_min, double *length);
 
 #ifdef __cplusplus
 }

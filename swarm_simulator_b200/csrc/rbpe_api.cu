@@ -11,6 +11,7 @@
 
 #include "../../include/rbpe.h"
 #include "rbpe_kernels.cuh"
+#include "rbpe_post.cuh"
 
 using namespace rbpe;
 
@@ -58,6 +59,7 @@ struct rbpe_handle {
     cudaEvent_t tev[2] = {nullptr, nullptr};
     int count = 0, N = 0, M = 0, sequential = 0, bs = 1, nbatch = 0, iteration = 1, nrec = 1, sweep = 0;
     DevBuf T, start, goal, radius, sfc_offs, sfc_base, sfc_box, sfc_t, rsfc_n, rsfc_t, init_traj;
+    DevBuf post_a, post_b, post_c, post_d, post_e;   // scratch of rbpe_corridor_rsfc / rbpe_safety_metrics
     DevBuf segbox, reln, segmat, ctrl, frozen, coef, qp_obj, qp_iters, qp_status, qp_res, status, scratch;
     rbpe_timing timing;
     std::vector<int> host_status;
@@ -149,7 +151,8 @@ extern "C" void rbpe_destroy(rbpe_handle *h) {
     cudaStreamSynchronize(h->stream);
     DevBuf *all[] = {&h->T, &h->start, &h->goal, &h->radius, &h->sfc_offs, &h->sfc_base, &h->sfc_box, &h->sfc_t,
                      &h->rsfc_n, &h->rsfc_t, &h->init_traj, &h->segbox, &h->reln, &h->segmat, &h->ctrl, &h->frozen,
-                     &h->coef, &h->qp_obj, &h->qp_iters, &h->qp_status, &h->qp_res, &h->status, &h->scratch};
+                     &h->coef, &h->qp_obj, &h->qp_iters, &h->qp_status, &h->qp_res, &h->status, &h->scratch, &h->post_a, &h->post_b, &h->post_c,
+                     &h->post_d, &h->post_e};
     for (DevBuf *b : all) b->release();
     for (int i = 0; i < 7; i++)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -465,5 +468,87 @@ extern "C" int rbpe_timer_stop(rbpe_handle *h, float *ms) {
     CU(cudaEventRecord(h->tev[1], h->stream));
     CU(cudaEventSynchronize(h->tev[1]));
     CU(cudaEventElapsedTime(ms, h->tev[0], h->tev[1]));
+    return RBPE_OK;
+}
+
+// Corridor::updateRelBox (rbp_corridor.hpp L338-L398) for `count` missions: host in, host out
+extern "C" int rbpe_corridor_rsfc(rbpe_handle *h, int N, int M, int count, const float *init_traj, const double *T,
+                                  double downwash, float *rsfc_n, double *rsfc_t, int *collided) {
+    if (!h) return RBPE_BAD_ARG;
+    if (N < 1 || M < 1 || count < 1 || !init_traj || !T || !collided || (N > 1 && (!rsfc_n || !rsfc_t)) || !(downwash > 0))
+        return fail(h, RBPE_BAD_ARG, "rbpe_corridor_rsfc: bad argument");
+    CU(cudaSetDevice(h->device));
+    const size_t P = (size_t)N * (N - 1) / 2;
+    const size_t b_traj = (size_t)count * N * (M + 1) * 3 * 4, b_T = (size_t)count * (M + 1) * 8;
+    const size_t b_n = (size_t)count * (P ? P : 1) * M * 3 * 4, b_t = (size_t)count * (P ? P : 1) * M * 8;
+    CU(h->post_a.reserve(b_traj)); CU(h->post_b.reserve(b_T)); CU(h->post_c.reserve(b_n)); CU(h->post_d.reserve(b_t));
+    CU(h->post_e.reserve((size_t)count * 4));
+    CU(cudaMemcpyAsync(h->post_a.p, init_traj, b_traj, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->post_b.p, T, b_T, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemsetAsync(h->post_e.p, 0, (size_t)count * 4, h->stream));
+    RsfcArgs A;
+    A.count = count; A.N = N; A.M = M; A.downwash = downwash;
+    A.init_traj = h->post_a.as<float>(); A.T = h->post_b.as<double>();
+    A.rsfc_n = h->post_c.as<float>(); A.rsfc_t = h->post_d.as<double>(); A.collided = h->post_e.as<int>();
+    long total = (long)count * N * N * M;
+    int blocks = (int)((total + 255) / 256), cap = h->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    rsfc_kernel<<<blocks, 256, 0, h->stream>>>(A);
+    CU(cudaGetLastError());
+    h->launches++;
+    if (P) {
+        CU(cudaMemcpyAsync(rsfc_n, h->post_c.p, (size_t)count * P * M * 3 * 4, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(rsfc_t, h->post_d.p, (size_t)count * P * M * 8, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU(cudaMemcpyAsync(collided, h->post_e.p, (size_t)count * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return RBPE_OK;
+}
+
+// RBPPublisher post-hoc checks (rbp_publisher.hpp L117-L127): safety_margin_ratio (collision-free iff >= 1), the time
+// of its minimum, and the total flight length, per mission.  coef [count][N][3][6M] as rbpe_result.coef / msgs_traj_coef.
+extern "C" int rbpe_safety_metrics(rbpe_handle *h, int N, int M, int count, const double *coef, const double *T,
+                                   const double *radius, double downwash, double dt, double *min_ratio, double *t_at_min,
+                                   double *length) {
+    if (!h) return RBPE_BAD_ARG;
+    if (N < 1 || M < 1 || count < 1 || !coef || !T || !radius || !(downwash > 0) || !(dt > 0) || !min_ratio || !t_at_min || !length)
+        return fail(h, RBPE_BAD_ARG, "rbpe_safety_metrics: bad argument");
+    CU(cudaSetDevice(h->device));
+    int nt_max = 1;
+    for (int c = 0; c < count; c++) {
+        int nt = (int)floor(T[(size_t)c * (M + 1) + M] / dt);
+        if (nt > nt_max) nt_max = nt;
+    }
+    const size_t b_coef = (size_t)count * N * 18 * M * 8, b_T = (size_t)count * (M + 1) * 8, b_r = (size_t)count * N * 8;
+    const size_t b_ratio = (size_t)count * nt_max * 8, b_len = (size_t)count * N * nt_max * 8;
+    CU(h->post_a.reserve(b_coef)); CU(h->post_b.reserve(b_T)); CU(h->post_c.reserve(b_r)); CU(h->post_d.reserve(b_ratio));
+    CU(h->post_e.reserve(b_len));
+    CU(cudaMemcpyAsync(h->post_a.p, coef, b_coef, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->post_b.p, T, b_T, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->post_c.p, radius, b_r, cudaMemcpyHostToDevice, h->stream));
+    MetricsArgs A;
+    A.count = count; A.N = N; A.M = M; A.nt_max = nt_max; A.downwash = downwash; A.dt = dt;
+    A.coef = h->post_a.as<double>(); A.T = h->post_b.as<double>(); A.radius = h->post_c.as<double>();
+    A.ratio_t = h->post_d.as<double>(); A.seglen = h->post_e.as<double>();
+    size_t smem = ((size_t)N * 6 + 8) * 8;
+    if (smem > h->smem_optin) return fail(h, RBPE_BAD_ARG, "rbpe_safety_metrics: N=%d needs %zu B of shared memory", N, smem);
+    cudaFuncSetAttribute(metrics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
+    metrics_kernel<<<dim3(nt_max, count), 256, smem, h->stream>>>(A);
+    CU(cudaGetLastError());
+    h->launches++;
+    std::vector<double> ratio((size_t)count * nt_max), seglen((size_t)count * N * nt_max);
+    CU(cudaMemcpyAsync(ratio.data(), h->post_d.p, b_ratio, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(seglen.data(), h->post_e.p, b_len, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (int c = 0; c < count; c++) {   // final reductions in the reference's loop order (L685-L695, L776-L797)
+        int nt = (int)floor(T[(size_t)c * (M + 1) + M] / dt);
+        double best = 1e9, tb = 0, len = 0;
+        for (int i = 0; i < nt; i++)
+            if (ratio[(size_t)c * nt_max + i] < best) { best = ratio[(size_t)c * nt_max + i]; tb = i * dt; }
+        for (int q = 0; q < N; q++)
+            for (int i = 0; i + 1 < nt; i++) len += seglen[((size_t)c * N + q) * nt_max + i];
+        min_ratio[c] = best; t_at_min[c] = tb; length[c] = len;
+    }
     return RBPE_OK;
 }

@@ -43,7 +43,8 @@ class RbpeTiming(C.Structure):
 
 EXPORTS = ["rbpe_create", "rbpe_destroy", "rbpe_last_error", "rbpe_set_batch", "rbpe_solve_many", "rbpe_solve",
            "rbpe_upload", "rbpe_assemble", "rbpe_run", "rbpe_run_jacobi_range", "rbpe_set_ctrl", "rbpe_download", "rbpe_device_ctrl",
-           "rbpe_device_coef", "rbpe_stream", "rbpe_sync", "rbpe_last_timing", "rbpe_timer_start", "rbpe_timer_stop"]
+           "rbpe_device_coef", "rbpe_stream", "rbpe_sync", "rbpe_last_timing", "rbpe_timer_start", "rbpe_timer_stop",
+           "rbpe_corridor_rsfc", "rbpe_safety_metrics"]
 
 _lib = None
 
@@ -96,6 +97,10 @@ def load_library(path=None):
     L.rbpe_sync.restype = C.c_int
     L.rbpe_last_timing.argtypes = [C.c_void_p, C.POINTER(RbpeTiming)]
     L.rbpe_last_timing.restype = C.c_int
+    L.rbpe_corridor_rsfc.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _fp, _dp, C.c_double, _fp, _dp, _ip]
+    L.rbpe_corridor_rsfc.restype = C.c_int
+    L.rbpe_safety_metrics.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, C.c_double, C.c_double, _dp, _dp, _dp]
+    L.rbpe_safety_metrics.restype = C.c_int
     if path is None:
         _lib = L
     return L
@@ -245,6 +250,34 @@ class Engine:
             raise RuntimeError("rbpe_download failed: %s" % self.last_error())
         r.rc = rc
         return r
+
+    def corridor_rsfc(self, init_traj, T, downwash=2.0):
+        """Corridor::updateRelBox on the device. init_traj [count,N,M+1,3] f32, T [count,M+1] -> (rsfc_n, rsfc_t, collided)."""
+        tr = np.ascontiguousarray(init_traj, np.float32)
+        T = np.ascontiguousarray(T, np.float64)
+        count, N, M = tr.shape[0], tr.shape[1], tr.shape[2] - 1
+        P = N * (N - 1) // 2
+        n = np.zeros((count, max(P, 1), M, 3), np.float32)
+        t = np.zeros((count, max(P, 1), M))
+        col = np.zeros(count, np.int32)
+        rc = self.lib.rbpe_corridor_rsfc(self.h, N, M, count, tr.ctypes.data_as(_fp), T.ctypes.data_as(_dp), float(downwash),
+                                         n.ctypes.data_as(_fp), t.ctypes.data_as(_dp), col.ctypes.data_as(_ip))
+        if rc != OK:
+            raise RuntimeError("rbpe_corridor_rsfc failed (%d): %s" % (rc, self.last_error()))
+        return n[:, :P], t[:, :P], col
+
+    def safety_metrics(self, coef, T, radius, downwash=2.0, dt=0.1):
+        """RBPPublisher checks on the device. coef [count,N,3,6M] -> (min_ratio, t_at_min, length), each [count]."""
+        c = np.ascontiguousarray(coef, np.float64)
+        T = np.ascontiguousarray(T, np.float64)
+        r = np.ascontiguousarray(radius, np.float64)
+        count, N, M = c.shape[0], c.shape[1], T.shape[1] - 1
+        a, b, l = np.zeros(count), np.zeros(count), np.zeros(count)
+        rc = self.lib.rbpe_safety_metrics(self.h, N, M, count, c.ctypes.data_as(_dp), T.ctypes.data_as(_dp), r.ctypes.data_as(_dp),
+                                          float(downwash), float(dt), a.ctypes.data_as(_dp), b.ctypes.data_as(_dp), l.ctypes.data_as(_dp))
+        if rc != OK:
+            raise RuntimeError("rbpe_safety_metrics failed (%d): %s" % (rc, self.last_error()))
+        return a, b, l
 
     def sync(self):
         return self.lib.rbpe_sync(self.h)
