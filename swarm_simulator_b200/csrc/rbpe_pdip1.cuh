@@ -21,9 +21,9 @@ __host__ __device__ inline size_t w1_smem_doubles(int M) {  // per warp
     return al2(6 * 3 * ncp) + al2(6 * ncp) + al2((size_t)(M > 1 ? M - 1 : 1) * 81) + al2((size_t)(M > 2 ? M - 2 : 1) * 81) + 3 * al2(nr) + 36;
 }
 __host__ __device__ inline size_t w1_scratch_doubles(int N, int M) {  // per warp, global arena
-    size_t nslot = (6 * (size_t)M + 31) / 32, NE = (size_t)(N > 1 ? N - 1 : 0);
-    size_t rows = nslot * NE * 32, boxs = nslot * 32 * 3;
-    return 3 * rows + 8 * boxs + al2((size_t)M * NE * 3) + 8;
+    size_t nslot = (6 * (size_t)M + 31) / 32, NR = (size_t)(N > 1 ? N - 1 : 0) + 6;   // + the 6 box rows of a control point
+    size_t rows = nslot * NR * 32;
+    return 3 * rows + al2((size_t)M * NR * 3) + 8;
 }
 
 #if defined(__CUDACC__) || defined(RBPE_EMU)
@@ -42,15 +42,16 @@ RBPE_DEV double rcp_nr(double a) {  // 1/a to double rounding: 20-bit hardware s
 }
 
 struct W1 {
-    int N, M, NE, ncp, nslot, nr, qa, mi, sequential;
+    int N, M, NE, NR, ncp, nslot, nr, qa, mi, sequential;
     const double *start, *goal, *radius, *segbox, *segmat;
     const float *reln;
     const double *ctrl_src;
     // shared memory (per warp); x-space index v = m*18 + k*6 + i
     double *x, *dxa, *dx, *rdx, *vA, *vB, *Dcp, *Wd, *Wo, *sg, *sg2, *dinv, *QB;
     // global arena (per warp)
-    double *he, *se, *ze;                                   // [slot][e][lane]
-    double *ub, *lbn, *sub, *zub, *slb, *zlb;                // [slot][k][lane]
+    // rows of a control point: e < NE the RSFC rows against the other agents, e = NE + 2k + side its box rows
+    // (x_k <= ub, -x_k <= -lb) written as ordinary rows with unit normals, so that every pass is ONE loop (code size)
+    double *he, *se, *ze;                                   // [slot][e][lane], e < NR = NE + 6
     double *nrm;                                            // [m][e][3], sign folded in (FP64: no per-row F2F)
 };
 
@@ -133,10 +134,10 @@ RBPE_DEV void w1_pass(const W1 &c, double sa, double sb, Acc &out) {
         double vA0 = 0, vA1 = 0, vA2 = 0, vB0 = 0, vB1 = 0, vB2 = 0;
         double Dxx = 0, Dxy = 0, Dxz = 0, Dyy = 0, Dyz = 0, Dzz = 0;
         if (on) {
-            const double *nm = c.nrm + (size_t)m * c.NE * 3;
-            const size_t rb = (size_t)slot * c.NE * 32 + lane;
+            const double *nm = c.nrm + (size_t)m * c.NR * 3;
+            const size_t rb = (size_t)slot * c.NR * 32 + lane;
 #pragma unroll 2
-            for (int e = 0; e < c.NE; e++) {
+            for (int e = 0; e < c.NR; e++) {
                 const size_t r = rb + (size_t)e * 32;
                 double n0 = nm[e * 3], n1 = nm[e * 3 + 1], n2 = nm[e * 3 + 2];
                 double h = c.he[r], s = c.se[r], z = c.ze[r], cA, cB, w;
@@ -149,24 +150,6 @@ RBPE_DEV void w1_pass(const W1 &c, double sa, double sb, Acc &out) {
                     double w0 = w * n0, w1 = w * n1, w2 = w * n2;
                     Dxx += w0 * n0; Dxy += w0 * n1; Dxz += w0 * n2; Dyy += w1 * n1; Dyz += w1 * n2; Dzz += w2 * n2;
                 }
-            }
-            // box rows of the three axes: x <= ub, -x <= -lb
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                const size_t b = ((size_t)slot * 3 + k) * 32 + lane;
-                double xk = k == 0 ? x0 : (k == 1 ? x1 : x2), ak = k == 0 ? a0 : (k == 1 ? a1 : a2), dk = k == 0 ? d0 : (k == 1 ? d1 : d2);
-                double cA, cB, w, s, z, tA = 0, tB = 0, tw = 0;
-                s = c.sub[b]; z = c.zub[b];
-                row_eval1<MODE>(c.ub[b], s, z, xk, ak, dk, sa, sb, cA, cB, w, acc);
-                if (WR) { c.sub[b] = s; c.zub[b] = z; }
-                tA += cA; tB += cB; tw += w;
-                s = c.slb[b]; z = c.zlb[b];
-                row_eval1<MODE>(c.lbn[b], s, z, -xk, -ak, -dk, sa, sb, cA, cB, w, acc);
-                if (WR) { c.slb[b] = s; c.zlb[b] = z; }
-                tA -= cA; tB -= cB; tw += w;
-                if (k == 0) { vA0 += tA; vB0 += tB; Dxx += tw; }
-                if (k == 1) { vA1 += tA; vB1 += tB; Dyy += tw; }
-                if (k == 2) { vA2 += tA; vB2 += tB; Dzz += tw; }
             }
             if (VEC) { c.vA[v0] = vA0; c.vA[v0 + 6] = vA1; c.vA[v0 + 12] = vA2; }
             if (MODE == P_RES) { c.vB[v0] = vB0; c.vB[v0 + 6] = vB1; c.vB[v0 + 12] = vB2; }
@@ -183,11 +166,109 @@ RBPE_DEV void w1_pass(const W1 &c, double sa, double sb, Acc &out) {
     out = acc;
 }
 
+// Rolled (compact-code) versions of factor_bt9 / solve_bt9: the kernel is instruction-fetch bound (ncu r1: GPC
+// instruction cache at 79 % of its request rate, SM I-cache hit rate 70 %), so code size matters more than a few
+// extra moves.  Column loop rolled with a register rotation: a[0] always holds the current column of the lane's row.
+RBPE_NOINLINE bool factor_bt9r(int nblk, double *Dall, double *Oall, double *dinv) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const bool isD = lane < 9, isO = lane >= 9 && lane < 18;
+    const int row = isD ? lane : (isO ? lane - 9 : 0);
+    bool ok = true;
+#pragma unroll 1
+    for (int t = 0; t < nblk; t++) {
+        double *D = Dall + t * 81, *O = Oall + t * 81;
+        const bool hasO = t < nblk - 1;
+        double a[9];
+#pragma unroll
+        for (int c = 0; c < 9; c++) a[c] = isD ? D[row * 9 + c] : ((isO && hasO) ? O[row * 9 + c] : 0.0);
+        if (t > 0) {  // D_t -= L_{t,t-1} L_{t,t-1}'
+            const double *P = Oall + (t - 1) * 81;
+#pragma unroll 1
+            for (int k = 0; k < 9; k++) {
+                double pk = isD ? P[row * 9 + k] : 0.0;
+#pragma unroll
+                for (int c = 0; c < 9; c++) a[c] -= pk * P[c * 9 + k];
+            }
+        }
+#pragma unroll 1
+        for (int j = 0; j < 9; j++) {
+            double piv = __shfl_sync(FULL, a[0], j);
+            if (!(piv > 0)) { ok = false; piv = 1.0; }
+            double inv = rsqrt(piv);
+            double a0 = a[0] * inv;                 // column j of L_tt (rows >= j) and of L_{t+1,t}
+            if (isD) D[row * 9 + j] = (j <= row) ? a0 : 0.0;
+            else if (isO && hasO) O[row * 9 + j] = a0;
+            if (lane == j) dinv[t * 9 + j] = inv;
+#pragma unroll
+            for (int k = 1; k < 9; k++) {
+                double lk = __shfl_sync(FULL, a0, (j + k) & 31);   // L[j+k][j] from the lane of row j+k (unused beyond 8)
+                a[k - 1] = a[k] - a0 * lk;                        // update column j+k and rotate it into slot k-1
+            }
+            a[8] = 0.0;
+        }
+        __syncwarp();
+    }
+    return ok;
+}
+
+RBPE_NOINLINE void solve_bt9r(int nblk, const double *Dall, const double *Oall, const double *dinv, double *g) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const bool act = lane < 9;
+    const int row = act ? lane : 0;
+    double prev = 0;
+#pragma unroll 1
+    for (int t = 0; t < nblk; t++) {  // L w = g
+        const double *L = Dall + t * 81;
+        double gv = act ? g[t * 9 + row] : 0.0, di = act ? dinv[t * 9 + row] : 0.0;
+        if (t > 0) {
+            const double *P = Oall + (t - 1) * 81;
+            double sm = 0;
+#pragma unroll 1
+            for (int k = 0; k < 9; k++) sm += P[row * 9 + k] * __shfl_sync(FULL, prev, k);
+            gv -= sm;
+        }
+#pragma unroll 1
+        for (int j = 0; j < 9; j++) {
+            if (lane == j) gv *= di;
+            double gj = __shfl_sync(FULL, gv, j);
+            if (act && lane > j) gv -= L[row * 9 + j] * gj;
+        }
+        prev = gv;
+        if (act) g[t * 9 + row] = gv;
+    }
+    double next = 0;
+#pragma unroll 1
+    for (int t = nblk - 1; t >= 0; t--) {  // L' y = w
+        const double *L = Dall + t * 81;
+        double gv = act ? g[t * 9 + row] : 0.0, di = act ? dinv[t * 9 + row] : 0.0;
+        if (t < nblk - 1) {
+            const double *P = Oall + t * 81;
+            double sm = 0;
+#pragma unroll 1
+            for (int k = 0; k < 9; k++) sm += P[k * 9 + row] * __shfl_sync(FULL, next, k);
+            gv -= sm;
+        }
+#pragma unroll 1
+        for (int j = 8; j >= 0; j--) {
+            if (lane == j) gv *= di;
+            double gj = __shfl_sync(FULL, gv, j);
+            if (act && lane < j) gv -= L[j * 9 + row] * gj;
+        }
+        next = gv;
+        if (act) g[t * 9 + row] = gv;
+    }
+    __syncwarp();
+}
+
+// The helpers below are single non-inlined copies (instruction-cache footprint) and take plain arguments, so that the
+// context struct never has its address taken and stays in registers.
 // out (nr) = Z' vec (x-space)
-RBPE_DEV void w1_Zt(const W1 &c, const double *vec, double *out) {
-    for (int r = threadIdx.x & 31; r < c.nr; r += 32) {
+RBPE_NOINLINE void w1_Zt(const double *segmat, int nr, const double *vec, double *out) {
+    for (int r = threadIdx.x & 31; r < nr; r += 32) {
         int t = r / 9 + 1, cc = r % 9, k = cc / 3, d = cc % 3;
-        const double *CR = c.segmat + (t - 1) * SEGMAT + SEGMAT_CR, *CL = c.segmat + t * SEGMAT + SEGMAT_CL;
+        const double *CR = segmat + (t - 1) * SEGMAT + SEGMAT_CR, *CL = segmat + t * SEGMAT + SEGMAT_CL;
         const double *vl = vec + (t - 1) * 18 + k * 6 + 3, *vr = vec + t * 18 + k * 6;
         double s = 0;
         for (int j = 0; j < 3; j++) s += CR[j * 3 + d] * vl[j] + CL[j * 3 + d] * vr[j];
@@ -196,64 +277,68 @@ RBPE_DEV void w1_Zt(const W1 &c, const double *vec, double *out) {
     __syncwarp();
 }
 // out (x-space) = Z sg
-RBPE_DEV void w1_Z(const W1 &c, const double *sg, double *out) {
-    const int nv = 18 * c.M;
+RBPE_NOINLINE void w1_Z(const double *segmat, int M, const double *sg, double *out) {
+    const int nv = 18 * M;
     for (int v = threadIdx.x & 31; v < nv; v += 32) {
         int m = v / 18, r = v % 18, k = r / 6, i = r % 6;
         double s = 0;
         if (i < 3) {
             if (m > 0) {
-                const double *C = c.segmat + m * SEGMAT + SEGMAT_CL + i * 3, *g = sg + (m - 1) * 9 + k * 3;
+                const double *C = segmat + m * SEGMAT + SEGMAT_CL + i * 3, *g = sg + (m - 1) * 9 + k * 3;
                 s = C[0] * g[0] + C[1] * g[1] + C[2] * g[2];
             }
-        } else if (m < c.M - 1) {
-            const double *C = c.segmat + m * SEGMAT + SEGMAT_CR + (i - 3) * 3, *g = sg + m * 9 + k * 3;
+        } else if (m < M - 1) {
+            const double *C = segmat + m * SEGMAT + SEGMAT_CR + (i - 3) * 3, *g = sg + m * 9 + k * 3;
             s = C[0] * g[0] + C[1] * g[1] + C[2] * g[2];
         }
         out[v] = s;
     }
     __syncwarp();
 }
-RBPE_DEV void w1_build_W(const W1 &c) {
-    const int M = c.M;
+RBPE_NOINLINE void w1_build_W(const double *segmat, int M, const double *Dcp, double *Wd, double *Wo) {
     for (int idx = threadIdx.x & 31; idx < (M - 1) * 81; idx += 32) {
         int t = idx / 81 + 1, r = (idx % 81) / 9, cc = idx % 9;
         double s = 0;
         if (cc <= r) {
             int k = r / 3, d = r % 3, k2 = cc / 3, d2 = cc % 3;
-            const double *CR = c.segmat + (t - 1) * SEGMAT + SEGMAT_CR, *CL = c.segmat + t * SEGMAT + SEGMAT_CL;
+            const double *CR = segmat + (t - 1) * SEGMAT + SEGMAT_CR, *CL = segmat + t * SEGMAT + SEGMAT_CL;
             int e = sym6(k, k2);
-            const double *Dl = c.Dcp + ((size_t)(t - 1) * 6 + 3) * 6 + e, *Dr = c.Dcp + ((size_t)t * 6) * 6 + e;
+            const double *Dl = Dcp + ((size_t)(t - 1) * 6 + 3) * 6 + e, *Dr = Dcp + ((size_t)t * 6) * 6 + e;
             for (int j = 0; j < 3; j++) s += CR[j * 3 + d] * CR[j * 3 + d2] * Dl[j * 6] + CL[j * 3 + d] * CL[j * 3 + d2] * Dr[j * 6];
-            if (k == k2) s += c.segmat[(t - 1) * SEGMAT + SEGMAT_RQ + (3 + d) * 6 + 3 + d2] + c.segmat[t * SEGMAT + SEGMAT_RQ + d * 6 + d2];
+            if (k == k2) s += segmat[(t - 1) * SEGMAT + SEGMAT_RQ + (3 + d) * 6 + 3 + d2] + segmat[t * SEGMAT + SEGMAT_RQ + d * 6 + d2];
         }
-        c.Wd[idx] = s;
+        Wd[idx] = s;
     }
     for (int idx = threadIdx.x & 31; idx < (M - 2) * 81; idx += 32) {
         int t = idx / 81 + 1, r = (idx % 81) / 9, cc = idx % 9;
-        c.Wo[idx] = (r / 3 == cc / 3) ? c.segmat[t * SEGMAT + SEGMAT_RQ + (3 + r % 3) * 6 + cc % 3] : 0.0;
+        Wo[idx] = (r / 3 == cc / 3) ? segmat[t * SEGMAT + SEGMAT_RQ + (3 + r % 3) * 6 + cc % 3] : 0.0;
     }
     __syncwarp();
 }
 // dxout = Z (Z'HZ)^-1 Z' r
 RBPE_DEV void w1_solve(const W1 &c, const double *r, double *dxout) {
-    w1_Zt(c, r, c.sg);
-    solve_bt9(c.M - 1, c.Wd, c.Wo, c.dinv, c.sg);
-    w1_Z(c, c.sg, dxout);
+    w1_Zt(c.segmat, c.nr, r, c.sg);
+    solve_bt9r(c.M - 1, c.Wd, c.Wo, c.dinv, c.sg);
+    w1_Z(c.segmat, c.M, c.sg, dxout);
 }
-// rdx = 2 Q x + vA, partial sums of the objective and max|Px|
-RBPE_DEV void w1_dual(const W1 &c, double &obj, double &mpx) {
-    const int nv = 18 * c.M;
+// rdx = 2 Q x + vA; returns the lane-partial objective and max|Px|
+struct ObjMpx { double obj, mpx; };
+RBPE_NOINLINE ObjMpx w1_dual(const double *segmat, int M, const double *QB, const double *x, const double *vA, double *rdx) {
+    const int nv = 18 * M;
+    double obj = 0, mpx = 0;
     for (int v = threadIdx.x & 31; v < nv; v += 32) {
         int m = v / 18, i = v % 6, b6 = v - i;
         double s = 0;
-        for (int j = 0; j < 6; j++) s += c.QB[i * 6 + j] * c.x[b6 + j];
-        double pxv = 2.0 * c.segmat[m * SEGMAT + SEGMAT_QS] * s;
-        c.rdx[v] = pxv + c.vA[v];
-        obj += 0.5 * c.x[v] * pxv;
+        for (int j = 0; j < 6; j++) s += QB[i * 6 + j] * x[b6 + j];
+        double pxv = 2.0 * segmat[m * SEGMAT + SEGMAT_QS] * s;
+        rdx[v] = pxv + vA[v];
+        obj += 0.5 * x[v] * pxv;
         mpx = fmax(mpx, fabs(pxv));
     }
     __syncwarp();
+    ObjMpx r;
+    r.obj = obj; r.mpx = mpx;
+    return r;
 }
 
 RBPE_DEV void w1_setup(const W1 &c) {
@@ -271,13 +356,23 @@ RBPE_DEV void w1_setup(const W1 &c) {
         }
         c.x[v] = xp; c.dxa[v] = 0; c.dx[v] = 0; c.vA[v] = 0; c.vB[v] = 0; c.rdx[v] = 0;
     }
-    // signed normals of the RSFC rows against every other agent: g = sg*n, sg = +1 if qa < qo
-    for (int idx = lane; idx < M * c.NE; idx += 32) {
-        int m = idx / c.NE, e = idx % c.NE, qo = (e < c.qa) ? e : e + 1;
-        long it = (c.qa < qo) ? pair_index(N, c.qa, qo) : pair_index(N, qo, c.qa);
-        const float *nf = c.reln + ((size_t)it * M + m) * 3;
-        double sg = (c.qa < qo) ? 1.0 : -1.0;
-        c.nrm[idx * 3] = sg * (double)nf[0]; c.nrm[idx * 3 + 1] = sg * (double)nf[1]; c.nrm[idx * 3 + 2] = sg * (double)nf[2];
+    // signed normals of the RSFC rows against every other agent (g = sg*n, sg = +1 if qa < qo), then the 6 unit
+    // normals of the box rows
+    for (int idx = lane; idx < M * c.NR; idx += 32) {
+        int m = idx / c.NR, e = idx % c.NR;
+        double n0, n1, n2;
+        if (e < c.NE) {
+            int qo = (e < c.qa) ? e : e + 1;
+            long it = (c.qa < qo) ? pair_index(N, c.qa, qo) : pair_index(N, qo, c.qa);
+            const float *nf = c.reln + ((size_t)it * M + m) * 3;
+            double sg = (c.qa < qo) ? 1.0 : -1.0;
+            n0 = sg * (double)nf[0]; n1 = sg * (double)nf[1]; n2 = sg * (double)nf[2];
+        } else {
+            int k = (e - c.NE) >> 1;
+            double sg = ((e - c.NE) & 1) ? -1.0 : 1.0;
+            n0 = k == 0 ? sg : 0.0; n1 = k == 1 ? sg : 0.0; n2 = k == 2 ? sg : 0.0;
+        }
+        c.nrm[idx * 3] = n0; c.nrm[idx * 3 + 1] = n1; c.nrm[idx * 3 + 2] = n2;
     }
     __syncwarp();
     for (int slot = 0; slot < c.nslot; slot++) {
@@ -285,21 +380,22 @@ RBPE_DEV void w1_setup(const W1 &c) {
         if (cp >= c.ncp) continue;
         const int m = cp / 6, i = cp % 6;
         const double *box = c.segbox + ((size_t)c.qa * M + m) * 6;
-        for (int k = 0; k < 3; k++) {
-            const size_t b = ((size_t)slot * 3 + k) * 32 + lane;
-            c.ub[b] = box[3 + k]; c.lbn[b] = -box[k];
-            c.sub[b] = 1; c.zub[b] = 1; c.slb[b] = 1; c.zlb[b] = 1;
-        }
-        const double *nm = c.nrm + (size_t)m * c.NE * 3;
-        const size_t rb = (size_t)slot * c.NE * 32 + lane;
-        for (int e = 0; e < c.NE; e++) {
-            int qo = (e < c.qa) ? e : e + 1;
-            const double *co = c.ctrl_src + (size_t)qo * 18 * M + m * 6 + i;
-            // h = sg*n.dummy_other - (r_a + r_other), accumulated in the reference's order (L643-L668)
-            double h = -(c.radius[c.qa] + c.radius[qo]);
-            h += nm[e * 3] * co[0];
-            h += nm[e * 3 + 1] * co[6 * M];
-            h += nm[e * 3 + 2] * co[12 * M];
+        const double *nm = c.nrm + (size_t)m * c.NR * 3;
+        const size_t rb = (size_t)slot * c.NR * 32 + lane;
+        for (int e = 0; e < c.NR; e++) {
+            double h;
+            if (e < c.NE) {
+                int qo = (e < c.qa) ? e : e + 1;
+                const double *co = c.ctrl_src + (size_t)qo * 18 * M + m * 6 + i;
+                // h = sg*n.dummy_other - (r_a + r_other), accumulated in the reference's order (L643-L668)
+                h = -(c.radius[c.qa] + c.radius[qo]);
+                h += nm[e * 3] * co[0];
+                h += nm[e * 3 + 1] * co[6 * M];
+                h += nm[e * 3 + 2] * co[12 * M];
+            } else {   // x_k <= ub ; -x_k <= -lb (L626-L635)
+                int k = (e - c.NE) >> 1;
+                h = ((e - c.NE) & 1) ? -box[k] : box[3 + k];
+            }
             const size_t r = rb + (size_t)e * 32;
             c.he[r] = h; c.se[r] = 1; c.ze[r] = 1;
         }
@@ -318,7 +414,7 @@ RBPE_DEV int w1_solve_qp(const W1 &c, int max_iter, double tol_gap, double tol_r
     if (acc.mx > PRESOLVE_FEAS_TOL) { status = ST_INFEASIBLE; go = false; }
     if (go && c.nr == 0) {
         double o = 0, mpx = 0, d1 = 0, d2 = 0;
-        w1_dual(c, o, mpx);
+        o = w1_dual(c.segmat, c.M, c.QB, c.x, c.vA, c.rdx).obj;
         warp_reduce<1>(o, d1, mpx, d2);
         obj = o; status = ST_OK; go = false;
     }
@@ -327,22 +423,17 @@ RBPE_DEV int w1_solve_qp(const W1 &c, int max_iter, double tol_gap, double tol_r
         for (int slot = 0; slot < c.nslot; slot++) {
             const int cp = slot * 32 + lane;
             if (cp >= c.ncp || w1_dead(c, cp)) continue;
-            for (int k = 0; k < 3; k++) {
-                const size_t b = ((size_t)slot * 3 + k) * 32 + lane;
-                mh = fmax(mh, fmax(fabs(c.ub[b]), fabs(c.lbn[b])));
-            }
-            const size_t rb = (size_t)slot * c.NE * 32 + lane;
-            for (int e = 0; e < c.NE; e++) mh = fmax(mh, fabs(c.he[rb + (size_t)e * 32]));
+            const size_t rb = (size_t)slot * c.NR * 32 + lane;
+            for (int e = 0; e < c.NR; e++) mh = fmax(mh, fabs(c.he[rb + (size_t)e * 32]));
         }
         warp_reduce<4>(d0, d1, mh, d2);
         hn = mh;
         w1_pass<P_INIT>(c, 0, 0, acc);
-        w1_build_W(c);
-        if (!factor_bt9(c.M - 1, c.Wd, c.Wo, c.dinv)) go = false;
+        w1_build_W(c.segmat, c.M, c.Dcp, c.Wd, c.Wo);
+        if (!factor_bt9r(c.M - 1, c.Wd, c.Wo, c.dinv)) go = false;
     }
     if (go) {
-        double o = 0, mpx = 0;
-        w1_dual(c, o, mpx);   // rdx = P x_p + vA
+        w1_dual(c.segmat, c.M, c.QB, c.x, c.vA, c.rdx);   // rdx = P x_p + vA
         for (int v = lane; v < 18 * c.M; v += 32) c.rdx[v] = 2.0 * c.vA[v] - c.rdx[v];
         __syncwarp();
         w1_solve(c, c.rdx, c.dx);
@@ -362,10 +453,10 @@ RBPE_DEV int w1_solve_qp(const W1 &c, int max_iter, double tol_gap, double tol_r
         }
         double mu = acc.s1 / mi, hz = acc.s2;
         nrg = fmax(acc.mx, 0.0);
-        double o = 0, mpx = 0;
-        w1_dual(c, o, mpx);
-        w1_Zt(c, c.rdx, c.sg);
-        w1_Zt(c, c.vA, c.sg2);
+        ObjMpx om = w1_dual(c.segmat, c.M, c.QB, c.x, c.vA, c.rdx);
+        double o = om.obj, mpx = om.mpx;
+        w1_Zt(c.segmat, c.nr, c.rdx, c.sg);
+        w1_Zt(c.segmat, c.nr, c.vA, c.sg2);
         double mr = 0, mc = 0;
         for (int r = lane; r < c.nr; r += 32) { mr = fmax(mr, fabs(c.sg[r])); mc = fmax(mc, fabs(c.sg2[r])); }
         double d1 = 0;
@@ -376,8 +467,8 @@ RBPE_DEV int w1_solve_qp(const W1 &c, int max_iter, double tol_gap, double tol_r
         if (!(mu == mu) || !(nrd == nrd)) { status = ST_NOT_CONVERGED; break; }
         if (gap <= tol_gap * fmax(1.0, fabs(obj)) && nrg <= tol_res * (1 + hn) && nrd <= tol_res * (1.0 + mpx)) { status = ST_OK; break; }
         if (hz < 0 && mc / (-hz) < 1e-8) { status = ST_INFEASIBLE; break; }
-        w1_build_W(c);
-        if (!factor_bt9(c.M - 1, c.Wd, c.Wo, c.dinv)) { status = ST_NOT_CONVERGED; break; }
+        w1_build_W(c.segmat, c.M, c.Dcp, c.Wd, c.Wo);
+        if (!factor_bt9r(c.M - 1, c.Wd, c.Wo, c.dinv)) { status = ST_NOT_CONVERGED; break; }
         for (int v = lane; v < 18 * c.M; v += 32) c.vB[v] = -c.rdx[v] + c.vB[v];
         __syncwarp();
         w1_solve(c, c.vB, c.dxa);
@@ -439,6 +530,7 @@ __global__ void __launch_bounds__(W1_WARPS * 32, 4) pdip1_kernel(SolveArgs S) { 
     W1 c;
     c.N = N; c.M = M; c.sequential = S.sequential;
     c.NE = S.sequential ? N - 1 : 0;
+    c.NR = c.NE + 6;
     c.ncp = 6 * M; c.nslot = (c.ncp + 31) / 32; c.nr = 9 * (M > 1 ? M - 1 : 0);
     c.mi = (6 * M - 6) * (6 + c.NE);
     c.start = S.start + (size_t)cidx * N * 9;
@@ -464,10 +556,8 @@ __global__ void __launch_bounds__(W1_WARPS * 32, 4) pdip1_kernel(SolveArgs S) { 
     }
     {   // global arena of this warp
         double *g = S.scratch + (size_t)unit * S.scratch_stride;
-        const size_t rows = (size_t)c.nslot * c.NE * 32, boxs = (size_t)c.nslot * 32 * 3;
+        const size_t rows = (size_t)c.nslot * c.NR * 32;
         c.he = g; c.se = g + rows; c.ze = g + 2 * rows; g += 3 * rows;
-        c.ub = g; c.lbn = g + boxs; c.sub = g + 2 * boxs; c.zub = g + 3 * boxs; c.slb = g + 4 * boxs; c.zlb = g + 5 * boxs;
-        g += 8 * boxs;
         c.nrm = g;
     }
     const int iters = (S.mode == 0) ? S.iteration : 1;
