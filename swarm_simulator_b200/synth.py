@@ -437,7 +437,8 @@ def _try_mission(N, M, rho, rng, p, wxy):
         return None
     return dict(N=N, M=M, T=T, start=start, goal=goal, radius=np.full(N, r), max_vel=np.full((N, 3), p["max_vel"]),
                 max_acc=np.full((N, 3), p["max_acc"]), sfc=sfc, rsfc_n=rsfc_n, rsfc_t=rsfc_t, init_traj=init_traj,
-                world_xy=np.array(wxy), n_pillars=int(round(rho * area)), downwash=p["downwash"])
+                world_xy=np.array(wxy), n_pillars=int(round(rho * area)), downwash=p["downwash"],
+                edt=world.edt, edt_k0=world.k0.copy(), world_z=(p["world_z_min"], p["world_z_max"]), resolution=res)
 
 
 def pack(missions):
@@ -488,3 +489,19 @@ def dump_text(m, path):
         for p in range(N * (N - 1) // 2):
             for ri in range(M):
                 f.write(" ".join(repr(float(v)) for v in list(m["rsfc_n"][p, ri]) + [m["rsfc_t"][p, ri]]) + "\n")
+
+
+def dump_world_text(m, path):
+    """Text dump of world + mission + initTraj for swarm_simulator_b200/host/corridor_cli (format in corridor_cli.cpp)."""
+    edt = m["edt"]
+    with open(path, "w") as f:
+        f.write("%r %d %d %d %d %d %d\n" % (float(m["resolution"]), m["edt_k0"][0], m["edt_k0"][1], m["edt_k0"][2], *edt.shape))
+        f.write(" ".join("%.9g" % v for v in edt.reshape(-1)) + "\n")
+        wxy = m["world_xy"]
+        f.write("%r %r %r %r %r %r\n" % (float(wxy[0]), float(wxy[1]), float(m["world_z"][0]), float(wxy[2]), float(wxy[3]), float(m["world_z"][1])))
+        f.write("%d %d\n" % (m["N"], m["M"]))
+        f.write(" ".join(repr(float(t)) for t in m["T"]) + "\n")
+        f.write(" ".join(repr(float(r)) for r in m["radius"]) + "\n")
+        for qi in range(m["N"]):
+            for j in range(m["M"] + 1):
+                f.write(" ".join(repr(float(v)) for v in m["init_traj"][qi, j]) + "\n")

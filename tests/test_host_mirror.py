@@ -88,3 +88,30 @@ def test_rbp_planner_update_drop_in(built, tmp_path):
     tt = np.linspace(0, scale, 201)
     vel = sum(row[..., j, None] * (5 - j) * tt ** (4 - j) for j in range(5))
     assert np.abs(vel).max() <= 0.3 * 1.1 + 1e-9
+
+
+@pytest.mark.gpu
+def test_corridor_update_drop_in(built, tmp_path):
+    """Corridor(distmap, mission, param).update(log, &planResult) through the C++ mirror: SFC boxes and end times equal the
+    workload generator's restatement of updateObsBox (exact doubles), RSFC equals the float32 oracle bit for bit."""
+    import oracle
+    from swarm_simulator_b200 import synth
+    m = synth.synth_mission(10, 5, 0.3, 77)
+    synth.dump_world_text(m, str(tmp_path / "world.txt"))
+    out = subprocess.check_output([os.path.join(HOST, "corridor_cli"), str(tmp_path / "world.txt"), "box/xy_res=0.1", "box/z_res=0.1",
+                                   "plan/downwash=2.0"], text=True).splitlines()
+    assert out[0] == "update=true"
+    i = 1
+    for qi in range(10):
+        tag, q, nb = out[i].split()
+        assert tag == "SFC" and int(q) == qi
+        boxes, tend = m["sfc"][qi]
+        assert int(nb) == len(tend)
+        for b in range(int(nb)):
+            vals = np.array(out[i + 1 + b].split(), float)
+            assert np.array_equal(vals[:6], boxes[b]) and vals[6] == tend[b]
+        i += 1 + int(nb)
+    rows = np.array([l.split()[1:] for l in out[i:]], float)
+    no, to, _ = oracle.rsfc(m["init_traj"], m["T"], 2.0)
+    assert np.array_equal(rows[:, :3].astype(np.float32).reshape(no.shape), no)
+    assert np.array_equal(rows[:, 3].reshape(to.shape), to)

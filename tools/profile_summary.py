@@ -5,6 +5,7 @@ from collections import defaultdict
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag, launches, rep, kname = sys.argv[1:5]
+missions = int(sys.argv[5]) if len(sys.argv) > 5 else 1184
 out_dir = os.path.join(ROOT, "profiles")
 os.makedirs(out_dir, exist_ok=True)
 
@@ -19,7 +20,7 @@ for r in rows[1:]:
 tot = sum(sum(v) for v in d.values())
 with open(os.path.join(out_dir, "%s_launches.md" % tag), "w") as f:
     f.write("# %s: every kernel launch of `ncu --metrics gpu__time_duration.sum --clock-control none python bench.py "
-            "--steps 2 --warmup 3 --missions 1184 --no-cpu-baseline --jacobi-missions 0`\n\n" % tag)
+            "--steps 2 --warmup 3 --missions %d --no-cpu-baseline --jacobi-missions 0`\n\n" % (tag, missions))
     f.write("Cold-cache, serialised launch times: compare SHARES, not absolutes.\n\n| kernel | launches | total ms | mean ms | share |\n|---|---|---|---|---|\n")
     for k, v in sorted(d.items(), key=lambda kv: -sum(kv[1])):
         f.write("| `%s` | %d | %.3f | %.3f | %.4f |\n" % (k[:70], len(v), sum(v) / 1e6, sum(v) / len(v) / 1e6, sum(v) / tot))
@@ -43,7 +44,8 @@ want = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio"]
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "sm__icc_request_hit_rate.pct", "gcc__cache_requests_type_instruction.sum.pct_of_peak_sustained_elapsed"]
 got = {}
 for i, name in enumerate(h):
     if name in want:
@@ -56,10 +58,10 @@ def to_bytes(name):
     x = num(v) or 0.0
     return x * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
 traffic = to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum")
-json.dump({"kernel": kname, "dram_bytes_per_launch": traffic, "metrics": {k: {"value": v, "unit": u} for k, (v, u) in got.items()}},
+json.dump({"kernel": kname, "missions": missions, "dram_bytes_per_launch": traffic, "metrics": {k: {"value": v, "unit": u} for k, (v, u) in got.items()}},
           open(os.path.join(out_dir, "%s_%s_ncu.json" % (tag, kname)), "w"), indent=1)
 with open(os.path.join(out_dir, "%s_%s_ncu.md" % (tag, kname)), "w") as f:
-    f.write("# %s: `ncu --set full --clock-control none --import-source on -k regex:%s` (one launch, 1184 missions x 64 agents)\n\n" % (tag, kname))
+    f.write("# %s: `ncu --set full --clock-control none --import-source on -k regex:%s` (one launch, %d missions x 64 agents)\n\n" % (tag, kname, missions))
     f.write("| metric | value | unit |\n|---|---|---|\n")
     for k in want:
         if k in got:
