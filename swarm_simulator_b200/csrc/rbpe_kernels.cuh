@@ -418,6 +418,9 @@ RBPE_DEV void block_reduce6(double *v, double *red) {
 
 enum { P_INIT = 0, P_START, P_SHIFT, P_RES, P_AFF, P_COR, P_STEP, P_DEAD };
 
+// right-hand side marker of a row removed by the bound-based redundancy presolve
+constexpr double ROW_PRUNED = 1e300;
+
 struct Acc {  // lane-local reductions of a row pass
     double s1, s2, mx, mx2, mn;
 };
@@ -496,6 +499,7 @@ RBPE_DEV void cp_task(const QP &q, int m, int a, int i, double sa, double sb, Ac
             size_t r = rb + e;
             double n0 = q.nex[r], n1 = q.ney[r], n2 = q.nez[r];
             double h = q.he[r], s = q.se[r], z = q.ze[r], t = q.te[r], cA, cB, w;
+            if (h >= ROW_PRUNED) continue;   // dropped by the presolve (see setup_rows)
             row_eval<MODE>(h, s, z, t, n0 * x0 + n1 * x1 + n2 * x2, n0 * a0 + n1 * a1 + n2 * a2,
                            n0 * d0 + n1 * d1 + n2 * d2, sa, sb, true, cA, cB, w, acc);
             if (WR) { q.se[r] = s; q.ze[r] = z; q.te[r] = t; }
@@ -518,6 +522,7 @@ RBPE_DEV void cp_task(const QP &q, int m, int a, int i, double sa, double sb, Ac
         double ga = n0 * (a0 - q.dxa[vo]) + n1 * (a1 - q.dxa[vo + 6]) + n2 * (a2 - q.dxa[vo + 12]);
         double gd = n0 * (d0 - q.dx[vo]) + n1 * (d1 - q.dx[vo + 6]) + n2 * (d2 - q.dx[vo + 12]);
         double h = q.hi[r], s = q.si[r], z = q.zi[r], t = q.ti[r], cA, cB, w;
+        if (h >= ROW_PRUNED) continue;
         bool own = (a == lo);
         row_eval<MODE>(h, s, z, t, gx, ga, gd, sa, sb, own, cA, cB, w, acc);
         if (WR && own) {
@@ -911,6 +916,17 @@ RBPE_DEV void setup_rows(const QP &q) {
         h += sg * ((double)f2 * co[12 * M]);
         if (sg < 0) { f0 = -f0; f1 = -f1; f2 = -f2; }
         q.nex[r] = f0; q.ney[r] = f1; q.nez[r] = f2;
+        if (!cp_dead(q, m, i)) {
+            // Bound-based row redundancy (standard presolve): if the largest value of g.x over the SFC box of the control
+            // point stays below h the row can never be active and is dropped; the feasible set is unchanged.
+            const double *box = q.segbox + ((size_t)qa * M + m) * 6;
+            double gg[3] = {(double)f0, (double)f1, (double)f2}, amax = 0;
+            for (int k = 0; k < 3; k++) {
+                double a1 = gg[k] * box[3 + k], b1 = gg[k] * box[k];
+                amax += (a1 > b1) ? a1 : b1;
+            }
+            if (amax < h - 1e-9 * fmax(1.0, fabs(h))) h = ROW_PRUNED;
+        }
         q.he[r] = h; q.se[r] = 1; q.ze[r] = 1; q.te[r] = 1;
     }
     // RSFC rows between two batch agents lo<hi: n.x_lo - n.x_hi <= -(r_lo + r_hi)
@@ -922,7 +938,22 @@ RBPE_DEV void setup_rows(const QP &q) {
         long it = pair_index(N, q.q0 + lo, q.q0 + hi);
         const float *nf = q.reln + ((size_t)it * M + m) * 3;
         q.nix[r] = nf[0]; q.niy[r] = nf[1]; q.niz[r] = nf[2];
-        q.hi[r] = -(q.radius[q.q0 + lo] + q.radius[q.q0 + hi]);
+        double hh = -(q.radius[q.q0 + lo] + q.radius[q.q0 + hi]);
+        if (!cp_dead(q, m, j % 6)) {   // same presolve over the boxes of both control points (g = +n on lo, -n on hi)
+            const double *bl = q.segbox + ((size_t)(q.q0 + lo) * M + m) * 6, *bh = q.segbox + ((size_t)(q.q0 + hi) * M + m) * 6;
+            double amax = 0;
+            for (int k = 0; k < 3; k++) {
+                double g = (double)nf[k];
+                if (g == 0) continue;
+                double a1 = g * bl[3 + k], b1 = g * bl[k];
+                amax += (a1 > b1) ? a1 : b1;
+                a1 = -g * bh[3 + k]; b1 = -g * bh[k];
+                amax += (a1 > b1) ? a1 : b1;
+            }
+            if (amax < hh - 1e-9 * fmax(1.0, fabs(hh))) hh = ROW_PRUNED;
+        }
+        q.hi[r] = hh;
+        for (int e6 = 0; e6 < 6; e6++) q.Dint[(size_t)r * 6 + e6] = 0.0;   // a dropped row contributes no coupling block
         q.si[r] = 1; q.zi[r] = 1; q.ti[r] = 1;
     }
 }
@@ -976,15 +1007,21 @@ RBPE_DEV int pdip_solve(const QP &q_in, int max_iter, double tol_gap, double tol
             int m = v / q.n, i = v % 6;
             if (!cp_dead(q, m, i)) mh = fmax(mh, fmax(fabs(q.ub[v]), fabs(q.lbn[v])));
         }
+        double live = 0;
         for (int r = tid; r < q.nrext; r += nt) {
             int rest = r / q.NE, i = rest % 6, m = (rest / 6) % q.M;
-            if (!cp_dead(q, m, i)) mh = fmax(mh, fabs(q.he[r]));
+            if (!cp_dead(q, m, i) && q.he[r] < ROW_PRUNED) { mh = fmax(mh, fabs(q.he[r])); live += 1; }
         }
         for (int r = tid; r < q.nrint; r += nt) {
             int j = r % (6 * q.M);
-            if (!cp_dead(q, j / 6, j % 6)) mh = fmax(mh, fabs(q.hi[r]));
+            if (!cp_dead(q, j / 6, j % 6) && q.hi[r] < ROW_PRUNED) { mh = fmax(mh, fabs(q.hi[r])); live += 1; }
         }
-        hn = block_max(mh, q.red);
+        {
+            double rr[6] = {live, 0, mh, -1e300, -1e300, 1e300};
+            block_reduce6<1 + 4>(rr, q.red);
+            hn = rr[2];
+            q.mi = (int)(rr[0] + 0.5) + q.nb * (6 * q.M - 6) * 6;   // kept RSFC rows + the box rows of the live control points
+        }
         // ---- initial point: W = I,  min 1/2 x'(P + G'G)x - (G'h)'x  over x = x_p + Z sigma ----
         row_pass<P_INIT>(q, 0, 0, acc);   // vA = G'(h - G x_p), Dcp/Dint with unit weights
         if (!kkt_factor(q)) go = false;

@@ -18,12 +18,12 @@ constexpr int W1_WARPS = 4;
 
 __host__ __device__ inline size_t w1_smem_doubles(int M) {  // per warp
     size_t ncp = 6 * (size_t)M, nr = 9 * (size_t)(M > 1 ? M - 1 : 0);
-    return al2(6 * 3 * ncp) + al2(6 * ncp) + al2((size_t)(M > 1 ? M - 1 : 1) * 81) + al2((size_t)(M > 2 ? M - 2 : 1) * 81) + 3 * al2(nr) + 36;
+    return al2(6 * 3 * ncp) + al2(6 * ncp) + al2((size_t)(M > 1 ? M - 1 : 1) * 81) + al2((size_t)(M > 2 ? M - 2 : 1) * 81) + 3 * al2(nr) + 36 + al2((6 * (size_t)M + 31) / 32);
 }
 __host__ __device__ inline size_t w1_scratch_doubles(int N, int M) {  // per warp, global arena
     size_t nslot = (6 * (size_t)M + 31) / 32, NR = (size_t)(N > 1 ? N - 1 : 0) + 6;   // + the 6 box rows of a control point
     size_t rows = nslot * NR * 32;
-    return 3 * rows + al2((size_t)M * NR * 3) + 8;
+    return 3 * rows + al2((rows + 1) / 2) + al2(nslot * 16) + al2((size_t)M * NR * 3) + 8;
 }
 
 #if defined(__CUDACC__) || defined(RBPE_EMU)
@@ -48,10 +48,15 @@ struct W1 {
     const double *ctrl_src;
     // shared memory (per warp); x-space index v = m*18 + k*6 + i
     double *x, *dxa, *dx, *rdx, *vA, *vB, *Dcp, *Wd, *Wo, *sg, *sg2, *dinv, *QB;
+    int *cmax;   // [nslot] largest kept-row count of a slot (warp-uniform loop bound)
     // global arena (per warp)
     // rows of a control point: e < NE the RSFC rows against the other agents, e = NE + 2k + side its box rows
     // (x_k <= ub, -x_k <= -lb) written as ordinary rows with unit normals, so that every pass is ONE loop (code size)
-    double *he, *se, *ze;                                   // [slot][e][lane], e < NR = NE + 6
+    // Presolve: an RSFC row whose maximal activity over the box of its control point stays below its right-hand side can
+    // never be active (bound-based row redundancy) and is not stored; a lane keeps cnt <= NR rows, compacted.
+    double *he, *se, *ze;                                   // [slot][j][lane], j < cnt[slot][lane]
+    int *ridx;                                              // [slot][j][lane] row number e of the kept row (normal look-up)
+    int *cnt;                                               // [slot][lane]
     double *nrm;                                            // [m][e][3], sign folded in (FP64: no per-row F2F)
 };
 
@@ -136,9 +141,11 @@ RBPE_DEV void w1_pass(const W1 &c, double sa, double sb, Acc &out) {
         if (on) {
             const double *nm = c.nrm + (size_t)m * c.NR * 3;
             const size_t rb = (size_t)slot * c.NR * 32 + lane;
+            const int cnt = c.cnt[slot * 32 + lane];
 #pragma unroll 2
-            for (int e = 0; e < c.NR; e++) {
-                const size_t r = rb + (size_t)e * 32;
+            for (int j = 0; j < cnt; j++) {
+                const size_t r = rb + (size_t)j * 32;
+                const int e = c.ridx[r];
                 double n0 = nm[e * 3], n1 = nm[e * 3 + 1], n2 = nm[e * 3 + 2];
                 double h = c.he[r], s = c.se[r], z = c.ze[r], cA, cB, w;
                 row_eval1<MODE>(h, s, z, n0 * x0 + n1 * x1 + n2 * x2, n0 * a0 + n1 * a1 + n2 * a2, n0 * d0 + n1 * d1 + n2 * d2,
@@ -341,7 +348,7 @@ RBPE_NOINLINE ObjMpx w1_dual(const double *segmat, int M, const double *QB, cons
     return r;
 }
 
-RBPE_DEV void w1_setup(const W1 &c) {
+RBPE_DEV int w1_setup(const W1 &c) {   // returns the number of live (kept, non-constant) inequality rows
     const int lane = threadIdx.x & 31, M = c.M, N = c.N, nv = 18 * M;
     for (int v = lane; v < nv; v += 32) {
         int m = v / 18, r = v % 18, k = r / 6, i = r % 6;
@@ -375,38 +382,58 @@ RBPE_DEV void w1_setup(const W1 &c) {
         c.nrm[idx * 3] = n0; c.nrm[idx * 3 + 1] = n1; c.nrm[idx * 3 + 2] = n2;
     }
     __syncwarp();
+    int live_rows = 0;
     for (int slot = 0; slot < c.nslot; slot++) {
         const int cp = slot * 32 + lane;
-        if (cp >= c.ncp) continue;
-        const int m = cp / 6, i = cp % 6;
-        const double *box = c.segbox + ((size_t)c.qa * M + m) * 6;
-        const double *nm = c.nrm + (size_t)m * c.NR * 3;
-        const size_t rb = (size_t)slot * c.NR * 32 + lane;
-        for (int e = 0; e < c.NR; e++) {
-            double h;
-            if (e < c.NE) {
-                int qo = (e < c.qa) ? e : e + 1;
-                const double *co = c.ctrl_src + (size_t)qo * 18 * M + m * 6 + i;
-                // h = sg*n.dummy_other - (r_a + r_other), accumulated in the reference's order (L643-L668)
-                h = -(c.radius[c.qa] + c.radius[qo]);
-                h += nm[e * 3] * co[0];
-                h += nm[e * 3 + 1] * co[6 * M];
-                h += nm[e * 3 + 2] * co[12 * M];
-            } else {   // x_k <= ub ; -x_k <= -lb (L626-L635)
-                int k = (e - c.NE) >> 1;
-                h = ((e - c.NE) & 1) ? -box[k] : box[3 + k];
+        int kept = 0;
+        if (cp < c.ncp) {
+            const int m = cp / 6, i = cp % 6;
+            const bool dead = w1_dead(c, cp);
+            const double *box = c.segbox + ((size_t)c.qa * M + m) * 6;
+            const double *nm = c.nrm + (size_t)m * c.NR * 3;
+            const size_t rb = (size_t)slot * c.NR * 32 + lane;
+            for (int e = 0; e < c.NR; e++) {
+                double h;
+                if (e < c.NE) {
+                    int qo = (e < c.qa) ? e : e + 1;
+                    const double *co = c.ctrl_src + (size_t)qo * 18 * M + m * 6 + i;
+                    // h = sg*n.dummy_other - (r_a + r_other), accumulated in the reference's order (L643-L668)
+                    h = -(c.radius[c.qa] + c.radius[qo]);
+                    h += nm[e * 3] * co[0];
+                    h += nm[e * 3 + 1] * co[6 * M];
+                    h += nm[e * 3 + 2] * co[12 * M];
+                    if (!dead) {   // bound-based redundancy: max of g.x over the control point's box
+                        double amax = 0;
+                        for (int k = 0; k < 3; k++) {
+                            double g = nm[e * 3 + k], a = g * box[3 + k], b = g * box[k];
+                            amax += (a > b) ? a : b;
+                        }
+                        if (amax < h - 1e-9 * fmax(1.0, fabs(h))) continue;
+                    }
+                } else {   // x_k <= ub ; -x_k <= -lb (L626-L635)
+                    int k = (e - c.NE) >> 1;
+                    h = ((e - c.NE) & 1) ? -box[k] : box[3 + k];
+                }
+                const size_t r = rb + (size_t)kept * 32;
+                c.he[r] = h; c.se[r] = 1; c.ze[r] = 1; c.ridx[r] = e;
+                kept++;
             }
-            const size_t r = rb + (size_t)e * 32;
-            c.he[r] = h; c.se[r] = 1; c.ze[r] = 1;
+            if (!dead) live_rows += kept;
+            c.cnt[slot * 32 + lane] = kept;
         }
+        int mx = kept;
+        for (int o = 16; o > 0; o >>= 1) { int t = __shfl_xor_sync(0xffffffffu, mx, o); mx = t > mx ? t : mx; }
+        if (lane == 0) c.cmax[slot] = mx;
     }
+    for (int o = 16; o > 0; o >>= 1) live_rows += __shfl_xor_sync(0xffffffffu, live_rows, o);
     __syncwarp();
+    return live_rows;
 }
 
 RBPE_DEV int w1_solve_qp(const W1 &c, int max_iter, double tol_gap, double tol_res, double *obj_out, int *it_out, double *res_out) {
     const int lane = threadIdx.x & 31;
     Acc acc;
-    w1_setup(c);
+    const int live_rows = w1_setup(c);
     int status = ST_NOT_CONVERGED, it = 0;
     double obj = 0, gap = 0, nrd = 0, nrg = 0, hn = 0;
     bool go = true;
@@ -424,7 +451,8 @@ RBPE_DEV int w1_solve_qp(const W1 &c, int max_iter, double tol_gap, double tol_r
             const int cp = slot * 32 + lane;
             if (cp >= c.ncp || w1_dead(c, cp)) continue;
             const size_t rb = (size_t)slot * c.NR * 32 + lane;
-            for (int e = 0; e < c.NR; e++) mh = fmax(mh, fabs(c.he[rb + (size_t)e * 32]));
+            const int cnt = c.cnt[slot * 32 + lane];
+            for (int j = 0; j < cnt; j++) mh = fmax(mh, fabs(c.he[rb + (size_t)j * 32]));
         }
         warp_reduce<4>(d0, d1, mh, d2);
         hn = mh;
@@ -444,7 +472,7 @@ RBPE_DEV int w1_solve_qp(const W1 &c, int max_iter, double tol_gap, double tol_r
         w1_pass<P_SHIFT>(c, ap >= 0 ? 1.0 + ap : 0.0, ad >= 0 ? 1.0 + ad : 0.0, acc);
     }
     double sigmu = 0, al = 0;
-    const double mi = c.mi > 0 ? (double)c.mi : 1.0;
+    const double mi = live_rows > 0 ? (double)live_rows : 1.0;
     for (it = 0; go && it < max_iter; it++) {
         w1_pass<P_RES>(c, sigmu, al, acc);
         if (al != 0.0) {
@@ -550,7 +578,8 @@ __global__ void __launch_bounds__(W1_WARPS * 32, 4) pdip1_kernel(SolveArgs S) { 
         c.Wd = p; p += al2((size_t)(M > 1 ? M - 1 : 1) * 81);
         c.Wo = p; p += al2((size_t)(M > 2 ? M - 2 : 1) * 81);
         c.sg = p; p += al2(c.nr); c.sg2 = p; p += al2(c.nr); c.dinv = p; p += al2(c.nr);
-        c.QB = p;
+        c.QB = p; p += 36;
+        c.cmax = (int *)p;
         for (int e = lane; e < 36; e += 32) c.QB[e] = q_base_entry(e / 6, e % 6);
         __syncwarp();
     }
@@ -558,6 +587,8 @@ __global__ void __launch_bounds__(W1_WARPS * 32, 4) pdip1_kernel(SolveArgs S) { 
         double *g = S.scratch + (size_t)unit * S.scratch_stride;
         const size_t rows = (size_t)c.nslot * c.NR * 32;
         c.he = g; c.se = g + rows; c.ze = g + 2 * rows; g += 3 * rows;
+        c.ridx = (int *)g; g += al2((rows + 1) / 2);
+        c.cnt = (int *)g; g += al2((size_t)c.nslot * 16);
         c.nrm = g;
     }
     const int iters = (S.mode == 0) ? S.iteration : 1;
