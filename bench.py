@@ -191,7 +191,7 @@ def main():
     pool = make_pool(args.pool, rank)
     packed = pin(synth.pack([pool[i % len(pool)] for i in range(count)]))
     prob = E.PackedProblem(packed, sequential=True, batch_size=1)
-    res = E.Result(prob)
+    res = E.Result(prob, want_ctrl=False)   # the reference's update() returns coefficients (msgs_traj_coef); `dummy` stays on the device
     eng = E.Engine(device=local)
     h2d, d2h = prob.h2d_bytes(), res.d2h_bytes()
     nqp = count * N_AGENTS
@@ -317,10 +317,10 @@ def main():
             "executed_structured_tflops": f_struct / (kernel_ms * 1e-3) / 1e12,
             "kernel_ms_per_launch": kernel_ms,
             "traffic_note": "ncu dram__bytes_read+write of one launch (profiles/r1_pdip1_ncu.md): the L2-resident row-state "
-                            "arena spills (L2 hit 90%); inputs+outputs of a launch are only 0.37 GB",
-            "fp64_pipe_pct_ncu": 16.2,
+                            "arena partly spills (L2 hit 78%); inputs + outputs of a launch are 0.75 GB",
+            "fp64_pipe_pct_ncu": 13.0,
             "note": "round-1 kernel is FP64 SIMT (no tensor cores): one-agent QPs reduce to 36x36 block tridiagonal systems; "
-                    "issue/latency bound (ncu: issue slots 22% busy, FP64 pipe 16%), see DESIGN.md section 6",
+                    "instruction-fetch / latency bound (ncu: issue slots 29% busy, FP64 pipe 13%, GPC I-cache 94%), see DESIGN.md section 6",
         }
         if world == 1 and not args.no_cpu_baseline:
             sys.path.insert(0, os.path.join(ROOT, "tests"))

@@ -151,25 +151,25 @@ class PackedProblem:
 
 
 class Result:
-    def __init__(self, prob):
+    def __init__(self, prob, want_ctrl=True):
         c, N, M = prob.count, prob.N, prob.M
         _, bi = prob.effective_batching()
         nrec = max(1, prob.iteration * bi)
         self.nrec = prob.iteration * bi
         self.coef = np.zeros((c, N, 3, 6 * M))
-        self.ctrl = np.zeros((c, N, 3, 6 * M))
+        self.ctrl = np.zeros((c, N, 3, 6 * M)) if want_ctrl else None
         self.qp_obj = np.zeros((c, nrec))
         self.qp_iters = np.zeros((c, nrec), np.int32)
         self.qp_status = np.zeros((c, nrec), np.int32)
         self.qp_res = np.zeros((c, nrec, 4))
         self.status = np.zeros(c, np.int32)
-        self.c = RbpeResult(self.coef.ctypes.data_as(_dp), self.ctrl.ctypes.data_as(_dp),
+        self.c = RbpeResult(self.coef.ctypes.data_as(_dp), self.ctrl.ctypes.data_as(_dp) if want_ctrl else None,
                             self.qp_obj.ctypes.data_as(_dp), self.qp_iters.ctypes.data_as(_ip),
                             self.qp_status.ctypes.data_as(_ip), self.qp_res.ctypes.data_as(_dp),
                             self.status.ctypes.data_as(_ip))
 
     def d2h_bytes(self):
-        return int(self.coef.nbytes + self.ctrl.nbytes + self.qp_obj.nbytes + self.qp_iters.nbytes
+        return int(self.coef.nbytes + (self.ctrl.nbytes if self.ctrl is not None else 0) + self.qp_obj.nbytes + self.qp_iters.nbytes
                    + self.qp_status.nbytes + self.qp_res.nbytes + self.status.nbytes)
 
 
