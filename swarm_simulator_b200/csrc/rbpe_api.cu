@@ -45,6 +45,9 @@ char g_create_error[512] = "";
 struct rbpe_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;   // copy streams of the pipelined rbpe_solve_many
+    std::vector<cudaEvent_t> pev;                    // per-chunk events of the pipeline
+    int chunk = 2368;                                // missions per pipeline stage (RBPE_CHUNK)
     cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int max_iter = 100;
     double tol_gap = 1e-10, tol_res = 1e-9;
@@ -127,6 +130,7 @@ extern "C" int rbpe_create(const rbpe_config *cfg, rbpe_handle **out) {
     // tuning overrides (documented in DESIGN.md): RBPE_THREADS, RBPE_SMEM_KB
     if (const char *e = getenv("RBPE_THREADS")) { int th = atoi(e); if (th >= 32 && th <= CTA_THREADS && th % 32 == 0) h->threads = th; }
     if (const char *e = getenv("RBPE_KERNEL")) h->force_cta = (strcmp(e, "cta") == 0);
+    if (const char *e = getenv("RBPE_CHUNK")) { int c = atoi(e); if (c > 0) h->chunk = c; }
     if (const char *e = getenv("RBPE_SMEM_KB")) { long kb = atol(e); if (kb > 0) h->smem_budget = (size_t)kb * 1024; }
     if (h->smem_budget == 0) h->smem_budget = 48 * 1024;
     if (h->smem_budget > h->smem_optin) h->smem_budget = h->smem_optin;
@@ -158,6 +162,9 @@ extern "C" void rbpe_destroy(rbpe_handle *h) {
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i < 2; i++)
         if (h->tev[i]) cudaEventDestroy(h->tev[i]);
+    for (cudaEvent_t e : h->pev) cudaEventDestroy(e);
+    if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
+    if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -411,7 +418,151 @@ extern "C" int rbpe_download(rbpe_handle *h, rbpe_result *r) {
     return rc;
 }
 
+// ---- pipelined whole-path call: missions are cut into chunks; chunk k+1 is uploaded (copy stream) while chunk k is being
+// assembled / solved / converted (engine stream) and chunk k-1 is downloaded (second copy stream).  Reference semantics
+// only (Gauss-Seidel inside every mission); missions are independent, so the chunking changes nothing in the results.
+static int solve_many_pipelined(rbpe_handle *h, const rbpe_problem *p, int count, rbpe_result *r) {
+    CU(cudaSetDevice(h->device));
+    const int N = p->N, M = p->M;
+    const size_t P = (size_t)N * (N - 1) / 2, per = (size_t)N * 18 * M;
+    h->resident = false;
+    h->count = count; h->N = N; h->M = M; h->sequential = p->sequential ? 1 : 0; h->iteration = p->iteration;
+    rbpe_set_batch(N, h->sequential, p->batch_size, p->batch_iter, &h->bs, &h->nbatch);
+    h->nrec = h->iteration * h->nbatch;
+    if (h->nrec < 1) h->nrec = 1;
+    const size_t nrec = h->nrec, nr_out = (size_t)h->iteration * h->nbatch;
+    const size_t nbox = (size_t)p->sfc_base[count];
+    if (!h->s_h2d) CU(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+    if (!h->s_d2h) CU(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+    const int nchunk = (count + h->chunk - 1) / h->chunk;
+    while ((int)h->pev.size() < 2 * nchunk) {
+        cudaEvent_t e;
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->pev.push_back(e);
+    }
+    // device buffers for the whole call
+    CU(h->T.reserve((size_t)count * (M + 1) * 8)); CU(h->start.reserve((size_t)count * N * 9 * 8));
+    CU(h->goal.reserve((size_t)count * N * 9 * 8)); CU(h->radius.reserve((size_t)count * N * 8));
+    CU(h->sfc_offs.reserve((size_t)count * (N + 1) * 4)); CU(h->sfc_base.reserve((size_t)(count + 1) * 4));
+    CU(h->sfc_box.reserve(nbox * 6 * 8)); CU(h->sfc_t.reserve(nbox * 8));
+    CU(h->rsfc_n.reserve((size_t)count * (P ? P : 1) * M * 3 * 4)); CU(h->rsfc_t.reserve((size_t)count * (P ? P : 1) * M * 8));
+    CU(h->init_traj.reserve((size_t)count * N * (M + 1) * 3 * 4));
+    CU(h->segbox.reserve((size_t)count * N * M * 6 * 8)); CU(h->reln.reserve((size_t)count * (P ? P : 1) * M * 3 * 4));
+    CU(h->segmat.reserve((size_t)count * M * SEGMAT * 8));
+    CU(h->ctrl.reserve(count * per * 8)); CU(h->frozen.reserve(count * per * 8)); CU(h->coef.reserve(count * per * 8));
+    CU(h->qp_obj.reserve((size_t)count * nrec * 8)); CU(h->qp_iters.reserve((size_t)count * nrec * 4));
+    CU(h->qp_status.reserve((size_t)count * nrec * 4)); CU(h->qp_res.reserve((size_t)count * nrec * 32));
+    CU(h->status.reserve((size_t)count * 4));
+    h->host_status.resize(count);
+    CU(cudaEventRecord(h->ev[0], h->stream));
+    CU(cudaStreamWaitEvent(h->s_h2d, h->ev[0], 0));   // the copy stream starts after whatever the engine stream was doing
+    CU(cudaMemcpyAsync(h->sfc_base.p, p->sfc_base, (size_t)(count + 1) * 4, cudaMemcpyHostToDevice, h->s_h2d));
+    for (int k = 0; k < nchunk; k++) {
+        const int c0 = k * h->chunk, c1 = (c0 + h->chunk < count) ? c0 + h->chunk : count, n = c1 - c0;
+        const size_t b0 = (size_t)p->sfc_base[c0], b1 = (size_t)p->sfc_base[c1];
+        // ---- H2D of the chunk (copy stream) ----
+#define H2D(buf, src, elem_bytes, per_mission)                                                                            \
+    CU(cudaMemcpyAsync((char *)h->buf.p + (size_t)c0 * (per_mission) * (elem_bytes), (const char *)(src) + (size_t)c0 * (per_mission) * (elem_bytes), \
+                       (size_t)n * (per_mission) * (elem_bytes), cudaMemcpyHostToDevice, h->s_h2d))
+        H2D(T, p->T, 8, (size_t)(M + 1));
+        H2D(start, p->start, 8, (size_t)N * 9);
+        H2D(goal, p->goal, 8, (size_t)N * 9);
+        H2D(radius, p->radius, 8, (size_t)N);
+        H2D(sfc_offs, p->sfc_offs, 4, (size_t)(N + 1));
+        if (b1 > b0) {
+            CU(cudaMemcpyAsync((char *)h->sfc_box.p + b0 * 48, (const char *)p->sfc_box + b0 * 48, (b1 - b0) * 48, cudaMemcpyHostToDevice, h->s_h2d));
+            CU(cudaMemcpyAsync((char *)h->sfc_t.p + b0 * 8, (const char *)p->sfc_t + b0 * 8, (b1 - b0) * 8, cudaMemcpyHostToDevice, h->s_h2d));
+        }
+        if (P) {
+            H2D(rsfc_n, p->rsfc_n, 4, P * M * 3);
+            H2D(rsfc_t, p->rsfc_t, 8, P * M);
+        }
+        if (p->sequential) H2D(init_traj, p->init_traj, 4, (size_t)N * (M + 1) * 3);
+#undef H2D
+        CU(cudaEventRecord(h->pev[2 * k], h->s_h2d));
+        // ---- kernels of the chunk (engine stream) ----
+        CU(cudaStreamWaitEvent(h->stream, h->pev[2 * k], 0));
+        CU(cudaMemsetAsync((char *)h->status.p + (size_t)c0 * 4, 0, (size_t)n * 4, h->stream));
+        CU(cudaMemsetAsync((char *)h->qp_obj.p + (size_t)c0 * nrec * 8, 0, (size_t)n * nrec * 8, h->stream));
+        CU(cudaMemsetAsync((char *)h->qp_iters.p + (size_t)c0 * nrec * 4, 0, (size_t)n * nrec * 4, h->stream));
+        CU(cudaMemsetAsync((char *)h->qp_status.p + (size_t)c0 * nrec * 4, 0, (size_t)n * nrec * 4, h->stream));
+        CU(cudaMemsetAsync((char *)h->qp_res.p + (size_t)c0 * nrec * 32, 0, (size_t)n * nrec * 32, h->stream));
+        AssembleArgs A;
+        A.count = n; A.N = N; A.M = M; A.sequential = h->sequential;
+        A.T = h->T.as<double>() + (size_t)c0 * (M + 1); A.sfc_offs = h->sfc_offs.as<int>() + (size_t)c0 * (N + 1);
+        A.sfc_base = h->sfc_base.as<int>() + c0; A.sfc_box = h->sfc_box.as<double>(); A.sfc_t = h->sfc_t.as<double>();
+        A.rsfc_n = h->rsfc_n.as<float>() + (size_t)c0 * P * M * 3; A.rsfc_t = h->rsfc_t.as<double>() + (size_t)c0 * P * M;
+        A.init_traj = h->init_traj.as<float>() + (size_t)c0 * N * (M + 1) * 3;
+        A.segbox = h->segbox.as<double>() + (size_t)c0 * N * M * 6; A.reln = h->reln.as<float>() + (size_t)c0 * P * M * 3;
+        A.ctrl = h->ctrl.as<double>() + c0 * per; A.segmat = h->segmat.as<double>() + (size_t)c0 * M * SEGMAT;
+        A.status = h->status.as<int>() + c0;
+        {
+            const long per_mission = (long)N + (long)P * M + (long)per + M;
+            long total = per_mission * n;
+            int blocks = (int)((total + 255) / 256), cap = h->sm_count * 16;
+            if (blocks > cap) blocks = cap;
+            if (blocks < 1) blocks = 1;
+            assemble_kernel<<<blocks, 256, 0, h->stream>>>(A);
+            CU(cudaGetLastError());
+            h->launches++;
+        }
+        if (h->nbatch > 0 && h->iteration > 0) {
+            SolveArgs S;
+            int rc;
+            if ((rc = fill_solve_args(h, S, 0, 1))) return rc;
+            S.count = n;
+            S.start += (size_t)c0 * N * 9; S.goal += (size_t)c0 * N * 9; S.radius += (size_t)c0 * N;
+            S.segbox += (size_t)c0 * N * M * 6; S.reln += (size_t)c0 * P * M * 3; S.segmat += (size_t)c0 * M * SEGMAT;
+            S.ctrl += c0 * per; S.ctrl_frozen += c0 * per;
+            S.qp_obj += (size_t)c0 * nrec; S.qp_iters += (size_t)c0 * nrec; S.qp_status += (size_t)c0 * nrec;
+            S.qp_res += (size_t)c0 * nrec * 4; S.status += c0;
+            if ((rc = launch_pdip_prepared(h, S, n))) return rc;
+        }
+        {
+            ConvertArgs C;
+            C.count = n; C.N = N; C.M = M;
+            C.ctrl = h->ctrl.as<double>() + c0 * per; C.segmat = h->segmat.as<double>() + (size_t)c0 * M * SEGMAT;
+            C.coef = h->coef.as<double>() + c0 * per;
+            long total = (long)n * per;
+            int blocks = (int)((total + 255) / 256), cap = h->sm_count * 16;
+            if (blocks > cap) blocks = cap;
+            convert_kernel<<<blocks, 256, 0, h->stream>>>(C);
+            CU(cudaGetLastError());
+            h->launches++;
+        }
+        CU(cudaEventRecord(h->pev[2 * k + 1], h->stream));
+        // ---- D2H of the chunk (second copy stream) ----
+        CU(cudaStreamWaitEvent(h->s_d2h, h->pev[2 * k + 1], 0));
+        if (r->coef) CU(cudaMemcpyAsync(r->coef + c0 * per, (char *)h->coef.p + c0 * per * 8, n * per * 8, cudaMemcpyDeviceToHost, h->s_d2h));
+        if (r->ctrl) CU(cudaMemcpyAsync(r->ctrl + c0 * per, (char *)h->ctrl.p + c0 * per * 8, n * per * 8, cudaMemcpyDeviceToHost, h->s_d2h));
+        if (nr_out) {   // host records are [count][iteration*batch_iter] == the device layout (nrec == nr_out when nr_out > 0)
+            if (r->qp_obj) CU(cudaMemcpyAsync(r->qp_obj + (size_t)c0 * nr_out, (char *)h->qp_obj.p + (size_t)c0 * nrec * 8, (size_t)n * nr_out * 8, cudaMemcpyDeviceToHost, h->s_d2h));
+            if (r->qp_iters) CU(cudaMemcpyAsync(r->qp_iters + (size_t)c0 * nr_out, (char *)h->qp_iters.p + (size_t)c0 * nrec * 4, (size_t)n * nr_out * 4, cudaMemcpyDeviceToHost, h->s_d2h));
+            if (r->qp_status) CU(cudaMemcpyAsync(r->qp_status + (size_t)c0 * nr_out, (char *)h->qp_status.p + (size_t)c0 * nrec * 4, (size_t)n * nr_out * 4, cudaMemcpyDeviceToHost, h->s_d2h));
+            if (r->qp_res) CU(cudaMemcpyAsync(r->qp_res + (size_t)c0 * nr_out * 4, (char *)h->qp_res.p + (size_t)c0 * nrec * 32, (size_t)n * nr_out * 32, cudaMemcpyDeviceToHost, h->s_d2h));
+        }
+        CU(cudaMemcpyAsync(h->host_status.data() + c0, (char *)h->status.p + (size_t)c0 * 4, (size_t)n * 4, cudaMemcpyDeviceToHost, h->s_d2h));
+    }
+    CU(cudaStreamSynchronize(h->s_d2h));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaStreamSynchronize(h->s_h2d));
+    h->resident = true;
+    h->assembled = true;
+    h->sweep = 0;
+    int rc = RBPE_OK;
+    for (int i = 0; i < count; i++) {
+        if (r->status) r->status[i] = h->host_status[i];
+        if (rc == RBPE_OK && h->host_status[i] != RBPE_OK) rc = h->host_status[i];
+    }
+    if (rc != RBPE_OK) snprintf(h->err, sizeof(h->err), "a mission ended with status %d (1 infeasible, 2 not converged, 3 bad input)", rc);
+    return rc;
+}
+
 extern "C" int rbpe_solve_many(rbpe_handle *h, const rbpe_problem *p, int count, int mode, rbpe_result *r) {
+    if (h && p && r && mode == RBPE_MODE_GAUSS_SEIDEL && count >= 2 * h->chunk && p->N > 0 && p->M > 0 && p->M <= MAX_M &&
+        p->batch_size > 0 && p->iteration >= 0 && p->T && p->start && p->goal && p->radius && p->sfc_offs && p->sfc_base &&
+        p->sfc_box && p->sfc_t && (p->N == 1 || (p->rsfc_n && p->rsfc_t)) && (!p->sequential || p->init_traj))
+        return solve_many_pipelined(h, p, count, r);
     int rc = rbpe_upload(h, p, count);
     if (rc) return rc;
     if ((rc = rbpe_run(h, mode))) return rc;

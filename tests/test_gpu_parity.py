@@ -209,3 +209,24 @@ def test_many_missions_in_one_call(eng):
         assert np.array_equal(r.ctrl[c], r.ctrl[c % 5])                             # deterministic, bit for bit
     single = eng.solve_many(E.PackedProblem(synth.pack(ms[:1]), sequential=True, batch_size=1))
     assert np.array_equal(single.ctrl[0], r.ctrl[0])
+
+
+def test_pipelined_call_equals_plain_call(monkeypatch):
+    """rbpe_solve_many overlaps H2D / kernels / D2H over chunks of missions when the call is large enough; the chunking
+    must not change a single bit of the results (missions are independent)."""
+    ms = [synth.synth_mission(8, 5, 0.2, 700 + i) for i in range(4)]
+    packed = synth.pack([ms[i % 4] for i in range(11)])
+    plain = E.Engine()
+    r0 = plain.solve_many(E.PackedProblem(packed, sequential=True, batch_size=1))
+    r0b = plain.solve_many(E.PackedProblem(packed, sequential=True, batch_size=2))
+    plain.close()
+    monkeypatch.setenv("RBPE_CHUNK", "3")            # 11 missions -> chunks of 3, 3, 3, 2
+    piped = E.Engine()
+    r1 = piped.solve_many(E.PackedProblem(packed, sequential=True, batch_size=1))
+    r1b = piped.solve_many(E.PackedProblem(packed, sequential=True, batch_size=2))
+    piped.close()
+    for a, b in ((r0, r1), (r0b, r1b)):
+        assert a.rc == b.rc == E.OK
+        assert np.array_equal(a.coef, b.coef) and np.array_equal(a.ctrl, b.ctrl)
+        assert np.array_equal(a.qp_iters, b.qp_iters) and np.array_equal(a.qp_obj, b.qp_obj)
+        assert np.array_equal(a.status, b.status)
