@@ -176,3 +176,8 @@ inline int atomicCAS(int *addr, int cmp, int val) {
     if (old == cmp) *addr = val;
     return old;
 }
+inline int atomicAdd(int *addr, int val) {
+    int old = *addr;
+    *addr = old + val;
+    return old;
+}
