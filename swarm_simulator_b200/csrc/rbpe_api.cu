@@ -62,7 +62,6 @@ struct rbpe_handle {
     cudaEvent_t tev[2] = {nullptr, nullptr};
     int count = 0, N = 0, M = 0, sequential = 0, bs = 1, nbatch = 0, iteration = 1, nrec = 1, sweep = 0;
     DevBuf T, start, goal, radius, sfc_offs, sfc_base, sfc_box, sfc_t, rsfc_n, rsfc_t, init_traj;
-    DevBuf work_counter;
     DevBuf post_a, post_b, post_c, post_d, post_e;   // scratch of rbpe_corridor_rsfc / rbpe_safety_metrics
     DevBuf segbox, reln, segmat, ctrl, frozen, coef, qp_obj, qp_iters, qp_status, qp_res, status, scratch;
     rbpe_timing timing;
@@ -157,7 +156,7 @@ extern "C" void rbpe_destroy(rbpe_handle *h) {
     DevBuf *all[] = {&h->T, &h->start, &h->goal, &h->radius, &h->sfc_offs, &h->sfc_base, &h->sfc_box, &h->sfc_t,
                      &h->rsfc_n, &h->rsfc_t, &h->init_traj, &h->segbox, &h->reln, &h->segmat, &h->ctrl, &h->frozen,
                      &h->coef, &h->qp_obj, &h->qp_iters, &h->qp_status, &h->qp_res, &h->status, &h->scratch, &h->post_a, &h->post_b, &h->post_c,
-                     &h->post_d, &h->post_e, &h->work_counter};
+                     &h->post_d, &h->post_e};
     for (DevBuf *b : all) b->release();
     for (int i = 0; i < 7; i++)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -314,12 +313,7 @@ static int warps_per_cta(const rbpe_handle *h) {
 static int launch_pdip_prepared(rbpe_handle *h, SolveArgs &S, long units) {
     int wpc = warps_per_cta(h);
     if (wpc > 0) {
-        long grid = (units + wpc - 1) / wpc, resident = (long)h->sm_count * 4;   // persistent warps: 4 CTAs per SM pull work
-        if (grid > resident) grid = resident;
-        CU(h->work_counter.reserve(16));
-        CU(cudaMemsetAsync(h->work_counter.p, 0, 4, h->stream));
-        S.work_counter = h->work_counter.as<int>();
-        S.total_units = units;
+        long grid = (units + wpc - 1) / wpc;
         S.scratch_stride = w1_scratch_doubles(h->N, h->M);
         S.smem_bytes = (unsigned)(wpc * w1_smem_doubles(h->M) * 8);
         CU(h->scratch.reserve(S.scratch_stride * 8 * (size_t)grid * wpc));

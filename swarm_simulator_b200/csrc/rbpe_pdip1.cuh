@@ -542,15 +542,7 @@ RBPE_DEV int w1_solve_qp(const W1 &c, int max_iter, double tol_gap, double tol_r
 __global__ void __launch_bounds__(W1_WARPS * 32, 4) pdip1_kernel(SolveArgs S) {   // blockDim.x = 32 * (QPs per CTA) <= W1_WARPS * 32
     RBPE_DYN_SMEM(smem);
     const int N = S.N, M = S.M, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // Persistent warps: the grid is sized to what is resident (4 CTAs per SM) and every warp pulls the next work item
-    // -- a mission's whole QP chain (mode 0) or one (mission, agent) QP (mode 1) -- from a global counter.  The scratch
-    // arena is per resident warp, so its footprint does not grow with the size of the call.
-    const long slot = (long)blockIdx.x * (blockDim.x >> 5) + warp;
-  for (;;) {
-    long unit = 0;
-    if (lane == 0) unit = (long)atomicAdd(S.work_counter, 1);
-    unit = __shfl_sync(0xffffffffu, unit, 0);
-    if (unit >= S.total_units) return;
+    const long unit = (long)blockIdx.x * (blockDim.x >> 5) + warp;   // one QP chain (mode 0) or one QP (mode 1) per warp
     int cidx, l_begin, l_end;
     if (S.mode == 0) {
         cidx = (int)unit; l_begin = 0; l_end = S.nbatch;
@@ -560,8 +552,8 @@ __global__ void __launch_bounds__(W1_WARPS * 32, 4) pdip1_kernel(SolveArgs S) { 
         l_begin = S.batch_begin + (int)(unit % per);
         l_end = l_begin + 1;
     }
-    if (cidx >= S.count) return;
-    if (S.status[cidx] != ST_OK && S.mode == 0) continue;
+    if (cidx >= S.count) return;   // whole warps only; no block-level barrier is used in this kernel
+    if (S.status[cidx] != ST_OK && S.mode == 0) return;
     const long P = (long)N * (N - 1) / 2;
     W1 c;
     c.N = N; c.M = M; c.sequential = S.sequential;
@@ -592,7 +584,7 @@ __global__ void __launch_bounds__(W1_WARPS * 32, 4) pdip1_kernel(SolveArgs S) { 
         __syncwarp();
     }
     {   // global arena of this warp
-        double *g = S.scratch + (size_t)slot * S.scratch_stride;
+        double *g = S.scratch + (size_t)unit * S.scratch_stride;
         const size_t rows = (size_t)c.nslot * c.NR * 32;
         c.he = g; c.se = g + rows; c.ze = g + 2 * rows; g += 3 * rows;
         c.ridx = (int *)g; g += al2((rows + 1) / 2);
@@ -600,9 +592,8 @@ __global__ void __launch_bounds__(W1_WARPS * 32, 4) pdip1_kernel(SolveArgs S) { 
         c.nrm = g;
     }
     const int iters = (S.mode == 0) ? S.iteration : 1;
-    bool abort_chain = false;
-    for (int iter = 0; iter < iters && !abort_chain; iter++)
-        for (int l = l_begin; l < l_end && !abort_chain; l++) {
+    for (int iter = 0; iter < iters; iter++)
+        for (int l = l_begin; l < l_end; l++) {
             c.qa = l;   // batch l of one-agent batches = agent l
             if (c.qa >= N) continue;
             int rec = (S.mode == 0 ? iter * S.nbatch : S.rec_offset) + l;
@@ -613,7 +604,7 @@ __global__ void __launch_bounds__(W1_WARPS * 32, 4) pdip1_kernel(SolveArgs S) { 
                 if (st != ST_OK) atomicCAS(&S.status[cidx], (int)ST_OK, st);
             }
             if (st != ST_OK) {
-                if (S.mode == 0) abort_chain = true;   // RBPPlanner::update() aborts on the first failed batch (L158-L161)
+                if (S.mode == 0) return;
                 continue;
             }
             for (int v = lane; v < 18 * M; v += 32) {   // dummy <- vals (L182-L184)
@@ -622,7 +613,6 @@ __global__ void __launch_bounds__(W1_WARPS * 32, 4) pdip1_kernel(SolveArgs S) { 
             }
             __syncwarp();
         }
-  }
 }
 
 #endif

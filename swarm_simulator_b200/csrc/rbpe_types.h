@@ -66,8 +66,6 @@ struct SolveArgs {
     double *scratch;        // per-CTA global scratch
     size_t scratch_stride;  // doubles per CTA
     unsigned smem_bytes;    // dynamic shared memory given to the kernel
-    int *work_counter;      // pdip1_kernel: next unclaimed work item (persistent warps pull work; zeroed before the launch)
-    long total_units;       // pdip1_kernel: number of work items
 };
 
 struct ConvertArgs {

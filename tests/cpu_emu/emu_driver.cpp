@@ -53,10 +53,6 @@ extern "C" int emu_solve_many(const rbpe_problem *p, int count, int mode, rbpe_r
     auto launch = [&](long units) {
         if (warp_kernel) {
             long grid = (units + wpc - 1) / wpc;
-            if (grid > 2) grid = 2;                       // fewer resident warps than work items: exercises the work counter
-            int counter = 0;
-            S.work_counter = &counter;
-            S.total_units = units;
             S.scratch_stride = w1_scratch_doubles(N, M);
             S.smem_bytes = (unsigned)(wpc * w1_smem_doubles(M) * 8);
             std::vector<double> scratch(S.scratch_stride * grid * wpc);
