@@ -144,7 +144,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
-    ap.add_argument("--missions", type=int, default=0, help="missions per rank per step (0 = 32 per SM: 4736 = two pipeline chunks of 16 warp-resident QP chains per SM)")
+    ap.add_argument("--missions", type=int, default=0, help="missions per rank per step (0 = 48 per SM: 7104 = three pipeline chunks of 16 warp-resident QP chains per SM)")
     ap.add_argument("--pool", type=int, default=8, help="distinct synthetic missions generated per rank (tiled to --missions)")
     ap.add_argument("--ref-missions", type=int, default=64, help="missions per step of the CPU arm")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
@@ -187,7 +187,7 @@ def main():
     barrier()
     from swarm_simulator_b200 import engine as E, synth
 
-    count = args.missions or 32 * 148
+    count = args.missions or 48 * 148
     pool = make_pool(args.pool, rank)
     packed = pin(synth.pack([pool[i % len(pool)] for i in range(count)]))
     prob = E.PackedProblem(packed, sequential=True, batch_size=1)
@@ -223,7 +223,10 @@ def main():
         flush()
         eng.timer_start()
         eng.run()
-        t_dev += eng.timer_stop()
+        dt_step = eng.timer_stop()
+        t_dev += dt_step
+        if rank == 0:
+            print("resident step: %.2f ms  %s" % (dt_step, eng.timing()), file=sys.stderr)
     barrier()
     eng.download(prob, res)
     kernel_ms = eng.timing()["solve_ms"]          # PDIP + conversion kernels of the last step (events on the stream)
