@@ -295,21 +295,6 @@ RBPE_DEV void bwd_vec(TM tm, int n, const double *L, int ld, double *u) {
     for (int j = tm.rank(); j < n; j += tm.size()) u[j] /= L[(size_t)j * ld + j];
     tm.sync();
 }
-// B (n x nc, row-major, ld = ldb) <- L^-1 B ; one thread per column, no barriers inside
-template <class TM>
-RBPE_DEV void trsm_cols(TM tm, int n, const double *L, int ld, int nc, double *B, int ldb, const int *first_row) {
-    for (int c = tm.rank(); c < nc; c += tm.size()) {
-        int r0 = first_row ? first_row[c] : 0;
-        for (int r = r0; r < n; r++) {
-            double v = B[(size_t)r * ldb + c];
-            const double *Lr = L + (size_t)r * ld;
-            for (int t = r0; t < r; t++) v -= Lr[t] * B[(size_t)t * ldb + c];
-            B[(size_t)r * ldb + c] = v / Lr[r];
-        }
-    }
-    tm.sync();
-}
-
 struct QP {
     int N, M, nb, q0, NE, n, kb, nv, nr, nrext, nrint, mi;
     int c;  // mission

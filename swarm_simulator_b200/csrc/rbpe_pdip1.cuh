@@ -42,7 +42,7 @@ RBPE_DEV double rcp_nr(double a) {  // 1/a to double rounding: 20-bit hardware s
 }
 
 struct W1 {
-    int N, M, NE, NR, ncp, nslot, nr, qa, mi, sequential;
+    int N, M, NE, NR, ncp, nslot, nr, qa, sequential;
     const double *start, *goal, *radius, *segbox, *segmat;
     const float *reln;
     const double *ctrl_src;
@@ -560,7 +560,6 @@ __global__ void __launch_bounds__(W1_WARPS * 32, 4) pdip1_kernel(SolveArgs S) { 
     c.NE = S.sequential ? N - 1 : 0;
     c.NR = c.NE + 6;
     c.ncp = 6 * M; c.nslot = (c.ncp + 31) / 32; c.nr = 9 * (M > 1 ? M - 1 : 0);
-    c.mi = (6 * M - 6) * (6 + c.NE);
     c.start = S.start + (size_t)cidx * N * 9;
     c.goal = S.goal + (size_t)cidx * N * 9;
     c.radius = S.radius + (size_t)cidx * N;
