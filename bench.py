@@ -161,6 +161,8 @@ def main():
         run_reference(args, rank, world)
         return
 
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -215,8 +217,8 @@ def main():
     clocks.start()
     # ---- region A: inputs resident in HBM, K steps back to back on the engine's stream ----
     eng.upload(prob)
+    eng.run()            # untimed: sizes the scratch arena of the resident path (the warm-up above went through the pipelined call)
     eng.sync()
-    solve_ms = []
     barrier()
     t_dev = 0.0
     for _ in range(args.steps):
