@@ -142,7 +142,7 @@ RBPE_DEV void w1_pass(const W1 &c, double sa, double sb, Acc &out) {
             const double *nm = c.nrm + (size_t)m * c.NR * 3;
             const size_t rb = (size_t)slot * c.NR * 32 + lane;
             const int cnt = c.cnt[slot * 32 + lane];
-#pragma unroll 2
+#pragma unroll 1
             for (int j = 0; j < cnt; j++) {
                 const size_t r = rb + (size_t)j * 32;
                 const int e = c.ridx[r];
