@@ -52,6 +52,20 @@ __host__ __device__ inline double q_base_entry(int a, int b) {
         }
     return rint(3600.0 * s);
 }
+// The same matrix in exact integer arithmetic (3600/5 = 720 and C(4,k) divides 720), usable in constant expressions.
+constexpr int binom_i(int n, int k) { return k == 0 ? 1 : binom_i(n, k - 1) * (n - k + 1) / k; }
+constexpr int q_base_int(int a, int b) {
+    int s = 0;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            int ca = a - i, cb = b - j;
+            if (ca < 0 || ca > 3 || cb < 0 || cb > 3) continue;
+            int sa = (ca == 0 || ca == 2) ? (ca == 0 ? -1 : -3) : (ca == 1 ? 3 : 1);
+            int sb = (cb == 0 || cb == 2) ? (cb == 0 ? -1 : -3) : (cb == 1 ? 3 : 1);
+            s += sa * binom_i(2, i) * binom_i(2, j) * (720 / binom_i(4, i + j)) * sb;
+        }
+    return s;
+}
 __host__ __device__ inline double basis_entry(int i, int j) {  // coefficient of t^(5-j) in B_i^5
     int pw = 5 - j, l = pw - i;
     if (l < 0 || l > 5 - i) return 0.0;

@@ -16,9 +16,17 @@ namespace rbpe {
 
 constexpr int W1_WARPS = 4;
 
+#define QROW(a) q_base_int(a, 0), q_base_int(a, 1), q_base_int(a, 2), q_base_int(a, 3), q_base_int(a, 4), q_base_int(a, 5)
+#if defined(__CUDACC__)
+__constant__ double c_QB[36] = {QROW(0), QROW(1), QROW(2), QROW(3), QROW(4), QROW(5)};   // Q_base (build_Q_base L327-L347)
+#else
+static const double c_QB[36] = {QROW(0), QROW(1), QROW(2), QROW(3), QROW(4), QROW(5)};
+#endif
+#undef QROW
+
 __host__ __device__ inline size_t w1_smem_doubles(int M) {  // per warp
     size_t ncp = 6 * (size_t)M, nr = 9 * (size_t)(M > 1 ? M - 1 : 0);
-    return al2(6 * 3 * ncp) + al2(6 * ncp) + al2((size_t)(M > 1 ? M - 1 : 1) * 81) + al2((size_t)(M > 2 ? M - 2 : 1) * 81) + 3 * al2(nr) + 36 + al2((6 * (size_t)M + 31) / 32);
+    return al2(6 * 3 * ncp) + al2(6 * ncp) + al2((size_t)(M > 1 ? M - 1 : 1) * 81) + al2((size_t)(M > 2 ? M - 2 : 1) * 81) + 3 * al2(nr) + al2((6 * (size_t)M + 31) / 32);
 }
 __host__ __device__ inline size_t w1_scratch_doubles(int N, int M) {  // per warp, global arena
     size_t nslot = (6 * (size_t)M + 31) / 32, NR = (size_t)(N > 1 ? N - 1 : 0) + 6;   // + the 6 box rows of a control point
@@ -47,7 +55,8 @@ struct W1 {
     const float *reln;
     const double *ctrl_src;
     // shared memory (per warp); x-space index v = m*18 + k*6 + i
-    double *x, *dxa, *dx, *rdx, *vA, *vB, *Dcp, *Wd, *Wo, *sg, *sg2, *dinv, *QB;
+    double *x, *dxa, *dx, *rdx, *vA, *vB, *Dcp, *Wd, *Wo, *sg, *sg2, *dinv;
+    const double *QB;
     int *cmax;   // [nslot] largest kept-row count of a slot (warp-uniform loop bound)
     // global arena (per warp)
     // rows of a control point: e < NE the RSFC rows against the other agents, e = NE + 2k + side its box rows
@@ -577,10 +586,8 @@ __global__ void __launch_bounds__(W1_WARPS * 32, 4) pdip1_kernel(SolveArgs S) { 
         c.Wd = p; p += al2((size_t)(M > 1 ? M - 1 : 1) * 81);
         c.Wo = p; p += al2((size_t)(M > 2 ? M - 2 : 1) * 81);
         c.sg = p; p += al2(c.nr); c.sg2 = p; p += al2(c.nr); c.dinv = p; p += al2(c.nr);
-        c.QB = p; p += 36;
+        c.QB = c_QB;
         c.cmax = (int *)p;
-        for (int e = lane; e < 36; e += 32) c.QB[e] = q_base_entry(e / 6, e % 6);
-        __syncwarp();
     }
     {   // global arena of this warp
         double *g = S.scratch + (size_t)unit * S.scratch_stride;
