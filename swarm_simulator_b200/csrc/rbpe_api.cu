@@ -53,6 +53,7 @@ struct rbpe_handle {
     double tol_gap = 1e-10, tol_res = 1e-9;
     size_t smem_budget = 0, smem_optin = 0;
     int threads = 128;
+    int threads_forced = 0;   // RBPE_THREADS / rbpe_config.reserved[0] given: applies to joint batches too
     int force_cta = 0;   // RBPE_KERNEL=cta: never use the warp-per-QP kernel (A/B testing)
     int sm_count = 0;
     char err[512] = "";
@@ -125,10 +126,10 @@ extern "C" int rbpe_create(const rbpe_config *cfg, rbpe_handle **out) {
         if (cfg->tol_res > 0) h->tol_res = cfg->tol_res;
         h->smem_budget = cfg->smem_budget;
         int th = cfg->reserved[0];   // CTA size of the PDIP kernel (tuning knob): 32..256, multiple of 32
-        if (th >= 32 && th <= CTA_THREADS && th % 32 == 0) h->threads = th;
+        if (th >= 32 && th <= CTA_THREADS && th % 32 == 0) { h->threads = th; h->threads_forced = 1; }
     }
     // tuning overrides (documented in DESIGN.md): RBPE_THREADS, RBPE_SMEM_KB
-    if (const char *e = getenv("RBPE_THREADS")) { int th = atoi(e); if (th >= 32 && th <= CTA_THREADS && th % 32 == 0) h->threads = th; }
+    if (const char *e = getenv("RBPE_THREADS")) { int th = atoi(e); if (th >= 32 && th <= CTA_THREADS && th % 32 == 0) { h->threads = th; h->threads_forced = 1; } }
     if (const char *e = getenv("RBPE_KERNEL")) h->force_cta = (strcmp(e, "cta") == 0);
     if (const char *e = getenv("RBPE_CHUNK")) { int c = atoi(e); if (c > 0) h->chunk = c; }
     if (const char *e = getenv("RBPE_SMEM_KB")) { long kb = atol(e); if (kb > 0) h->smem_budget = (size_t)kb * 1024; }
@@ -324,7 +325,9 @@ static int launch_pdip_prepared(rbpe_handle *h, SolveArgs &S, long units) {
         S.smem_bytes = (unsigned)smem_for(h, S.scratch_stride);
         CU(h->scratch.reserve(S.scratch_stride * 8 * (size_t)units));
         S.scratch = h->scratch.as<double>();
-        pdip_kernel<<<(unsigned)units, h->threads, S.smem_bytes, h->stream>>>(S);
+        // joint batches use the full CTA (CTA-wide DMMA factorisation); one-agent batches through this kernel keep the knob
+        const int threads = (h->bs > 1 && !h->threads_forced) ? CTA_THREADS : h->threads;
+        pdip_kernel<<<(unsigned)units, threads, S.smem_bytes, h->stream>>>(S);
     }
     CU(cudaGetLastError());
     h->launches++;

@@ -99,6 +99,9 @@ __host__ __device__ inline long pair_index(int N, int qi, int qj) {  // lexicogr
 // per-QP scratch size (doubles) for a batch of bs agents; must match Layout below
 // ------------------------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t al2(size_t nd) { return (nd + 1) & ~(size_t)1; }
+// leading dimension of the reduced-Hessian blocks: 9 for one-agent batches (register routines), else 9b rounded up to
+// a multiple of 8 (DMMA tiles, rbpe_blockla.cuh)
+__host__ __device__ inline size_t kp_of(int nb) { return nb <= 1 ? 9 : (size_t)((9 * nb + 7) & ~7); }
 __host__ __device__ inline size_t scratch_doubles(int N, int M, int bs) {
     size_t n = 18 * (size_t)bs, kb = 9 * (size_t)bs, nv = n * M, nr = kb * (size_t)(M > 1 ? M - 1 : 0);
     size_t NE = (size_t)(N - bs > 0 ? N - bs : 0), rext = (size_t)bs * M * 6 * NE;
@@ -107,10 +110,12 @@ __host__ __device__ inline size_t scratch_doubles(int N, int M, int bs) {
         if (rl > rext) rext = rl;
     }
     size_t rint_ = (size_t)bs * (bs - 1) / 2 * 6 * M;
+    size_t kp = kp_of(bs), ninv = (kp + 31) / 32;
     size_t t = 64 + 36;
     t += 14 * al2(nv) + 3 * al2(nr);
     t += al2((size_t)M * bs * 36) + al2(rint_ * 6);                  // Dcp, Dint
-    t += al2((size_t)(M > 1 ? M - 1 : 1) * kb * kb) + al2((size_t)(M > 2 ? M - 2 : 1) * kb * kb);
+    t += al2((size_t)(M > 1 ? M - 1 : 1) * kp * kp) + al2((size_t)(M > 2 ? M - 2 : 1) * kp * kp);
+    if (bs > 1) t += al2((size_t)(M > 1 ? M - 1 : 1) * ninv * 1024) + al2((size_t)(M > 1 ? M - 1 : 1) * kp) + al2(kp + 32);   // Linv, wk, yk
     t += 4 * al2(rext) + 3 * al2((rext + 1) / 2);
     t += 7 * al2(rint_) + 3 * al2((rint_ + 1) / 2);
     return t;
@@ -123,6 +128,10 @@ __host__ __device__ inline size_t scratch_doubles(int N, int M, int bs) {
 #define RBPE_DEV inline
 #define RBPE_NOINLINE inline
 #endif
+
+}  // namespace rbpe
+#include "rbpe_blockla.cuh"
+namespace rbpe {
 
 #if defined(__CUDACC__) || defined(RBPE_EMU)
 
@@ -241,76 +250,8 @@ __global__ void convert_kernel(ConvertArgs A) {
 // ------------------------------------------------------------------------------------------------------------
 // k2: PDIP
 // ------------------------------------------------------------------------------------------------------------
-struct CtaTeam {
-    RBPE_DEV int rank() const { return threadIdx.x; }
-    RBPE_DEV int size() const { return blockDim.x; }
-    RBPE_DEV void sync() const { __syncthreads(); }
-};
-struct WarpTeam {
-    RBPE_DEV int rank() const { return threadIdx.x & 31; }
-    RBPE_DEV int size() const { return 32; }
-    RBPE_DEV void sync() const { __syncwarp(); }
-};
-
-// In-place lower Cholesky of a row-major n x n matrix (only the lower triangle is read or written).
-// Right-looking with deferred scaling: one team barrier per column.  Returns false on a non-positive pivot.
-template <class TM>
-RBPE_DEV bool chol_lower(TM tm, int n, double *A, int ld) {
-    bool ok = true;
-    for (int j = 0; j < n; j++) {
-        tm.sync();
-        double d = A[(size_t)j * ld + j];
-        if (!(d > 0)) { ok = false; d = 1.0; }
-        double inv = 1.0 / d;
-        int w = n - j - 1;
-        for (int idx = tm.rank(); idx < w * w; idx += tm.size()) {
-            int i = j + 1 + idx / w, k = j + 1 + idx % w;
-            if (k <= i) A[(size_t)i * ld + k] -= A[(size_t)i * ld + j] * A[(size_t)k * ld + j] * inv;
-        }
-    }
-    tm.sync();
-    for (int idx = tm.rank(); idx < n * n; idx += tm.size()) {
-        int i = idx / n, j = idx % n;
-        if (j < i) {
-            double d = A[(size_t)j * ld + j];
-            A[(size_t)i * ld + j] *= (d > 0) ? 1.0 / sqrt(d) : 0.0;
-        }
-    }
-    tm.sync();
-    for (int j = tm.rank(); j < n; j += tm.size()) {
-        double d = A[(size_t)j * ld + j];
-        A[(size_t)j * ld + j] = (d > 0) ? sqrt(d) : 1.0;
-    }
-    tm.sync();
-    return ok;
-}
-
-// u <- L^-1 u
-template <class TM>
-RBPE_DEV void fwd_vec(TM tm, int n, const double *L, int ld, double *u) {
-    for (int j = 0; j < n; j++) {
-        tm.sync();
-        double uj = u[j] / L[(size_t)j * ld + j];
-        for (int i = j + 1 + tm.rank(); i < n; i += tm.size()) u[i] -= L[(size_t)i * ld + j] * uj;
-    }
-    tm.sync();
-    for (int j = tm.rank(); j < n; j += tm.size()) u[j] /= L[(size_t)j * ld + j];
-    tm.sync();
-}
-// u <- L^-T u
-template <class TM>
-RBPE_DEV void bwd_vec(TM tm, int n, const double *L, int ld, double *u) {
-    for (int j = n - 1; j >= 0; j--) {
-        tm.sync();
-        double uj = u[j] / L[(size_t)j * ld + j];
-        for (int i = tm.rank(); i < j; i += tm.size()) u[i] -= L[(size_t)j * ld + i] * uj;
-    }
-    tm.sync();
-    for (int j = tm.rank(); j < n; j += tm.size()) u[j] /= L[(size_t)j * ld + j];
-    tm.sync();
-}
 struct QP {
-    int N, M, nb, q0, NE, n, kb, nv, nr, nrext, nrint, mi;
+    int N, M, nb, q0, NE, n, kb, kp, nv, nr, nrext, nrint, mi;   // kp: leading dimension of the Wd / Wo blocks (kp_of)
     int c;  // mission
     const double *start, *goal, *radius, *segbox, *segmat;
     const float *reln;
@@ -320,7 +261,8 @@ struct QP {
     // knot-space vectors (nr): r = (t-1)*9nb + (a*3+k)*3 + d, t = 1..M-1
     double *sg, *sg2;
     double *dinv;        // [nr] reciprocal Cholesky diagonal (one-agent batches)
-    double *Wd, *Wo;     // reduced Hessian Z'HZ: (M-1) diagonal blocks, (M-2) blocks (t+1,t), each 9nb x 9nb
+    double *Wd, *Wo;     // reduced Hessian Z'HZ: (M-1) diagonal blocks, (M-2) blocks (t+1,t), each kp x kp (9nb used)
+    double *Linv, *wk, *yk;   // joint batches: inverted 32 x 32 diagonal blocks of the factor, solve work vectors (rbpe_blockla.cuh)
     double *Dcp;         // [M*nb*6][6]  sum_rows w g g' restricted to one control point (3x3 symmetric over axes)
     double *Dint;        // [nrint][6]   -w n n' of a row between two batch agents
     double *he, *se, *ze, *te;   // per row: right-hand side, slack, multiplier, t = 1/(s z)  (1/s = t z, 1/z = t s)
@@ -365,8 +307,14 @@ RBPE_DEV void layout(QP &q, unsigned char *smem, size_t smem_bytes, double *gscr
     q.dinv = a.take(q.nr);
     q.Dcp = a.take((size_t)q.M * q.nb * 36);
     q.Dint = a.take((size_t)q.nrint * 6);
-    q.Wd = a.take((size_t)(q.M > 1 ? q.M - 1 : 1) * q.kb * q.kb);
-    q.Wo = a.take((size_t)(q.M > 2 ? q.M - 2 : 1) * q.kb * q.kb);
+    q.Wd = a.take((size_t)(q.M > 1 ? q.M - 1 : 1) * q.kp * q.kp);
+    q.Wo = a.take((size_t)(q.M > 2 ? q.M - 2 : 1) * q.kp * q.kp);
+    q.Linv = q.wk = q.yk = nullptr;
+    if (q.nb > 1) {
+        q.Linv = a.take((size_t)(q.M > 1 ? q.M - 1 : 1) * bla_ninv(q.kp) * BLA_W * BLA_W);
+        q.wk = a.take((size_t)(q.M > 1 ? q.M - 1 : 1) * q.kp);
+        q.yk = a.take((size_t)q.kp + 32);
+    }
     q.he = a.take(q.nrext); q.se = a.take(q.nrext); q.ze = a.take(q.nrext); q.te = a.take(q.nrext);
     q.nex = (float *)a.take(((size_t)q.nrext + 1) / 2);
     q.ney = (float *)a.take(((size_t)q.nrext + 1) / 2);
@@ -636,11 +584,13 @@ RBPE_DEV void Z_apply(const QP &q, const double *sg, double *out) {
 
 // reduced Hessian Z'(2Q + G'WG)Z from the per-control-point blocks left by the last P_INIT / P_RES pass
 RBPE_DEV void build_W(const QP &q) {
-    const int kb = q.kb, kk = kb * kb, M = q.M;
+    const int kb = q.kb, kp = q.kp, kk = kp * kp, M = q.M;
     for (int idx = threadIdx.x; idx < (M - 1) * kk; idx += blockDim.x) {
-        int t = idx / kk + 1, r = (idx % kk) / kb, c = idx % kb;
+        int t = idx / kk + 1, r = (idx % kk) / kp, c = idx % kp;
         double s = 0;
-        if (c <= r) {
+        if (r >= kb || c >= kb) {
+            s = (r == c) ? 1.0 : 0.0;   // identity padding up to a multiple of 8
+        } else if (c <= r) {
             int a = r / 9, k = (r % 9) / 3, d = r % 3, a2 = c / 9, k2 = (c % 9) / 3, d2 = c % 3;
             const double *CR = q.segmat + (t - 1) * SEGMAT + SEGMAT_CR, *CL = q.segmat + t * SEGMAT + SEGMAT_CL;
             int e = sym6(k, k2);
@@ -661,71 +611,10 @@ RBPE_DEV void build_W(const QP &q) {
     }
     // blocks (t+1, t), t = 1..M-2: only the cost couples neighbouring knots, per (agent, axis)
     for (int idx = threadIdx.x; idx < (M - 2) * kk; idx += blockDim.x) {
-        int t = idx / kk + 1, r = (idx % kk) / kb, c = idx % kb;
+        int t = idx / kk + 1, r = (idx % kk) / kp, c = idx % kp;
         double s = 0;
-        if (r / 3 == c / 3) s = q.segmat[t * SEGMAT + SEGMAT_RQ + (3 + r % 3) * 6 + c % 3];
+        if (r < kb && c < kb && r / 3 == c / 3) s = q.segmat[t * SEGMAT + SEGMAT_RQ + (3 + r % 3) * 6 + c % 3];
         q.Wo[idx] = s;
-    }
-}
-
-// block tridiagonal Cholesky of nblk diagonal blocks D (kb x kb, lower) and nblk-1 blocks O = (t+1, t)
-template <class TM>
-RBPE_DEV bool factor_bt(TM tm, int nblk, int kb, double *Dall, double *Oall) {
-    const int kk = kb * kb;
-    bool ok = true;
-    for (int t = 0; t < nblk; t++) {
-        double *D = Dall + (size_t)t * kk;
-        if (t > 0) {
-            const double *Lo = Oall + (size_t)(t - 1) * kk;
-            for (int idx = tm.rank(); idx < kk; idx += tm.size()) {
-                int r = idx / kb, c = idx % kb;
-                if (c <= r) {
-                    double s = 0;
-                    for (int k = 0; k < kb; k++) s += Lo[r * kb + k] * Lo[c * kb + k];
-                    D[idx] -= s;
-                }
-            }
-        }
-        ok = chol_lower(tm, kb, D, kb) && ok;
-        if (t < nblk - 1) {  // O_t <- O_t D^-T : row-wise forward substitution, one thread per row
-            double *O = Oall + (size_t)t * kk;
-            for (int r = tm.rank(); r < kb; r += tm.size()) {
-                for (int c = 0; c < kb; c++) {
-                    double v = O[r * kb + c];
-                    for (int k = 0; k < c; k++) v -= O[r * kb + k] * D[c * kb + k];
-                    O[r * kb + c] = v / D[c * kb + c];
-                }
-            }
-            tm.sync();
-        }
-    }
-    return ok;
-}
-
-template <class TM>
-RBPE_DEV void solve_bt(TM tm, int nblk, int kb, const double *Dall, const double *Oall, double *g) {
-    const int kk = kb * kb;
-    for (int t = 0; t < nblk; t++) {
-        if (t > 0) {
-            const double *Lo = Oall + (size_t)(t - 1) * kk;
-            for (int r = tm.rank(); r < kb; r += tm.size()) {
-                double s = 0;
-                for (int k = 0; k < kb; k++) s += Lo[r * kb + k] * g[(t - 1) * kb + k];
-                g[t * kb + r] -= s;
-            }
-        }
-        fwd_vec(tm, kb, Dall + (size_t)t * kk, kb, g + t * kb);
-    }
-    for (int t = nblk - 1; t >= 0; t--) {
-        if (t < nblk - 1) {
-            const double *Lo = Oall + (size_t)t * kk;
-            for (int c = tm.rank(); c < kb; c += tm.size()) {
-                double s = 0;
-                for (int k = 0; k < kb; k++) s += Lo[k * kb + c] * g[(t + 1) * kb + k];
-                g[t * kb + c] -= s;
-            }
-        }
-        bwd_vec(tm, kb, Dall + (size_t)t * kk, kb, g + t * kb);
     }
 }
 
@@ -839,7 +728,7 @@ RBPE_DEV void solve_bt9(int nblk, const double *Dall, const double *Oall, const 
     __syncwarp();
 }
 
-// factorisation verdict travels through q.red[60] (written by the factoring warp / thread 0, read after a barrier)
+// one-agent batches: warp 0 factors out of registers, verdict through q.red[60]; joint batches: CTA-wide DMMA routines
 RBPE_DEV bool kkt_factor(const QP &q) {
     __syncthreads();
     build_W(q);
@@ -849,17 +738,10 @@ RBPE_DEV bool kkt_factor(const QP &q) {
             bool ok = factor_bt9(q.M - 1, q.Wd, q.Wo, q.dinv);
             if (threadIdx.x == 0) q.red[60] = ok ? 0.0 : 1.0;
         }
-    } else if (q.kb <= 36) {
-        if ((threadIdx.x >> 5) == 0) {
-            bool ok = factor_bt(WarpTeam(), q.M - 1, q.kb, q.Wd, q.Wo);
-            if (threadIdx.x == 0) q.red[60] = ok ? 0.0 : 1.0;
-        }
-    } else {
-        bool ok = factor_bt(CtaTeam(), q.M - 1, q.kb, q.Wd, q.Wo);
-        if (threadIdx.x == 0) q.red[60] = ok ? 0.0 : 1.0;
+        __syncthreads();
+        return q.red[60] == 0.0;
     }
-    __syncthreads();
-    return q.red[60] == 0.0;
+    return factor_bt_blk(q.M - 1, q.kp, q.Wd, q.Wo, q.Linv);
 }
 
 // dxout (nv) = Z (Z'HZ)^-1 Z' r   with r (nv) in x-space; uses q.sg
@@ -869,10 +751,8 @@ RBPE_DEV void kkt_solve(const QP &q, const double *r, double *dxout) {
     __syncthreads();
     if (q.kb == 9) {
         if ((threadIdx.x >> 5) == 0) solve_bt9(q.M - 1, q.Wd, q.Wo, q.dinv, q.sg);
-    } else if (q.kb <= 36) {
-        if ((threadIdx.x >> 5) == 0) solve_bt(WarpTeam(), q.M - 1, q.kb, q.Wd, q.Wo, q.sg);
     } else {
-        solve_bt(CtaTeam(), q.M - 1, q.kb, q.Wd, q.Wo, q.sg);
+        solve_bt_blk(q.M - 1, q.kb, q.kp, q.Wd, q.Wo, q.Linv, q.sg, q.wk, q.yk);
     }
     __syncthreads();
     Z_apply(q, q.sg, dxout);
@@ -1145,7 +1025,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) pdip_kernel(SolveArgs S) {
             q.nb = (q.q0 + S.bs <= N) ? S.bs : N - q.q0;
             if (q.nb <= 0) continue;
             q.NE = S.sequential ? N - q.nb : 0;
-            q.n = 18 * q.nb; q.kb = 9 * q.nb; q.nv = q.n * M; q.nr = q.kb * (M > 1 ? M - 1 : 0);
+            q.n = 18 * q.nb; q.kb = 9 * q.nb; q.kp = (int)kp_of(q.nb); q.nv = q.n * M; q.nr = q.kb * (M > 1 ? M - 1 : 0);
             q.nrext = q.nb * M * 6 * q.NE;
             q.nrint = q.nb * (q.nb - 1) / 2 * 6 * M;
             {   // live rows: every row on the 6M-6 control points per agent that the endpoints do not fix

@@ -12,6 +12,8 @@ _EMU_DIR = os.path.join(_HERE, "cpu_emu")
 _EMU_LIB = os.path.join(_EMU_DIR, "librbpe_emu.so")
 _SRCS = [os.path.join(_EMU_DIR, "emu_driver.cpp"), os.path.join(_EMU_DIR, "cuda_emu.h"),
          os.path.join(_HERE, "..", "swarm_simulator_b200", "csrc", "rbpe_kernels.cuh"),
+         os.path.join(_HERE, "..", "swarm_simulator_b200", "csrc", "rbpe_blockla.cuh"),
+         os.path.join(_HERE, "..", "swarm_simulator_b200", "csrc", "rbpe_pdip1.cuh"),
          os.path.join(_HERE, "..", "swarm_simulator_b200", "csrc", "rbpe_types.h")]
 
 

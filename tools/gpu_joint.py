@@ -1,0 +1,39 @@
+"""Exploratory GPU probe (not a test): joint-batch (b > 1) workloads of BASELINE configs 1, 2, 4 and the launch default b=4:
+parity against the oracle on one mission, then kernel time over `count` tiled missions."""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+from swarm_simulator_b200 import engine as E, synth
+import oracle_util
+
+CASES = ((4, 3, 0.0, False, 4, 1001, 1184), (16, 5, 0.2, False, 16, 2001, 592), (64, 5, 0.2, True, 4, 3001, 296),
+         (64, 5, 0.2, True, 16, 3001, 148), (256, 5, 0.4, True, 32, 4001, 8))
+
+
+def main():
+    only = os.environ.get("JOINT_CASES")
+    eng = E.Engine(device=0)
+    for ci, (N, M, rho, seq, bs, seed, count) in enumerate(CASES):
+        if only and str(ci) not in only.split(","):
+            continue
+        m = synth.synth_mission(N, M, rho, seed)
+        prob1 = E.PackedProblem(synth.pack([m]), sequential=seq, batch_size=bs)
+        t = time.time(); r = eng.solve_many(prob1); dt1 = time.time() - t
+        err = float("nan"); same = None; dto = 0.0
+        if N <= 64:
+            t = time.time(); ro = oracle_util.oracle_problem(m, sequential=seq, batch_size=bs).update(); dto = time.time() - t
+            err = float(np.abs(r.ctrl[0] - ro["ctrl"]).max()); same = bool((r.qp_iters[0] == ro["batch_iters"]).all())
+        prob = E.PackedProblem(synth.pack([m] * count), sequential=seq, batch_size=bs)
+        eng.upload(prob)
+        best = 1e9
+        for rep in range(2):
+            eng.timer_start(); eng.run(); best = min(best, eng.timer_stop())
+        rr = eng.download(prob)
+        print("N=%d M=%d b=%d: rc=%d/%d iters=%s same_iters=%s err=%.2e | one mission %.1f ms (oracle %.1f ms) | %d missions: kernel %.1f ms -> %.0f agent-QPs/s" % (
+            N, M, bs, r.rc, rr.rc, r.qp_iters[0][:8], same, err, dt1 * 1e3, dto * 1e3, count, best, count * N / best * 1e3), flush=True)
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()
