@@ -134,7 +134,8 @@ extern "C" int rbpe_create(const rbpe_config *cfg, rbpe_handle **out) {
     if (const char *e = getenv("RBPE_CHUNK")) { int c = atoi(e); if (c > 0) h->chunk = c; }
     if (const char *e = getenv("RBPE_SMEM_KB")) { long kb = atol(e); if (kb > 0) h->smem_budget = (size_t)kb * 1024; }
     if (h->smem_budget == 0) h->smem_budget = 48 * 1024;
-    if (h->smem_budget > h->smem_optin) h->smem_budget = h->smem_optin;
+    // the joint-batch factorisation holds 17 KB of static shared memory next to the dynamic budget
+    if (h->smem_budget + 20 * 1024 > h->smem_optin) h->smem_budget = h->smem_optin - 20 * 1024;
     memset(&h->timing, 0, sizeof(h->timing));
     if ((e = cudaSetDevice(dev)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
         fail(nullptr, RBPE_CUDA_ERROR, "stream creation: %s", cudaGetErrorString(e));
@@ -144,7 +145,7 @@ extern "C" int rbpe_create(const rbpe_config *cfg, rbpe_handle **out) {
     for (int i = 0; i < 7; i++) cudaEventCreate(&h->ev[i]);
     cudaEventCreate(&h->tev[0]);
     cudaEventCreate(&h->tev[1]);
-    cudaFuncSetAttribute(pdip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
+    cudaFuncSetAttribute(pdip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin - 20 * 1024);
     cudaFuncSetAttribute(pdip1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
     *out = h;
     return RBPE_OK;
@@ -706,3 +707,13 @@ extern "C" int rbpe_safety_metrics(rbpe_handle *h, int N, int M, int count, cons
     }
     return RBPE_OK;
 }
+
+#ifdef RBPE_PROFILE
+// profile builds only (tools/): cumulative clock64 ticks of thread 0 per phase {setup, row passes, factor, solves, other}
+extern "C" int rbpe_prof_read(unsigned long long *out, int reset) {
+    unsigned long long z[16] = {0}; z[13] = ~0ull;
+    if (cudaMemcpyFromSymbol(out, rbpe::g_prof, sizeof(z)) != cudaSuccess) return RBPE_CUDA_ERROR;
+    if (reset && cudaMemcpyToSymbol(rbpe::g_prof, z, sizeof(z)) != cudaSuccess) return RBPE_CUDA_ERROR;
+    return RBPE_OK;
+}
+#endif

@@ -9,9 +9,10 @@
 //               rows 0..kp-1 are the diagonal block (lower triangle), rows kp..2kp-1 the block (t+1, t), which so
 //               becomes L_{t+1,t} = O_t L_tt^-T without a separate triangular solve.  The update of a block column
 //               (all earlier columns, plus L_{t,t-1} L_{t,t-1}' of the previous knot) is one DMMA k-loop per
-//               8 x 32 strip, operands straight from L1/L2; the 8-column panels inside are factored in registers.
-//   tri_inverse the 32 x 32 diagonal blocks of L_tt are inverted once per factorisation so that the two solves of an
-//               interior-point iteration are matrix-vector products (2 barriers per 32 unknowns instead of 64).
+//               8 x 32 strip, operands straight from L1/L2.
+//   chol32_warp the 32 x 32 diagonal block of a block column is factored AND inverted by one warp out of registers;
+//               the rows below then become L21 = A21 L11^-T = A21 X' by DMMA as well, and the two solves of an
+//               interior-point iteration reuse X as matrix-vector products (2 barriers per 32 unknowns).
 //   solve_bt_blk forward / backward block substitution.
 //
 // Matrices are row-major with leading dimension kp = kb rounded up to a multiple of 8 (identity padding).
@@ -44,11 +45,11 @@ RBPE_DEV void dmma884(double &d0, double &d1, double a, double b) {
 
 // acc[jt] (8 x 8 tiles jt < ntj of the strip rows A0.., columns = rows B0 + 8 jt.. of Bm) += A0[.][0..klen) * Bm[.][0..klen)'
 // tiles with jt > jt_max are skipped (upper triangle).  Warp-uniform arguments.
-RBPE_DEV void strip_mma(double (&acc)[4][2], const double *A0, const double *B0, int ld, int klen, int ntj, int jt_max) {
+RBPE_DEV void strip_mma(double (&acc)[4][2], const double *A0, const double *B0, int ld, int ldb, int klen, int ntj, int jt_max) {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const double *ap = A0 + (size_t)g * ld + t;
-    const double *bp = B0 + (size_t)g * ld + t;
-    const size_t tile = (size_t)8 * ld;
+    const double *bp = B0 + (size_t)g * ldb + t;
+    const size_t tile = (size_t)8 * ldb;
     const bool u0 = ntj > 0 && jt_max >= 0, u1 = ntj > 1 && jt_max >= 1, u2 = ntj > 2 && jt_max >= 2, u3 = ntj > 3 && jt_max >= 3;
 #pragma unroll 2
     for (int k0 = 0; k0 < klen; k0 += 4) {
@@ -60,147 +61,169 @@ RBPE_DEV void strip_mma(double (&acc)[4][2], const double *A0, const double *B0,
     }
 }
 
-// Cholesky of the 8 x 8 tile held packed (lower, row-major: l[r(r+1)/2 + c]) in registers; returns false on a
-// non-positive pivot.  On exit l holds L and di[c] = 1 / L[c][c].
-RBPE_DEV bool chol8_reg(double (&l)[36], double (&di)[8]) {
+// One warp: Cholesky of the wJ x wJ (wJ <= 32) diagonal block at Db (leading dimension ld, lower triangle) and its
+// inverse X (32 x 32, row-major; identity beyond wJ).  Compact rolled code (the kernel is instruction-fetch bound):
+// lane i owns row i of the trailing matrix in a register window that rotates by one column per step; the columns of L
+// are exchanged through a shared-memory tile Ls (64 x 32, rows 32..63 zero so that the window can run past the block)
+// as warp-wide broadcast loads.  No global memory traffic inside the two loops (a store followed by __syncwarp costs a
+// full L2 round trip).  The inverse is a second pass of the same shape (lane c owns column c of L^-1).
+// Returns false on a non-positive pivot.
+RBPE_NOINLINE bool chol32_warp(double *Db, int ld, int wJ, double *X) {
+    RBPE_STATIC_SMEM(double, Ls, 64 * 32 + 32);
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
     bool ok = true;
+    double a[32];
+    PROF_DECL;
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-        double d = l[j * (j + 1) / 2 + j];
+    for (int k = 0; k < 32; k++) {
+        a[k] = (lane < wJ && k <= lane) ? Db[(size_t)lane * ld + k] : ((k == lane) ? 1.0 : 0.0);
+        Ls[(32 + k) * 32 + lane] = 0.0;
+    }
+    PROF(10);
+#pragma unroll 1
+    for (int j = 0; j < wJ; j++) {
+        double piv = __shfl_sync(FULL, a[0], j);
+        if (!(piv > 0)) { ok = false; piv = 1.0; }
+        const double inv = rsqrt(piv);
+        const double a0 = a[0] * inv;                    // L[lane][j] for lane >= j
+        Ls[lane * 32 + j] = (lane >= j) ? a0 : 0.0;
+        if (lane == j) Ls[2048 + j] = inv;
+        __syncwarp();
+        const double *col = Ls + j * 33;                 // col[k * 32] = L[j + k][j]
+        // loads staged 8 at a time ahead of their FMAs (at the 128-register cap the compiler otherwise pairs every
+        // load with its FMA and exposes the shared-memory latency 31 times per column)
 #pragma unroll
-        for (int k = 0; k < j; k++) d -= l[j * (j + 1) / 2 + k] * l[j * (j + 1) / 2 + k];
-        if (!(d > 0)) { ok = false; d = 1.0; }
-        const double inv = rsqrt(d);
-        di[j] = inv;
-        l[j * (j + 1) / 2 + j] = d * inv;
+        for (int k0 = 0; k0 < 32; k0 += 8) {
+            double c[8];
 #pragma unroll
-        for (int r = j + 1; r < 8; r++) {
-            double v = l[r * (r + 1) / 2 + j];
+            for (int k = 0; k < 8; k++) c[k] = col[(k0 + k + 1) * 32];   // row 32 + j of Ls is zero
 #pragma unroll
-            for (int k = 0; k < j; k++) v -= l[r * (r + 1) / 2 + k] * l[j * (j + 1) / 2 + k];
-            l[r * (r + 1) / 2 + j] = v * inv;
+            for (int k = 0; k < 8; k++) a[k0 + k] = ((k0 + k + 1 < 32) ? a[(k0 + k + 1) & 31] : 0.0) - a0 * c[k];
         }
     }
+    __syncwarp();
+#if defined(RBPE_PROFILE) && defined(__CUDACC__)
+    if (threadIdx.x == 0 && wJ == 32) { unsigned long long d = (unsigned long long)(clock64() - prof_t0); atomicMin(&g_prof[13], d); atomicMax(&g_prof[14], d); atomicAdd(&g_prof[15], 1ull); }
+#endif
+    PROF(11);
+    // inverse: a = residual of column `lane` of L X = I, window rotating with the row index
+#pragma unroll
+    for (int k = 0; k < 32; k++) a[k] = (k == lane) ? 1.0 : 0.0;
+#pragma unroll 1
+    for (int j = 0; j < 32; j++) {
+        double xj = a[0];
+        if (j < wJ) {   // warp-uniform
+            xj *= Ls[2048 + j];
+            const double *col = Ls + j * 33;
+#pragma unroll
+            for (int k0 = 0; k0 < 32; k0 += 8) {
+                double c[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) c[k] = col[(k0 + k + 1) * 32];
+#pragma unroll
+                for (int k = 0; k < 8; k++) a[k0 + k] = ((k0 + k + 1 < 32) ? a[(k0 + k + 1) & 31] : 0.0) - c[k] * xj;
+            }
+        } else {
+#pragma unroll
+            for (int k = 1; k < 32; k++) a[k - 1] = a[k];
+            a[31] = 0.0;
+        }
+        X[j * BLA_W + lane] = xj;
+    }
+#pragma unroll 1
+    for (int r = 0; r < wJ; r++)
+        if (lane <= r) Db[(size_t)r * ld + lane] = Ls[r * 32 + lane];
+    __syncwarp();
+    PROF(12);
     return ok;
 }
 
 // Factor the tall matrix [D; O] (see the header).  Pm = L_{t,t-1} of the previous knot (kp x kp) or null.
 // Linv receives the inverses of the 32 x 32 diagonal blocks of L ([bla_ninv][32*32], row-major, lower).
-// Every thread factors the same diagonal tiles, so the verdict is uniform.  All threads of the CTA must call.
-RBPE_DEV bool chol_tall(int kp, double *D, double *O, const double *Pm, double *Linv) {
+// `flag`: one double of shared / global scratch for the verdict of warp 0.  All threads of the CTA must call.
+RBPE_NOINLINE bool chol_tall(int kp, double *D, double *O, const double *Pm, double *Linv, double *flag) {
     const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, nw = nt >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
     const int ntile = kp >> 3;
-    bool ok = true;
+    PROF_DECL;
+    if (tid == 0) *flag = 0.0;
     for (int j0 = 0; j0 < kp; j0 += BLA_W) {
         const int wJ = (kp - j0 < BLA_W) ? kp - j0 : BLA_W, ntJ = wJ >> 3;
-        // ---- 1. left-looking update of the block column ----
-        if (j0 > 0 || Pm) {
-            const int nsD = (kp - j0) >> 3, nsO = O ? ntile : 0;
-            for (int s = warp; s < nsD + nsO; s += nw) {
-                const bool isO = s >= nsD;
-                const int i0 = isO ? (s - nsD) * 8 : j0 + s * 8;
-                double *C0 = (isO ? O : D) + (size_t)i0 * kp;
-                const int jt_max = isO ? 3 : (i0 - j0) >> 3;
-                double acc[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
-                if (j0 > 0) strip_mma(acc, C0, D + (size_t)j0 * kp, kp, j0, ntJ, jt_max);
-                if (!isO && Pm) strip_mma(acc, Pm + (size_t)i0 * kp, Pm + (size_t)j0 * kp, kp, kp, ntJ, jt_max);
-#pragma unroll
-                for (int jt = 0; jt < 4; jt++)
-                    if (jt < ntJ && jt <= jt_max) {
-                        double *c = C0 + (size_t)g * kp + j0 + 8 * jt + 2 * t4;
-                        c[0] -= acc[jt][0];
-                        c[1] -= acc[jt][1];
-                    }
-            }
-            __syncthreads();
-        }
-        // ---- 2. the block column itself, 8 columns at a time ----
-        for (int s8 = 0; s8 < ntJ; s8++) {
-            const int c0 = j0 + 8 * s8;
-            double l[36], di[8];
-#pragma unroll
-            for (int r = 0; r < 8; r++)
-#pragma unroll
-                for (int c = 0; c <= r; c++) l[r * (r + 1) / 2 + c] = D[(size_t)(c0 + r) * kp + c0 + c];
-            if (!chol8_reg(l, di)) ok = false;
-            const int nrD = kp - c0 - 8, nrT = nrD + (O ? kp : 0);
-            for (int r = tid; r < nrT; r += nt) {   // rows below the tile: v <- v L11^-T
-                double *rp = (r < nrD) ? D + (size_t)(c0 + 8 + r) * kp + c0 : O + (size_t)(r - nrD) * kp + c0;
-                double v[8];
-#pragma unroll
-                for (int c = 0; c < 8; c++) v[c] = rp[c];
-#pragma unroll
-                for (int c = 0; c < 8; c++) {
-                    double sm = v[c];
-#pragma unroll
-                    for (int k = 0; k < c; k++) sm -= v[k] * l[c * (c + 1) / 2 + k];
-                    v[c] = sm * di[c];
-                }
-#pragma unroll
-                for (int c = 0; c < 8; c++) rp[c] = v[c];
-            }
-            __syncthreads();   // every thread has read the diagonal tile
-            if (tid == 0) {
-#pragma unroll
-                for (int r = 0; r < 8; r++)
-#pragma unroll
-                    for (int c = 0; c < 8; c++) D[(size_t)(c0 + r) * kp + c0 + c] = (c <= r) ? l[r * (r + 1) / 2 + c] : 0.0;
-            }
-            // in-panel update of the remaining columns of the block column (k = 8)
-            if (s8 + 1 < ntJ) {
-                const int r0 = c0 + 8, nsD = (kp - r0) >> 3, nsO = O ? ntile : 0, ntj = ntJ - s8 - 1;
-                for (int s = warp; s < nsD + nsO; s += nw) {
+        double *X = Linv + (size_t)(j0 / BLA_W) * BLA_W * BLA_W;
+        // ---- 1. left-looking update of the block column: C -= L[., 0..j0) L[J, 0..j0)'  (+ the previous knot's block).
+        // 1a: the strips of the diagonal block (all warps), barrier; 1b: the remaining strips by warps 1.., overlapped
+        // with 2: warp 0 factors and inverts the diagonal block (a serial 32-step chain).
+        const int nsD = (kp - j0) >> 3, nsO = O ? ntile : 0;
+        const bool upd = (j0 > 0 || Pm);
+        for (int pass = 0; pass < 2; pass++) {
+            const bool solo = nw < 2;   // a one-warp CTA (tuning knob) cannot overlap: everything in pass 0
+            const int s_begin = pass == 0 ? 0 : ntJ, s_end = (pass == 0 && !solo) ? ntJ : nsD + nsO;
+            const int w = pass == 0 ? warp : warp - 1, wn = pass == 0 ? nw : nw - 1;
+            if (upd && w >= 0 && !(solo && pass == 1))
+                for (int s = s_begin + w; s < s_end; s += wn) {
                     const bool isO = s >= nsD;
-                    const int i0 = isO ? (s - nsD) * 8 : r0 + s * 8;
+                    const int i0 = isO ? (s - nsD) * 8 : j0 + s * 8;
                     double *C0 = (isO ? O : D) + (size_t)i0 * kp;
-                    const int jt_max = isO ? 3 : (i0 - r0) >> 3;
+                    const int jt_max = isO ? 3 : (i0 - j0) >> 3;
                     double acc[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
-                    strip_mma(acc, C0 + c0, D + (size_t)r0 * kp + c0, kp, 8, ntj, jt_max);
+                    if (j0 > 0) strip_mma(acc, C0, D + (size_t)j0 * kp, kp, kp, j0, ntJ, jt_max);
+                    if (!isO && Pm) strip_mma(acc, Pm + (size_t)i0 * kp, Pm + (size_t)j0 * kp, kp, kp, kp, ntJ, jt_max);
 #pragma unroll
-                    for (int jt = 0; jt < 3; jt++)
-                        if (jt < ntj && jt <= jt_max) {
-                            double *c = C0 + (size_t)g * kp + r0 + 8 * jt + 2 * t4;
+                    for (int jt = 0; jt < 4; jt++)
+                        if (jt < ntJ && jt <= jt_max) {
+                            double *c = C0 + (size_t)g * kp + j0 + 8 * jt + 2 * t4;
                             c[0] -= acc[jt][0];
                             c[1] -= acc[jt][1];
                         }
                 }
+            if (pass == 0) {
+                if (upd) __syncthreads();
+                PROF(6);
+                // ---- 2. diagonal block: factor + invert, one warp ----
+                if (warp == 0) {
+                    bool ok = chol32_warp(D + (size_t)j0 * kp + j0, kp, wJ, X);
+                    if (!ok && lane == 0) *flag = 1.0;
+                }
             }
-            __syncthreads();
         }
-    }
-    // ---- inverses of the 32 x 32 diagonal blocks: one warp per block, one lane per column ----
-    const int ninv = bla_ninv(kp);
-    for (int J = warp; J < ninv; J += nw) {
-        const int j0 = J * BLA_W, wJ = (kp - j0 < BLA_W) ? kp - j0 : BLA_W;
-        double *X = Linv + (size_t)J * BLA_W * BLA_W;
-        const int c = lane;
-        for (int r = 0; r < BLA_W; r++) {
-            double v = 0.0;
-            if (c < wJ && r < wJ && r >= c) {
-                const double *Lr = D + (size_t)(j0 + r) * kp + j0;
-                double sm = (r == c) ? 1.0 : 0.0;
-                for (int k = c; k < r; k++) sm -= Lr[k] * X[k * BLA_W + c];
-                v = sm / Lr[r];
+        __syncthreads();
+        PROF(7);
+        // ---- 3. rows below: L21 = A21 L11^-T = A21 X'  (DMMA, k = wJ) ----
+        {
+            const int r0 = j0 + wJ, nsD = (kp - r0) >> 3, nsO = O ? ntile : 0;
+            for (int s = warp; s < nsD + nsO; s += nw) {
+                const bool isO = s >= nsD;
+                const int i0 = isO ? (s - nsD) * 8 : r0 + s * 8;
+                double *C0 = (isO ? O : D) + (size_t)i0 * kp + j0;
+                double acc[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+                strip_mma(acc, C0, X, kp, BLA_W, wJ, ntJ, 3);
+#pragma unroll
+                for (int jt = 0; jt < 4; jt++)
+                    if (jt < ntJ) {
+                        double *c = C0 + (size_t)g * kp + 8 * jt + 2 * t4;
+                        c[0] = acc[jt][0];
+                        c[1] = acc[jt][1];
+                    }
             }
-            X[r * BLA_W + c] = v;   // a lane only ever re-reads its own column
         }
+        __syncthreads();
+        PROF(8);
     }
-    __syncthreads();
-    return ok;
+    return *flag == 0.0;
 }
 
 // block tridiagonal Cholesky: Dall (nblk diagonal blocks, lower), Oall (nblk-1 blocks (t+1, t)), ld = kp
-RBPE_DEV bool factor_bt_blk(int nblk, int kp, double *Dall, double *Oall, double *Linv) {
+RBPE_DEV bool factor_bt_blk(int nblk, int kp, double *Dall, double *Oall, double *Linv, double *flag) {
     const size_t kk = (size_t)kp * kp, li = (size_t)bla_ninv(kp) * BLA_W * BLA_W;
     bool ok = true;
     for (int t = 0; t < nblk; t++)
         ok = chol_tall(kp, Dall + t * kk, (t < nblk - 1) ? Oall + t * kk : nullptr, (t > 0) ? Oall + (t - 1) * kk : nullptr,
-                       Linv + t * li) && ok;
+                       Linv + t * li, flag) && ok;
     return ok;
 }
 
 // g (nblk blocks of kb, stride kb) <- (L L')^-1 g.  w: nblk*kp work doubles, y: kp + 32 work doubles.
-RBPE_DEV void solve_bt_blk(int nblk, int kb, int kp, const double *Dall, const double *Oall, const double *Linv, double *g,
+RBPE_NOINLINE void solve_bt_blk(int nblk, int kb, int kp, const double *Dall, const double *Oall, const double *Linv, double *g,
                            double *w, double *y) {
     const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, nw = nt >> 5, lane = tid & 31;
     const size_t kk = (size_t)kp * kp, li = (size_t)bla_ninv(kp) * BLA_W * BLA_W;
@@ -280,6 +303,105 @@ RBPE_DEV void solve_bt_blk(int nblk, int kb, int kp, const double *Dall, const d
     }
     __syncthreads();
 }
+
+// ---- one-agent batches (9 x 9 blocks): the whole block tridiagonal system handled by one warp out of registers ----
+// lanes 0..8 hold the rows of the diagonal block D_t, lanes 9..17 the rows of O_t = block (t+1, t).  On exit D holds
+// L_tt (lower), O holds L_{t+1,t}, dinv[t*9+j] = 1 / L_tt[j][j].  Rolled (compact code): the kernels are instruction-fetch bound (ncu r1: GPC
+// instruction cache at 79 % of its request rate, SM I-cache hit rate 70 %), so code size matters more than a few
+// extra moves.  Column loop rolled with a register rotation: a[0] always holds the current column of the lane's row.
+RBPE_NOINLINE bool factor_bt9r(int nblk, double *Dall, double *Oall, double *dinv) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const bool isD = lane < 9, isO = lane >= 9 && lane < 18;
+    const int row = isD ? lane : (isO ? lane - 9 : 0);
+    bool ok = true;
+#pragma unroll 1
+    for (int t = 0; t < nblk; t++) {
+        double *D = Dall + t * 81, *O = Oall + t * 81;
+        const bool hasO = t < nblk - 1;
+        double a[9];
+#pragma unroll
+        for (int c = 0; c < 9; c++) a[c] = isD ? D[row * 9 + c] : ((isO && hasO) ? O[row * 9 + c] : 0.0);
+        if (t > 0) {  // D_t -= L_{t,t-1} L_{t,t-1}'
+            const double *P = Oall + (t - 1) * 81;
+#pragma unroll 1
+            for (int k = 0; k < 9; k++) {
+                double pk = isD ? P[row * 9 + k] : 0.0;
+#pragma unroll
+                for (int c = 0; c < 9; c++) a[c] -= pk * P[c * 9 + k];
+            }
+        }
+#pragma unroll 1
+        for (int j = 0; j < 9; j++) {
+            double piv = __shfl_sync(FULL, a[0], j);
+            if (!(piv > 0)) { ok = false; piv = 1.0; }
+            double inv = rsqrt(piv);
+            double a0 = a[0] * inv;                 // column j of L_tt (rows >= j) and of L_{t+1,t}
+            if (isD) D[row * 9 + j] = (j <= row) ? a0 : 0.0;
+            else if (isO && hasO) O[row * 9 + j] = a0;
+            if (lane == j) dinv[t * 9 + j] = inv;
+#pragma unroll
+            for (int k = 1; k < 9; k++) {
+                double lk = __shfl_sync(FULL, a0, (j + k) & 31);   // L[j+k][j] from the lane of row j+k (unused beyond 8)
+                a[k - 1] = a[k] - a0 * lk;                        // update column j+k and rotate it into slot k-1
+            }
+            a[8] = 0.0;
+        }
+        __syncwarp();
+    }
+    return ok;
+}
+
+RBPE_NOINLINE void solve_bt9r(int nblk, const double *Dall, const double *Oall, const double *dinv, double *g) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const bool act = lane < 9;
+    const int row = act ? lane : 0;
+    double prev = 0;
+#pragma unroll 1
+    for (int t = 0; t < nblk; t++) {  // L w = g
+        const double *L = Dall + t * 81;
+        double gv = act ? g[t * 9 + row] : 0.0, di = act ? dinv[t * 9 + row] : 0.0;
+        if (t > 0) {
+            const double *P = Oall + (t - 1) * 81;
+            double sm = 0;
+#pragma unroll 1
+            for (int k = 0; k < 9; k++) sm += P[row * 9 + k] * __shfl_sync(FULL, prev, k);
+            gv -= sm;
+        }
+#pragma unroll 1
+        for (int j = 0; j < 9; j++) {
+            if (lane == j) gv *= di;
+            double gj = __shfl_sync(FULL, gv, j);
+            if (act && lane > j) gv -= L[row * 9 + j] * gj;
+        }
+        prev = gv;
+        if (act) g[t * 9 + row] = gv;
+    }
+    double next = 0;
+#pragma unroll 1
+    for (int t = nblk - 1; t >= 0; t--) {  // L' y = w
+        const double *L = Dall + t * 81;
+        double gv = act ? g[t * 9 + row] : 0.0, di = act ? dinv[t * 9 + row] : 0.0;
+        if (t < nblk - 1) {
+            const double *P = Oall + t * 81;
+            double sm = 0;
+#pragma unroll 1
+            for (int k = 0; k < 9; k++) sm += P[k * 9 + row] * __shfl_sync(FULL, next, k);
+            gv -= sm;
+        }
+#pragma unroll 1
+        for (int j = 8; j >= 0; j--) {
+            if (lane == j) gv *= di;
+            double gj = __shfl_sync(FULL, gv, j);
+            if (act && lane < j) gv -= L[j * 9 + row] * gj;
+        }
+        next = gv;
+        if (act) g[t * 9 + row] = gv;
+    }
+    __syncwarp();
+}
+
 
 #endif
 }  // namespace rbpe

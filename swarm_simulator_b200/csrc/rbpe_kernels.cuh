@@ -124,9 +124,21 @@ __host__ __device__ inline size_t scratch_doubles(int N, int M, int bs) {
 #ifdef __CUDACC__
 #define RBPE_DEV __device__ __forceinline__
 #define RBPE_NOINLINE __device__ __noinline__
+#define RBPE_STATIC_SMEM(type, name, n) __shared__ __align__(16) type name[n]
 #else
 #define RBPE_DEV inline
 #define RBPE_NOINLINE inline
+#define RBPE_STATIC_SMEM(type, name, n) static type name[n]   /* emulator: blocks run one after another */
+#endif
+
+// Phase timers of the CTA-per-QP kernel (tools/gpu_joint.py with a -DRBPE_PROFILE build; never in the product build)
+#if defined(RBPE_PROFILE) && defined(__CUDACC__)
+__device__ unsigned long long g_prof[16];
+#define PROF_DECL long long prof_t0 = clock64()
+#define PROF(slot) do { if (threadIdx.x == 0) { long long t1_ = clock64(); atomicAdd(&g_prof[slot], (unsigned long long)(t1_ - prof_t0)); prof_t0 = t1_; } } while (0)
+#else
+#define PROF_DECL
+#define PROF(slot)
 #endif
 
 }  // namespace rbpe
@@ -618,139 +630,31 @@ RBPE_DEV void build_W(const QP &q) {
     }
 }
 
-// ---- one-agent batches (9x9 blocks): the whole block tridiagonal system handled by one warp out of registers -------
-// lanes 0..8 hold the rows of the diagonal block D_t, lanes 9..17 the rows of O_t = block (t+1, t).
-// On exit D holds L_tt (lower), O holds L_{t+1,t}, dinv[t*9+j] = 1 / L_tt[j][j].
-RBPE_DEV bool factor_bt9(int nblk, double *Dall, double *Oall, double *dinv) {
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const bool isD = lane < 9, isO = lane >= 9 && lane < 18;
-    const int row = isD ? lane : lane - 9;
-    bool ok = true;
-    for (int t = 0; t < nblk; t++) {
-        double *D = Dall + t * 81, *O = Oall + t * 81;
-        const bool hasO = t < nblk - 1;
-        double a[9];
-#pragma unroll
-        for (int c = 0; c < 9; c++) a[c] = isD ? D[row * 9 + c] : ((isO && hasO) ? O[row * 9 + c] : 0.0);
-        if (t > 0 && isD) {  // D_t -= L_{t,t-1} L_{t,t-1}'
-            const double *P = Oall + (t - 1) * 81;
-            double pr[9];
-#pragma unroll
-            for (int k = 0; k < 9; k++) pr[k] = P[row * 9 + k];
-#pragma unroll
-            for (int c = 0; c < 9; c++) {
-                double sm = 0;
-#pragma unroll
-                for (int k = 0; k < 9; k++) sm += pr[k] * P[c * 9 + k];
-                a[c] -= sm;
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 9; j++) {
-            double piv = __shfl_sync(FULL, a[j], j);
-            if (!(piv > 0)) { ok = false; piv = 1.0; }
-            double inv = rsqrt(piv);
-            a[j] *= inv;                       // column j of L_tt (rows >= j) and of L_{t+1,t}
-            if (lane == j) dinv[t * 9 + j] = inv;
-#pragma unroll
-            for (int k = j + 1; k < 9; k++) {
-                double lkj = __shfl_sync(FULL, a[j], k);
-                a[k] -= a[j] * lkj;            // only entries on or below the diagonal are meaningful for D rows
-            }
-        }
-        if (isD) {
-#pragma unroll
-            for (int c = 0; c < 9; c++) D[row * 9 + c] = (c <= row) ? a[c] : 0.0;
-        } else if (isO && hasO) {
-#pragma unroll
-            for (int c = 0; c < 9; c++) O[row * 9 + c] = a[c];
-        }
-        __syncwarp();
-    }
-    return ok;
-}
-
-RBPE_DEV void solve_bt9(int nblk, const double *Dall, const double *Oall, const double *dinv, double *g) {
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const bool act = lane < 9;
-    double prev = 0;
-    for (int t = 0; t < nblk; t++) {  // L w = g
-        const double *L = Dall + t * 81;
-        double gv = act ? g[t * 9 + lane] : 0.0, di = act ? dinv[t * 9 + lane] : 0.0, lrow[9];
-#pragma unroll
-        for (int c = 0; c < 9; c++) lrow[c] = act ? L[lane * 9 + c] : 0.0;
-        if (t > 0) {
-            const double *P = Oall + (t - 1) * 81;
-            double sm = 0;
-#pragma unroll
-            for (int k = 0; k < 9; k++) {
-                double gk = __shfl_sync(FULL, prev, k);
-                if (act) sm += P[lane * 9 + k] * gk;
-            }
-            gv -= sm;
-        }
-#pragma unroll
-        for (int j = 0; j < 9; j++) {
-            if (lane == j) gv *= di;
-            double gj = __shfl_sync(FULL, gv, j);
-            if (act && lane > j) gv -= lrow[j] * gj;
-        }
-        prev = gv;
-        if (act) g[t * 9 + lane] = gv;
-    }
-    double next = 0;
-    for (int t = nblk - 1; t >= 0; t--) {  // L' y = w
-        const double *L = Dall + t * 81;
-        double gv = act ? g[t * 9 + lane] : 0.0, di = act ? dinv[t * 9 + lane] : 0.0, lcol[9];
-#pragma unroll
-        for (int j = 0; j < 9; j++) lcol[j] = act ? L[j * 9 + lane] : 0.0;
-        if (t < nblk - 1) {
-            const double *P = Oall + t * 81;
-            double sm = 0;
-#pragma unroll
-            for (int k = 0; k < 9; k++) {
-                double yk = __shfl_sync(FULL, next, k);
-                if (act) sm += P[k * 9 + lane] * yk;
-            }
-            gv -= sm;
-        }
-#pragma unroll
-        for (int j = 8; j >= 0; j--) {
-            if (lane == j) gv *= di;
-            double gj = __shfl_sync(FULL, gv, j);
-            if (act && lane < j) gv -= lcol[j] * gj;
-        }
-        next = gv;
-        if (act) g[t * 9 + lane] = gv;
-    }
-    __syncwarp();
-}
-
 // one-agent batches: warp 0 factors out of registers, verdict through q.red[60]; joint batches: CTA-wide DMMA routines
-RBPE_DEV bool kkt_factor(const QP &q) {
+RBPE_NOINLINE bool kkt_factor(const QP &q) {
+    PROF_DECL;
     __syncthreads();
     build_W(q);
     __syncthreads();
+    PROF(5);
     if (q.kb == 9) {
         if ((threadIdx.x >> 5) == 0) {
-            bool ok = factor_bt9(q.M - 1, q.Wd, q.Wo, q.dinv);
+            bool ok = factor_bt9r(q.M - 1, q.Wd, q.Wo, q.dinv);
             if (threadIdx.x == 0) q.red[60] = ok ? 0.0 : 1.0;
         }
         __syncthreads();
         return q.red[60] == 0.0;
     }
-    return factor_bt_blk(q.M - 1, q.kp, q.Wd, q.Wo, q.Linv);
+    return factor_bt_blk(q.M - 1, q.kp, q.Wd, q.Wo, q.Linv, q.red + 60);
 }
 
 // dxout (nv) = Z (Z'HZ)^-1 Z' r   with r (nv) in x-space; uses q.sg
-RBPE_DEV void kkt_solve(const QP &q, const double *r, double *dxout) {
+RBPE_NOINLINE void kkt_solve(const QP &q, const double *r, double *dxout) {
     __syncthreads();
     Zt_apply(q, r, q.sg);
     __syncthreads();
     if (q.kb == 9) {
-        if ((threadIdx.x >> 5) == 0) solve_bt9(q.M - 1, q.Wd, q.Wo, q.dinv, q.sg);
+        if ((threadIdx.x >> 5) == 0) solve_bt9r(q.M - 1, q.Wd, q.Wo, q.dinv, q.sg);
     } else {
         solve_bt_blk(q.M - 1, q.kb, q.kp, q.Wd, q.Wo, q.Linv, q.sg, q.wk, q.yk);
     }
@@ -863,8 +767,10 @@ RBPE_DEV int pdip_solve(const QP &q_in, int max_iter, double tol_gap, double tol
     QP q = q_in;
     const int tid = threadIdx.x, nt = blockDim.x;
     Acc acc;
+    PROF_DECL;
     setup_rows(q);
     __syncthreads();
+    PROF(0);
     int status = ST_NOT_CONVERGED, it = 0;
     double obj = 0, gap = 0, nrd = 0, nrg = 0, hn = 0;
     bool go = true;
@@ -921,7 +827,9 @@ RBPE_DEV int pdip_solve(const QP &q_in, int max_iter, double tol_gap, double tol
     double sigmu = 0, al = 0;   // pending step of the previous iteration, applied inside the next residual pass
     for (it = 0; go && it < max_iter; it++) {
         // ---- residuals (with the previous step's s, z update fused in) ----
+        PROF(4);
         row_pass<P_RES>(q, sigmu, al, acc);  // vA = G'z, vB = G't_aff, Dcp/Dint; s1 = s'z, s2 = h'z, mx = |rg|
+        PROF(1);
         { double *t1 = q.si; q.si = q.si_w; q.si_w = t1; t1 = q.zi; q.zi = q.zi_w; q.zi_w = t1; t1 = q.ti; q.ti = q.ti_w; q.ti_w = t1; }
         if (al != 0.0) {
             for (int v = tid; v < q.nv; v += nt) q.x[v] += al * q.dx[v];
@@ -949,20 +857,27 @@ RBPE_DEV int pdip_solve(const QP &q_in, int max_iter, double tol_gap, double tol
         }
         if (hz < 0 && mcert / (-hz) < 1e-8) { status = ST_INFEASIBLE; break; }  // Farkas certificate (reduced problem)
         // ---- factor with W = z/s ----
+        PROF(4);
         if (!kkt_factor(q)) { status = ST_NOT_CONVERGED; break; }
+        PROF(2);
         // ---- affine direction ----
         for (int v = tid; v < q.nv; v += nt) q.vB[v] = -q.rdx[v] + q.vB[v];
         kkt_solve(q, q.vB, q.dxa);
+        PROF(3);
         row_pass<P_AFF>(q, 0, 0, acc);       // mx = ratio test (max form); s1, s2 = linear / quadratic coefficient of mu_aff(a)
+        PROF(1);
         double aa = (acc.mx > 1.0) ? 1.0 / acc.mx : 1.0;
         double mua = (mu * (q.mi > 0 ? q.mi : 1) + aa * acc.s1 + aa * aa * acc.s2) / (q.mi > 0 ? q.mi : 1);
         double sigma = (mu > 0) ? (mua / mu) * (mua / mu) * (mua / mu) : 0.0;
         sigmu = sigma * mu;
         // ---- corrector ----
         row_pass<P_COR>(q, sigmu, 0, acc);
+        PROF(1);
         for (int v = tid; v < q.nv; v += nt) q.vA[v] = -q.rdx[v] + q.vA[v];
         kkt_solve(q, q.vA, q.dx);
+        PROF(3);
         row_pass<P_STEP>(q, sigmu, 0, acc);
+        PROF(1);
         al = (0.99 < acc.mx) ? 0.99 / acc.mx : 1.0;   // min(1, 0.99 * max step); s, z, x advance at the top of the next iteration
     }
     __syncthreads();
@@ -992,7 +907,10 @@ RBPE_DEV int pdip_solve(const QP &q_in, int max_iter, double tol_gap, double tol
     return status;
 }
 
-__global__ void __launch_bounds__(CTA_THREADS, 2) pdip_kernel(SolveArgs S) {
+#ifndef RBPE_PDIP_MINB
+#define RBPE_PDIP_MINB 2
+#endif
+__global__ void __launch_bounds__(CTA_THREADS, RBPE_PDIP_MINB) pdip_kernel(SolveArgs S) {
     RBPE_DYN_SMEM(smem);
     const int N = S.N, M = S.M;
     int c, l_begin, l_end;

@@ -182,102 +182,6 @@ RBPE_DEV void w1_pass(const W1 &c, double sa, double sb, Acc &out) {
     out = acc;
 }
 
-// Rolled (compact-code) versions of factor_bt9 / solve_bt9: the kernel is instruction-fetch bound (ncu r1: GPC
-// instruction cache at 79 % of its request rate, SM I-cache hit rate 70 %), so code size matters more than a few
-// extra moves.  Column loop rolled with a register rotation: a[0] always holds the current column of the lane's row.
-RBPE_NOINLINE bool factor_bt9r(int nblk, double *Dall, double *Oall, double *dinv) {
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const bool isD = lane < 9, isO = lane >= 9 && lane < 18;
-    const int row = isD ? lane : (isO ? lane - 9 : 0);
-    bool ok = true;
-#pragma unroll 1
-    for (int t = 0; t < nblk; t++) {
-        double *D = Dall + t * 81, *O = Oall + t * 81;
-        const bool hasO = t < nblk - 1;
-        double a[9];
-#pragma unroll
-        for (int c = 0; c < 9; c++) a[c] = isD ? D[row * 9 + c] : ((isO && hasO) ? O[row * 9 + c] : 0.0);
-        if (t > 0) {  // D_t -= L_{t,t-1} L_{t,t-1}'
-            const double *P = Oall + (t - 1) * 81;
-#pragma unroll 1
-            for (int k = 0; k < 9; k++) {
-                double pk = isD ? P[row * 9 + k] : 0.0;
-#pragma unroll
-                for (int c = 0; c < 9; c++) a[c] -= pk * P[c * 9 + k];
-            }
-        }
-#pragma unroll 1
-        for (int j = 0; j < 9; j++) {
-            double piv = __shfl_sync(FULL, a[0], j);
-            if (!(piv > 0)) { ok = false; piv = 1.0; }
-            double inv = rsqrt(piv);
-            double a0 = a[0] * inv;                 // column j of L_tt (rows >= j) and of L_{t+1,t}
-            if (isD) D[row * 9 + j] = (j <= row) ? a0 : 0.0;
-            else if (isO && hasO) O[row * 9 + j] = a0;
-            if (lane == j) dinv[t * 9 + j] = inv;
-#pragma unroll
-            for (int k = 1; k < 9; k++) {
-                double lk = __shfl_sync(FULL, a0, (j + k) & 31);   // L[j+k][j] from the lane of row j+k (unused beyond 8)
-                a[k - 1] = a[k] - a0 * lk;                        // update column j+k and rotate it into slot k-1
-            }
-            a[8] = 0.0;
-        }
-        __syncwarp();
-    }
-    return ok;
-}
-
-RBPE_NOINLINE void solve_bt9r(int nblk, const double *Dall, const double *Oall, const double *dinv, double *g) {
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const bool act = lane < 9;
-    const int row = act ? lane : 0;
-    double prev = 0;
-#pragma unroll 1
-    for (int t = 0; t < nblk; t++) {  // L w = g
-        const double *L = Dall + t * 81;
-        double gv = act ? g[t * 9 + row] : 0.0, di = act ? dinv[t * 9 + row] : 0.0;
-        if (t > 0) {
-            const double *P = Oall + (t - 1) * 81;
-            double sm = 0;
-#pragma unroll 1
-            for (int k = 0; k < 9; k++) sm += P[row * 9 + k] * __shfl_sync(FULL, prev, k);
-            gv -= sm;
-        }
-#pragma unroll 1
-        for (int j = 0; j < 9; j++) {
-            if (lane == j) gv *= di;
-            double gj = __shfl_sync(FULL, gv, j);
-            if (act && lane > j) gv -= L[row * 9 + j] * gj;
-        }
-        prev = gv;
-        if (act) g[t * 9 + row] = gv;
-    }
-    double next = 0;
-#pragma unroll 1
-    for (int t = nblk - 1; t >= 0; t--) {  // L' y = w
-        const double *L = Dall + t * 81;
-        double gv = act ? g[t * 9 + row] : 0.0, di = act ? dinv[t * 9 + row] : 0.0;
-        if (t < nblk - 1) {
-            const double *P = Oall + t * 81;
-            double sm = 0;
-#pragma unroll 1
-            for (int k = 0; k < 9; k++) sm += P[k * 9 + row] * __shfl_sync(FULL, next, k);
-            gv -= sm;
-        }
-#pragma unroll 1
-        for (int j = 8; j >= 0; j--) {
-            if (lane == j) gv *= di;
-            double gj = __shfl_sync(FULL, gv, j);
-            if (act && lane < j) gv -= L[j * 9 + row] * gj;
-        }
-        next = gv;
-        if (act) g[t * 9 + row] = gv;
-    }
-    __syncwarp();
-}
-
 // The helpers below are single non-inlined copies (instruction-cache footprint) and take plain arguments, so that the
 // context struct never has its address taken and stays in registers.
 // out (nr) = Z' vec (x-space)

@@ -5,6 +5,8 @@
 #include <stdint.h>
 
 #include "cuda_emu.h"
+namespace rbpe { long g_emu_dmma = 0; }
+extern "C" long emu_dmma_count() { return rbpe::g_emu_dmma; }
 #define RBPE_EMU 1
 #include "../../swarm_simulator_b200/csrc/rbpe_kernels.cuh"
 #include "../../include/rbpe.h"

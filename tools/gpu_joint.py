@@ -11,8 +11,20 @@ CASES = ((4, 3, 0.0, False, 4, 1001, 1184), (16, 5, 0.2, False, 16, 2001, 592), 
          (64, 5, 0.2, True, 16, 3001, 148), (256, 5, 0.4, True, 32, 4001, 8))
 
 
+def prof_read(reset=True):
+    import ctypes as C
+    lib = E.load_library()
+    if not hasattr(lib, "rbpe_prof_read"):
+        return None
+    buf = (C.c_ulonglong * 16)()
+    lib.rbpe_prof_read(buf, 1 if reset else 0)
+    return [int(v) for v in buf]
+
+
 def main():
     only = os.environ.get("JOINT_CASES")
+    if os.environ.get("JOINT_LIB"):       # e.g. a -DRBPE_PROFILE build: swarm_simulator_b200/librbpe_prof.so
+        E.LIB_PATH = os.path.join(ROOT, os.environ["JOINT_LIB"])
     eng = E.Engine(device=0)
     for ci, (N, M, rho, seq, bs, seed, count) in enumerate(CASES):
         if only and str(ci) not in only.split(","):
@@ -27,9 +39,19 @@ def main():
         prob = E.PackedProblem(synth.pack([m] * count), sequential=seq, batch_size=bs)
         eng.upload(prob)
         best = 1e9
+        eng.run(); eng.sync()            # warm (clocks, scratch)
+        prof_read()
         for rep in range(2):
             eng.timer_start(); eng.run(); best = min(best, eng.timer_stop())
+        pr = prof_read()
         rr = eng.download(prob)
+        if pr:
+            tot = float(sum(pr[:5])) or 1.0
+            print("   phases (thread-0 clocks summed over CTAs, steady state): setup %.1f%% rows %.1f%% factor %.1f%% solves %.1f%% other %.1f%%" % (
+                100 * pr[0] / tot, 100 * pr[1] / tot, 100 * pr[2] / tot, 100 * pr[3] / tot, 100 * pr[4] / tot))
+            print("   inside factor: build_W %.1f%% | update %.1f%% chol32 %.1f%% trsm %.1f%% (of total)" % tuple(
+                100 * pr[i] / tot for i in (5, 6, 7, 8)))
+            print("   chol32 pass-1 cycles per 32-step call: min %d max %d mean-all-phases %.0f" % (pr[13], pr[14], (pr[10] + pr[11] + pr[12]) / max(1, pr[15])))
         print("N=%d M=%d b=%d: rc=%d/%d iters=%s same_iters=%s err=%.2e | one mission %.1f ms (oracle %.1f ms) | %d missions: kernel %.1f ms -> %.0f agent-QPs/s" % (
             N, M, bs, r.rc, rr.rc, r.qp_iters[0][:8], same, err, dt1 * 1e3, dto * 1e3, count, best, count * N / best * 1e3), flush=True)
     eng.close()
