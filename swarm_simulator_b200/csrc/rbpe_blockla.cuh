@@ -304,12 +304,18 @@ RBPE_NOINLINE void solve_bt_blk(int nblk, int kb, int kp, const double *Dall, co
     __syncthreads();
 }
 
-// ---- one-agent batches (9 x 9 blocks): the whole block tridiagonal system handled by one warp out of registers ----
-// lanes 0..8 hold the rows of the diagonal block D_t, lanes 9..17 the rows of O_t = block (t+1, t).  On exit D holds
-// L_tt (lower), O holds L_{t+1,t}, dinv[t*9+j] = 1 / L_tt[j][j].  Rolled (compact code): the kernels are instruction-fetch bound (ncu r1: GPC
-// instruction cache at 79 % of its request rate, SM I-cache hit rate 70 %), so code size matters more than a few
-// extra moves.  Column loop rolled with a register rotation: a[0] always holds the current column of the lane's row.
-RBPE_NOINLINE bool factor_bt9r(int nblk, double *Dall, double *Oall, double *dinv) {
+// ---- one-agent batches (9 x 9 blocks): the whole block tridiagonal system handled by one warp ---------------------
+// The one-agent kernel is instruction-issue bound and, after the row presolve, spends most of its instructions here
+// (ncu r1), so the routines are organised for few instructions, not few flops:
+//   * the factorisation produces, per knot, the INVERSE of the diagonal factor L_tt (in place of D_t) together with
+//     L_{t+1,t} (in place of O_t): lanes 0..8 hold the rows of D_t, lanes 9..17 the rows of O_t in a register window
+//     that rotates by one column per step (compact rolled code); column j of L is broadcast through `cb` (shared
+//     memory) instead of shuffles, and the same broadcast drives the forward substitution L X = I (lane c owns column c
+//     of X), so the inverse costs 8 more FMAs per column;
+//   * the two solves of an interior-point iteration are then 9 x 9 matrix-vector products (one lane per row, no
+//     shuffles, no 9-step substitution chains).
+// D_t -= L_{t,t-1} L_{t,t-1}' runs on 27 lanes (3 entries each).  cb: >= 32 doubles of shared memory.
+RBPE_NOINLINE bool factor_bt9v(int nblk, double *Dall, double *Oall, double *cb) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const bool isD = lane < 9, isO = lane >= 9 && lane < 18;
@@ -319,89 +325,91 @@ RBPE_NOINLINE bool factor_bt9r(int nblk, double *Dall, double *Oall, double *din
     for (int t = 0; t < nblk; t++) {
         double *D = Dall + t * 81, *O = Oall + t * 81;
         const bool hasO = t < nblk - 1;
-        double a[9];
-#pragma unroll
-        for (int c = 0; c < 9; c++) a[c] = isD ? D[row * 9 + c] : ((isO && hasO) ? O[row * 9 + c] : 0.0);
-        if (t > 0) {  // D_t -= L_{t,t-1} L_{t,t-1}'
+        if (t > 0) {
             const double *P = Oall + (t - 1) * 81;
-#pragma unroll 1
-            for (int k = 0; k < 9; k++) {
-                double pk = isD ? P[row * 9 + k] : 0.0;
+            if (lane < 27) {
+                const int r = lane / 3, c0 = 3 * (lane % 3);
+                double s0 = D[r * 9 + c0], s1 = D[r * 9 + c0 + 1], s2 = D[r * 9 + c0 + 2];
 #pragma unroll
-                for (int c = 0; c < 9; c++) a[c] -= pk * P[c * 9 + k];
+                for (int k = 0; k < 9; k++) {
+                    const double pk = P[r * 9 + k];
+                    s0 -= pk * P[c0 * 9 + k]; s1 -= pk * P[(c0 + 1) * 9 + k]; s2 -= pk * P[(c0 + 2) * 9 + k];
+                }
+                D[r * 9 + c0] = s0; D[r * 9 + c0 + 1] = s1; D[r * 9 + c0 + 2] = s2;
             }
+            __syncwarp();
         }
+        double a[9], v[9];
+#pragma unroll
+        for (int c = 0; c < 9; c++) {
+            a[c] = isD ? D[row * 9 + c] : ((isO && hasO) ? O[row * 9 + c] : 0.0);
+            v[c] = (c == lane) ? 1.0 : 0.0;
+        }
+        __syncwarp();   // rows are in registers: D may now be overwritten by the inverse
 #pragma unroll 1
         for (int j = 0; j < 9; j++) {
             double piv = __shfl_sync(FULL, a[0], j);
             if (!(piv > 0)) { ok = false; piv = 1.0; }
-            double inv = rsqrt(piv);
-            double a0 = a[0] * inv;                 // column j of L_tt (rows >= j) and of L_{t+1,t}
-            if (isD) D[row * 9 + j] = (j <= row) ? a0 : 0.0;
-            else if (isO && hasO) O[row * 9 + j] = a0;
-            if (lane == j) dinv[t * 9 + j] = inv;
+            const double inv = rsqrt(piv);
+            const double a0 = a[0] * inv;                  // L_tt[lane][j] (lanes j..8), L_{t+1,t}[lane-9][j] (lanes 9..17)
+            const double xj = v[0] * inv;                  // X[j][lane]
+            cb[(lane - j) & 31] = (isD && lane >= j) ? a0 : 0.0;   // cb[k] = L_tt[j+k][j], zero beyond the block
+            if (isO && hasO) O[row * 9 + j] = a0;
+            if (isD) D[j * 9 + lane] = xj;                 // zero above the diagonal
+            __syncwarp();
 #pragma unroll
             for (int k = 1; k < 9; k++) {
-                double lk = __shfl_sync(FULL, a0, (j + k) & 31);   // L[j+k][j] from the lane of row j+k (unused beyond 8)
-                a[k - 1] = a[k] - a0 * lk;                        // update column j+k and rotate it into slot k-1
+                const double l = cb[k];
+                a[k - 1] = a[k] - a0 * l;
+                v[k - 1] = v[k] - l * xj;
             }
-            a[8] = 0.0;
+            a[8] = 0.0; v[8] = 0.0;
+            __syncwarp();
         }
-        __syncwarp();
     }
     return ok;
 }
 
-RBPE_NOINLINE void solve_bt9r(int nblk, const double *Dall, const double *Oall, const double *dinv, double *g) {
-    const unsigned FULL = 0xffffffffu;
+// g <- (L L')^-1 g with Dall = inverses of the diagonal factor blocks, Oall = L_{t+1,t} (factor_bt9v)
+RBPE_NOINLINE void solve_bt9v(int nblk, const double *Dall, const double *Oall, double *g, double *cb) {
     const int lane = threadIdx.x & 31;
     const bool act = lane < 9;
     const int row = act ? lane : 0;
-    double prev = 0;
 #pragma unroll 1
-    for (int t = 0; t < nblk; t++) {  // L w = g
-        const double *L = Dall + t * 81;
-        double gv = act ? g[t * 9 + row] : 0.0, di = act ? dinv[t * 9 + row] : 0.0;
+    for (int t = 0; t < nblk; t++) {   // w_t = X_t (g_t - L_{t,t-1} w_{t-1})
+        const double *X = Dall + t * 81;
+        double s = g[t * 9 + row];
         if (t > 0) {
-            const double *P = Oall + (t - 1) * 81;
-            double sm = 0;
-#pragma unroll 1
-            for (int k = 0; k < 9; k++) sm += P[row * 9 + k] * __shfl_sync(FULL, prev, k);
-            gv -= sm;
+            const double *P = Oall + (t - 1) * 81 + row * 9, *wp = g + (t - 1) * 9;
+#pragma unroll
+            for (int k = 0; k < 9; k++) s -= P[k] * wp[k];
         }
-#pragma unroll 1
-        for (int j = 0; j < 9; j++) {
-            if (lane == j) gv *= di;
-            double gj = __shfl_sync(FULL, gv, j);
-            if (act && lane > j) gv -= L[row * 9 + j] * gj;
-        }
-        prev = gv;
-        if (act) g[t * 9 + row] = gv;
+        if (act) cb[row] = s;
+        __syncwarp();
+        double w = 0;
+#pragma unroll
+        for (int c = 0; c < 9; c++) w += X[row * 9 + c] * cb[c];
+        if (act) g[t * 9 + row] = w;
+        __syncwarp();
     }
-    double next = 0;
 #pragma unroll 1
-    for (int t = nblk - 1; t >= 0; t--) {  // L' y = w
-        const double *L = Dall + t * 81;
-        double gv = act ? g[t * 9 + row] : 0.0, di = act ? dinv[t * 9 + row] : 0.0;
+    for (int t = nblk - 1; t >= 0; t--) {   // u_t = X_t' (w_t - L_{t+1,t}' u_{t+1})
+        const double *X = Dall + t * 81;
+        double s = g[t * 9 + row];
         if (t < nblk - 1) {
-            const double *P = Oall + t * 81;
-            double sm = 0;
-#pragma unroll 1
-            for (int k = 0; k < 9; k++) sm += P[k * 9 + row] * __shfl_sync(FULL, next, k);
-            gv -= sm;
+            const double *P = Oall + t * 81 + row, *un = g + (t + 1) * 9;
+#pragma unroll
+            for (int k = 0; k < 9; k++) s -= P[k * 9] * un[k];
         }
-#pragma unroll 1
-        for (int j = 8; j >= 0; j--) {
-            if (lane == j) gv *= di;
-            double gj = __shfl_sync(FULL, gv, j);
-            if (act && lane < j) gv -= L[j * 9 + row] * gj;
-        }
-        next = gv;
-        if (act) g[t * 9 + row] = gv;
+        if (act) cb[row] = s;
+        __syncwarp();
+        double u = 0;
+#pragma unroll
+        for (int r = 0; r < 9; r++) u += X[r * 9 + row] * cb[r];
+        if (act) g[t * 9 + row] = u;
+        __syncwarp();
     }
-    __syncwarp();
 }
-
 
 #endif
 }  // namespace rbpe

@@ -112,7 +112,7 @@ __host__ __device__ inline size_t scratch_doubles(int N, int M, int bs) {
     size_t rint_ = (size_t)bs * (bs - 1) / 2 * 6 * M;
     size_t kp = kp_of(bs), ninv = (kp + 31) / 32;
     size_t t = 64 + 36;
-    t += 14 * al2(nv) + 3 * al2(nr);
+    t += 14 * al2(nv) + 2 * al2(nr) + al2(nr > 32 ? nr : 32);
     t += al2((size_t)M * bs * 36) + al2(rint_ * 6);                  // Dcp, Dint
     t += al2((size_t)(M > 1 ? M - 1 : 1) * kp * kp) + al2((size_t)(M > 2 ? M - 2 : 1) * kp * kp);
     if (bs > 1) t += al2((size_t)(M > 1 ? M - 1 : 1) * ninv * 1024) + al2((size_t)(M > 1 ? M - 1 : 1) * kp) + al2(kp + 32);   // Linv, wk, yk
@@ -272,7 +272,7 @@ struct QP {
     double *x, *dxa, *dx, *rdx, *ub, *lbn, *sub, *zub, *slb, *zlb, *vA, *vB, *tub, *tlb;
     // knot-space vectors (nr): r = (t-1)*9nb + (a*3+k)*3 + d, t = 1..M-1
     double *sg, *sg2;
-    double *dinv;        // [nr] reciprocal Cholesky diagonal (one-agent batches)
+    double *dinv;        // [max(nr, 32)] column exchange buffer of the 9 x 9 routines (one-agent batches)
     double *Wd, *Wo;     // reduced Hessian Z'HZ: (M-1) diagonal blocks, (M-2) blocks (t+1,t), each kp x kp (9nb used)
     double *Linv, *wk, *yk;   // joint batches: inverted 32 x 32 diagonal blocks of the factor, solve work vectors (rbpe_blockla.cuh)
     double *Dcp;         // [M*nb*6][6]  sum_rows w g g' restricted to one control point (3x3 symmetric over axes)
@@ -316,7 +316,7 @@ RBPE_DEV void layout(QP &q, unsigned char *smem, size_t smem_bytes, double *gscr
     for (int i = 0; i < 14; i++) *vv[i] = a.take(q.nv);
     q.sg = a.take(q.nr);
     q.sg2 = a.take(q.nr);
-    q.dinv = a.take(q.nr);
+    q.dinv = a.take(q.nr > 32 ? q.nr : 32);
     q.Dcp = a.take((size_t)q.M * q.nb * 36);
     q.Dint = a.take((size_t)q.nrint * 6);
     q.Wd = a.take((size_t)(q.M > 1 ? q.M - 1 : 1) * q.kp * q.kp);
@@ -639,7 +639,7 @@ RBPE_NOINLINE bool kkt_factor(const QP &q) {
     PROF(5);
     if (q.kb == 9) {
         if ((threadIdx.x >> 5) == 0) {
-            bool ok = factor_bt9r(q.M - 1, q.Wd, q.Wo, q.dinv);
+            bool ok = factor_bt9v(q.M - 1, q.Wd, q.Wo, q.dinv);
             if (threadIdx.x == 0) q.red[60] = ok ? 0.0 : 1.0;
         }
         __syncthreads();
@@ -654,7 +654,7 @@ RBPE_NOINLINE void kkt_solve(const QP &q, const double *r, double *dxout) {
     Zt_apply(q, r, q.sg);
     __syncthreads();
     if (q.kb == 9) {
-        if ((threadIdx.x >> 5) == 0) solve_bt9r(q.M - 1, q.Wd, q.Wo, q.dinv, q.sg);
+        if ((threadIdx.x >> 5) == 0) solve_bt9v(q.M - 1, q.Wd, q.Wo, q.sg, q.dinv);
     } else {
         solve_bt_blk(q.M - 1, q.kb, q.kp, q.Wd, q.Wo, q.Linv, q.sg, q.wk, q.yk);
     }

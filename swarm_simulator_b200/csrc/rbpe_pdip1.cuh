@@ -15,6 +15,10 @@
 namespace rbpe {
 
 constexpr int W1_WARPS = 4;
+#ifndef RBPE_W1_UNROLL
+#define RBPE_W1_UNROLL 1
+#endif
+constexpr int W1_UNROLL = RBPE_W1_UNROLL;   // unroll factor of the row loop (tuning; 1 = smallest code)
 
 #define QROW(a) q_base_int(a, 0), q_base_int(a, 1), q_base_int(a, 2), q_base_int(a, 3), q_base_int(a, 4), q_base_int(a, 5)
 #if defined(__CUDACC__)
@@ -26,7 +30,7 @@ static const double c_QB[36] = {QROW(0), QROW(1), QROW(2), QROW(3), QROW(4), QRO
 
 __host__ __device__ inline size_t w1_smem_doubles(int M) {  // per warp
     size_t ncp = 6 * (size_t)M, nr = 9 * (size_t)(M > 1 ? M - 1 : 0);
-    return al2(6 * 3 * ncp) + al2(6 * ncp) + al2((size_t)(M > 1 ? M - 1 : 1) * 81) + al2((size_t)(M > 2 ? M - 2 : 1) * 81) + 3 * al2(nr) + al2((6 * (size_t)M + 31) / 32);
+    return al2(6 * 3 * ncp) + al2(6 * ncp) + al2((size_t)(M > 1 ? M - 1 : 1) * 81) + al2((size_t)(M > 2 ? M - 2 : 1) * 81) + 2 * al2(nr) + al2(nr > 32 ? nr : 32) + al2((6 * (size_t)M + 31) / 32);
 }
 __host__ __device__ inline size_t w1_scratch_doubles(int N, int M) {  // per warp, global arena
     size_t nslot = (6 * (size_t)M + 31) / 32, NR = (size_t)(N > 1 ? N - 1 : 0) + 6;   // + the 6 box rows of a control point
@@ -151,10 +155,12 @@ RBPE_DEV void w1_pass(const W1 &c, double sa, double sb, Acc &out) {
             const double *nm = c.nrm + (size_t)m * c.NR * 3;
             const size_t rb = (size_t)slot * c.NR * 32 + lane;
             const int cnt = c.cnt[slot * 32 + lane];
-#pragma unroll 1
+            int e_next = cnt > 0 ? c.ridx[rb] : 0;   // row number fetched one iteration ahead: one L2 round trip per row, not two
+#pragma unroll W1_UNROLL
             for (int j = 0; j < cnt; j++) {
                 const size_t r = rb + (size_t)j * 32;
-                const int e = c.ridx[r];
+                const int e = e_next;
+                e_next = (j + 1 < cnt) ? c.ridx[r + 32] : 0;
                 double n0 = nm[e * 3], n1 = nm[e * 3 + 1], n2 = nm[e * 3 + 2];
                 double h = c.he[r], s = c.se[r], z = c.ze[r], cA, cB, w;
                 row_eval1<MODE>(h, s, z, n0 * x0 + n1 * x1 + n2 * x2, n0 * a0 + n1 * a1 + n2 * a2, n0 * d0 + n1 * d1 + n2 * d2,
@@ -238,7 +244,7 @@ RBPE_NOINLINE void w1_build_W(const double *segmat, int M, const double *Dcp, do
 // dxout = Z (Z'HZ)^-1 Z' r
 RBPE_DEV void w1_solve(const W1 &c, const double *r, double *dxout) {
     w1_Zt(c.segmat, c.nr, r, c.sg);
-    solve_bt9r(c.M - 1, c.Wd, c.Wo, c.dinv, c.sg);
+    solve_bt9v(c.M - 1, c.Wd, c.Wo, c.sg, c.dinv);
     w1_Z(c.segmat, c.M, c.sg, dxout);
 }
 // rdx = 2 Q x + vA; returns the lane-partial objective and max|Px|
@@ -371,7 +377,7 @@ RBPE_DEV int w1_solve_qp(const W1 &c, int max_iter, double tol_gap, double tol_r
         hn = mh;
         w1_pass<P_INIT>(c, 0, 0, acc);
         w1_build_W(c.segmat, c.M, c.Dcp, c.Wd, c.Wo);
-        if (!factor_bt9r(c.M - 1, c.Wd, c.Wo, c.dinv)) go = false;
+        if (!factor_bt9v(c.M - 1, c.Wd, c.Wo, c.dinv)) go = false;
     }
     if (go) {
         w1_dual(c.segmat, c.M, c.QB, c.x, c.vA, c.rdx);   // rdx = P x_p + vA
@@ -409,7 +415,7 @@ RBPE_DEV int w1_solve_qp(const W1 &c, int max_iter, double tol_gap, double tol_r
         if (gap <= tol_gap * fmax(1.0, fabs(obj)) && nrg <= tol_res * (1 + hn) && nrd <= tol_res * (1.0 + mpx)) { status = ST_OK; break; }
         if (hz < 0 && mc / (-hz) < 1e-8) { status = ST_INFEASIBLE; break; }
         w1_build_W(c.segmat, c.M, c.Dcp, c.Wd, c.Wo);
-        if (!factor_bt9r(c.M - 1, c.Wd, c.Wo, c.dinv)) { status = ST_NOT_CONVERGED; break; }
+        if (!factor_bt9v(c.M - 1, c.Wd, c.Wo, c.dinv)) { status = ST_NOT_CONVERGED; break; }
         for (int v = lane; v < 18 * c.M; v += 32) c.vB[v] = -c.rdx[v] + c.vB[v];
         __syncwarp();
         w1_solve(c, c.vB, c.dxa);
@@ -452,7 +458,10 @@ RBPE_DEV int w1_solve_qp(const W1 &c, int max_iter, double tol_gap, double tol_r
     return status;
 }
 
-__global__ void __launch_bounds__(W1_WARPS * 32, 4) pdip1_kernel(SolveArgs S) {   // blockDim.x = 32 * (QPs per CTA) <= W1_WARPS * 32
+#ifndef RBPE_W1_MINB
+#define RBPE_W1_MINB 4
+#endif
+__global__ void __launch_bounds__(W1_WARPS * 32, RBPE_W1_MINB) pdip1_kernel(SolveArgs S) {   // blockDim.x = 32 * (QPs per CTA) <= W1_WARPS * 32
     RBPE_DYN_SMEM(smem);
     const int N = S.N, M = S.M, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long unit = (long)blockIdx.x * (blockDim.x >> 5) + warp;   // one QP chain (mode 0) or one QP (mode 1) per warp
@@ -489,7 +498,7 @@ __global__ void __launch_bounds__(W1_WARPS * 32, 4) pdip1_kernel(SolveArgs S) { 
         c.Dcp = p; p += al2(6 * (size_t)c.ncp);
         c.Wd = p; p += al2((size_t)(M > 1 ? M - 1 : 1) * 81);
         c.Wo = p; p += al2((size_t)(M > 2 ? M - 2 : 1) * 81);
-        c.sg = p; p += al2(c.nr); c.sg2 = p; p += al2(c.nr); c.dinv = p; p += al2(c.nr);
+        c.sg = p; p += al2(c.nr); c.sg2 = p; p += al2(c.nr); c.dinv = p; p += al2(c.nr > 32 ? c.nr : 32);
         c.QB = c_QB;
         c.cmax = (int *)p;
     }
