@@ -252,31 +252,48 @@ def main():
     e2e = world * nqp / (ms_e2e * 1e-3)
 
     # ---- secondary leg: Jacobi mode (north-star's agent sharding): the SAME missions on every rank, each rank solves its
-    # range of agents of every mission against the frozen table, one NCCL all-gather of control points per sweep ----
+    # range of agents of every mission against the frozen table; the exchange of the solved control points is fused into the
+    # sweep kernel (peer stores over NVLink), with the NCCL all-gather variant timed beside it ----
     jac = None
     if args.jacobi_missions > 0:
         from swarm_simulator_b200 import dist as D
         jpool = make_pool(min(args.pool, 4), 0)
         jprob = E.PackedProblem(pin(synth.pack([jpool[i % len(jpool)] for i in range(args.jacobi_missions)])),
                                 sequential=True, batch_size=1, iteration=args.jacobi_sweeps)
-        jeng = E.Engine(device=local)
         dev = torch.device("cuda", local)
-        D.jacobi_solve(jeng, jprob, args.jacobi_sweeps, device=dev)          # warm-up (also allocates)
-        jeng.sync()
-        l0 = jeng.timing()["kernel_launches"]
-        barrier()
-        jeng.timer_start()                                   # CUDA events on the engine's stream; every phase in between
-        for _ in range(args.steps):                          # (H2D, sweeps, all-gathers) is stream- or host-synchronised
-            D.jacobi_solve(jeng, jprob, args.jacobi_sweeps, device=dev)
-        ms_j = max_over_ranks(jeng.timer_stop() / args.steps)
-        barrier()
-        jr = jeng.download(jprob)
+
+        def jacobi_leg(fused):
+            jeng = E.Engine(device=local)
+            if fused:
+                D.jacobi_attach_peers(jeng, jprob)                            # one-time exchange of IPC handles (host side)
+            D.jacobi_solve(jeng, jprob, args.jacobi_sweeps, device=dev, fused=fused)   # warm-up (also allocates)
+            jeng.sync()
+            l0 = jeng.timing()["kernel_launches"]
+            barrier()
+            jeng.timer_start()                               # CUDA events on the engine's stream; every phase in between
+            for _ in range(args.steps):                      # (H2D, sweeps, exchange) is stream- or host-synchronised
+                D.jacobi_solve(jeng, jprob, args.jacobi_sweeps, device=dev, fused=fused)
+            ms_j = max_over_ranks(jeng.timer_stop() / args.steps)
+            barrier()
+            jr = jeng.download(jprob)
+            if fused:
+                jeng.peer_status()
+            out = (ms_j, int(jeng.timing()["kernel_launches"] - l0), int((jr.status != 0).sum()))
+            jeng.close()
+            return out
+
+        ms_j, jl, jfail = jacobi_leg(fused=world > 1)
         jac = {"value": args.jacobi_missions * N_AGENTS * args.jacobi_sweeps / (ms_j * 1e-3), "unit": UNIT,
                "scaling": "strong", "missions": args.jacobi_missions, "sweeps": args.jacobi_sweeps, "ms_per_step": ms_j,
-               "collective": "1 all-gather of control points per sweep (%d B per agent)" % (18 * M_SEG * 8),
-               "includes": "H2D of inputs, assembly, %d sweeps, all-gathers" % args.jacobi_sweeps,
-               "gpu_launches": int(jeng.timing()["kernel_launches"] - l0), "failed": int((jr.status != 0).sum())}
-        jeng.close()
+               "exchange": ("fused into the sweep kernel: stores of the solved control points (%d B per agent) into every rank's "
+                            "next table over NVLink peer memory + flag words; no collective call" % (18 * M_SEG * 8)) if world > 1
+                           else "single GPU: none",
+               "includes": "H2D of inputs, assembly, %d sweeps, exchange" % args.jacobi_sweeps,
+               "gpu_launches": jl, "failed": jfail}
+        if world > 1:   # the baseline it replaces: sweep kernel, then one NCCL all-gather of control points per sweep
+            ms_ag, _, _ = jacobi_leg(fused=False)
+            jac["allgather_baseline"] = {"value": args.jacobi_missions * N_AGENTS * args.jacobi_sweeps / (ms_ag * 1e-3),
+                                         "ms_per_step": ms_ag, "collective": "1 NCCL all-gather of control points per sweep"}
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -110,6 +110,24 @@ int rbpe_run(rbpe_handle *h, int mode);                                      /* 
 /* Jacobi sweep restricted to batches [batch_begin, batch_end) of every resident mission (agent sharding);
  * needs rbpe_upload + rbpe_assemble first; does not reset the control-point table */
 int rbpe_run_jacobi_range(rbpe_handle *h, int batch_begin, int batch_end);
+/* ---- Jacobi exchange over NVLink peer memory (one process per GPU, or several handles in one process) ----
+ * Replaces "sweep, then all-gather of control points" (the exchange step the north-star names; the reference itself
+ * has no such step: rbp_planner.hpp L140-L201 is a Gauss-Seidel chain) by ONE sweep kernel whose epilogue stores every
+ * solved batch straight into the next table of every rank and raises a flag there.
+ *   rbpe_peer_export   after rbpe_upload + rbpe_assemble: pins the two table buffers and the flag words and returns
+ *                      their 3 IPC handles (3 x RBPE_IPC_HANDLE_BYTES bytes); exchange them between ranks with any
+ *                      host-side transport (bench.py / dist.py use torch.distributed.all_gather_object)
+ *   rbpe_peer_attach   all_handles = [world][3][RBPE_IPC_HANDLE_BYTES], rank order
+ *   rbpe_peer_attach_local  same, for handles living in the calling process (raw device pointers)
+ *   rbpe_run_jacobi_fused   one sweep over batches [batch_begin, batch_end) of every resident mission; every rank
+ *                      must call it the same number of times (ranks with an empty range included)
+ *   rbpe_peer_status   RBPE_CUDA_ERROR after a flag wait timed out (a peer died) */
+#define RBPE_IPC_HANDLE_BYTES 64
+int rbpe_peer_export(rbpe_handle *h, unsigned char *handles);
+int rbpe_peer_attach(rbpe_handle *h, int rank, int world, const unsigned char *all_handles);
+int rbpe_peer_attach_local(rbpe_handle *h, int rank, int world, rbpe_handle *const *peers);
+int rbpe_run_jacobi_fused(rbpe_handle *h, int batch_begin, int batch_end);
+int rbpe_peer_status(rbpe_handle *h);
 int rbpe_set_ctrl(rbpe_handle *h, const double *ctrl);                       /* H2D: overwrite `dummy` [count][N][3][6M] */
 int rbpe_download(rbpe_handle *h, rbpe_result *r);                           /* D2H of results */
 /* device pointers of the resident control-point table [count][N][3][6M] (f64) and coefficient table */

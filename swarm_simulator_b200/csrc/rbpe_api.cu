@@ -20,8 +20,10 @@ namespace {
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
+    bool pinned = false;   // exported to peers (IPC): must not be reallocated
     cudaError_t reserve(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
+        if (pinned) return cudaErrorInvalidValue;
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
@@ -67,6 +69,14 @@ struct rbpe_handle {
     DevBuf segbox, reln, segmat, ctrl, frozen, coef, qp_obj, qp_iters, qp_status, qp_res, status, scratch;
     rbpe_timing timing;
     std::vector<int> host_status;
+    // Jacobi exchange over peer memory (rbpe_peer_*): tables[0] / tables[1] are the two physical control-point buffers of
+    // every rank as exported (ctrl, frozen); `phys_cur` tells which one currently is h->ctrl
+    int peer_rank = -1, peer_world = 0, phys_cur = 0;
+    double *peer_tables[2][RBPE_MAX_PEERS] = {};
+    unsigned long long *peer_flags[RBPE_MAX_PEERS] = {};
+    std::vector<void *> ipc_opened;
+    DevBuf flags;   // [RBPE_MAX_PEERS] u64 flag words, then u32 done counter, then i32 error
+    unsigned long long sweep_id = 0;
 };
 
 static int fail(rbpe_handle *h, int code, const char *fmt, ...) {
@@ -158,7 +168,8 @@ extern "C" void rbpe_destroy(rbpe_handle *h) {
     DevBuf *all[] = {&h->T, &h->start, &h->goal, &h->radius, &h->sfc_offs, &h->sfc_base, &h->sfc_box, &h->sfc_t,
                      &h->rsfc_n, &h->rsfc_t, &h->init_traj, &h->segbox, &h->reln, &h->segmat, &h->ctrl, &h->frozen,
                      &h->coef, &h->qp_obj, &h->qp_iters, &h->qp_status, &h->qp_res, &h->status, &h->scratch, &h->post_a, &h->post_b, &h->post_c,
-                     &h->post_d, &h->post_e};
+                     &h->post_d, &h->post_e, &h->flags};
+    for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
     for (DevBuf *b : all) b->release();
     for (int i = 0; i < 7; i++)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -293,6 +304,8 @@ static int fill_solve_args(rbpe_handle *h, SolveArgs &S, int mode, int grid) {
     S.ctrl = h->ctrl.as<double>(); S.ctrl_frozen = h->frozen.as<double>();
     S.qp_obj = h->qp_obj.as<double>(); S.qp_iters = h->qp_iters.as<int>(); S.qp_status = h->qp_status.as<int>();
     S.qp_res = h->qp_res.as<double>(); S.nrec = h->nrec; S.status = h->status.as<int>();
+    S.npeer = 0; S.peer_rank = 0; S.sweep_id = 0; S.done_counter = nullptr; S.work_items = 0;
+    for (int p = 0; p < RBPE_MAX_PEERS; p++) { S.peer_ctrl[p] = nullptr; S.peer_flags[p] = nullptr; }
     S.scratch_stride = scratch_doubles(h->N, h->M, h->bs);
     S.smem_bytes = (unsigned)smem_for(h, S.scratch_stride);
     CU(h->scratch.reserve(S.scratch_stride * 8 * (size_t)grid));
@@ -314,6 +327,7 @@ static int warps_per_cta(const rbpe_handle *h) {
 // S must have been filled by fill_solve_args (mode, ranges, record offsets already set by the caller)
 static int launch_pdip_prepared(rbpe_handle *h, SolveArgs &S, long units) {
     int wpc = warps_per_cta(h);
+    S.work_items = (unsigned)units;
     if (wpc > 0) {
         long grid = (units + wpc - 1) / wpc;
         S.scratch_stride = w1_scratch_doubles(h->N, h->M);
@@ -383,6 +397,143 @@ extern "C" int rbpe_run_jacobi_range(rbpe_handle *h, int b0, int b1) {
     h->sweep++;
     if ((rc = launch_convert(h))) return rc;
     CU(cudaEventRecord(h->ev[4], h->stream));
+    return RBPE_OK;
+}
+
+
+// ---- Jacobi exchange over NVLink peer memory ---------------------------------------------------------------------
+static int peer_prepare(rbpe_handle *h) {
+    if (!h->resident || !h->assembled) return fail(h, RBPE_BAD_ARG, "rbpe_peer_*: call rbpe_upload and rbpe_assemble first");
+    CU(cudaSetDevice(h->device));
+    CU(h->flags.reserve(RBPE_MAX_PEERS * 8 + 64));
+    CU(cudaMemsetAsync(h->flags.p, 0, RBPE_MAX_PEERS * 8 + 64, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    {   // no allocation may happen once peers spin on our flags (cudaMalloc can wait for running kernels): size the
+        // scratch arena for a sweep over every batch now
+        const long units = (long)h->count * (h->nbatch > 0 ? h->nbatch : 1);
+        const int wpc = warps_per_cta(h);
+        size_t bytes = wpc > 0 ? w1_scratch_doubles(h->N, h->M) * 8 * (size_t)((units + wpc - 1) / wpc) * wpc
+                               : scratch_doubles(h->N, h->M, h->bs) * 8 * (size_t)units;
+        CU(h->scratch.reserve(bytes));
+    }
+    h->ctrl.pinned = h->frozen.pinned = h->flags.pinned = true;
+    h->sweep_id = 0;
+    h->phys_cur = 0;
+    return RBPE_OK;
+}
+
+extern "C" int rbpe_peer_export(rbpe_handle *h, unsigned char *handles) {
+    if (!h || !handles) return RBPE_BAD_ARG;
+    int rc = peer_prepare(h);
+    if (rc) return rc;
+    cudaIpcMemHandle_t m[3];
+    CU(cudaIpcGetMemHandle(&m[0], h->ctrl.p));
+    CU(cudaIpcGetMemHandle(&m[1], h->frozen.p));
+    CU(cudaIpcGetMemHandle(&m[2], h->flags.p));
+    static_assert(sizeof(cudaIpcMemHandle_t) == RBPE_IPC_HANDLE_BYTES, "IPC handle size");
+    memcpy(handles, m, sizeof(m));
+    return RBPE_OK;
+}
+
+extern "C" int rbpe_peer_attach(rbpe_handle *h, int rank, int world, const unsigned char *all_handles) {
+    if (!h || !all_handles || world < 1 || world > RBPE_MAX_PEERS || rank < 0 || rank >= world)
+        return fail(h, RBPE_BAD_ARG, "rbpe_peer_attach: bad rank / world (%d / %d, at most %d ranks)", rank, world, RBPE_MAX_PEERS);
+    if (!h->ctrl.pinned) return fail(h, RBPE_BAD_ARG, "rbpe_peer_attach: call rbpe_peer_export first");
+    CU(cudaSetDevice(h->device));
+    for (int p = 0; p < world; p++) {
+        if (p == rank) {
+            h->peer_tables[0][p] = h->ctrl.as<double>(); h->peer_tables[1][p] = h->frozen.as<double>();
+            h->peer_flags[p] = h->flags.as<unsigned long long>();
+            continue;
+        }
+        cudaIpcMemHandle_t m[3];
+        memcpy(m, all_handles + (size_t)p * 3 * RBPE_IPC_HANDLE_BYTES, sizeof(m));
+        void *ptr[3];
+        for (int i = 0; i < 3; i++) {
+            CU(cudaIpcOpenMemHandle(&ptr[i], m[i], cudaIpcMemLazyEnablePeerAccess));
+            h->ipc_opened.push_back(ptr[i]);
+        }
+        h->peer_tables[0][p] = (double *)ptr[0]; h->peer_tables[1][p] = (double *)ptr[1];
+        h->peer_flags[p] = (unsigned long long *)ptr[2];
+    }
+    h->peer_rank = rank; h->peer_world = world;
+    return RBPE_OK;
+}
+
+// same-process variant (several handles of one process, e.g. the single-GPU tests): raw device pointers, no IPC
+extern "C" int rbpe_peer_attach_local(rbpe_handle *h, int rank, int world, rbpe_handle *const *peers) {
+    if (!h || !peers || world < 1 || world > RBPE_MAX_PEERS || rank < 0 || rank >= world || peers[rank] != h)
+        return fail(h, RBPE_BAD_ARG, "rbpe_peer_attach_local: bad rank / world / peer list");
+    for (int p = 0; p < world; p++)
+        if (!peers[p] || !peers[p]->ctrl.pinned) return fail(h, RBPE_BAD_ARG, "rbpe_peer_attach_local: peer %d not exported", p);
+    CU(cudaSetDevice(h->device));
+    for (int p = 0; p < world; p++) {
+        if (peers[p]->device != h->device) {
+            int can = 0;
+            CU(cudaDeviceCanAccessPeer(&can, h->device, peers[p]->device));
+            if (!can) return fail(h, RBPE_CUDA_ERROR, "device %d cannot access device %d", h->device, peers[p]->device);
+            cudaError_t e = cudaDeviceEnablePeerAccess(peers[p]->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CU(e);
+            cudaGetLastError();
+        }
+        h->peer_tables[0][p] = peers[p]->ctrl.as<double>(); h->peer_tables[1][p] = peers[p]->frozen.as<double>();
+        h->peer_flags[p] = peers[p]->flags.as<unsigned long long>();
+    }
+    h->peer_rank = rank; h->peer_world = world;
+    return RBPE_OK;
+}
+
+// One Jacobi sweep over batches [b0, b1) with the exchange fused into the sweep kernel: the kernel reads the current
+// table, stores every solved batch into the NEXT table of every rank over peer memory, and its last work item raises
+// this rank's flag on every peer; a one-CTA kernel then waits for all ranks' flags (no host synchronisation, no
+// collective call), the tables swap roles and the conversion kernel runs on the completed table.
+extern "C" int rbpe_run_jacobi_fused(rbpe_handle *h, int b0, int b1) {
+    if (!h) return RBPE_BAD_ARG;
+    if (!h->resident || !h->assembled) return fail(h, RBPE_BAD_ARG, "rbpe_run_jacobi_fused: call rbpe_upload and rbpe_assemble first");
+    if (h->peer_world < 1) return fail(h, RBPE_BAD_ARG, "rbpe_run_jacobi_fused: no peers attached");
+    if ((long)h->nbatch * h->bs < h->N)
+        return fail(h, RBPE_BAD_ARG, "rbpe_run_jacobi_fused: truncated schedules (batch_iter < ceil(N/batch_size)) leave the next table incomplete");
+    if (b0 < 0 || b1 > h->nbatch || b0 > b1) return fail(h, RBPE_BAD_ARG, "batch range [%d,%d) outside [0,%d)", b0, b1, h->nbatch);
+    CU(cudaSetDevice(h->device));
+    CU(cudaEventRecord(h->ev[3], h->stream));
+    int rc;
+    h->sweep_id++;
+    unsigned long long *fl = h->flags.as<unsigned long long>();
+    int *err = (int *)(fl + RBPE_MAX_PEERS) + 1;
+    if (b1 > b0) {
+        SolveArgs S;
+        if ((rc = fill_solve_args(h, S, 1, 1))) return rc;
+        S.batch_begin = b0; S.batch_end = b1;
+        S.rec_offset = (h->iteration > 0 ? h->sweep % h->iteration : 0) * h->nbatch;
+        S.ctrl_frozen = h->ctrl.as<double>();   // the complete current table; nothing is written to it during the sweep
+        S.npeer = h->peer_world; S.peer_rank = h->peer_rank; S.sweep_id = h->sweep_id;
+        for (int p = 0; p < h->peer_world; p++) { S.peer_ctrl[p] = h->peer_tables[h->phys_cur ^ 1][p]; S.peer_flags[p] = h->peer_flags[p]; }
+        S.done_counter = (unsigned int *)(fl + RBPE_MAX_PEERS);
+        if ((rc = launch_pdip_prepared(h, S, (long)h->count * (b1 - b0)))) return rc;
+    } else {   // nothing to solve on this rank: only raise the flags (host-issued peer copies on the stream)
+        for (int p = 0; p < h->peer_world; p++)
+            CU(cudaMemcpyAsync(h->peer_flags[p] + h->peer_rank, &h->sweep_id, 8, cudaMemcpyHostToDevice, h->stream));
+    }
+    peer_wait_kernel<<<1, 32, 0, h->stream>>>(fl, h->peer_world, h->sweep_id, err);
+    CU(cudaGetLastError());
+    h->launches++;
+    std::swap(h->ctrl, h->frozen);
+    h->phys_cur ^= 1;
+    h->sweep++;
+    if ((rc = launch_convert(h))) return rc;
+    CU(cudaEventRecord(h->ev[4], h->stream));
+    return RBPE_OK;
+}
+
+// 0 when every flag wait so far has completed in time; RBPE_CUDA_ERROR after a timeout (a peer died or fell behind by > 2 s)
+extern "C" int rbpe_peer_status(rbpe_handle *h) {
+    if (!h) return RBPE_BAD_ARG;
+    if (!h->flags.p) return RBPE_OK;
+    CU(cudaSetDevice(h->device));
+    int e = 0;
+    CU(cudaMemcpyAsync(&e, (int *)(h->flags.as<unsigned long long>() + RBPE_MAX_PEERS) + 1, 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (e) return fail(h, RBPE_CUDA_ERROR, "peer flag wait timed out");
     return RBPE_OK;
 }
 

@@ -131,6 +131,42 @@ __host__ __device__ inline size_t scratch_doubles(int N, int M, int bs) {
 #define RBPE_STATIC_SMEM(type, name, n) static type name[n]   /* emulator: blocks run one after another */
 #endif
 
+
+// ---- Jacobi exchange over peer memory (fused epilogue of the sweep kernels) -------------------------------------
+// One work item (a warp of pdip1_kernel, a CTA of pdip_kernel) has finished: make its stores visible system-wide, count
+// it, and let the last one raise this rank's flag in every peer's flag array (stores over NVLink, no collective call).
+RBPE_DEV void peer_signal_done(const SolveArgs &S, bool leader) {
+#if defined(__CUDACC__)
+    if (S.npeer <= 0 || !leader) return;
+    __threadfence_system();
+    unsigned int prev = atomicAdd(S.done_counter, 1u);
+    if (prev + 1 == S.work_items) {
+        *S.done_counter = 0;
+        __threadfence_system();
+        for (int p = 0; p < S.npeer; p++) {
+            volatile unsigned long long *f = S.peer_flags[p] + S.peer_rank;
+            *f = S.sweep_id;
+        }
+        __threadfence_system();
+    }
+#endif
+}
+
+// waits until every rank has raised its flag to `sweep_id` in OUR flag array; err[0] = 1 on timeout (about 2 s)
+__global__ void peer_wait_kernel(const unsigned long long *flags, int world, unsigned long long sweep_id, int *err) {
+#if defined(__CUDACC__)
+    const int p = threadIdx.x;
+    if (p >= world) return;
+    const long long t0 = clock64();
+    const volatile unsigned long long *f = flags + p;
+    while (*f < sweep_id) {
+        if (clock64() - t0 > 4000000000LL) { atomicExch(err, 1); return; }
+        __nanosleep(200);
+    }
+    __threadfence_system();
+#endif
+}
+
 // Phase timers of the CTA-per-QP kernel (tools/gpu_joint.py with a -DRBPE_PROFILE build; never in the product build)
 #if defined(RBPE_PROFILE) && defined(__CUDACC__)
 __device__ unsigned long long g_prof[16];
@@ -960,17 +996,20 @@ __global__ void __launch_bounds__(CTA_THREADS, RBPE_PDIP_MINB) pdip_kernel(Solve
                 S.qp_status[(size_t)c * S.nrec + rec] = st;
                 if (st != ST_OK && S.status[c] == ST_OK) S.status[c] = st;
             }
-            if (st != ST_OK) {
-                if (S.mode == 0) return;  // RBPPlanner::update() aborts on the first failed batch (L158-L161)
-                continue;
-            }
-            // dummy <- vals for the agents of the batch (L182-L184)
+            if (st != ST_OK && S.mode == 0) return;  // RBPPlanner::update() aborts on the first failed batch (L158-L161)
+            if (st != ST_OK && S.npeer <= 0) continue;
+            // dummy <- vals for the agents of the batch (L182-L184); with peers: into the next table of every rank (a
+            // failed batch carries its old control points over, so that the next table is complete)
             for (int v = threadIdx.x; v < q.nv; v += blockDim.x) {
                 int m = v / q.n, r = v % q.n, a = r / 18, k = (r % 18) / 6, i = r % 6;
-                ctrl[(size_t)(q.q0 + a) * 18 * M + (size_t)k * 6 * M + m * 6 + i] = q.x[v];
+                const size_t at = (size_t)(q.q0 + a) * 18 * M + (size_t)k * 6 * M + m * 6 + i;
+                if (S.npeer <= 0) { ctrl[at] = q.x[v]; continue; }
+                const double val = (st == ST_OK) ? q.x[v] : q.ctrl_src[at];
+                for (int p = 0; p < S.npeer; p++) S.peer_ctrl[p][(size_t)c * N * 18 * M + at] = val;
             }
             __syncthreads();
         }
+    peer_signal_done(S, threadIdx.x == 0);
 }
 
 #endif  // __CUDACC__ || RBPE_EMU

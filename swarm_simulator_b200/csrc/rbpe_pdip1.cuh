@@ -522,16 +522,18 @@ __global__ void __launch_bounds__(W1_WARPS * 32, RBPE_W1_MINB) pdip1_kernel(Solv
                 S.qp_status[(size_t)cidx * S.nrec + rec] = st;
                 if (st != ST_OK) atomicCAS(&S.status[cidx], (int)ST_OK, st);
             }
-            if (st != ST_OK) {
-                if (S.mode == 0) return;
-                continue;
-            }
-            for (int v = lane; v < 18 * M; v += 32) {   // dummy <- vals (L182-L184)
+            if (st != ST_OK && S.mode == 0) return;
+            if (st != ST_OK && S.npeer <= 0) continue;
+            for (int v = lane; v < 18 * M; v += 32) {   // dummy <- vals (L182-L184); with peers: next table of every rank
                 int m = v / 18, r = v % 18, k = r / 6, i = r % 6;
-                ctrl[(size_t)c.qa * 18 * M + (size_t)k * 6 * M + m * 6 + i] = c.x[v];
+                const size_t at = (size_t)c.qa * 18 * M + (size_t)k * 6 * M + m * 6 + i;
+                if (S.npeer <= 0) { ctrl[at] = c.x[v]; continue; }
+                const double val = (st == ST_OK) ? c.x[v] : c.ctrl_src[at];
+                for (int p = 0; p < S.npeer; p++) S.peer_ctrl[p][(size_t)cidx * N * 18 * M + at] = val;
             }
             __syncwarp();
         }
+    peer_signal_done(S, lane == 0);
 }
 
 #endif

@@ -7,6 +7,7 @@ namespace rbpe {
 constexpr int NCP = 6;            // n+1 control points per segment (n = 5 only: rbp_planner.hpp L328, L361)
 constexpr int CTA_THREADS = 256;  // PDIP kernel block size
 constexpr int MAX_M = 64;
+constexpr int RBPE_MAX_PEERS = 8;   // one node: up to 8 GPUs behind one NVSwitch
 
 // status codes == include/rbpe.h
 enum { ST_OK = 0, ST_INFEASIBLE = 1, ST_NOT_CONVERGED = 2, ST_BAD_ARG = 3 };
@@ -63,6 +64,15 @@ struct SolveArgs {
     double *qp_res;         // [count][nrec][4]
     int nrec;
     int *status;            // [count] mission status (assembly may already have set BAD_ARG)
+    // Jacobi exchange fused into the sweep (multi-GPU, NVLink peer memory): every solved batch is stored into the next
+    // table of every rank (own one included), and the last work item of the launch raises this rank's flag on every peer
+    int npeer;              // 0: single-GPU behaviour (results go to `ctrl` only)
+    int peer_rank;
+    double *peer_ctrl[RBPE_MAX_PEERS];               // next control-point table [count][N][3][6M] of every rank
+    unsigned long long *peer_flags[RBPE_MAX_PEERS];  // flag words [RBPE_MAX_PEERS] of every rank; slot [peer_rank] is ours there
+    unsigned long long sweep_id;                     // value to raise (monotone)
+    unsigned int *done_counter;                      // work items finished in this launch (reset by the last one)
+    unsigned int work_items;
     double *scratch;        // per-CTA global scratch
     size_t scratch_stride;  // doubles per CTA
     unsigned smem_bytes;    // dynamic shared memory given to the kernel

@@ -65,15 +65,40 @@ def engine_ctrl_tensor(eng, count, N, M, device):
     return torch.as_tensor(_DevicePtr(eng.device_ctrl_ptr(), (count, N, 3, 6 * M)), device=device)
 
 
-def jacobi_solve(eng, prob, sweeps, group=None, device=None):
-    """Jacobi mode on the ranks of `group`: inputs replicated, batches sharded, one all-gather per sweep.
-    Returns the number of kernel launches issued by this rank."""
+def jacobi_attach_peers(eng, prob, group=None):
+    """One-time set-up of the fused exchange: upload + assemble (allocates the tables), export the IPC handles of the
+    two table buffers and the flag words, gather them over the process group (host side, any backend) and open the
+    peers' buffers.  Afterwards `jacobi_solve(..., fused=True)` needs no collective at all."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    eng.upload(prob)
+    eng.assemble()
+    mine = eng.peer_export()
+    handles = [None] * world
+    if world > 1:
+        dist.all_gather_object(handles, mine, group=group)
+    else:
+        handles[0] = mine
+    eng.peer_attach(rank, world, handles)
+    if world > 1:
+        dist.barrier(group=group)      # every rank has opened every buffer before the first remote store
+
+
+def jacobi_solve(eng, prob, sweeps, group=None, device=None, fused=False):
+    """Jacobi mode on the ranks of `group`: inputs replicated, batches sharded.
+    fused=False: one NCCL all-gather of the solved control points per sweep (`exchange_ctrl`).
+    fused=True (after `jacobi_attach_peers`): the sweep kernel's epilogue stores the solved control points into every
+    rank's next table over NVLink peer memory and raises a flag there; no collective call, no host synchronisation."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     bs, nbatch = prob.effective_batching()
     b0, b1 = batch_range(nbatch, world, rank)
     eng.upload(prob)
     eng.assemble()
+    if fused:
+        for _ in range(sweeps):
+            eng.run_jacobi_fused(b0, b1)
+        return eng
     table = engine_ctrl_tensor(eng, prob.count, prob.N, prob.M, device) if world > 1 else None
     for _ in range(sweeps):
         eng.run_jacobi_range(b0, b1)

@@ -44,7 +44,9 @@ class RbpeTiming(C.Structure):
 EXPORTS = ["rbpe_create", "rbpe_destroy", "rbpe_last_error", "rbpe_set_batch", "rbpe_solve_many", "rbpe_solve",
            "rbpe_upload", "rbpe_assemble", "rbpe_run", "rbpe_run_jacobi_range", "rbpe_set_ctrl", "rbpe_download", "rbpe_device_ctrl",
            "rbpe_device_coef", "rbpe_stream", "rbpe_sync", "rbpe_last_timing", "rbpe_timer_start", "rbpe_timer_stop",
-           "rbpe_corridor_rsfc", "rbpe_safety_metrics"]
+           "rbpe_corridor_rsfc", "rbpe_safety_metrics", "rbpe_peer_export", "rbpe_peer_attach", "rbpe_peer_attach_local",
+           "rbpe_run_jacobi_fused", "rbpe_peer_status"]
+IPC_HANDLE_BYTES = 64
 
 _lib = None
 
@@ -83,6 +85,16 @@ def load_library(path=None):
     L.rbpe_run.restype = C.c_int
     L.rbpe_run_jacobi_range.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.rbpe_run_jacobi_range.restype = C.c_int
+    L.rbpe_run_jacobi_fused.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.rbpe_run_jacobi_fused.restype = C.c_int
+    L.rbpe_peer_export.argtypes = [C.c_void_p, C.c_char_p]
+    L.rbpe_peer_export.restype = C.c_int
+    L.rbpe_peer_attach.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p]
+    L.rbpe_peer_attach.restype = C.c_int
+    L.rbpe_peer_attach_local.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    L.rbpe_peer_attach_local.restype = C.c_int
+    L.rbpe_peer_status.argtypes = [C.c_void_p]
+    L.rbpe_peer_status.restype = C.c_int
     L.rbpe_set_ctrl.argtypes = [C.c_void_p, _dp]
     L.rbpe_set_ctrl.restype = C.c_int
     L.rbpe_download.argtypes = [C.c_void_p, C.POINTER(RbpeResult)]
@@ -235,6 +247,40 @@ class Engine:
         if rc == CUDA_ERROR or rc == BAD_ARG:
             raise RuntimeError("rbpe_run_jacobi_range failed (%d): %s" % (rc, self.last_error()))
         return rc
+
+    # ---- Jacobi exchange over peer memory (include/rbpe.h, rbpe_peer_*) ----
+    def peer_export(self):
+        """Pins the table buffers and returns their IPC handles (bytes, 3 x 64)."""
+        buf = C.create_string_buffer(3 * IPC_HANDLE_BYTES)
+        rc = self.lib.rbpe_peer_export(self.h, buf)
+        if rc != OK:
+            raise RuntimeError("rbpe_peer_export failed (%d): %s" % (rc, self.last_error()))
+        return buf.raw
+
+    def peer_attach(self, rank, world, all_handles):
+        """all_handles: list of `world` byte strings from peer_export, rank order (other processes)."""
+        blob = b"".join(all_handles)
+        assert len(blob) == world * 3 * IPC_HANDLE_BYTES
+        rc = self.lib.rbpe_peer_attach(self.h, rank, world, blob)
+        if rc != OK:
+            raise RuntimeError("rbpe_peer_attach failed (%d): %s" % (rc, self.last_error()))
+
+    def peer_attach_local(self, rank, engines):
+        """engines: the Engine objects of all ranks living in THIS process, rank order."""
+        arr = (C.c_void_p * len(engines))(*[e.h for e in engines])
+        rc = self.lib.rbpe_peer_attach_local(self.h, rank, len(engines), arr)
+        if rc != OK:
+            raise RuntimeError("rbpe_peer_attach_local failed (%d): %s" % (rc, self.last_error()))
+
+    def run_jacobi_fused(self, b0, b1):
+        rc = self.lib.rbpe_run_jacobi_fused(self.h, b0, b1)
+        if rc != OK:
+            raise RuntimeError("rbpe_run_jacobi_fused failed (%d): %s" % (rc, self.last_error()))
+
+    def peer_status(self):
+        rc = self.lib.rbpe_peer_status(self.h)
+        if rc != OK:
+            raise RuntimeError("peer exchange failed (%d): %s" % (rc, self.last_error()))
 
     def set_ctrl(self, ctrl):
         c = np.ascontiguousarray(ctrl, np.float64)

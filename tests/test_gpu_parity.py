@@ -159,6 +159,38 @@ def test_jacobi_sweep_matches_per_batch_oracle_solves(eng):
         assert np.abs(got - ctrl.transpose(1, 0, 2)).max() < CTRL_TOL
 
 
+@pytest.mark.parametrize("N,bs,split", [(12, 1, 5), (10, 2, 2), (6, 1, 0)])
+def test_jacobi_fused_peer_exchange_equals_sweep_plus_copy(N, bs, split):
+    """The exchange fused into the sweep kernel (stores into every rank's next table over peer memory + flag words,
+    include/rbpe.h rbpe_peer_*) gives bit-identical tables to the plain Jacobi sweeps.  Two "ranks" = two engine handles
+    of this process on one GPU (raw device pointers instead of IPC handles); split = first batch of rank 1 (0 = rank 0
+    has nothing to solve and only raises its flags)."""
+    import __graft_entry__ as G
+    G.build()
+    ms = [synth.synth_mission(N, 4, 0.2, 500 + i) for i in range(3)]
+    sweeps = 3
+    prob = E.PackedProblem(synth.pack(ms), sequential=True, batch_size=bs, iteration=sweeps)
+    _, nbatch = prob.effective_batching()
+    ref = E.Engine(device=0)
+    ref.upload(prob); ref.assemble()
+    for _ in range(sweeps):
+        ref.run_jacobi_range(0, nbatch)
+    r0 = ref.download(prob)
+    ref.close()
+    ea, eb = E.Engine(device=0), E.Engine(device=0)
+    for e in (ea, eb):
+        e.upload(prob); e.assemble(); e.peer_export()
+    ea.peer_attach_local(0, [ea, eb]); eb.peer_attach_local(1, [ea, eb])
+    for _ in range(sweeps):          # both ranks enqueue asynchronously; the flag waits run on the streams
+        ea.run_jacobi_fused(0, split)
+        eb.run_jacobi_fused(split, nbatch)
+    ra, rb = ea.download(prob), eb.download(prob)
+    ea.peer_status(); eb.peer_status()
+    assert np.array_equal(ra.ctrl, r0.ctrl) and np.array_equal(rb.ctrl, r0.ctrl)
+    assert np.array_equal(ra.coef, r0.coef) and np.array_equal(rb.coef, r0.coef)
+    ea.close(); eb.close()
+
+
 def test_fixture_batch15_matches_cplex_csv(eng, golden):
     """The reference's only frozen CPLEX run: log/QPmodel.lp (batch 15 of a 64-agent, 36-segment mission) and
     log/coef61..64.csv.  The engine assembles batch 15 from the recovered inputs with agents 0..59 frozen at CPLEX's own
