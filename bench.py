@@ -149,6 +149,7 @@ def main():
     ap.add_argument("--ref-missions", type=int, default=64, help="missions per step of the CPU arm")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--joint-missions", type=int, default=592, help="missions of the joint-batch leg (configs[1]); 0 = skip")
     ap.add_argument("--jacobi-missions", type=int, default=64, help="missions (replicated on every rank) of the Jacobi leg; 0 = skip")
     ap.add_argument("--jacobi-sweeps", type=int, default=2)
     args = ap.parse_args()
@@ -161,8 +162,11 @@ def main():
         run_reference(args, rank, world)
         return
 
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+    # rank 0 prints exactly ONE JSON line on stdout: native libraries (NCCL's version banner) write to fd 1 directly, so
+    # fd 1 is pointed at stderr for the whole run and the result goes to the saved descriptor
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -251,6 +255,28 @@ def main():
     value = world * nqp / (ms_step * 1e-3)
     e2e = world * nqp / (ms_e2e * 1e-3)
 
+    # ---- secondary leg: BASELINE configs[1] (16 agents, forest 0.2, 5 segments, ONE joint QP per mission: nv = 1440, K = 2304);
+    # CTA-per-QP kernel, block tridiagonal factorisation of 144 x 144 blocks on the FP64 tensor pipe (DMMA) ----
+    joint = None
+    if args.joint_missions > 0:
+        jm = [synth.synth_mission(16, M_SEG, RHO, 2000 + rank * 64 + i) for i in range(2)]
+        jp = E.PackedProblem(pin(synth.pack([jm[i % 2] for i in range(args.joint_missions)])), sequential=False, batch_size=16)
+        je = E.Engine(device=local)
+        je.upload(jp); je.run(); je.sync()
+        barrier()
+        je.timer_start()
+        for _ in range(2):
+            je.run()
+        ms_joint = max_over_ranks(je.timer_stop() / 2)
+        jr = je.download(jp)
+        it_j = int(jr.qp_iters.sum())
+        joint = {"workload": "16 agents, random forest rho=0.2, 5-segment, one joint batch of 16 (BASELINE configs[1])",
+                 "value": world * args.joint_missions * 16 / (ms_joint * 1e-3), "unit": UNIT, "ms_per_step": ms_joint,
+                 "missions_per_gpu": args.joint_missions, "ipm_iterations_mean": float(jr.qp_iters.mean()), "failed": int((jr.status != 0).sum()),
+                 "dense_tflops": dense_flops_per_iter(16, M_SEG) * it_j / (ms_joint * 1e-3) / 1e12,
+                 "kernel": "pdip_kernel (256 threads per QP; DMMA m8n8k4 block Cholesky, rbpe_blockla.cuh)"}
+        je.close()
+
     # ---- secondary leg: Jacobi mode (north-star's agent sharding): the SAME missions on every rank, each rank solves its
     # range of agents of every mission against the frozen table; the exchange of the solved control points is fused into the
     # sweep kernel (peer stores over NVLink), with the NCCL all-gather variant timed beside it ----
@@ -309,6 +335,8 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clk,
     }
+    if joint:
+        out["joint_batch"] = joint
     if jac:
         out["jacobi_mode"] = jac
     if rank == 0:
@@ -318,30 +346,55 @@ def main():
         except Exception:
             pass
         bf16 = peaks.get("bf16_tflops_sustained") or 1400.0
-        tf32_peak = bf16 / 2.0
+        tf32_peak, tf32_src = bf16 / 2.0, ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 dense proxy)" if peaks
+                                           else "fallback 1.4 PFLOP/s bf16 / 2")
+        fp64_peak = None
+        try:   # the two peaks this path is judged against, measured here (after the timed regions): cuBLAS TF32 and FP64 GEMMs
+            def gemm_tflops(dtype, n, reps):
+                a_ = torch.randn(n, n, device="cuda", dtype=dtype); b_ = torch.randn(n, n, device="cuda", dtype=dtype)
+                torch.matmul(a_, b_); torch.cuda.synchronize()
+                best = 1e9
+                for _ in range(reps):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(); torch.matmul(a_, b_); e1.record(); torch.cuda.synchronize()
+                    best = min(best, e0.elapsed_time(e1))
+                return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+            torch.backends.cuda.matmul.allow_tf32 = True
+            tf32_peak, tf32_src = gemm_tflops(torch.float32, 8192, 5), "measured in this run: torch.matmul TF32 8192^3, best of 5 (CUDA events)"
+            fp64_peak = gemm_tflops(torch.float64, 4096, 3)
+        except Exception as ex:   # keep the fallback
+            print("peak measurement skipped: %r" % (ex,), file=sys.stderr)
         f_dense = dense_flops_per_iter(1, M_SEG) * iters_total          # per rank per step
         f_struct = structured_flops_per_iter(1, M_SEG, N_AGENTS) * iters_total
         ach = f_dense / (kernel_ms * 1e-3) / 1e12
-        traffic = None
-        try:   # DRAM bytes of one launch of the dominant kernel, from the committed ncu --set full capture (same mission count)
+        traffic, ncu = None, {}
+        try:   # DRAM bytes of one launch of the dominant kernel from the committed ncu --set full capture, scaled to this
+            # launch's mission count (missions are independent work items of identical shape)
             prof = json.load(open(os.path.join(ROOT, "profiles", "r1_pdip1_ncu.json")))
-            if count == prof.get("missions", 1184):
-                traffic = prof["dram_bytes_per_launch"]
+            traffic = prof["dram_bytes_per_launch"] * count / float(prof.get("missions", 2368))
+            ncu = {k: float(v["value"].replace(",", "")) for k, v in prof["metrics"].items() if k.endswith(".pct") or "pct_of_peak" in k}
         except Exception:
             pass
         out["roofline"] = {
             "bound": "tensor", "kernel": "pdip1_kernel", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",
-            "frac": ach / tf32_peak, "traffic": traffic,
-            "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 dense proxy; TF32 itself not measured)"
-                            if peaks else "fallback 1.4 PFLOP/s bf16 / 2"),
-            "algorithmic": "dense reduced-KKT flops (SURVEY 8d) x iterations executed: %.3e per launch" % f_dense,
+            "frac": ach / tf32_peak, "traffic": traffic, "peak_source": tf32_src,
+            "algorithmic": "dense reduced-KKT flops (SURVEY 8d: nv^3/3 + nv^2 ne + nv ne^2 + ne^3/3 = 0.995 MFLOP per iteration at "
+                           "b=1, M=5) x iterations executed: %.3e per launch" % f_dense,
             "executed_structured_tflops": f_struct / (kernel_ms * 1e-3) / 1e12,
+            "executed_structured_note": "block tridiagonal factor / solves + 40 flops per inequality row and pass, counted over ALL rows "
+                                        "of populatebyrow; the presolve drops 60-95% of the RSFC rows, so this is an upper bound",
+            "fp64_peak_tflops": fp64_peak,
+            "executed_fraction_of_fp64_peak": (f_struct / (kernel_ms * 1e-3) / 1e12 / fp64_peak) if fp64_peak else None,
             "kernel_ms_per_launch": kernel_ms,
-            "traffic_note": "ncu dram__bytes_read+write of one launch (profiles/r1_pdip1_ncu.md): the L2-resident row-state "
-                            "arena partly spills (L2 hit 78%); inputs + outputs of a launch are 0.75 GB",
-            "fp64_pipe_pct_ncu": 13.0,
-            "note": "round-1 kernel is FP64 SIMT (no tensor cores): one-agent QPs reduce to 36x36 block tridiagonal systems; "
-                    "instruction-fetch / latency bound (ncu: issue slots 29% busy, FP64 pipe 13%, GPC I-cache 94%), see DESIGN.md section 6",
+            "traffic_note": "ncu dram__bytes_read+write of one launch (profiles/r1_pdip1_ncu.md, %d missions) scaled to %d missions; "
+                            "far above the %.2f GB of inputs + outputs because the per-warp row-state arena is written once per "
+                            "QP and spills from L2" % (2368, count, (h2d + d2h) / 1e9),
+            "ncu": {"issue_active_pct": ncu.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                    "fp64_pipe_pct": ncu.get("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+                    "l2_hit_pct": ncu.get("lts__t_sector_hit_rate.pct")},
+            "note": "one-agent QPs (K = 144) reduce to 36x36 block tridiagonal systems: FP64 SIMT, issue/latency bound, no tensor "
+                    "work by design (SURVEY section 7 'tiny matrices'); the joint-batch kernel (b > 1) runs its factorisation on the "
+                    "FP64 tensor pipe (DMMA), see the joint_batch leg and DESIGN.md section 4",
         }
         if world == 1 and not args.no_cpu_baseline:
             sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -360,7 +413,8 @@ def main():
                                    "sample": "%d missions (the %d distinct ones, repeated) in %.1f s, OpenMP over missions"
                                              % (n, len(pool), dt),
                                    "note": "CPU oracle (not CPLEX: proprietary, absent)"}
-        print(json.dumps(out), flush=True)
+        sys.stdout.flush()
+        os.write(result_fd, (json.dumps(out) + "\n").encode())
     eng.close()
     if world > 1:
         dist.destroy_process_group()

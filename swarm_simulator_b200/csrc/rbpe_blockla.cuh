@@ -315,6 +315,7 @@ RBPE_NOINLINE void solve_bt_blk(int nblk, int kb, int kp, const double *Dall, co
 //   * the two solves of an interior-point iteration are then 9 x 9 matrix-vector products (one lane per row, no
 //     shuffles, no 9-step substitution chains).
 // D_t -= L_{t,t-1} L_{t,t-1}' runs on 27 lanes (3 entries each).  cb: >= 32 doubles of shared memory.
+template <int TAG>   // TAG: one private copy per kernel (a copy shared by two kernels changed the one-agent kernel's layout: -12%)
 RBPE_NOINLINE bool factor_bt9v(int nblk, double *Dall, double *Oall, double *cb) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -371,6 +372,7 @@ RBPE_NOINLINE bool factor_bt9v(int nblk, double *Dall, double *Oall, double *cb)
 }
 
 // g <- (L L')^-1 g with Dall = inverses of the diagonal factor blocks, Oall = L_{t+1,t} (factor_bt9v)
+template <int TAG>
 RBPE_NOINLINE void solve_bt9v(int nblk, const double *Dall, const double *Oall, double *g, double *cb) {
     const int lane = threadIdx.x & 31;
     const bool act = lane < 9;

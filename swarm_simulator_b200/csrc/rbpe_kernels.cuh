@@ -675,7 +675,7 @@ RBPE_NOINLINE bool kkt_factor(const QP &q) {
     PROF(5);
     if (q.kb == 9) {
         if ((threadIdx.x >> 5) == 0) {
-            bool ok = factor_bt9v(q.M - 1, q.Wd, q.Wo, q.dinv);
+            bool ok = factor_bt9v<0>(q.M - 1, q.Wd, q.Wo, q.dinv);
             if (threadIdx.x == 0) q.red[60] = ok ? 0.0 : 1.0;
         }
         __syncthreads();
@@ -690,7 +690,7 @@ RBPE_NOINLINE void kkt_solve(const QP &q, const double *r, double *dxout) {
     Zt_apply(q, r, q.sg);
     __syncthreads();
     if (q.kb == 9) {
-        if ((threadIdx.x >> 5) == 0) solve_bt9v(q.M - 1, q.Wd, q.Wo, q.sg, q.dinv);
+        if ((threadIdx.x >> 5) == 0) solve_bt9v<0>(q.M - 1, q.Wd, q.Wo, q.sg, q.dinv);
     } else {
         solve_bt_blk(q.M - 1, q.kb, q.kp, q.Wd, q.Wo, q.Linv, q.sg, q.wk, q.yk);
     }

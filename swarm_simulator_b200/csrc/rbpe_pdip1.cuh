@@ -73,14 +73,22 @@ struct W1 {
     double *nrm;                                            // [m][e][3], sign folded in (FP64: no per-row F2F)
 };
 
-template <int MASK>
-RBPE_DEV void warp_reduce(double &s1, double &s2, double &mx, double &mx2) {
+// Warp all-reduce of (sum, sum, max, max, max) -- ONE non-inlined copy with a rolled butterfly: the inlined templated
+// version accounted for a third of the kernel's code (64-bit shuffles are two SHFLs plus packing each), and the kernel is
+// instruction-fetch bound (ncu r1: no_instruction is the top stall whenever the text grows past ~125 KB).
+struct Red5 { double s1, s2, mx, mx2, mx3; };
+RBPE_NOINLINE Red5 warp_reduce5(double s1, double s2, double mx, double mx2, double mx3) {
+#pragma unroll 1
     for (int o = 16; o > 0; o >>= 1) {
-        if (MASK & 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-        if (MASK & 2) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-        if (MASK & 4) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        if (MASK & 8) mx2 = fmax(mx2, __shfl_xor_sync(0xffffffffu, mx2, o));
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        mx2 = fmax(mx2, __shfl_xor_sync(0xffffffffu, mx2, o));
+        mx3 = fmax(mx3, __shfl_xor_sync(0xffffffffu, mx3, o));
     }
+    Red5 r;
+    r.s1 = s1; r.s2 = s2; r.mx = mx; r.mx2 = mx2; r.mx3 = mx3;
+    return r;
 }
 
 // same row algebra as row_eval (rbpe_kernels.cuh); t = 1/(s z) computed here
@@ -181,9 +189,10 @@ RBPE_DEV void w1_pass(const W1 &c, double sa, double sb, Acc &out) {
             }
         }
     }
-    if (MODE == P_RES || MODE == P_AFF) warp_reduce<1 + 2 + 4>(acc.s1, acc.s2, acc.mx, acc.mx2);
-    if (MODE == P_START) warp_reduce<4 + 8>(acc.s1, acc.s2, acc.mx, acc.mx2);
-    if (MODE == P_STEP || MODE == P_DEAD) warp_reduce<4>(acc.s1, acc.s2, acc.mx, acc.mx2);
+    if (MODE == P_RES || MODE == P_AFF || MODE == P_START || MODE == P_STEP || MODE == P_DEAD) {
+        Red5 r = warp_reduce5(acc.s1, acc.s2, acc.mx, acc.mx2, 0.0);
+        acc.s1 = r.s1; acc.s2 = r.s2; acc.mx = r.mx; acc.mx2 = r.mx2;
+    }
     __syncwarp();
     out = acc;
 }
@@ -244,7 +253,7 @@ RBPE_NOINLINE void w1_build_W(const double *segmat, int M, const double *Dcp, do
 // dxout = Z (Z'HZ)^-1 Z' r
 RBPE_DEV void w1_solve(const W1 &c, const double *r, double *dxout) {
     w1_Zt(c.segmat, c.nr, r, c.sg);
-    solve_bt9v(c.M - 1, c.Wd, c.Wo, c.sg, c.dinv);
+    solve_bt9v<1>(c.M - 1, c.Wd, c.Wo, c.sg, c.dinv);
     w1_Z(c.segmat, c.M, c.sg, dxout);
 }
 // rdx = 2 Q x + vA; returns the lane-partial objective and max|Px|
@@ -361,29 +370,33 @@ RBPE_DEV int w1_solve_qp(const W1 &c, int max_iter, double tol_gap, double tol_r
     if (go && c.nr == 0) {
         double o = 0, mpx = 0, d1 = 0, d2 = 0;
         o = w1_dual(c.segmat, c.M, c.QB, c.x, c.vA, c.rdx).obj;
-        warp_reduce<1>(o, d1, mpx, d2);
+        o = warp_reduce5(o, 0.0, 0.0, 0.0, 0.0).s1;
         obj = o; status = ST_OK; go = false;
     }
     if (go) {
         double mh = 0, d0 = 0, d1 = 0, d2 = 0;
+        #pragma unroll 1
         for (int slot = 0; slot < c.nslot; slot++) {
             const int cp = slot * 32 + lane;
             if (cp >= c.ncp || w1_dead(c, cp)) continue;
             const size_t rb = (size_t)slot * c.NR * 32 + lane;
             const int cnt = c.cnt[slot * 32 + lane];
+            #pragma unroll 1
             for (int j = 0; j < cnt; j++) mh = fmax(mh, fabs(c.he[rb + (size_t)j * 32]));
         }
-        warp_reduce<4>(d0, d1, mh, d2);
+        mh = warp_reduce5(0.0, 0.0, mh, 0.0, 0.0).mx;
         hn = mh;
         w1_pass<P_INIT>(c, 0, 0, acc);
         w1_build_W(c.segmat, c.M, c.Dcp, c.Wd, c.Wo);
-        if (!factor_bt9v(c.M - 1, c.Wd, c.Wo, c.dinv)) go = false;
+        if (!factor_bt9v<1>(c.M - 1, c.Wd, c.Wo, c.dinv)) go = false;
     }
     if (go) {
         w1_dual(c.segmat, c.M, c.QB, c.x, c.vA, c.rdx);   // rdx = P x_p + vA
+        #pragma unroll 1
         for (int v = lane; v < 18 * c.M; v += 32) c.rdx[v] = 2.0 * c.vA[v] - c.rdx[v];
         __syncwarp();
         w1_solve(c, c.rdx, c.dx);
+        #pragma unroll 1
         for (int v = lane; v < 18 * c.M; v += 32) { c.x[v] += c.dx[v]; c.dx[v] = 0; }
         __syncwarp();
         w1_pass<P_START>(c, 0, 0, acc);
@@ -395,6 +408,7 @@ RBPE_DEV int w1_solve_qp(const W1 &c, int max_iter, double tol_gap, double tol_r
     for (it = 0; go && it < max_iter; it++) {
         w1_pass<P_RES>(c, sigmu, al, acc);
         if (al != 0.0) {
+            #pragma unroll 1
             for (int v = lane; v < 18 * c.M; v += 32) c.x[v] += al * c.dx[v];
             __syncwarp();
         }
@@ -405,17 +419,18 @@ RBPE_DEV int w1_solve_qp(const W1 &c, int max_iter, double tol_gap, double tol_r
         w1_Zt(c.segmat, c.nr, c.rdx, c.sg);
         w1_Zt(c.segmat, c.nr, c.vA, c.sg2);
         double mr = 0, mc = 0;
+        #pragma unroll 1
         for (int r = lane; r < c.nr; r += 32) { mr = fmax(mr, fabs(c.sg[r])); mc = fmax(mc, fabs(c.sg2[r])); }
         double d1 = 0;
-        warp_reduce<1 + 4 + 8>(o, d1, mpx, mr);
-        warp_reduce<4>(d1, d1, mc, d1);
+        { Red5 r = warp_reduce5(o, 0.0, mpx, mr, mc); o = r.s1; mpx = r.mx; mr = r.mx2; mc = r.mx3; }
         obj = o; nrd = mr;
         gap = mu;
         if (!(mu == mu) || !(nrd == nrd)) { status = ST_NOT_CONVERGED; break; }
         if (gap <= tol_gap * fmax(1.0, fabs(obj)) && nrg <= tol_res * (1 + hn) && nrd <= tol_res * (1.0 + mpx)) { status = ST_OK; break; }
         if (hz < 0 && mc / (-hz) < 1e-8) { status = ST_INFEASIBLE; break; }
         w1_build_W(c.segmat, c.M, c.Dcp, c.Wd, c.Wo);
-        if (!factor_bt9v(c.M - 1, c.Wd, c.Wo, c.dinv)) { status = ST_NOT_CONVERGED; break; }
+        if (!factor_bt9v<1>(c.M - 1, c.Wd, c.Wo, c.dinv)) { status = ST_NOT_CONVERGED; break; }
+        #pragma unroll 1
         for (int v = lane; v < 18 * c.M; v += 32) c.vB[v] = -c.rdx[v] + c.vB[v];
         __syncwarp();
         w1_solve(c, c.vB, c.dxa);
@@ -425,6 +440,7 @@ RBPE_DEV int w1_solve_qp(const W1 &c, int max_iter, double tol_gap, double tol_r
         double sigma = (mu > 0) ? (mua / mu) * (mua / mu) * (mua / mu) : 0.0;
         sigmu = sigma * mu;
         w1_pass<P_COR>(c, sigmu, 0, acc);
+        #pragma unroll 1
         for (int v = lane; v < 18 * c.M; v += 32) c.vA[v] = -c.rdx[v] + c.vA[v];
         __syncwarp();
         w1_solve(c, c.vA, c.dx);
@@ -433,6 +449,7 @@ RBPE_DEV int w1_solve_qp(const W1 &c, int max_iter, double tol_gap, double tol_r
     }
     // |Ax - b| for the record
     double mrp = 0;
+    #pragma unroll 1
     for (int e = lane; e < 9 * (c.M + 1); e += 32) {
         int t = e / 9, cc = e % 9, k = cc / 3, d = cc % 3;
         double sm = 0;
@@ -449,7 +466,7 @@ RBPE_DEV int w1_solve_qp(const W1 &c, int max_iter, double tol_gap, double tol_r
         mrp = fmax(mrp, fabs(sm));
     }
     double d0 = 0, d1 = 0, d2 = 0;
-    warp_reduce<4>(d0, d1, mrp, d2);
+    mrp = warp_reduce5(0.0, 0.0, mrp, 0.0, 0.0).mx;
     if (lane == 0) {
         *obj_out = obj;
         *it_out = it;
@@ -524,11 +541,16 @@ __global__ void __launch_bounds__(W1_WARPS * 32, RBPE_W1_MINB) pdip1_kernel(Solv
             }
             if (st != ST_OK && S.mode == 0) return;
             if (st != ST_OK && S.npeer <= 0) continue;
+            #pragma unroll 1
             for (int v = lane; v < 18 * M; v += 32) {   // dummy <- vals (L182-L184); with peers: next table of every rank
                 int m = v / 18, r = v % 18, k = r / 6, i = r % 6;
                 const size_t at = (size_t)c.qa * 18 * M + (size_t)k * 6 * M + m * 6 + i;
+#ifdef RBPE_NO_PEER1
+                ctrl[at] = c.x[v]; continue;
+#endif
                 if (S.npeer <= 0) { ctrl[at] = c.x[v]; continue; }
                 const double val = (st == ST_OK) ? c.x[v] : c.ctrl_src[at];
+                #pragma unroll 1
                 for (int p = 0; p < S.npeer; p++) S.peer_ctrl[p][(size_t)cidx * N * 18 * M + at] = val;
             }
             __syncwarp();

@@ -85,16 +85,17 @@ def load_library(path=None):
     L.rbpe_run.restype = C.c_int
     L.rbpe_run_jacobi_range.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.rbpe_run_jacobi_range.restype = C.c_int
-    L.rbpe_run_jacobi_fused.argtypes = [C.c_void_p, C.c_int, C.c_int]
-    L.rbpe_run_jacobi_fused.restype = C.c_int
-    L.rbpe_peer_export.argtypes = [C.c_void_p, C.c_char_p]
-    L.rbpe_peer_export.restype = C.c_int
-    L.rbpe_peer_attach.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p]
-    L.rbpe_peer_attach.restype = C.c_int
-    L.rbpe_peer_attach_local.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
-    L.rbpe_peer_attach_local.restype = C.c_int
-    L.rbpe_peer_status.argtypes = [C.c_void_p]
-    L.rbpe_peer_status.restype = C.c_int
+    if path is None or hasattr(L, "rbpe_run_jacobi_fused"):   # (tools/gpu_ab.py may load older builds of the library)
+        L.rbpe_run_jacobi_fused.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.rbpe_run_jacobi_fused.restype = C.c_int
+        L.rbpe_peer_export.argtypes = [C.c_void_p, C.c_char_p]
+        L.rbpe_peer_export.restype = C.c_int
+        L.rbpe_peer_attach.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p]
+        L.rbpe_peer_attach.restype = C.c_int
+        L.rbpe_peer_attach_local.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.rbpe_peer_attach_local.restype = C.c_int
+        L.rbpe_peer_status.argtypes = [C.c_void_p]
+        L.rbpe_peer_status.restype = C.c_int
     L.rbpe_set_ctrl.argtypes = [C.c_void_p, _dp]
     L.rbpe_set_ctrl.restype = C.c_int
     L.rbpe_download.argtypes = [C.c_void_p, C.POINTER(RbpeResult)]

@@ -5,8 +5,6 @@
 #include <stdint.h>
 
 #include "cuda_emu.h"
-namespace rbpe { long g_emu_dmma = 0; }
-extern "C" long emu_dmma_count() { return rbpe::g_emu_dmma; }
 #define RBPE_EMU 1
 #include "../../swarm_simulator_b200/csrc/rbpe_kernels.cuh"
 #include "../../include/rbpe.h"
@@ -37,6 +35,7 @@ extern "C" int emu_solve_many(const rbpe_problem *p, int count, int mode, rbpe_r
     std::vector<double> obj((size_t)count * nrec, 0.0), res((size_t)count * nrec * 4, 0.0);
     std::vector<int> its((size_t)count * nrec, 0), qst((size_t)count * nrec, 0);
     SolveArgs S;
+    S.npeer = 0; S.peer_rank = 0; S.sweep_id = 0; S.done_counter = nullptr; S.work_items = 0;
     S.count = count; S.N = N; S.M = M; S.bs = bs; S.nbatch = nbatch; S.iteration = p->iteration;
     S.sequential = p->sequential; S.mode = mode; S.batch_begin = 0; S.batch_end = nbatch; S.rec_offset = 0;
     S.max_iter = max_iter > 0 ? max_iter : 100;
@@ -110,4 +109,19 @@ extern "C" int rbpe_set_batch(int N, int sequential, int batch_size, int batch_i
     *ebs = batch_size;
     *ebi = batch_iter;
     return bmax;
+}
+
+// Block tridiagonal factorisation / solve of rbpe_blockla.cuh on caller-provided blocks (test_emu_kernels.py compares with
+// numpy): Dall [nblk][kp*kp] (lower triangles used), Oall [nblk-1][kp*kp], g [nblk*kb] -> in place: factor, solution.
+extern "C" int emu_block_tridiag(int nblk, int kb, double *Dall, double *Oall, double *g, int threads) {
+    const int kp = bla_kp(kb);
+    std::vector<double> Linv((size_t)nblk * bla_ninv(kp) * BLA_W * BLA_W), w((size_t)nblk * kp), y(kp + 32), flag(1);
+    int ok = 1;
+    emu::launch([&] {
+        bool f = factor_bt_blk(nblk, kp, Dall, Oall, Linv.data(), flag.data());
+        if (threadIdx.x == 0) ok = f ? 1 : 0;
+        __syncthreads();
+        solve_bt_blk(nblk, kb, kp, Dall, Oall, Linv.data(), g, w.data(), y.data());
+    }, 1, threads, 0);
+    return ok;
 }

@@ -38,3 +38,19 @@ def emu_solve_many(prob, mode=0, smem_bytes=48 * 1024, max_iter=0, tol_gap=0.0, 
     r.rc = _lib.emu_solve_many(C.byref(prob.c), prob.count, mode, C.byref(r.c), smem_bytes, max_iter, tol_gap,
                                tol_res, threads)
     return r
+
+
+def emu_block_tridiag(D, O, g, threads=64):
+    """D [nblk, kp, kp], O [nblk-1, kp, kp] (kp = kb rounded up to a multiple of 8, identity padded), g [nblk, kb]:
+    factor + solve with the product routines of rbpe_blockla.cuh under the emulator; returns (ok, x, L_diag_blocks, L_off_blocks)."""
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+    _lib.emu_block_tridiag.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    _lib.emu_block_tridiag.restype = C.c_int
+    nblk, kb = g.shape
+    Dc, Oc, gc = np.ascontiguousarray(D, np.float64).copy(), np.ascontiguousarray(O, np.float64).copy(), np.ascontiguousarray(g, np.float64).copy()
+    if Oc.size == 0:
+        Oc = np.zeros((1,) + Dc.shape[1:])
+    ok = _lib.emu_block_tridiag(nblk, kb, Dc.ctypes.data, Oc.ctypes.data, gc.ctypes.data, threads)
+    return bool(ok), gc, Dc, Oc

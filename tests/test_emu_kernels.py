@@ -22,3 +22,35 @@ def test_emulated_kernels_match_oracle(N, M, rho, seq, bs, smem):
     assert np.array_equal(r.qp_iters[0], ro["batch_iters"][:r.qp_iters.shape[1]])
     assert np.abs(r.ctrl[0] - ro["ctrl"]).max() < 1e-9
     assert np.abs(r.coef[0] - ro["coef"]).max() < 1e-9
+
+
+@pytest.mark.parametrize("kb,nblk,threads", [(18, 3, 64), (36, 2, 64), (45, 3, 96), (72, 2, 128), (27, 1, 32)])
+def test_emulated_block_tridiagonal_factor_and_solve(kb, nblk, threads):
+    """rbpe_blockla.cuh (DMMA tile updates, warp-level 32 x 32 diagonal blocks + inverses, blocked substitution) against
+    numpy on a random SPD block tridiagonal system, for block orders that are / are not multiples of 8 and of 32."""
+    rng = np.random.default_rng(kb * 10 + nblk)
+    n = kb * nblk
+    G = rng.standard_normal((n, n))
+    A = G @ G.T + n * np.eye(n)
+    for i in range(nblk):            # keep the block tridiagonal part only (diagonally dominant enough to stay SPD)
+        for j in range(nblk):
+            if abs(i - j) > 1:
+                A[i * kb:(i + 1) * kb, j * kb:(j + 1) * kb] = 0
+    A += np.eye(n) * np.abs(A).sum(1).max()
+    kp = (kb + 7) // 8 * 8
+    D = np.zeros((nblk, kp, kp)); O = np.zeros((max(nblk - 1, 0), kp, kp))
+    for t in range(nblk):
+        D[t] = np.eye(kp)
+        D[t, :kb, :kb] = np.tril(A[t * kb:(t + 1) * kb, t * kb:(t + 1) * kb])
+        if t + 1 < nblk:
+            O[t, :kb, :kb] = A[(t + 1) * kb:(t + 2) * kb, t * kb:(t + 1) * kb]
+    g = rng.standard_normal((nblk, kb))
+    ok, x, Lf, Lo = emu_util.emu_block_tridiag(D, O, g, threads=threads)
+    assert ok
+    x_ref = np.linalg.solve(A, g.reshape(-1))
+    assert np.abs(x.reshape(-1) - x_ref).max() < 1e-11 * max(1.0, np.abs(x_ref).max())
+    L = np.linalg.cholesky(A)
+    for t in range(nblk):
+        assert np.abs(np.tril(Lf[t, :kb, :kb]) - L[t * kb:(t + 1) * kb, t * kb:(t + 1) * kb]).max() < 1e-10 * np.abs(L).max()
+        if t + 1 < nblk:
+            assert np.abs(Lo[t, :kb, :kb] - L[(t + 1) * kb:(t + 2) * kb, t * kb:(t + 1) * kb]).max() < 1e-10 * np.abs(L).max()

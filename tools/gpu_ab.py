@@ -8,8 +8,7 @@ ms = [synth.synth_mission(64, 5, 0.2, 3000 + i) for i in range(8)]
 count = int(os.environ.get("AB_COUNT", 2368))
 packed = synth.pack([ms[i % 8] for i in range(count)])
 for lib in sys.argv[1:]:
-    E._lib = None
-    E.LIB_PATH = os.path.join(ROOT, lib)
+    E._lib = E.load_library(os.path.join(ROOT, lib))
     eng = E.Engine()
     prob = E.PackedProblem(packed, sequential=True, batch_size=1)
     eng.upload(prob)
