@@ -14,7 +14,10 @@
 
 namespace rbpe {
 
-constexpr int W1_WARPS = 4;
+#ifndef RBPE_W1_WARPS
+#define RBPE_W1_WARPS 4
+#endif
+constexpr int W1_WARPS = RBPE_W1_WARPS;   // QPs (warps) per CTA; 16 warps per SM either way (registers, shared memory)
 #ifndef RBPE_W1_UNROLL
 #define RBPE_W1_UNROLL 1
 #endif
@@ -30,7 +33,7 @@ static const double c_QB[36] = {QROW(0), QROW(1), QROW(2), QROW(3), QROW(4), QRO
 
 __host__ __device__ inline size_t w1_smem_doubles(int M) {  // per warp
     size_t ncp = 6 * (size_t)M, nr = 9 * (size_t)(M > 1 ? M - 1 : 0);
-    return al2(6 * 3 * ncp) + al2(6 * ncp) + al2((size_t)(M > 1 ? M - 1 : 1) * 81) + al2((size_t)(M > 2 ? M - 2 : 1) * 81) + 2 * al2(nr) + al2(nr > 32 ? nr : 32) + al2((6 * (size_t)M + 31) / 32);
+    return al2(6 * 3 * ncp) + al2(6 * ncp) + al2((size_t)(M > 1 ? M - 1 : 1) * 81) + al2((size_t)(M > 2 ? M - 2 : 1) * 81) + al2(nr) + al2(nr > 32 ? nr : 32) + al2((6 * (size_t)M + 31) / 32);
 }
 __host__ __device__ inline size_t w1_scratch_doubles(int N, int M) {  // per warp, global arena
     size_t nslot = (6 * (size_t)M + 31) / 32, NR = (size_t)(N > 1 ? N - 1 : 0) + 6;   // + the 6 box rows of a control point
@@ -476,7 +479,7 @@ RBPE_DEV int w1_solve_qp(const W1 &c, int max_iter, double tol_gap, double tol_r
 }
 
 #ifndef RBPE_W1_MINB
-#define RBPE_W1_MINB 4
+#define RBPE_W1_MINB (16 / RBPE_W1_WARPS)
 #endif
 __global__ void __launch_bounds__(W1_WARPS * 32, RBPE_W1_MINB) pdip1_kernel(SolveArgs S) {   // blockDim.x = 32 * (QPs per CTA) <= W1_WARPS * 32
     RBPE_DYN_SMEM(smem);
@@ -515,7 +518,7 @@ __global__ void __launch_bounds__(W1_WARPS * 32, RBPE_W1_MINB) pdip1_kernel(Solv
         c.Dcp = p; p += al2(6 * (size_t)c.ncp);
         c.Wd = p; p += al2((size_t)(M > 1 ? M - 1 : 1) * 81);
         c.Wo = p; p += al2((size_t)(M > 2 ? M - 2 : 1) * 81);
-        c.sg = p; p += al2(c.nr); c.sg2 = p; p += al2(c.nr); c.dinv = p; p += al2(c.nr > 32 ? c.nr : 32);
+        c.sg = p; p += al2(c.nr); c.sg2 = p; c.dinv = p; p += al2(c.nr > 32 ? c.nr : 32);   // the column exchange buffer of the 9x9 routines shares sg2 (dead by then)
         c.QB = c_QB;
         c.cmax = (int *)p;
     }
