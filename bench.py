@@ -197,7 +197,7 @@ def main():
     pool = make_pool(args.pool, rank)
     packed = pin(synth.pack([pool[i % len(pool)] for i in range(count)]))
     prob = E.PackedProblem(packed, sequential=True, batch_size=1)
-    res = E.Result(prob, want_ctrl=False)   # the reference's update() returns coefficients (msgs_traj_coef); `dummy` stays on the device
+    res = E.Result(prob, want_ctrl=False, pinned=True)   # page-locked like the inputs; the reference's update() returns coefficients (msgs_traj_coef); `dummy` stays on the device
     eng = E.Engine(device=local)
     h2d, d2h = prob.h2d_bytes(), res.d2h_bytes()
     nqp = count * N_AGENTS

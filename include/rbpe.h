@@ -91,6 +91,11 @@ int rbpe_create(const rbpe_config *cfg, rbpe_handle **out);
 void rbpe_destroy(rbpe_handle *h);
 const char *rbpe_last_error(const rbpe_handle *h); /* never NULL; h may be NULL (creation errors) */
 
+/* Page-locked host memory for input / result buffers (optional; any host memory works).  With pageable buffers the
+ * asynchronous copies of the pipelined rbpe_solve_many degrade to blocking ones and copies stop overlapping kernels. */
+void *rbpe_host_alloc(size_t bytes);
+void rbpe_host_free(void *p);
+
 /* effective batch partition of RBPPlanner::setBatch (L849-L872): returns ceil(N/batch_size) */
 int rbpe_set_batch(int N, int sequential, int batch_size, int batch_iter, int *eff_batch_size, int *eff_batch_iter);
 

@@ -48,6 +48,7 @@ struct rbpe_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;   // copy streams of the pipelined rbpe_solve_many
+    cudaStream_t s_k2 = nullptr;                     // second compute stream: kernels of consecutive chunks overlap (no tail gaps)
     std::vector<cudaEvent_t> pev;                    // per-chunk events of the pipeline
     int chunk = 2368;                                // missions per pipeline stage (RBPE_CHUNK)
     cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -68,7 +69,21 @@ struct rbpe_handle {
     DevBuf post_a, post_b, post_c, post_d, post_e;   // scratch of rbpe_corridor_rsfc / rbpe_safety_metrics
     DevBuf segbox, reln, segmat, ctrl, frozen, coef, qp_obj, qp_iters, qp_status, qp_res, status, scratch;
     rbpe_timing timing;
-    std::vector<int> host_status;
+    struct PinnedInts {   // page-locked (a pageable destination would make the per-chunk status copies blocking)
+        int *p = nullptr;
+        size_t cap = 0;
+        bool resize(size_t n) {
+            if (n <= cap) return true;
+            if (p) cudaFreeHost(p);
+            p = nullptr; cap = 0;
+            if (cudaHostAlloc((void **)&p, (n + 64) * sizeof(int), cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return false; }
+            cap = n + 64;
+            return true;
+        }
+        int *data() { return p; }
+        int &operator[](size_t i) { return p[i]; }
+        ~PinnedInts() { if (p) cudaFreeHost(p); }
+    } host_status;
     // Jacobi exchange over peer memory (rbpe_peer_*): tables[0] / tables[1] are the two physical control-point buffers of
     // every rank as exported (ctrl, frozen); `phys_cur` tells which one currently is h->ctrl
     int peer_rank = -1, peer_world = 0, phys_cur = 0;
@@ -178,11 +193,23 @@ extern "C" void rbpe_destroy(rbpe_handle *h) {
     for (cudaEvent_t e : h->pev) cudaEventDestroy(e);
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+    if (h->s_k2) cudaStreamDestroy(h->s_k2);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
 
 extern "C" const char *rbpe_last_error(const rbpe_handle *h) { return h ? h->err : g_create_error; }
+
+// page-locked host memory for the caller's input / result buffers: with pageable buffers every cudaMemcpyAsync of the
+// pipelined rbpe_solve_many blocks the host, and the chunks' copies and kernels no longer overlap
+extern "C" void *rbpe_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void rbpe_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
 
 static int up(rbpe_handle *h, DevBuf &b, const void *src, size_t bytes) {
     if (bytes == 0) return RBPE_OK;
@@ -325,24 +352,28 @@ static int warps_per_cta(const rbpe_handle *h) {
 
 // launches k2 over `units` independent work items (missions in mode 0, (mission, batch) pairs in mode 1)
 // S must have been filled by fill_solve_args (mode, ranges, record offsets already set by the caller)
-static int launch_pdip_prepared(rbpe_handle *h, SolveArgs &S, long units) {
+// `st`: stream to launch on (default: the engine's); `slot0` / `slots`: this launch uses work-item slots [slot0, slot0 + units)
+// of a scratch arena sized for `slots` items (pipelined call: chunks in flight on two streams must not share scratch)
+static int launch_pdip_prepared(rbpe_handle *h, SolveArgs &S, long units, cudaStream_t st = nullptr, long slot0 = 0, long slots = 0) {
     int wpc = warps_per_cta(h);
     S.work_items = (unsigned)units;
+    if (!st) st = h->stream;
+    if (slots < units) slots = units;
     if (wpc > 0) {
         long grid = (units + wpc - 1) / wpc;
         S.scratch_stride = w1_scratch_doubles(h->N, h->M);
         S.smem_bytes = (unsigned)(wpc * w1_smem_doubles(h->M) * 8);
-        CU(h->scratch.reserve(S.scratch_stride * 8 * (size_t)grid * wpc));
-        S.scratch = h->scratch.as<double>();
-        pdip1_kernel<<<(unsigned)grid, wpc * 32, S.smem_bytes, h->stream>>>(S);
+        CU(h->scratch.reserve(S.scratch_stride * 8 * (size_t)(slots + wpc)));
+        S.scratch = h->scratch.as<double>() + (size_t)slot0 * S.scratch_stride;
+        pdip1_kernel<<<(unsigned)grid, wpc * 32, S.smem_bytes, st>>>(S);
     } else {
         S.scratch_stride = scratch_doubles(h->N, h->M, h->bs);
         S.smem_bytes = (unsigned)smem_for(h, S.scratch_stride);
-        CU(h->scratch.reserve(S.scratch_stride * 8 * (size_t)units));
-        S.scratch = h->scratch.as<double>();
+        CU(h->scratch.reserve(S.scratch_stride * 8 * (size_t)slots));
+        S.scratch = h->scratch.as<double>() + (size_t)slot0 * S.scratch_stride;
         // joint batches use the full CTA (CTA-wide DMMA factorisation); one-agent batches through this kernel keep the knob
         const int threads = (h->bs > 1 && !h->threads_forced) ? CTA_THREADS : h->threads;
-        pdip_kernel<<<(unsigned)units, threads, S.smem_bytes, h->stream>>>(S);
+        pdip_kernel<<<(unsigned)units, threads, S.smem_bytes, st>>>(S);
     }
     CU(cudaGetLastError());
     h->launches++;
@@ -552,7 +583,7 @@ extern "C" int rbpe_download(rbpe_handle *h, rbpe_result *r) {
         if (r->qp_status) CU(cudaMemcpyAsync(r->qp_status, h->qp_status.p, c * nr * 4, cudaMemcpyDeviceToHost, h->stream));
         if (r->qp_res) CU(cudaMemcpyAsync(r->qp_res, h->qp_res.p, c * nr * 32, cudaMemcpyDeviceToHost, h->stream));
     }
-    h->host_status.resize(c);
+    if (!h->host_status.resize(c)) return fail(h, RBPE_CUDA_ERROR, "cudaHostAlloc failed");
     CU(cudaMemcpyAsync(h->host_status.data(), h->status.p, c * 4, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaEventRecord(h->ev[5], h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -589,6 +620,7 @@ static int solve_many_pipelined(rbpe_handle *h, const rbpe_problem *p, int count
     const size_t nbox = (size_t)p->sfc_base[count];
     if (!h->s_h2d) CU(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
     if (!h->s_d2h) CU(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+    if (!h->s_k2) CU(cudaStreamCreateWithFlags(&h->s_k2, cudaStreamNonBlocking));
     const int nchunk = (count + h->chunk - 1) / h->chunk;
     while ((int)h->pev.size() < 2 * nchunk) {
         cudaEvent_t e;
@@ -608,9 +640,10 @@ static int solve_many_pipelined(rbpe_handle *h, const rbpe_problem *p, int count
     CU(h->qp_obj.reserve((size_t)count * nrec * 8)); CU(h->qp_iters.reserve((size_t)count * nrec * 4));
     CU(h->qp_status.reserve((size_t)count * nrec * 4)); CU(h->qp_res.reserve((size_t)count * nrec * 32));
     CU(h->status.reserve((size_t)count * 4));
-    h->host_status.resize(count);
+    if (!h->host_status.resize(count)) return fail(h, RBPE_CUDA_ERROR, "cudaHostAlloc failed");
     CU(cudaEventRecord(h->ev[0], h->stream));
     CU(cudaStreamWaitEvent(h->s_h2d, h->ev[0], 0));   // the copy stream starts after whatever the engine stream was doing
+    CU(cudaStreamWaitEvent(h->s_k2, h->ev[0], 0));
     CU(cudaMemcpyAsync(h->sfc_base.p, p->sfc_base, (size_t)(count + 1) * 4, cudaMemcpyHostToDevice, h->s_h2d));
     for (int k = 0; k < nchunk; k++) {
         const int c0 = k * h->chunk, c1 = (c0 + h->chunk < count) ? c0 + h->chunk : count, n = c1 - c0;
@@ -635,13 +668,14 @@ static int solve_many_pipelined(rbpe_handle *h, const rbpe_problem *p, int count
         if (p->sequential) H2D(init_traj, p->init_traj, 4, (size_t)N * (M + 1) * 3);
 #undef H2D
         CU(cudaEventRecord(h->pev[2 * k], h->s_h2d));
-        // ---- kernels of the chunk (engine stream) ----
-        CU(cudaStreamWaitEvent(h->stream, h->pev[2 * k], 0));
-        CU(cudaMemsetAsync((char *)h->status.p + (size_t)c0 * 4, 0, (size_t)n * 4, h->stream));
-        CU(cudaMemsetAsync((char *)h->qp_obj.p + (size_t)c0 * nrec * 8, 0, (size_t)n * nrec * 8, h->stream));
-        CU(cudaMemsetAsync((char *)h->qp_iters.p + (size_t)c0 * nrec * 4, 0, (size_t)n * nrec * 4, h->stream));
-        CU(cudaMemsetAsync((char *)h->qp_status.p + (size_t)c0 * nrec * 4, 0, (size_t)n * nrec * 4, h->stream));
-        CU(cudaMemsetAsync((char *)h->qp_res.p + (size_t)c0 * nrec * 32, 0, (size_t)n * nrec * 32, h->stream));
+        // ---- kernels of the chunk (alternating compute streams: the next chunk's CTAs fill the SMs as this one's drain) ----
+        cudaStream_t ks = (k & 1) ? h->s_k2 : h->stream;
+        CU(cudaStreamWaitEvent(ks, h->pev[2 * k], 0));
+        CU(cudaMemsetAsync((char *)h->status.p + (size_t)c0 * 4, 0, (size_t)n * 4, ks));
+        CU(cudaMemsetAsync((char *)h->qp_obj.p + (size_t)c0 * nrec * 8, 0, (size_t)n * nrec * 8, ks));
+        CU(cudaMemsetAsync((char *)h->qp_iters.p + (size_t)c0 * nrec * 4, 0, (size_t)n * nrec * 4, ks));
+        CU(cudaMemsetAsync((char *)h->qp_status.p + (size_t)c0 * nrec * 4, 0, (size_t)n * nrec * 4, ks));
+        CU(cudaMemsetAsync((char *)h->qp_res.p + (size_t)c0 * nrec * 32, 0, (size_t)n * nrec * 32, ks));
         AssembleArgs A;
         A.count = n; A.N = N; A.M = M; A.sequential = h->sequential;
         A.T = h->T.as<double>() + (size_t)c0 * (M + 1); A.sfc_offs = h->sfc_offs.as<int>() + (size_t)c0 * (N + 1);
@@ -657,7 +691,7 @@ static int solve_many_pipelined(rbpe_handle *h, const rbpe_problem *p, int count
             int blocks = (int)((total + 255) / 256), cap = h->sm_count * 16;
             if (blocks > cap) blocks = cap;
             if (blocks < 1) blocks = 1;
-            assemble_kernel<<<blocks, 256, 0, h->stream>>>(A);
+            assemble_kernel<<<blocks, 256, 0, ks>>>(A);
             CU(cudaGetLastError());
             h->launches++;
         }
@@ -671,7 +705,7 @@ static int solve_many_pipelined(rbpe_handle *h, const rbpe_problem *p, int count
             S.ctrl += c0 * per; S.ctrl_frozen += c0 * per;
             S.qp_obj += (size_t)c0 * nrec; S.qp_iters += (size_t)c0 * nrec; S.qp_status += (size_t)c0 * nrec;
             S.qp_res += (size_t)c0 * nrec * 4; S.status += c0;
-            if ((rc = launch_pdip_prepared(h, S, n))) return rc;
+            if ((rc = launch_pdip_prepared(h, S, n, ks, c0, count))) return rc;
         }
         {
             ConvertArgs C;
@@ -681,11 +715,11 @@ static int solve_many_pipelined(rbpe_handle *h, const rbpe_problem *p, int count
             long total = (long)n * per;
             int blocks = (int)((total + 255) / 256), cap = h->sm_count * 16;
             if (blocks > cap) blocks = cap;
-            convert_kernel<<<blocks, 256, 0, h->stream>>>(C);
+            convert_kernel<<<blocks, 256, 0, ks>>>(C);
             CU(cudaGetLastError());
             h->launches++;
         }
-        CU(cudaEventRecord(h->pev[2 * k + 1], h->stream));
+        CU(cudaEventRecord(h->pev[2 * k + 1], ks));
         // ---- D2H of the chunk (second copy stream) ----
         CU(cudaStreamWaitEvent(h->s_d2h, h->pev[2 * k + 1], 0));
         if (r->coef) CU(cudaMemcpyAsync(r->coef + c0 * per, (char *)h->coef.p + c0 * per * 8, n * per * 8, cudaMemcpyDeviceToHost, h->s_d2h));
@@ -700,6 +734,7 @@ static int solve_many_pipelined(rbpe_handle *h, const rbpe_problem *p, int count
     }
     CU(cudaStreamSynchronize(h->s_d2h));
     CU(cudaStreamSynchronize(h->stream));
+    CU(cudaStreamSynchronize(h->s_k2));
     CU(cudaStreamSynchronize(h->s_h2d));
     h->resident = true;
     h->assembled = true;

@@ -45,7 +45,7 @@ EXPORTS = ["rbpe_create", "rbpe_destroy", "rbpe_last_error", "rbpe_set_batch", "
            "rbpe_upload", "rbpe_assemble", "rbpe_run", "rbpe_run_jacobi_range", "rbpe_set_ctrl", "rbpe_download", "rbpe_device_ctrl",
            "rbpe_device_coef", "rbpe_stream", "rbpe_sync", "rbpe_last_timing", "rbpe_timer_start", "rbpe_timer_stop",
            "rbpe_corridor_rsfc", "rbpe_safety_metrics", "rbpe_peer_export", "rbpe_peer_attach", "rbpe_peer_attach_local",
-           "rbpe_run_jacobi_fused", "rbpe_peer_status"]
+           "rbpe_run_jacobi_fused", "rbpe_peer_status", "rbpe_host_alloc", "rbpe_host_free"]
 IPC_HANDLE_BYTES = 64
 
 _lib = None
@@ -85,6 +85,11 @@ def load_library(path=None):
     L.rbpe_run.restype = C.c_int
     L.rbpe_run_jacobi_range.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.rbpe_run_jacobi_range.restype = C.c_int
+    if path is None or hasattr(L, "rbpe_host_alloc"):
+        L.rbpe_host_alloc.argtypes = [C.c_size_t]
+        L.rbpe_host_alloc.restype = C.c_void_p
+        L.rbpe_host_free.argtypes = [C.c_void_p]
+        L.rbpe_host_free.restype = None
     if path is None or hasattr(L, "rbpe_run_jacobi_fused"):   # (tools/gpu_ab.py may load older builds of the library)
         L.rbpe_run_jacobi_fused.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.rbpe_run_jacobi_fused.restype = C.c_int
@@ -163,19 +168,46 @@ class PackedProblem:
                                                    "sfc_t", "rsfc_n", "rsfc_t", "init_traj")))
 
 
+class _PinnedPool:
+    """numpy arrays over page-locked memory from rbpe_host_alloc (freed when the pool dies)."""
+
+    def __init__(self):
+        self.lib = load_library()
+        self.ptrs = []
+
+    def zeros(self, shape, dtype=np.float64):
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = self.lib.rbpe_host_alloc(max(n, 1))
+        if not p:
+            raise MemoryError("rbpe_host_alloc(%d) failed" % n)
+        self.ptrs.append(p)
+        a = np.frombuffer((C.c_char * max(n, 1)).from_address(p), dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        a[...] = 0
+        return a
+
+    def __del__(self):
+        for p in self.ptrs:
+            self.lib.rbpe_host_free(p)
+        self.ptrs = []
+
+
 class Result:
-    def __init__(self, prob, want_ctrl=True):
+    def __init__(self, prob, want_ctrl=True, pinned=False):
+        """pinned=True: result arrays in page-locked memory (rbpe_host_alloc), so that the D2H copies of the pipelined
+        rbpe_solve_many are truly asynchronous."""
         c, N, M = prob.count, prob.N, prob.M
         _, bi = prob.effective_batching()
         nrec = max(1, prob.iteration * bi)
         self.nrec = prob.iteration * bi
-        self.coef = np.zeros((c, N, 3, 6 * M))
-        self.ctrl = np.zeros((c, N, 3, 6 * M)) if want_ctrl else None
-        self.qp_obj = np.zeros((c, nrec))
-        self.qp_iters = np.zeros((c, nrec), np.int32)
-        self.qp_status = np.zeros((c, nrec), np.int32)
-        self.qp_res = np.zeros((c, nrec, 4))
-        self.status = np.zeros(c, np.int32)
+        self._pool = _PinnedPool() if pinned else None
+        zeros = self._pool.zeros if pinned else (lambda shape, dtype=np.float64: np.zeros(shape, dtype))
+        self.coef = zeros((c, N, 3, 6 * M))
+        self.ctrl = zeros((c, N, 3, 6 * M)) if want_ctrl else None
+        self.qp_obj = zeros((c, nrec))
+        self.qp_iters = zeros((c, nrec), np.int32)
+        self.qp_status = zeros((c, nrec), np.int32)
+        self.qp_res = zeros((c, nrec, 4))
+        self.status = zeros(c, np.int32)
         self.c = RbpeResult(self.coef.ctypes.data_as(_dp), self.ctrl.ctypes.data_as(_dp) if want_ctrl else None,
                             self.qp_obj.ctypes.data_as(_dp), self.qp_iters.ctypes.data_as(_ip),
                             self.qp_status.ctypes.data_as(_ip), self.qp_res.ctypes.data_as(_dp),
