@@ -126,7 +126,7 @@ int rbpe_run_jacobi_range(rbpe_handle *h, int batch_begin, int batch_end);
  *   rbpe_peer_attach_local  same, for handles living in the calling process (raw device pointers)
  *   rbpe_run_jacobi_fused   one sweep over batches [batch_begin, batch_end) of every resident mission; every rank
  *                      must call it the same number of times (ranks with an empty range included)
- *   rbpe_peer_status   RBPE_CUDA_ERROR after a flag wait timed out (a peer died) */
+ *   rbpe_peer_status   RBPE_CUDA_ERROR after a flag wait timed out (about 20 s: a peer died) */
 #define RBPE_IPC_HANDLE_BYTES 64
 int rbpe_peer_export(rbpe_handle *h, unsigned char *handles);
 int rbpe_peer_attach(rbpe_handle *h, int rank, int world, const unsigned char *all_handles);

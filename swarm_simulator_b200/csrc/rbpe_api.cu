@@ -556,7 +556,7 @@ extern "C" int rbpe_run_jacobi_fused(rbpe_handle *h, int b0, int b1) {
     return RBPE_OK;
 }
 
-// 0 when every flag wait so far has completed in time; RBPE_CUDA_ERROR after a timeout (a peer died or fell behind by > 2 s)
+// 0 when every flag wait so far has completed in time; RBPE_CUDA_ERROR after a timeout (a peer died or fell behind by > 20 s)
 extern "C" int rbpe_peer_status(rbpe_handle *h) {
     if (!h) return RBPE_BAD_ARG;
     if (!h->flags.p) return RBPE_OK;

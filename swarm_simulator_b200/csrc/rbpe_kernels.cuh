@@ -152,7 +152,8 @@ RBPE_DEV void peer_signal_done(const SolveArgs &S, bool leader) {
 #endif
 }
 
-// waits until every rank has raised its flag to `sweep_id` in OUR flag array; err[0] = 1 on timeout (about 2 s)
+// waits until every rank has raised its flag to `sweep_id` in OUR flag array; err[0] = 1 on timeout (about 20 s: a peer
+// that is merely late -- first-touch allocations, a slower host thread -- must not be mistaken for a dead one)
 __global__ void peer_wait_kernel(const unsigned long long *flags, int world, unsigned long long sweep_id, int *err) {
 #if defined(__CUDACC__)
     const int p = threadIdx.x;
@@ -160,7 +161,7 @@ __global__ void peer_wait_kernel(const unsigned long long *flags, int world, uns
     const long long t0 = clock64();
     const volatile unsigned long long *f = flags + p;
     while (*f < sweep_id) {
-        if (clock64() - t0 > 4000000000LL) { atomicExch(err, 1); return; }
+        if (clock64() - t0 > 40000000000LL) { atomicExch(err, 1); return; }
         __nanosleep(200);
     }
     __threadfence_system();

@@ -73,15 +73,30 @@ def jacobi_attach_peers(eng, prob, group=None):
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     eng.upload(prob)
     eng.assemble()
-    mine = eng.peer_export()
+    err = None
+    try:
+        mine = eng.peer_export()
+    except RuntimeError as ex:
+        mine, err = None, ex
     handles = [None] * world
     if world > 1:
         dist.all_gather_object(handles, mine, group=group)
     else:
         handles[0] = mine
-    eng.peer_attach(rank, world, handles)
-    if world > 1:
-        dist.barrier(group=group)      # every rank has opened every buffer before the first remote store
+    if err is None and all(h is not None for h in handles):
+        try:
+            eng.peer_attach(rank, world, handles)
+        except RuntimeError as ex:
+            err = ex
+    elif err is None:
+        err = RuntimeError("a peer could not export its tables")
+    if world > 1:   # every rank learns whether every rank attached (also: nobody stores remotely before all have opened)
+        oks = [None] * world
+        dist.all_gather_object(oks, err is None, group=group)
+        if not all(oks) and err is None:
+            err = RuntimeError("peer attach failed on rank(s) %s" % [r for r, o in enumerate(oks) if not o])
+    if err is not None:
+        raise err
 
 
 def jacobi_solve(eng, prob, sweeps, group=None, device=None, fused=False):
