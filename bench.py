@@ -123,6 +123,8 @@ def run_reference(args, rank, world):
         _, _, st = oracle.update_many(probs, nthreads=cores)
         bad += int((st != 0).sum())
     dt = (time.perf_counter() - t0) / args.steps
+    bad //= max(args.steps, 1)
+    nqp = (len(probs) - bad) * N_AGENTS          # only the QPs of missions whose update() succeeds count
     val = nqp / dt
     sample = "%d missions x %d agents per step (%d distinct, seeds %d..), oracle.update_many, OpenMP over missions" % (
         len(probs), N_AGENTS, len(pool), 1000 * CONFIG_ID)
@@ -212,7 +214,11 @@ def main():
     # ---- warm-up (e2e path: exercises H2D, all three kernels, D2H) ----
     for _ in range(args.warmup):
         r = eng.solve_many(prob, result=res)
-    assert r.rc == E.OK, (r.rc, eng.last_error())
+    # a mission whose QP is infeasible / does not converge makes update() return false in the reference as well; such
+    # missions are reported and their QPs do not count (seeded pools at 4+ ranks contain one: the CPU oracle agrees on it)
+    assert r.rc in (E.OK, E.INFEASIBLE, E.NOT_CONVERGED), (r.rc, eng.last_error())
+    failed_missions = int((res.status != 0).sum())
+    nqp_ok = (count - failed_missions) * N_AGENTS
     iters_total = int(res.qp_iters.sum())
     iters_mean = float(res.qp_iters.mean())
     launches0 = eng.timing()["kernel_launches"]
@@ -246,14 +252,23 @@ def main():
         r = eng.solve_many(prob, result=res)
         t_e2e += eng.timer_stop()
     barrier()
-    assert r.rc == E.OK
+    assert r.rc in (E.OK, E.INFEASIBLE, E.NOT_CONVERGED)
     ms_e2e = max_over_ranks(t_e2e / args.steps)
     clk = clocks.stop()
     launches = eng.timing()["kernel_launches"] - launches0
     kernel_ms = max_over_ranks(kernel_ms)
 
-    value = world * nqp / (ms_step * 1e-3)
-    e2e = world * nqp / (ms_e2e * 1e-3)
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    nqp_all = sum_over_ranks(float(nqp_ok))          # converged agent-QPs per step over all ranks
+    failed_all = int(sum_over_ranks(float(failed_missions)))
+    value = nqp_all / (ms_step * 1e-3)
+    e2e = nqp_all / (ms_e2e * 1e-3)
 
     # ---- secondary leg: BASELINE configs[1] (16 agents, forest 0.2, 5 segments, ONE joint QP per mission: nv = 1440, K = 2304);
     # CTA-per-QP kernel, block tridiagonal factorisation of 144 x 144 blocks on the FP64 tensor pipe (DMMA) ----
@@ -333,7 +348,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": "64 agents, random forest rho=0.2, 5-segment degree-5, sequential batch_size=1 "
                                "(BASELINE configs[2]; reference Gauss-Seidel order)",
-                   "missions_per_step_per_gpu": count, "agent_qps_per_step": world * nqp, "distinct_missions_per_gpu": len(pool),
+                   "missions_per_step_per_gpu": count, "agent_qps_per_step": int(nqp_all), "failed_missions_per_step": failed_all, "distinct_missions_per_gpu": len(pool),
                    "parallelism": "missions sharded over %d GPU(s), no collective" % world, "cache": l2_note,
                    "ipm_iterations_mean": iters_mean, "tol_gap": 1e-10, "tol_res": 1e-9},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
