@@ -30,7 +30,7 @@ int main(int argc, char **argv) {
     Param param;
     // launch defaults of plan_rbp_random_forest.launch L29-L65 where they differ from Param's
     param.grid_xy_res = 0.5; param.grid_z_res = 1.0; param.sequential = true; param.batch_size = 4; param.batch_iter = -1;
-    param.world_z_min = 0; param.world_z_max = 2.5;
+    param.world_z_min = 0.3; param.world_z_max = 2.5;
     param.setParam(kv);
     Mission mission;
     if (!mission.setMission(argv[1])) { std::fprintf(stderr, "cannot read mission %s\n", argv[1]); return 2; }

@@ -170,6 +170,14 @@ def test_bt_reader_on_reference_worlds(built, world, tmp_path):
         assert 9 * 10 <= ncol <= 9 * 20
 
 
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference worlds not mounted")
+def test_reference_smoke_loop_stage_1_on_all_50_maps(built):
+    """Stage 1 of the reference's own smoke loop (swarm_traj_planner_rbp_test_all.cpp L49-L78, plan_rbp_test.launch): the
+    64-agent mission must get initial trajectories on every one of worlds/map1..50.bt (the loop returns -1 otherwise)."""
+    out = subprocess.run([os.sys.executable, os.path.join(ROOT, "tools", "plan_test_all.py"), REF, "stage=ecbs"], capture_output=True, text=True)
+    assert out.returncode == 0 and "50 / 50 maps planned" in out.stdout, out.stdout[-2000:]
+
+
 def test_distance_map_matches_scipy(built, tmp_path):
     """clamped_edt (Felzenszwalb) behind GridDistanceMap == scipy's exact EDT clamped at 1 m, probed through ECBS's obstacle
     rule: a grid point is an obstacle iff dist < r + grid_margin (ecbs_planner.hpp L99)."""
@@ -255,7 +263,7 @@ def test_whole_pipeline_on_a_forest_world(built, tmp_path):
     write_bt(tmp_path / "w.bt", occ, set())
     write_mission(tmp_path / "m.json", 8)
     for extra in (["plan/sequential=true", "plan/batch_size=4"], ["plan/sequential=true", "plan/batch_size=1"]):
-        out = run_cli(tmp_path / "m.json", tmp_path / "w.bt", tmp_path, "stage=all", *extra)
+        out = run_cli(tmp_path / "m.json", tmp_path / "w.bt", tmp_path, "stage=all", "world/z_min=0", *extra)
         assert "rbp=true" in out.stdout, out.stdout + out.stderr
         ratio = float(out.stdout.split("safety_margin_ratio=")[1].split()[0])
         assert ratio >= 1.0 - 1e-6
