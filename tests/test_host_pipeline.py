@@ -140,7 +140,7 @@ def test_bt_reader_matches_python_restatement(built, tmp_path):
     res, size, leaves = read_bt_python(tmp_path / "w.bt")
     assert size == n_nodes and sum(1 for l in leaves if l[4]) == len(occ)
     json.dump({"quadrotors": {}, "agents": []}, open(tmp_path / "m.json", "w"))
-    out = run_cli(tmp_path / "m.json", tmp_path / "w.bt", tmp_path, "stage=world").stdout.splitlines()
+    out = run_cli(tmp_path / "m.json", tmp_path / "w.bt", tmp_path, "stage=world", "world/z_min=0").stdout.splitlines()
     head = dict(kv.split("=") for kv in out[0].split()[1:])
     assert int(head["declared_nodes"]) == n_nodes == int(head["inner"]) + int(head["leaves"])
     assert int(head["occupied_leaves"]) == len(occ)
@@ -190,7 +190,7 @@ def test_distance_map_matches_scipy(built, tmp_path):
             grid[x + 50, y + 50, z] = True
     edt = np.minimum(distance_transform_edt(~grid) * 0.1, 1.0)
     agents = write_mission(tmp_path / "m.json", 2)
-    out = run_cli(tmp_path / "m.json", tmp_path / "w.bt", tmp_path, "stage=ecbs")
+    out = run_cli(tmp_path / "m.json", tmp_path / "w.bt", tmp_path, "stage=ecbs", "world/z_min=0")
     assert "ecbs=true" in out.stdout, out.stdout + out.stderr
     blocked = set()
     for i, x in enumerate(np.arange(-5, 5.0001, 0.5)):
@@ -235,7 +235,7 @@ def test_ecbs_paths_are_valid(built, tmp_path, n_agents, seed):
     occ = forest(seed)
     write_bt(tmp_path / "w.bt", occ, set())
     agents = write_mission(tmp_path / "m.json", n_agents)
-    out = run_cli(tmp_path / "m.json", tmp_path / "w.bt", tmp_path, "stage=ecbs", "ecbs/w=1.3")
+    out = run_cli(tmp_path / "m.json", tmp_path / "w.bt", tmp_path, "stage=ecbs", "ecbs/w=1.3", "world/z_min=0")
     assert "ecbs=true" in out.stdout, out.stdout + out.stderr
     M = int(out.stdout.split("M=")[1].split()[0])
     paths, cost = [], 0
