@@ -229,7 +229,7 @@ extern "C" int rbpe_upload(rbpe_handle *h, const rbpe_problem *p, int count) {
     CU(cudaSetDevice(h->device));
     h->resident = false;
     const int N = p->N, M = p->M;
-    const size_t P = (size_t)N * (N - 1) / 2, per = (size_t)N * 18 * M;
+    const size_t P = (size_t)N * (N - 1) / 2;
     h->count = count; h->N = N; h->M = M; h->sequential = p->sequential ? 1 : 0; h->iteration = p->iteration;
     rbpe_set_batch(N, h->sequential, p->batch_size, p->batch_iter, &h->bs, &h->nbatch);
     h->nrec = h->iteration * h->nbatch;

@@ -371,13 +371,13 @@ RBPE_DEV int w1_solve_qp(const W1 &c, int max_iter, double tol_gap, double tol_r
     w1_pass<P_DEAD>(c, 0, 0, acc);
     if (acc.mx > PRESOLVE_FEAS_TOL) { status = ST_INFEASIBLE; go = false; }
     if (go && c.nr == 0) {
-        double o = 0, mpx = 0, d1 = 0, d2 = 0;
+        double o = 0;
         o = w1_dual(c.segmat, c.M, c.QB, c.x, c.vA, c.rdx).obj;
         o = warp_reduce5(o, 0.0, 0.0, 0.0, 0.0).s1;
         obj = o; status = ST_OK; go = false;
     }
     if (go) {
-        double mh = 0, d0 = 0, d1 = 0, d2 = 0;
+        double mh = 0;
         #pragma unroll 1
         for (int slot = 0; slot < c.nslot; slot++) {
             const int cp = slot * 32 + lane;
@@ -424,7 +424,6 @@ RBPE_DEV int w1_solve_qp(const W1 &c, int max_iter, double tol_gap, double tol_r
         double mr = 0, mc = 0;
         #pragma unroll 1
         for (int r = lane; r < c.nr; r += 32) { mr = fmax(mr, fabs(c.sg[r])); mc = fmax(mc, fabs(c.sg2[r])); }
-        double d1 = 0;
         { Red5 r = warp_reduce5(o, 0.0, mpx, mr, mc); o = r.s1; mpx = r.mx; mr = r.mx2; mc = r.mx3; }
         obj = o; nrd = mr;
         gap = mu;
@@ -468,7 +467,6 @@ RBPE_DEV int w1_solve_qp(const W1 &c, int max_iter, double tol_gap, double tol_r
         if (t == c.M) sm -= c.goal[(size_t)c.qa * 9 + k + 3 * d];
         mrp = fmax(mrp, fabs(sm));
     }
-    double d0 = 0, d1 = 0, d2 = 0;
     mrp = warp_reduce5(0.0, 0.0, mrp, 0.0, 0.0).mx;
     if (lane == 0) {
         *obj_out = obj;
