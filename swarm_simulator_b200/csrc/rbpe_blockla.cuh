@@ -196,6 +196,13 @@ RBPE_NOINLINE bool chol_tall(int kp, double *D, double *O, const double *Pm, dou
                 const int i0 = isO ? (s - nsD) * 8 : r0 + s * 8;
                 double *C0 = (isO ? O : D) + (size_t)i0 * kp + j0;
                 double acc[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+#ifdef RBPE_BLA_STABLE
+                // experiment (off by default): one step of refinement of L21 = A21 L11^-T:  R = A21 - L21 L11',  L21 += R X'
+                double a21[4][2];
+#pragma unroll
+                for (int jt = 0; jt < 4; jt++)
+                    if (jt < ntJ) { const double *c = C0 + (size_t)g * kp + 8 * jt + 2 * t4; a21[jt][0] = c[0]; a21[jt][1] = c[1]; }
+#endif
                 strip_mma(acc, C0, X, kp, BLA_W, wJ, ntJ, 3);
 #pragma unroll
                 for (int jt = 0; jt < 4; jt++)
@@ -204,6 +211,44 @@ RBPE_NOINLINE bool chol_tall(int kp, double *D, double *O, const double *Pm, dou
                         c[0] = acc[jt][0];
                         c[1] = acc[jt][1];
                     }
+#ifdef RBPE_BLA_STABLE
+                {
+                    __syncwarp();
+                    double r[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+                    // L21 L11': B[k][n] = L11[n][k] (lower triangular: k <= n), masked because the strict upper triangle of the
+                    // diagonal block holds stale values
+                    const double *ap = C0 + (size_t)g * kp + t4;
+                    for (int k0 = 0; k0 < wJ; k0 += 4) {
+                        const double a = ap[k0];
+#pragma unroll
+                        for (int jt = 0; jt < 4; jt++)
+                            if (jt < ntJ) {
+                                const int n = 8 * jt + g, k = k0 + t4;
+                                const double b = (k <= n) ? D[(size_t)(j0 + n) * kp + j0 + k] : 0.0;
+                                dmma884(r[jt][0], r[jt][1], a, b);
+                            }
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int jt = 0; jt < 4; jt++)
+                        if (jt < ntJ) {   // the strip now holds the residual R; the first estimate stays in acc
+                            double *c = C0 + (size_t)g * kp + 8 * jt + 2 * t4;
+                            c[0] = a21[jt][0] - r[jt][0];
+                            c[1] = a21[jt][1] - r[jt][1];
+                        }
+                    __syncwarp();
+                    double d[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+                    strip_mma(d, C0, X, kp, BLA_W, wJ, ntJ, 3);
+                    __syncwarp();
+#pragma unroll
+                    for (int jt = 0; jt < 4; jt++)
+                        if (jt < ntJ) {
+                            double *c = C0 + (size_t)g * kp + 8 * jt + 2 * t4;
+                            c[0] = acc[jt][0] + d[jt][0];
+                            c[1] = acc[jt][1] + d[jt][1];
+                        }
+                }
+#endif
             }
         }
         __syncthreads();
@@ -249,11 +294,25 @@ RBPE_NOINLINE void solve_bt_blk(int nblk, int kb, int kp, const double *Dall, co
         for (int j0 = 0; j0 < kp; j0 += BLA_W) {
             const int wJ = (kp - j0 < BLA_W) ? kp - j0 : BLA_W;
             const double *X = Li + (size_t)(j0 / BLA_W) * BLA_W * BLA_W;
+#ifdef RBPE_BLA_STABLE
+            // experiment (off by default): substitution inside the 32-block by one warp instead of the product with the
+            // explicit inverse -- componentwise backward stable; X only supplies 1 / L_jj
+            if (warp == 0) {
+                double wv = (lane < wJ) ? wt[j0 + lane] : 0.0;
+                for (int j = 0; j < wJ; j++) {
+                    const double yj = __shfl_sync(0xffffffffu, wv, j) * X[j * BLA_W + j];
+                    if (lane == j) wv = yj;
+                    else if (lane > j && lane < wJ) wv -= L[(size_t)(j0 + lane) * kp + j0 + j] * yj;
+                }
+                y[lane] = wv;
+            }
+#else
             for (int r = warp; r < wJ; r += nw) {   // y = Linv_J w_J
                 double sm = (lane <= r) ? X[r * BLA_W + lane] * wt[j0 + lane] : 0.0;
                 for (int o = 16; o > 0; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
                 if (lane == 0) y[r] = sm;
             }
+#endif
             __syncthreads();
             for (int r = j0 + tid; r < kp; r += nt) {
                 if (r < j0 + wJ) { wt[r] = y[r - j0]; continue; }
@@ -281,12 +340,24 @@ RBPE_NOINLINE void solve_bt_blk(int nblk, int kb, int kp, const double *Dall, co
         for (int j0 = ((kp - 1) / BLA_W) * BLA_W; j0 >= 0; j0 -= BLA_W) {
             const int wJ = (kp - j0 < BLA_W) ? kp - j0 : BLA_W;
             const double *X = Li + (size_t)(j0 / BLA_W) * BLA_W * BLA_W;
+#ifdef RBPE_BLA_STABLE
+            if (warp == 0) {   // L_JJ' y = w_J by back substitution
+                double wv = (lane < wJ) ? wt[j0 + lane] : 0.0;
+                for (int j = wJ - 1; j >= 0; j--) {
+                    const double yj = __shfl_sync(0xffffffffu, wv, j) * X[j * BLA_W + j];
+                    if (lane == j) wv = yj;
+                    else if (lane < j) wv -= L[(size_t)(j0 + j) * kp + j0 + lane] * yj;
+                }
+                y[lane] = wv;
+            }
+#else
             if (warp == 0) {   // y = Linv_J' w_J
                 double sm = 0;
                 if (lane < wJ)
                     for (int r = lane; r < wJ; r++) sm += X[r * BLA_W + lane] * wt[j0 + r];
                 y[lane] = sm;
             }
+#endif
             __syncthreads();
             for (int r = tid; r < j0 + wJ; r += nt) {
                 if (r >= j0) { wt[r] = y[r - j0]; continue; }
