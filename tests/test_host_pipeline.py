@@ -255,6 +255,92 @@ def test_ecbs_paths_are_valid(built, tmp_path, n_agents, seed):
     assert _conflicts(paths, 0.15) == 0
 
 
+def _optimal_sum_of_costs(starts, goals, blocked, dims, radius=0.15, grid=0.5):
+    """Exact minimum sum of costs for two agents on a small 2-D grid under the reference's conflict rules (Dijkstra over joint
+    states; an agent that has committed to its goal stays there and stops paying)."""
+    import heapq
+    moves = [(0, 0), (-1, 0), (1, 0), (0, 1), (0, -1)]
+    def ok(c):
+        return 0 <= c[0] < dims[0] and 0 <= c[1] < dims[1] and c not in blocked
+    def vconf(a, b):
+        return a == b                                            # 2 r = 0.3 < grid
+    def econf(a0, a1, b0, b1):
+        return _conflicts([[a0 + (0,), a1 + (0,)], [b0 + (0,), b1 + (0,)]], radius, grid) > 0 and not vconf(a0, b0)
+    start = (tuple(starts[0]), tuple(starts[1]), False, False)
+    pq, best = [(0, start)], {start: 0}
+    while pq:
+        c, st = heapq.heappop(pq)
+        if c > best.get(st, 1e9):
+            continue
+        p, q, fp, fq = st
+        if fp and fq:
+            return c
+        for mp in ([(0, 0)] if fp else moves):
+            for mq in ([(0, 0)] if fq else moves):
+                np_, nq = (p[0] + mp[0], p[1] + mp[1]), (q[0] + mq[0], q[1] + mq[1])
+                if not ok(np_) or not ok(nq) or vconf(np_, nq):
+                    continue
+                # edge rule of environment.hpp L666-L681 between the two moves
+                a = np.array([q[0] - p[0], q[1] - p[1], 0.0]); b = np.array([nq[0] - np_[0], nq[1] - np_[1], 0.0])
+                d = np.linalg.norm(a)
+                if not np.array_equal(a, b):
+                    d = min(d, np.linalg.norm(b))
+                    n = (b - a) / np.linalg.norm(b - a)
+                    cc = a - n * a.dot(n)
+                    if (cc - a).dot(cc - b) < 0:
+                        d = min(d, np.linalg.norm(cc))
+                if d * grid <= 2 * radius:
+                    continue
+                step = (0 if fp else 1) + (0 if fq else 1)
+                for nfp in ([True] if fp else ([False, True] if np_ == tuple(goals[0]) else [False])):
+                    for nfq in ([True] if fq else ([False, True] if nq == tuple(goals[1]) else [False])):
+                        ns = (np_, nq, nfp, nfq)
+                        if c + step < best.get(ns, 1e9):
+                            best[ns] = c + step
+                            heapq.heappush(pq, (c + step, ns))
+    return None
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5])
+def test_ecbs_is_within_its_suboptimality_bound(built, tmp_path, seed):
+    """Two agents on a 7 x 7 grid with random blocked cells: cost of the ECBS solution is between the exact optimum
+    (joint-state Dijkstra above) and w times it (w = 1.3, ecbs.hpp focal bound)."""
+    rng = np.random.default_rng(100 + seed)
+    dims = (7, 7)
+    cells = [(x, y) for x in range(7) for y in range(7)]
+    pick = rng.permutation(len(cells))
+    s0, s1, g0, g1 = (cells[i] for i in pick[:4])
+    if seed % 2 == 0:
+        g0, g1 = s1, s0                                           # a swap: the hardest two-agent case
+    blocked = {cells[i] for i in pick[4:4 + 8]}
+    occ = set()
+    for (bx, by) in blocked:                                      # a pillar at the grid point (world = -1.5 + 0.5 * index)
+        ix, iy = int(math.floor((-1.5 + 0.5 * bx) / 0.1)), int(math.floor((-1.5 + 0.5 * by) / 0.1))
+        for z in range(0, 11):
+            occ.add((ix, iy, z))
+    write_bt(tmp_path / "w.bt", occ, set())
+    w2c = lambda c: [-1.5 + 0.5 * c[0], -1.5 + 0.5 * c[1], 0.0]
+    json.dump({"quadrotors": {"q": {"max_vel": [1.7] * 3, "max_acc": [6.2] * 3, "radius": 0.15, "speed": 1.0}},
+               "agents": [{"name": "q", "start": w2c(s0), "goal": w2c(g0), "radius": 0.15, "speed": 1.0},
+                          {"name": "q", "start": w2c(s1), "goal": w2c(g1), "radius": 0.15, "speed": 1.0}]}, open(tmp_path / "m.json", "w"))
+    # a pillar cell blocks its own grid point only: margin r + 0.2 = 0.35 m < 0.5 m grid pitch (cell centres are 0.05 m off)
+    out = run_cli(tmp_path / "m.json", tmp_path / "w.bt", tmp_path, "stage=ecbs", "ecbs/w=1.3", "world/x_min=-1.5", "world/x_max=1.5",
+                  "world/y_min=-1.5", "world/y_max=1.5", "world/z_min=0", "world/z_max=0.9", "grid/z_res=1.0")
+    opt = _optimal_sum_of_costs([s0, s1], [g0, g1], blocked, dims)
+    if "ecbs=true" not in out.stdout:
+        assert opt is None, out.stdout + out.stderr
+        return
+    cost = 0
+    for line in [l for l in out.stdout.splitlines() if l.startswith("traj")]:
+        v = [float(t) for t in line.split()[2:]]
+        cells_ = [(round((x + 1.5) / 0.5), round((y + 1.5) / 0.5)) for x, y in zip(v[0::3][1:], v[1::3][1:])]
+        last = cells_[-1]
+        moving = [i for i, c in enumerate(cells_) if c != last]
+        cost += (max(moving) + 1) if moving else 0
+    print("seed", seed, "optimal", opt, "ecbs", cost)
+    assert opt is not None and opt <= cost <= math.floor(1.3 * opt + 1e-9), (opt, cost, out.stdout)
+
+
 @pytest.mark.gpu
 def test_whole_pipeline_on_a_forest_world(built, tmp_path):
     """.bt world -> distance map -> ECBS -> Corridor (SFC on the host, RSFC kernel) -> RBPPlanner (B200 engine) ->
