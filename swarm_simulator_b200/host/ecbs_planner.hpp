@@ -294,47 +294,50 @@ private:
 
 }  // namespace ecbs
 
+// Planner stage with the reference's constructor / update() shape.  Grid conventions (init_traj_planner.hpp L17-L30): the
+// planning lattice is the set of multiples of the grid pitch inside the world box; lattice index = round((coord - min) / pitch).
 template <class DistMap>
 class ECBSPlannerT {
 public:
-    ECBSPlannerT(std::shared_ptr<DistMap> _distmap_obj, Mission _mission, Param _param)
-        : distmap_obj(std::move(_distmap_obj)), mission(std::move(_mission)), param(std::move(_param)) {
-        // InitTrajPlanner::InitTrajPlanner (init_traj_planner.hpp L17-L30)
-        grid_x_min = std::ceil((param.world_x_min - SP_EPSILON) / param.grid_xy_res) * param.grid_xy_res;
-        grid_y_min = std::ceil((param.world_y_min - SP_EPSILON) / param.grid_xy_res) * param.grid_xy_res;
-        grid_z_min = std::ceil((param.world_z_min - SP_EPSILON) / param.grid_z_res) * param.grid_z_res;
-        grid_x_max = std::floor((param.world_x_max + SP_EPSILON) / param.grid_xy_res) * param.grid_xy_res;
-        grid_y_max = std::floor((param.world_y_max + SP_EPSILON) / param.grid_xy_res) * param.grid_xy_res;
-        grid_z_max = std::floor((param.world_z_max + SP_EPSILON) / param.grid_z_res) * param.grid_z_res;
-        dimx = (int)std::round((grid_x_max - grid_x_min) / param.grid_xy_res) + 1;
-        dimy = (int)std::round((grid_y_max - grid_y_min) / param.grid_xy_res) + 1;
-        dimz = (int)std::round((grid_z_max - grid_z_min) / param.grid_z_res) + 1;
-        valid = setObstacles() && setWaypoints();
+    ECBSPlannerT(std::shared_ptr<DistMap> distmap, Mission mission_in, Param param_in)
+        : map_(std::move(distmap)), mission(std::move(mission_in)), param(std::move(param_in)) {
+        const double lo[3] = {param.world_x_min, param.world_y_min, param.world_z_min};
+        const double hi[3] = {param.world_x_max, param.world_y_max, param.world_z_max};
+        for (int a = 0; a < 3; a++) {
+            pitch_[a] = (a < 2) ? param.grid_xy_res : param.grid_z_res;
+            gmin_[a] = std::ceil((lo[a] - SP_EPSILON) / pitch_[a]) * pitch_[a];
+            gmax_[a] = std::floor((hi[a] + SP_EPSILON) / pitch_[a]) * pitch_[a];
+            dim_[a] = (int)std::round((gmax_[a] - gmin_[a]) / pitch_[a]) + 1;
+        }
+        valid = mark_obstacles() && place_agents();
     }
 
-    bool update(bool log, SwarmPlanning::PlanResult *planResult_ptr) {
+    // ecbs_planner.hpp L21-L74: search, then T = {0, dt, ..., (makespan + 2) dt} and initTraj = exact start, lattice states,
+    // exact goal repeated up to makespan + 2 points after the start
+    bool update(bool log, SwarmPlanning::PlanResult *out) {
         if (!valid) return false;
-        ecbs::Environment mapf(dimx, dimy, dimz, ecbs_obstacles, ecbs_goalLocations, mission.quad_size, param.grid_xy_res);
-        std::vector<ecbs::Path> solution;
-        if (!mapf.search(ecbs_startStates, param.ecbs_w, solution, log)) {
+        ecbs::Environment env(dim_[0], dim_[1], dim_[2], blocked_, goals_, mission.quad_size, param.grid_xy_res);
+        std::vector<ecbs::Path> paths;
+        if (!env.search(starts_, param.ecbs_w, paths, log)) {
             std::fprintf(stderr, "ECBSPlanner: ECBS Failed!\n");
             return false;
         }
-        int makespan = 0;                                                        // ecbs_planner.hpp L36-L46
-        for (const auto &s : solution) makespan = std::max<int>(makespan, s.cost);
-        planResult_ptr->T.clear();
-        for (int i = 0; i <= makespan + 2; i++) planResult_ptr->T.emplace_back(i * param.time_step);
-        planResult_ptr->initTraj.assign(solution.size(), {});
-        for (size_t a = 0; a < solution.size(); ++a) {                            // L52-L72
-            auto &traj = planResult_ptr->initTraj[a];
-            traj.emplace_back(octomap::point3d(mission.startState[a][0], mission.startState[a][1], mission.startState[a][2]));
-            for (const auto &st : solution[a].states)
-                traj.emplace_back(octomap::point3d(st.x * param.grid_xy_res + grid_x_min, st.y * param.grid_xy_res + grid_y_min,
-                                                   st.z * param.grid_z_res + grid_z_min));
-            while ((int)traj.size() <= makespan + 2)
-                traj.emplace_back(octomap::point3d(mission.goalState[a][0], mission.goalState[a][1], mission.goalState[a][2]));
+        high_level_expanded = env.high_level_expanded;
+        int makespan = 0;
+        for (const ecbs::Path &p : paths) makespan = std::max(makespan, p.cost);
+        const int npts = makespan + 3;
+        out->T.resize(npts);
+        for (int i = 0; i < npts; i++) out->T[i] = i * param.time_step;
+        out->initTraj.assign(paths.size(), {});
+        for (size_t q = 0; q < paths.size(); q++) {
+            auto &traj = out->initTraj[q];
+            traj.reserve(npts);
+            traj.emplace_back(mission.startState[q][0], mission.startState[q][1], mission.startState[q][2]);
+            for (const ecbs::State &st : paths[q].states)
+                traj.emplace_back(st.x * pitch_[0] + gmin_[0], st.y * pitch_[1] + gmin_[1], st.z * pitch_[2] + gmin_[2]);
+            const octomap::point3d goal(mission.goalState[q][0], mission.goalState[q][1], mission.goalState[q][2]);
+            while ((int)traj.size() < npts) traj.push_back(goal);
         }
-        high_level_expanded = mapf.high_level_expanded;
         return true;
     }
 
@@ -342,51 +345,52 @@ public:
     bool valid = false;
 
 private:
-    std::shared_ptr<DistMap> distmap_obj;
+    std::shared_ptr<DistMap> map_;
     Mission mission;
     Param param;
-    double grid_x_min, grid_y_min, grid_z_min, grid_x_max, grid_y_max, grid_z_max;
-    int dimx, dimy, dimz;
-    std::unordered_set<long long> ecbs_obstacles;
-    std::vector<ecbs::State> ecbs_startStates, ecbs_goalLocations;
+    double pitch_[3], gmin_[3], gmax_[3];
+    int dim_[3];
+    std::unordered_set<long long> blocked_;
+    std::vector<ecbs::State> starts_, goals_;
 
-    bool setObstacles() {                                                         // ecbs_planner.hpp L81-L110
-        double r = 0;
-        for (int qi = 0; qi < mission.qn; qi++) r = std::max(r, mission.quad_size[qi]);
-        for (double k = grid_z_min; k < grid_z_max + SP_EPSILON; k += param.grid_z_res)
-            for (double i = grid_x_min; i < grid_x_max + SP_EPSILON; i += param.grid_xy_res)
-                for (double j = grid_y_min; j < grid_y_max + SP_EPSILON; j += param.grid_xy_res) {
-                    octomap::point3d cur_point(i, j, k);
-                    float dist = distmap_obj->getDistance(cur_point);
-                    if (dist < 0) return false;
-                    if (dist < r + param.grid_margin) {
-                        int x = (int)std::round((i - grid_x_min) / param.grid_xy_res);
-                        int y = (int)std::round((j - grid_y_min) / param.grid_xy_res);
-                        int z = (int)std::round((k - grid_z_min) / param.grid_z_res);
-                        ecbs_obstacles.insert(ecbs::key3(x, y, z));
-                    }
+    int cell_of(double coord, int a) const { return (int)std::round((coord - gmin_[a]) / pitch_[a]); }
+
+    // ecbs_planner.hpp L81-L110: a lattice point is blocked when the distance map reads less than the largest radius plus
+    // grid_margin there.  The reference walks the lattice with running double sums (k += res); the same sums are formed here
+    // so that the points handed to getDistance are the same floats.
+    bool mark_obstacles() {
+        double rmax = 0;
+        for (double r : mission.quad_size) rmax = std::max(rmax, r);
+        const double clearance = rmax + param.grid_margin;
+        for (double z = gmin_[2]; z < gmax_[2] + SP_EPSILON; z += pitch_[2])
+            for (double x = gmin_[0]; x < gmax_[0] + SP_EPSILON; x += pitch_[0])
+                for (double y = gmin_[1]; y < gmax_[1] + SP_EPSILON; y += pitch_[1]) {
+                    const float d = map_->getDistance(octomap::point3d(x, y, z));
+                    if (d < 0) return false;                       // outside the distance map
+                    if (d < clearance) blocked_.insert(ecbs::key3(cell_of(x, 0), cell_of(y, 1), cell_of(z, 2)));
                 }
         return true;
     }
 
-    bool setWaypoints() {                                                         // ecbs_planner.hpp L113-L136
-        for (int i = 0; i < mission.qn; i++) {
-            int xig = (int)std::round((mission.startState[i][0] - grid_x_min) / param.grid_xy_res);
-            int yig = (int)std::round((mission.startState[i][1] - grid_y_min) / param.grid_xy_res);
-            int zig = (int)std::round((mission.startState[i][2] - grid_z_min) / param.grid_z_res);
-            int xfg = (int)std::round((mission.goalState[i][0] - grid_x_min) / param.grid_xy_res);
-            int yfg = (int)std::round((mission.goalState[i][1] - grid_y_min) / param.grid_xy_res);
-            int zfg = (int)std::round((mission.goalState[i][2] - grid_z_min) / param.grid_z_res);
-            if (ecbs_obstacles.count(ecbs::key3(xig, yig, zig))) {
-                std::fprintf(stderr, "ECBSPlanner: start of agent %d is occluded by obstacle\n", i);
+    // ecbs_planner.hpp L113-L136: nearest lattice point of every start / goal; a blocked one is an error
+    bool place_agents() {
+        for (int q = 0; q < mission.qn; q++) {
+            ecbs::State s{0, 0, 0, 0}, g{0, 0, 0, 0};
+            int *sc[3] = {&s.x, &s.y, &s.z}, *gc[3] = {&g.x, &g.y, &g.z};
+            for (int a = 0; a < 3; a++) {
+                *sc[a] = cell_of(mission.startState[q][a], a);
+                *gc[a] = cell_of(mission.goalState[q][a], a);
+            }
+            if (blocked_.count(ecbs::key3(s.x, s.y, s.z))) {
+                std::fprintf(stderr, "ECBSPlanner: start of agent %d is occluded by obstacle\n", q);
                 return false;
             }
-            if (ecbs_obstacles.count(ecbs::key3(xfg, yfg, zfg))) {
-                std::fprintf(stderr, "ECBSPlanner: goal of agent %d is occluded by obstacle\n", i);
+            if (blocked_.count(ecbs::key3(g.x, g.y, g.z))) {
+                std::fprintf(stderr, "ECBSPlanner: goal of agent %d is occluded by obstacle\n", q);
                 return false;
             }
-            ecbs_startStates.push_back(ecbs::State{0, xig, yig, zig});
-            ecbs_goalLocations.push_back(ecbs::State{0, xfg, yfg, zfg});
+            starts_.push_back(s);
+            goals_.push_back(g);
         }
         return true;
     }
