@@ -640,7 +640,7 @@ static double inf_norm(const double *v, int n) {
  * CPLEX's default feasibility tolerance 1e-6 and dropped, as a presolve would.  A start or goal lying on a face
  * of its SFC box, which the corridor generator produces routinely, would otherwise leave no strict interior. */
 #define PRESOLVE_FEAS_TOL 1e-6
-static int presolve_dead_rows(const nsp_t *K, unsigned char *dead, int *n_live) {
+static int presolve_dead_rows(const nsp_t *K, double *h, unsigned char *dead, int *n_live) {
     const oracle_qp *q = K->q;
     int rc = 0, live = 0;
     for (int r = 0; r < q->mi; r++) {
@@ -652,7 +652,7 @@ static int presolve_dead_rows(const nsp_t *K, unsigned char *dead, int *n_live) 
             gx += q->g_val[t] * K->xp[c];
         }
         dead[r] = (unsigned char)all;
-        if (all) { if (gx - q->h[r] > PRESOLVE_FEAS_TOL) rc = ORACLE_INFEASIBLE; }
+        if (all) { if (gx - h[r] > PRESOLVE_FEAS_TOL) rc = ORACLE_INFEASIBLE; }
     }
     /* Bound-based row redundancy (also a standard presolve reduction): the box rows are singleton rows, i.e. simple
      * bounds lb <= x <= ub on every variable.  A row with several columns whose maximal activity over those bounds,
@@ -666,9 +666,30 @@ static int presolve_dead_rows(const nsp_t *K, unsigned char *dead, int *n_live) 
         for (int r = 0; r < q->n_box_rows && r < q->mi; r++)   /* the box rows of populatebyrow (RP L626-L635) */
             if (q->g_ptr[r + 1] - q->g_ptr[r] == 1) {
                 int c = q->g_idx[q->g_ptr[r]];
-                double g = q->g_val[q->g_ptr[r]], b = q->h[r] / g;
+                double g = q->g_val[q->g_ptr[r]], b = h[r] / g;
                 if (g > 0) { if (b < ub[c]) ub[c] = b; } else if (g < 0) { if (b > lb[c]) lb[c] = b; }
             }
+        /* Bounds that leave no interior at the feasibility tolerance (|ub - lb| < 2e-6: a corridor box of zero width,
+         * e.g. an agent flying along the world boundary next to a pillar) would be a fixed variable to CPLEX's presolve,
+         * and any point within 1e-6 of the bounds is feasible to it.  The interior-point method needs an interior: such
+         * a pair of bounds is opened to [mid - 1e-6, mid + 1e-6]. */
+        for (int r = 0; r < q->n_box_rows && r < q->mi; r++)
+            if (!dead[r] && q->g_ptr[r + 1] - q->g_ptr[r] == 1) {
+                int c = q->g_idx[q->g_ptr[r]];
+                double g = q->g_val[q->g_ptr[r]], wdt = ub[c] - lb[c];
+                if (ub[c] < 1e300 && lb[c] > -1e300 && wdt < 2 * PRESOLVE_FEAS_TOL && wdt > -2 * PRESOLVE_FEAS_TOL) {
+                    double mid = 0.5 * (ub[c] + lb[c]);
+                    if (g > 0 && h[r] / g == ub[c]) h[r] = g * (mid + PRESOLVE_FEAS_TOL);
+                    if (g < 0 && h[r] / g == lb[c]) h[r] = g * (mid - PRESOLVE_FEAS_TOL);
+                }
+            }
+        for (int i = 0; i < nv; i++) {
+            double wdt = ub[i] - lb[i];
+            if (ub[i] < 1e300 && lb[i] > -1e300 && wdt < 2 * PRESOLVE_FEAS_TOL && wdt > -2 * PRESOLVE_FEAS_TOL) {
+                double mid = 0.5 * (ub[i] + lb[i]);
+                ub[i] = mid + PRESOLVE_FEAS_TOL; lb[i] = mid - PRESOLVE_FEAS_TOL;
+            }
+        }
         for (int r = q->n_box_rows; r < q->mi; r++) {          /* the RSFC rows (RP L636-L684) */
             if (dead[r] || q->g_ptr[r + 1] == q->g_ptr[r]) continue;
             double amax = 0;
@@ -680,7 +701,7 @@ static int presolve_dead_rows(const nsp_t *K, unsigned char *dead, int *n_live) 
                 double a = g * ub[c], b = g * lb[c];
                 amax += (a > b) ? a : b;
             }
-            if (bounded && amax < q->h[r] - 1e-9 * fmax(1.0, fabs(q->h[r]))) dead[r] = 2;
+            if (bounded && amax < h[r] - 1e-9 * fmax(1.0, fabs(h[r]))) dead[r] = 2;
         }
         free(ub); free(lb);
     }
@@ -689,6 +710,11 @@ static int presolve_dead_rows(const nsp_t *K, unsigned char *dead, int *n_live) 
     return rc;
 }
 
+#define TOL_DUAL_FLOOR 1e-6 /* CPLEX EpOpt default; see the acceptance rule in oracle_solve_qp */
+/* Farkas certificate z >= 0, h'z < 0: |(GZ)'z| / (-h'z) < ratio proves that no sigma with |sigma|_1 < 1/ratio satisfies the
+ * rows (knot states -- metres, m/s, m/s^2 -- beyond 1e6 are outside any mission). */
+#define CERT_RATIO 1e-6
+#define CERT_RATIO_BREAKDOWN 1e-4
 /* Mehrotra predictor-corrector on  min x'Qx  s.t. Ax=b, Gx+s=h, s>=0  (P = Q+Q'). */
 int oracle_solve_qp(const oracle_qp *q, const oracle_solver_opts *opts, double *x, double *obj_out,
                     int *iters_out, double *res_out) {
@@ -698,7 +724,8 @@ int oracle_solve_qp(const oracle_qp *q, const oracle_solver_opts *opts, double *
     double tol_res = (opts && opts->tol_res > 0) ? opts->tol_res : 1e-9;
     nsp_t K;
     int status = ORACLE_NOT_CONVERGED, it = 0, n_live = mi;
-    double gap = 0, obj = 0, nrd = 0, nrg = 0, hn = 0;
+    double gap = 0, obj = 0, nrd = 0, nrg = 0, hn = 0, nrd_prev = 1e300;
+    int acceptable = 0;
     if (nsp_init(&K, q)) {
         nsp_free(&K);
         if (obj_out) *obj_out = 0;
@@ -714,8 +741,10 @@ int oracle_solve_qp(const oracle_qp *q, const oracle_solver_opts *opts, double *
     double *gxa = (double *)malloc(sizeof(double) * (mi + 1)), *hs = (double *)malloc(sizeof(double) * (mi + 1));
     double *sg = (double *)malloc(sizeof(double) * (nr + 1)), *ax = (double *)malloc(sizeof(double) * (ne + 1));
     unsigned char *dead = (unsigned char *)calloc(mi + 1, 1);
-    if (presolve_dead_rows(&K, dead, &n_live)) { status = ORACLE_INFEASIBLE; goto done; }
-    for (int r = 0; r < mi; r++) if (!dead[r] && fabs(q->h[r]) > hn) hn = fabs(q->h[r]);
+    double *h = (double *)malloc(sizeof(double) * (mi + 1));   /* right-hand sides after presolve */
+    memcpy(h, q->h, sizeof(double) * mi);
+    if (presolve_dead_rows(&K, h, dead, &n_live)) { status = ORACLE_INFEASIBLE; goto done; }
+    for (int r = 0; r < mi; r++) if (!dead[r] && fabs(h[r]) > hn) hn = fabs(h[r]);
     for (int i = 0; i < nv; i++) x[i] = K.xp[i];
     if (nr == 0) { /* a single segment: start and goal fix everything */
         p_mulv(q, x, px);
@@ -725,7 +754,7 @@ int oracle_solve_qp(const oracle_qp *q, const oracle_solver_opts *opts, double *
     }
     /* reduced right-hand side h - G x_p (used by the infeasibility certificate) */
     csr_mulv(mi, q->g_ptr, q->g_idx, q->g_val, K.xp, hs);
-    for (int r = 0; r < mi; r++) hs[r] = q->h[r] - hs[r];
+    for (int r = 0; r < mi; r++) hs[r] = h[r] - hs[r];
 
     /* initial point (least-squares start, W = I): min 1/2 x'(P+G'G)x - (G'h)'x  s.t. Ax = b */
     for (int r = 0; r < mi; r++) K.w[r] = dead[r] ? 0.0 : 1.0;
@@ -741,7 +770,7 @@ int oracle_solve_qp(const oracle_qp *q, const oracle_solver_opts *opts, double *
     csr_mulv(mi, q->g_ptr, q->g_idx, q->g_val, x, gx);
     {
         double ap = -1e300, ad = -1e300;
-        for (int r = 0; r < mi; r++) { z[r] = gx[r] - q->h[r]; s[r] = -z[r]; }
+        for (int r = 0; r < mi; r++) { z[r] = gx[r] - h[r]; s[r] = -z[r]; }
         for (int r = 0; r < mi; r++) { if (dead[r]) continue; if (-s[r] > ap) ap = -s[r]; if (-z[r] > ad) ad = -z[r]; }
         for (int r = 0; r < mi; r++) {
             if (dead[r]) { s[r] = 1.0; z[r] = 0.0; continue; }
@@ -755,10 +784,11 @@ int oracle_solve_qp(const oracle_qp *q, const oracle_solver_opts *opts, double *
         for (int i = 0; i < nv; i++) rd[i] = px[i];
         csr_mulTv_add(mi, q->g_ptr, q->g_idx, q->g_val, z, rd);   /* rd = Px + G'z; its part in range(A') is the multiplier */
         csr_mulv(mi, q->g_ptr, q->g_idx, q->g_val, x, gx);
-        double mu = 0, hz = 0;
+        double mu = 0, hz = 0, zmax = 0;
         for (int r = 0; r < mi; r++) {
             if (dead[r]) { rg[r] = 0; continue; }
-            rg[r] = gx[r] + s[r] - q->h[r]; mu += s[r] * z[r]; hz += hs[r] * z[r];
+            rg[r] = gx[r] + s[r] - h[r]; mu += s[r] * z[r]; hz += hs[r] * z[r];
+            if (z[r] > zmax) zmax = z[r];
         }
         mu /= (n_live > 0 ? n_live : 1);
         obj = 0;
@@ -769,19 +799,39 @@ int oracle_solve_qp(const oracle_qp *q, const oracle_solver_opts *opts, double *
         nrg = inf_norm(rg, mi);
         double dscale = 1.0 + inf_norm(px, nv);
         if (!(mu == mu) || !(nrd == nrd)) { status = ORACLE_NOT_CONVERGED; break; }
-        if (gap <= tol_gap * fmax(1.0, fabs(obj)) && nrg <= tol_res * (1 + hn) && nrd <= tol_res * dscale) {
-            status = ORACLE_OK;
-            break;
+        {
+            int gap_ok = gap <= tol_gap * fmax(1.0, fabs(obj)) && nrg <= tol_res * (1 + hn);
+            if (gap_ok && nrd <= tol_res * dscale) { status = ORACLE_OK; break; }
+            /* Round-off floor of the dual residual.  On (nearly) degenerate QPs x converges like sqrt(mu) while the
+             * weights z/s of the active rows grow like 1/mu, so the multiplier step dz = .. - w (G dx) carries noise
+             * eps w |dx| that GROWS as mu falls: the strict dual test can become unreachable although complementarity
+             * and primal feasibility are converged (seeds 3029, 3194, 3220 of the 64-agent workload: strictly feasible
+             * by an independent LP, CPLEX solves them).  Such an iterate is accepted at CPLEX's own optimality
+             * tolerance (EpOpt, default 1e-6, relative to the gradient scale) as soon as the dual residual stops
+             * falling -- i.e. when further iterations can only add noise. */
+            acceptable = gap_ok && nrd <= TOL_DUAL_FLOOR * dscale;
+            if (acceptable && nrd >= nrd_prev) { status = ORACLE_OK; break; }
+            nrd_prev = nrd;
         }
-        /* infeasibility certificate of the reduced problem {G Z sigma <= h - G x_p}: z >= 0, (GZ)'z ~ 0, (h - G x_p)'z < 0 */
-        if (hz < 0) {
+        /* infeasibility certificate of the reduced problem {G Z sigma <= h - G x_p}: z >= 0, (GZ)'z ~ 0, (h - G x_p)'z < 0.
+         * By LP duality the largest uniform slack of the rows is min (h - G x_p)'z / sum(z) over such z, so the row set is
+         * infeasible beyond the feasibility tolerance only if (h - G x_p)'z < -1e-6 sum(z); sum(z) >= max(z) is used.  A
+         * QP whose rows have no interior but are consistent (slack exactly 0) must not be certified infeasible. */
+        double cert = 1e300;
+        if (hz < -PRESOLVE_FEAS_TOL * zmax) {
             for (int i = 0; i < nv; i++) r1[i] = 0;
             csr_mulTv_add(mi, q->g_ptr, q->g_idx, q->g_val, z, r1);
             nsp_Zt(&K, r1, sg);
-            if (inf_norm(sg, nr) / (-hz) < 1e-8) { status = ORACLE_INFEASIBLE; break; }
+            cert = inf_norm(sg, nr) / (-hz);
+            if (cert < CERT_RATIO) { status = ORACLE_INFEASIBLE; break; }
         }
         for (int r = 0; r < mi; r++) K.w[r] = dead[r] ? 0.0 : z[r] / s[r];
-        if (nsp_factor(&K, K.w)) { status = ORACLE_NOT_CONVERGED; break; }
+        if (nsp_factor(&K, K.w)) {
+            /* the weights of an infeasible QP diverge by orders of magnitude per iteration; if the factorisation gives up
+             * before the certificate is sharp, a certificate that already excludes every |sigma| < 1e4 decides */
+            status = acceptable ? ORACLE_OK : (cert < CERT_RATIO_BREAKDOWN ? ORACLE_INFEASIBLE : ORACLE_NOT_CONVERGED);
+            break;
+        }
         /* affine direction: rc = s.z  =>  G' coefficient -(w rg - z) */
         for (int r = 0; r < mi; r++) tt[r] = dead[r] ? 0.0 : -(K.w[r] * rg[r] - z[r]);
         for (int i = 0; i < nv; i++) r1[i] = -rd[i];
@@ -831,6 +881,7 @@ int oracle_solve_qp(const oracle_qp *q, const oracle_solver_opts *opts, double *
         double al = fmin(1.0, 0.99 * am);
         for (int i = 0; i < nv; i++) x[i] += al * dx[i];
         for (int r = 0; r < mi; r++) { if (dead[r]) continue; s[r] += al * tt[r]; z[r] += al * rg[r]; }
+        acceptable = 0;
     }
 done:
     if (res_out) {
@@ -845,7 +896,7 @@ done:
     if (iters_out) *iters_out = it;
     nsp_free(&K);
     free(s); free(z); free(rd); free(rg); free(r1); free(tt); free(dx); free(dxa); free(gx); free(px);
-    free(gxa); free(hs); free(sg); free(ax); free(dead);
+    free(gxa); free(hs); free(sg); free(ax); free(dead); free(h);
     return status;
 }
 

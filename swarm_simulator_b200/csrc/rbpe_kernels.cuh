@@ -414,6 +414,13 @@ RBPE_DEV void block_reduce6(double *v, double *red) {
 
 enum { P_INIT = 0, P_START, P_SHIFT, P_RES, P_AFF, P_COR, P_STEP, P_DEAD };
 
+constexpr double PRESOLVE_FEAS_TOL = 1e-6;  // CPLEX's default feasibility tolerance, for rows made constant by the endpoints
+// Dual-residual floor of the acceptance rule (CPLEX's optimality tolerance EpOpt, default 1e-6); see pdip_solve and
+// oracle/rbp_oracle.c (TOL_DUAL_FLOOR) for the reasoning.
+constexpr double TOL_DUAL_FLOOR = 1e-6;
+// Farkas certificate ratios |(GZ)'z| / (-h'z): regular test, and the looser one that decides when the factorisation of a
+// diverging (infeasible) QP breaks down first.  Reasoning in oracle/rbp_oracle.c (CERT_RATIO).
+constexpr double CERT_RATIO = 1e-6, CERT_RATIO_BREAKDOWN = 1e-4;
 // right-hand side marker of a row removed by the bound-based redundancy presolve
 constexpr double ROW_PRUNED = 1e300;
 
@@ -455,7 +462,7 @@ RBPE_DEV void row_eval(double h, double &s, double &z, double &t, double gx, dou
     if (MODE == P_RES) {
         cA = z;
         cB = -(w * rg - z);
-        if (owner) { acc.s1 += s * z; acc.s2 += h * z; acc.mx = fmax(acc.mx, fabs(rg)); }
+        if (owner) { acc.s1 += s * z; acc.s2 += h * z; acc.mx = fmax(acc.mx, fabs(rg)); acc.mx2 = fmax(acc.mx2, z); }
         return;
     }
     double rz = t * s;
@@ -592,7 +599,7 @@ RBPE_DEV void row_pass(const QP &q, double sa, double sb, Acc &out) {
     }
     if (MODE == P_SHIFT || MODE == P_COR || MODE == P_INIT) { __syncthreads(); return; }
     double v[6] = {acc.s1, acc.s2, acc.mx, acc.mx2, -1e300, acc.mn};
-    constexpr int MASK = (MODE == P_RES) ? (1 + 2 + 4) : (MODE == P_AFF) ? (1 + 2 + 4) : (MODE == P_START) ? (4 + 8) : 4;
+    constexpr int MASK = (MODE == P_RES) ? (1 + 2 + 4 + 8) : (MODE == P_AFF) ? (1 + 2 + 4) : (MODE == P_START) ? (4 + 8) : 4;
     block_reduce6<MASK>(v, q.red);
     out.s1 = v[0]; out.s2 = v[1]; out.mx = v[2]; out.mx2 = v[3]; out.mn = v[5];
 }
@@ -700,6 +707,19 @@ RBPE_NOINLINE void kkt_solve(const QP &q, const double *r, double *dxout) {
     __syncthreads();
 }
 
+// Bounds of one axis of a corridor box as the solver sees them.  A box of (numerically) zero width -- an agent flying
+// along the world boundary next to a pillar gets one -- is a fixed variable to CPLEX's presolve, and any point within its
+// feasibility tolerance (1e-6) of the bounds is feasible to it; an interior-point method needs an interior, so such a pair
+// of bounds is opened to [mid - 1e-6, mid + 1e-6].  Same rule in oracle/rbp_oracle.c (presolve_dead_rows).
+RBPE_DEV void box_bounds(const double *box, int k, double &lb, double &ub) {
+    lb = box[k]; ub = box[3 + k];
+    const double wdt = ub - lb;
+    if (wdt < 2 * PRESOLVE_FEAS_TOL && wdt > -2 * PRESOLVE_FEAS_TOL) {
+        const double mid = 0.5 * (ub + lb);
+        ub = mid + PRESOLVE_FEAS_TOL; lb = mid - PRESOLVE_FEAS_TOL;
+    }
+}
+
 // rows of populatebyrow for the batch starting at agent q0 (h, normals; s = z = 1 until the start point is known);
 // x <- particular solution x_p (fixed control points from the start / goal states, zero elsewhere)
 RBPE_DEV void setup_rows(const QP &q) {
@@ -707,8 +727,12 @@ RBPE_DEV void setup_rows(const QP &q) {
     for (int v = threadIdx.x; v < q.nv; v += blockDim.x) {
         int m = v / q.n, r = v % q.n, a = r / 18, k = (r % 18) / 6, i = r % 6;
         const double *box = q.segbox + ((size_t)(q.q0 + a) * M + m) * 6;
-        q.ub[v] = box[3 + k];
-        q.lbn[v] = -box[k];
+        {
+            double lb, ub;
+            box_bounds(box, k, lb, ub);
+            q.ub[v] = ub;
+            q.lbn[v] = -lb;
+        }
         q.sub[v] = 1; q.zub[v] = 1; q.slb[v] = 1; q.zlb[v] = 1; q.tub[v] = 1; q.tlb[v] = 1;
         double xp = 0;
         if (m == 0 && i < 3) {          // build_deq rows 0..2 (L408-L432): start pos / vel / acc
@@ -742,7 +766,9 @@ RBPE_DEV void setup_rows(const QP &q) {
             const double *box = q.segbox + ((size_t)qa * M + m) * 6;
             double gg[3] = {(double)f0, (double)f1, (double)f2}, amax = 0;
             for (int k = 0; k < 3; k++) {
-                double a1 = gg[k] * box[3 + k], b1 = gg[k] * box[k];
+                double lb, ub;
+                box_bounds(box, k, lb, ub);
+                double a1 = gg[k] * ub, b1 = gg[k] * lb;
                 amax += (a1 > b1) ? a1 : b1;
             }
             if (amax < h - 1e-9 * fmax(1.0, fabs(h))) h = ROW_PRUNED;
@@ -763,11 +789,13 @@ RBPE_DEV void setup_rows(const QP &q) {
             const double *bl = q.segbox + ((size_t)(q.q0 + lo) * M + m) * 6, *bh = q.segbox + ((size_t)(q.q0 + hi) * M + m) * 6;
             double amax = 0;
             for (int k = 0; k < 3; k++) {
-                double g = (double)nf[k];
+                double g = (double)nf[k], lb, ub;
                 if (g == 0) continue;
-                double a1 = g * bl[3 + k], b1 = g * bl[k];
+                box_bounds(bl, k, lb, ub);
+                double a1 = g * ub, b1 = g * lb;
                 amax += (a1 > b1) ? a1 : b1;
-                a1 = -g * bh[3 + k]; b1 = -g * bh[k];
+                box_bounds(bh, k, lb, ub);
+                a1 = -g * ub; b1 = -g * lb;
                 amax += (a1 > b1) ? a1 : b1;
             }
             if (amax < hh - 1e-9 * fmax(1.0, fabs(hh))) hh = ROW_PRUNED;
@@ -796,7 +824,6 @@ RBPE_DEV double block_max(double v, double *red) {
     return r[2];
 }
 
-constexpr double PRESOLVE_FEAS_TOL = 1e-6;  // CPLEX's default feasibility tolerance, for rows made constant by the endpoints
 
 // Solves the QP described by q. Returns status; x holds the solution.
 RBPE_DEV int pdip_solve(const QP &q_in, int max_iter, double tol_gap, double tol_res, double *obj_out, int *it_out,
@@ -809,8 +836,8 @@ RBPE_DEV int pdip_solve(const QP &q_in, int max_iter, double tol_gap, double tol
     __syncthreads();
     PROF(0);
     int status = ST_NOT_CONVERGED, it = 0;
-    double obj = 0, gap = 0, nrd = 0, nrg = 0, hn = 0;
-    bool go = true;
+    double obj = 0, gap = 0, nrd = 0, nrg = 0, hn = 0, nrd_prev = 1e300;
+    bool go = true, acceptable = false;
     // presolve: rows on fixed control points are constants; check them and leave them out
     row_pass<P_DEAD>(q, 0, 0, acc);
     if (acc.mx > PRESOLVE_FEAS_TOL) { status = ST_INFEASIBLE; go = false; }
@@ -888,14 +915,25 @@ RBPE_DEV int pdip_solve(const QP &q_in, int max_iter, double tol_gap, double tol
         double mcert = rr[4];
         gap = mu;
         if (!(mu == mu) || !(nrd == nrd)) { status = ST_NOT_CONVERGED; break; }
-        if (gap <= tol_gap * fmax(1.0, fabs(obj)) && nrg <= tol_res * (1 + hn) && nrd <= tol_res * (1.0 + mpx)) {
-            status = ST_OK;
-            break;
+        {
+            // Strict test first.  On (nearly) degenerate QPs the dual residual has a round-off floor that RISES as mu
+            // falls (multiplier noise eps w |dx| with w = z/s ~ 1/mu and |dx| ~ sqrt(mu)); once complementarity and primal
+            // feasibility are converged and the dual residual has stopped falling, the iterate is accepted at CPLEX's own
+            // optimality tolerance instead of iterating into a numerically singular factorisation.
+            const bool gap_ok = gap <= tol_gap * fmax(1.0, fabs(obj)) && nrg <= tol_res * (1 + hn);
+            if (gap_ok && nrd <= tol_res * (1.0 + mpx)) { status = ST_OK; break; }
+            acceptable = gap_ok && nrd <= TOL_DUAL_FLOOR * (1.0 + mpx);
+            if (acceptable && nrd >= nrd_prev) { status = ST_OK; break; }
+            nrd_prev = nrd;
         }
-        if (hz < 0 && mcert / (-hz) < 1e-8) { status = ST_INFEASIBLE; break; }  // Farkas certificate (reduced problem)
+        // Farkas certificate of the reduced problem.  The largest uniform slack of the rows equals min h'z / sum(z) over
+        // z >= 0 with (GZ)'z = 0, so "infeasible beyond the feasibility tolerance" needs h'z < -1e-6 sum(z) (max(z) is
+        // used); rows that are consistent but have no interior (slack exactly 0) are not certified infeasible.
+        const double cert = (hz < -PRESOLVE_FEAS_TOL * acc.mx2) ? mcert / (-hz) : 1e300;
+        if (cert < CERT_RATIO) { status = ST_INFEASIBLE; break; }
         // ---- factor with W = z/s ----
         PROF(4);
-        if (!kkt_factor(q)) { status = ST_NOT_CONVERGED; break; }
+        if (!kkt_factor(q)) { status = acceptable ? ST_OK : (cert < CERT_RATIO_BREAKDOWN ? ST_INFEASIBLE : ST_NOT_CONVERGED); break; }
         PROF(2);
         // ---- affine direction ----
         for (int v = tid; v < q.nv; v += nt) q.vB[v] = -q.rdx[v] + q.vB[v];

@@ -123,7 +123,7 @@ RBPE_DEV void row_eval1(double h, double &s, double &z, double gx, double ga, do
     if (MODE == P_RES) {
         cA = z;
         cB = -(w * rg - z);
-        acc.s1 += s * z; acc.s2 += h * z; acc.mx = fmax(acc.mx, fabs(rg));
+        acc.s1 += s * z; acc.s2 += h * z; acc.mx = fmax(acc.mx, fabs(rg)); acc.mx2 = fmax(acc.mx2, z);
         return;
     }
     double rz = t * s;
@@ -336,14 +336,18 @@ RBPE_DEV int w1_setup(const W1 &c) {   // returns the number of live (kept, non-
                     if (!dead) {   // bound-based redundancy: max of g.x over the control point's box
                         double amax = 0;
                         for (int k = 0; k < 3; k++) {
-                            double g = nm[e * 3 + k], a = g * box[3 + k], b = g * box[k];
+                            double lb, ub;
+                            box_bounds(box, k, lb, ub);
+                            double g = nm[e * 3 + k], a = g * ub, b = g * lb;
                             amax += (a > b) ? a : b;
                         }
                         if (amax < h - 1e-9 * fmax(1.0, fabs(h))) continue;
                     }
                 } else {   // x_k <= ub ; -x_k <= -lb (L626-L635)
                     int k = (e - c.NE) >> 1;
-                    h = ((e - c.NE) & 1) ? -box[k] : box[3 + k];
+                    double lb, ub;
+                    box_bounds(box, k, lb, ub);
+                    h = ((e - c.NE) & 1) ? -lb : ub;
                 }
                 const size_t r = rb + (size_t)kept * 32;
                 c.he[r] = h; c.se[r] = 1; c.ze[r] = 1; c.ridx[r] = e;
@@ -366,8 +370,8 @@ RBPE_DEV int w1_solve_qp(const W1 &c, int max_iter, double tol_gap, double tol_r
     Acc acc;
     const int live_rows = w1_setup(c);
     int status = ST_NOT_CONVERGED, it = 0;
-    double obj = 0, gap = 0, nrd = 0, nrg = 0, hn = 0;
-    bool go = true;
+    double obj = 0, gap = 0, nrd = 0, nrg = 0, hn = 0, nrd_prev = 1e300;
+    bool go = true, acceptable = false;
     w1_pass<P_DEAD>(c, 0, 0, acc);
     if (acc.mx > PRESOLVE_FEAS_TOL) { status = ST_INFEASIBLE; go = false; }
     if (go && c.nr == 0) {
@@ -428,10 +432,17 @@ RBPE_DEV int w1_solve_qp(const W1 &c, int max_iter, double tol_gap, double tol_r
         obj = o; nrd = mr;
         gap = mu;
         if (!(mu == mu) || !(nrd == nrd)) { status = ST_NOT_CONVERGED; break; }
-        if (gap <= tol_gap * fmax(1.0, fabs(obj)) && nrg <= tol_res * (1 + hn) && nrd <= tol_res * (1.0 + mpx)) { status = ST_OK; break; }
-        if (hz < 0 && mc / (-hz) < 1e-8) { status = ST_INFEASIBLE; break; }
+        {   // acceptance rule of pdip_solve (rbpe_kernels.cuh): strict test, else the round-off floor of the dual residual
+            const bool gap_ok = gap <= tol_gap * fmax(1.0, fabs(obj)) && nrg <= tol_res * (1 + hn);
+            if (gap_ok && nrd <= tol_res * (1.0 + mpx)) { status = ST_OK; break; }
+            acceptable = gap_ok && nrd <= TOL_DUAL_FLOOR * (1.0 + mpx);
+            if (acceptable && nrd >= nrd_prev) { status = ST_OK; break; }
+            nrd_prev = nrd;
+        }
+        const double cert = (hz < -PRESOLVE_FEAS_TOL * acc.mx2) ? mc / (-hz) : 1e300;
+        if (cert < CERT_RATIO) { status = ST_INFEASIBLE; break; }
         w1_build_W(c.segmat, c.M, c.Dcp, c.Wd, c.Wo);
-        if (!factor_bt9v<1>(c.M - 1, c.Wd, c.Wo, c.dinv)) { status = ST_NOT_CONVERGED; break; }
+        if (!factor_bt9v<1>(c.M - 1, c.Wd, c.Wo, c.dinv)) { status = acceptable ? ST_OK : (cert < CERT_RATIO_BREAKDOWN ? ST_INFEASIBLE : ST_NOT_CONVERGED); break; }
         #pragma unroll 1
         for (int v = lane; v < 18 * c.M; v += 32) c.vB[v] = -c.rdx[v] + c.vB[v];
         __syncwarp();
