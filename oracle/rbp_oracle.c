@@ -724,7 +724,7 @@ int oracle_solve_qp(const oracle_qp *q, const oracle_solver_opts *opts, double *
     double tol_res = (opts && opts->tol_res > 0) ? opts->tol_res : 1e-9;
     nsp_t K;
     int status = ORACLE_NOT_CONVERGED, it = 0, n_live = mi;
-    double gap = 0, obj = 0, nrd = 0, nrg = 0, hn = 0, nrd_prev = 1e300;
+    double gap = 0, obj = 0, nrd = 0, nrg = 0, hn = 0;
     int acceptable = 0;
     if (nsp_init(&K, q)) {
         nsp_free(&K);
@@ -806,12 +806,11 @@ int oracle_solve_qp(const oracle_qp *q, const oracle_solver_opts *opts, double *
              * weights z/s of the active rows grow like 1/mu, so the multiplier step dz = .. - w (G dx) carries noise
              * eps w |dx| that GROWS as mu falls: the strict dual test can become unreachable although complementarity
              * and primal feasibility are converged (seeds 3029, 3194, 3220 of the 64-agent workload: strictly feasible
-             * by an independent LP, CPLEX solves them).  Such an iterate is accepted at CPLEX's own optimality
-             * tolerance (EpOpt, default 1e-6, relative to the gradient scale) as soon as the dual residual stops
-             * falling -- i.e. when further iterations can only add noise. */
+             * by an independent LP, CPLEX solves them).  Once complementarity and primal feasibility meet their strict
+             * tolerances the iterate is therefore accepted at CPLEX's own optimality tolerance (EpOpt, default 1e-6,
+             * relative to the gradient scale) instead of iterating into a numerically singular factorisation. */
             acceptable = gap_ok && nrd <= TOL_DUAL_FLOOR * dscale;
-            if (acceptable && nrd >= nrd_prev) { status = ORACLE_OK; break; }
-            nrd_prev = nrd;
+            if (acceptable) { status = ORACLE_OK; break; }
         }
         /* infeasibility certificate of the reduced problem {G Z sigma <= h - G x_p}: z >= 0, (GZ)'z ~ 0, (h - G x_p)'z < 0.
          * By LP duality the largest uniform slack of the rows is min (h - G x_p)'z / sum(z) over such z, so the row set is
@@ -881,7 +880,6 @@ int oracle_solve_qp(const oracle_qp *q, const oracle_solver_opts *opts, double *
         double al = fmin(1.0, 0.99 * am);
         for (int i = 0; i < nv; i++) x[i] += al * dx[i];
         for (int r = 0; r < mi; r++) { if (dead[r]) continue; s[r] += al * tt[r]; z[r] += al * rg[r]; }
-        acceptable = 0;
     }
 done:
     if (res_out) {

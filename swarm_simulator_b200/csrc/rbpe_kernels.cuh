@@ -836,7 +836,7 @@ RBPE_DEV int pdip_solve(const QP &q_in, int max_iter, double tol_gap, double tol
     __syncthreads();
     PROF(0);
     int status = ST_NOT_CONVERGED, it = 0;
-    double obj = 0, gap = 0, nrd = 0, nrg = 0, hn = 0, nrd_prev = 1e300;
+    double obj = 0, gap = 0, nrd = 0, nrg = 0, hn = 0;
     bool go = true, acceptable = false;
     // presolve: rows on fixed control points are constants; check them and leave them out
     row_pass<P_DEAD>(q, 0, 0, acc);
@@ -918,13 +918,12 @@ RBPE_DEV int pdip_solve(const QP &q_in, int max_iter, double tol_gap, double tol
         {
             // Strict test first.  On (nearly) degenerate QPs the dual residual has a round-off floor that RISES as mu
             // falls (multiplier noise eps w |dx| with w = z/s ~ 1/mu and |dx| ~ sqrt(mu)); once complementarity and primal
-            // feasibility are converged and the dual residual has stopped falling, the iterate is accepted at CPLEX's own
-            // optimality tolerance instead of iterating into a numerically singular factorisation.
+            // feasibility meet their strict tolerances the iterate is accepted at CPLEX's own optimality tolerance (1e-6,
+            // relative to the gradient scale) instead of iterating into a numerically singular factorisation.
             const bool gap_ok = gap <= tol_gap * fmax(1.0, fabs(obj)) && nrg <= tol_res * (1 + hn);
             if (gap_ok && nrd <= tol_res * (1.0 + mpx)) { status = ST_OK; break; }
             acceptable = gap_ok && nrd <= TOL_DUAL_FLOOR * (1.0 + mpx);
-            if (acceptable && nrd >= nrd_prev) { status = ST_OK; break; }
-            nrd_prev = nrd;
+            if (acceptable) { status = ST_OK; break; }
         }
         // Farkas certificate of the reduced problem.  The largest uniform slack of the rows equals min h'z / sum(z) over
         // z >= 0 with (GZ)'z = 0, so "infeasible beyond the feasibility tolerance" needs h'z < -1e-6 sum(z) (max(z) is
@@ -1054,4 +1053,8 @@ __global__ void __launch_bounds__(CTA_THREADS, RBPE_PDIP_MINB) pdip_kernel(Solve
 #endif  // __CUDACC__ || RBPE_EMU
 }  // namespace rbpe
 
+#ifdef RBPE_W1_V1
+#include "rbpe_pdip1_v1.cuh"
+#else
 #include "rbpe_pdip1.cuh"
+#endif

@@ -1,9 +1,5 @@
 // rbpe_pdip1.cuh -- k2 for one-agent batches (plan/batch_size = 1, the per-agent QP of the north-star):
-// ONE WARP PER QP, ONE LANE PER CONTROL POINT.  (Round-2 layout of the code: ONE copy of the row loop with a run-time
-// pass mode and a phase machine around it, because the kernel is instruction-FETCH bound -- ncu r1/r2a: icc hit rate 69 %,
-// GPC instruction-cache requests at 92 % of peak, `no_instruction` the top stall -- while the B200's L0 / L1.5 instruction
-// caches hold ~6 KB / 32 KB: four template copies of the row loop, run by 16 warps in 16 different phases, do not fit.
-// The round-1 layout is kept as rbpe_pdip1_v1.cuh for A/B runs, -DRBPE_W1_V1.)
+// ONE WARP PER QP, ONE LANE PER CONTROL POINT.
 //
 // Same algorithm and row order as pdip_kernel (rbpe_kernels.cuh), different mapping:
 //   * lane <-> Bernstein control point (6M of them, 32 per "slot"); the lane walks the rows that touch its control
@@ -98,35 +94,71 @@ RBPE_NOINLINE Red5 warp_reduce5(double s1, double s2, double mx, double mx2, dou
     return r;
 }
 
+// same row algebra as row_eval (rbpe_kernels.cuh); t = 1/(s z) computed here
+template <int MODE>
+RBPE_DEV void row_eval1(double h, double &s, double &z, double gx, double ga, double gd, double sa, double sb, double &cA,
+                        double &cB, double &w, Acc &acc) {
+    cA = 0; cB = 0; w = 0;
+    if (MODE == P_DEAD) { acc.mx = fmax(acc.mx, gx - h); return; }
+    if (MODE == P_INIT) { w = 1.0; cA = h - gx; return; }
+    if (MODE == P_START) {
+        z = gx - h; s = -z;
+        acc.mx = fmax(acc.mx, -s); acc.mx2 = fmax(acc.mx2, -z);
+        return;
+    }
+    if (MODE == P_SHIFT) { s += sa; z += sb; return; }
+    double t = rcp_nr(s * z), rs = t * z;
+    if (MODE == P_RES && sb != 0.0) {  // pending step of the previous iteration, fused into the residual pass
+        double rgo = gx + s - h, wo = z * rs;
+        double dsa = -rgo - ga, dza = -z - wo * dsa;
+        double rc = s * z + dsa * dza - sa;
+        double ds = -rgo - gd, dz = (-rc - z * ds) * rs;
+        s += sb * ds; z += sb * dz;
+        gx += sb * gd;
+        t = rcp_nr(s * z);
+        rs = t * z;
+    }
+    double rg = gx + s - h;
+    w = z * rs;
+    if (MODE == P_RES) {
+        cA = z;
+        cB = -(w * rg - z);
+        acc.s1 += s * z; acc.s2 += h * z; acc.mx = fmax(acc.mx, fabs(rg)); acc.mx2 = fmax(acc.mx2, z);
+        return;
+    }
+    double rz = t * s;
+    double dsa = -rg - ga, dza = -z - w * dsa;
+    if (MODE == P_AFF) {
+        acc.mx = fmax(acc.mx, fmax(-dsa * rs, -dza * rz));
+        acc.s1 += s * dza + z * dsa; acc.s2 += dsa * dza;
+        return;
+    }
+    double rc = s * z + dsa * dza - sa;
+    if (MODE == P_COR) { cA = -(z * rg - rc) * rs; return; }
+    double ds = -rg - gd, dz = (-rc - z * ds) * rs;
+    if (MODE == P_STEP) acc.mx = fmax(acc.mx, fmax(-ds * rs, -dz * rz));
+}
 
 RBPE_DEV bool w1_dead(const W1 &c, int cp) { int m = cp / 6, i = cp % 6; return (m == 0 && i < 3) || (m == c.M - 1 && i >= 3); }
 
-// One pass over the kept inequality rows: the lane walks the rows of its control point.  `mode` is warp-uniform, every
-// branch on it is a uniform branch; same row algebra as row_eval (rbpe_kernels.cuh), t = 1/(s z) recomputed here:
-//   P_INIT   unit weights: vA = G'(h - G x), D = sum g g';                     acc.mx2 = max |h|
-//   P_START  z = G x - h, s = -z;                                             acc.mx = max(-s), acc.mx2 = max(-z)
-//   P_SHIFT  s += sa, z += sb
-//   P_RES    pending step (sa = its sigma mu, sb = its length) fused in; vA = G'z, vB = G' t_aff, D = sum w g g';
-//            acc.s1 = s'z, acc.s2 = h'z, acc.mx = max |rg|, acc.mx2 = max z
-//   P_AFF    ratio test of the affine direction (max form) in acc.mx; acc.s1, acc.s2 = coefficients of mu_aff(a)
-//   P_COR    vA = G'(corrector coefficients), sa = sigma mu
-//   P_STEP   ratio test of the final direction in acc.mx
-// Called from ONE place (w1_solve_qp's phase machine) so that a single copy of this loop exists in the kernel text.
-RBPE_DEV void w1_pass(const W1 &c, const int mode, const double sa, const double sb, Acc &out) {
+template <int MODE>
+RBPE_DEV void w1_pass(const W1 &c, double sa, double sb, Acc &out) {
+    constexpr bool WR = (MODE == P_START || MODE == P_SHIFT || MODE == P_RES);
+    constexpr bool VEC = (MODE == P_INIT || MODE == P_RES || MODE == P_COR);
+    constexpr bool MAT = (MODE == P_INIT || MODE == P_RES);
     const int lane = threadIdx.x & 31;
     Acc acc;
-    acc.s1 = 0; acc.s2 = 0; acc.mx = (mode == P_AFF || mode == P_STEP) ? 0.0 : -1e300; acc.mx2 = -1e300; acc.mn = 1e300;
-#pragma unroll 1
+    acc.s1 = 0; acc.s2 = 0; acc.mx = (MODE == P_AFF || MODE == P_STEP) ? 0.0 : -1e300; acc.mx2 = -1e300; acc.mn = 1e300;
     for (int slot = 0; slot < c.nslot; slot++) {
         const int cp = slot * 32 + lane;
-        const bool on = cp < c.ncp && !w1_dead(c, cp);
+        const bool on = cp < c.ncp && (w1_dead(c, cp) == (MODE == P_DEAD));
         if (!__any_sync(0xffffffffu, on)) continue;
         const int m = on ? cp / 6 : 0, i = on ? cp % 6 : 0, v0 = m * 18 + i;
         double x0 = 0, x1 = 0, x2 = 0, a0 = 0, a1 = 0, a2 = 0, d0 = 0, d1 = 0, d2 = 0;
         if (on) {
             x0 = c.x[v0]; x1 = c.x[v0 + 6]; x2 = c.x[v0 + 12];
-            a0 = c.dxa[v0]; a1 = c.dxa[v0 + 6]; a2 = c.dxa[v0 + 12];
-            d0 = c.dx[v0]; d1 = c.dx[v0 + 6]; d2 = c.dx[v0 + 12];
+            if (MODE == P_RES || MODE == P_AFF || MODE == P_COR || MODE == P_STEP) { a0 = c.dxa[v0]; a1 = c.dxa[v0 + 6]; a2 = c.dxa[v0 + 12]; }
+            if (MODE == P_RES || MODE == P_STEP) { d0 = c.dx[v0]; d1 = c.dx[v0 + 6]; d2 = c.dx[v0 + 12]; }
         }
         double vA0 = 0, vA1 = 0, vA2 = 0, vB0 = 0, vB1 = 0, vB2 = 0;
         double Dxx = 0, Dxy = 0, Dxz = 0, Dyy = 0, Dyz = 0, Dzz = 0;
@@ -135,92 +167,39 @@ RBPE_DEV void w1_pass(const W1 &c, const int mode, const double sa, const double
             const size_t rb = (size_t)slot * c.NR * 32 + lane;
             const int cnt = c.cnt[slot * 32 + lane];
             int e_next = cnt > 0 ? c.ridx[rb] : 0;   // row number fetched one iteration ahead: one L2 round trip per row, not two
-#pragma unroll 1
+#pragma unroll W1_UNROLL
             for (int j = 0; j < cnt; j++) {
                 const size_t r = rb + (size_t)j * 32;
                 const int e = e_next;
                 e_next = (j + 1 < cnt) ? c.ridx[r + 32] : 0;
-                const double n0 = nm[e * 3], n1 = nm[e * 3 + 1], n2 = nm[e * 3 + 2];
-                const double h = c.he[r];
-                double s = c.se[r], z = c.ze[r];
-                double gx = n0 * x0 + n1 * x1 + n2 * x2;
-                double cA, w;
-                if (mode <= P_SHIFT) {
-                    if (mode != P_INIT) {
-                        if (mode == P_START) {
-                            z = gx - h; s = -z;
-                            acc.mx = fmax(acc.mx, -s); acc.mx2 = fmax(acc.mx2, -z);
-                        } else {
-                            s += sa; z += sb;
-                        }
-                        c.se[r] = s; c.ze[r] = z;
-                        continue;
-                    }
-                    w = 1.0; cA = h - gx;
-                    acc.mx2 = fmax(acc.mx2, fabs(h));
-                } else {
-                    const double ga = n0 * a0 + n1 * a1 + n2 * a2, gd = n0 * d0 + n1 * d1 + n2 * d2;
-                    double t = rcp_nr(s * z), rs = t * z;
-                    if (mode == P_RES) {
-                        if (sb != 0.0) {   // pending step of the previous iteration, fused into the residual pass
-                            double rgo = gx + s - h, wo = z * rs;
-                            double dsa = -rgo - ga, dza = -z - wo * dsa;
-                            double rc = s * z + dsa * dza - sa;
-                            double ds = -rgo - gd, dz = (-rc - z * ds) * rs;
-                            s += sb * ds; z += sb * dz;
-                            gx += sb * gd;
-                            t = rcp_nr(s * z);
-                            rs = t * z;
-                            c.se[r] = s; c.ze[r] = z;
-                        }
-                        const double rg = gx + s - h;
-                        w = z * rs;
-                        cA = z;
-                        const double cB = -(w * rg - z);
-                        acc.s1 += s * z; acc.s2 += h * z; acc.mx = fmax(acc.mx, fabs(rg)); acc.mx2 = fmax(acc.mx2, z);
-                        vB0 += cB * n0; vB1 += cB * n1; vB2 += cB * n2;
-                    } else {
-                        const double rg = gx + s - h;
-                        w = z * rs;
-                        const double rz = t * s;
-                        const double dsa = -rg - ga, dza = -z - w * dsa;
-                        if (mode == P_AFF) {
-                            acc.mx = fmax(acc.mx, fmax(-dsa * rs, -dza * rz));
-                            acc.s1 += s * dza + z * dsa; acc.s2 += dsa * dza;
-                            continue;
-                        }
-                        const double rc = s * z + dsa * dza - sa;
-                        if (mode == P_STEP) {
-                            const double ds = -rg - gd, dz = (-rc - z * ds) * rs;
-                            acc.mx = fmax(acc.mx, fmax(-ds * rs, -dz * rz));
-                            continue;
-                        }
-                        cA = -(z * rg - rc) * rs;   // P_COR
-                        vA0 += cA * n0; vA1 += cA * n1; vA2 += cA * n2;
-                        continue;
-                    }
-                }
-                vA0 += cA * n0; vA1 += cA * n1; vA2 += cA * n2;
-                {
-                    const double w0 = w * n0, w1 = w * n1, w2 = w * n2;
+                double n0 = nm[e * 3], n1 = nm[e * 3 + 1], n2 = nm[e * 3 + 2];
+                double h = c.he[r], s = c.se[r], z = c.ze[r], cA, cB, w;
+                row_eval1<MODE>(h, s, z, n0 * x0 + n1 * x1 + n2 * x2, n0 * a0 + n1 * a1 + n2 * a2, n0 * d0 + n1 * d1 + n2 * d2,
+                                sa, sb, cA, cB, w, acc);
+                if (WR) { c.se[r] = s; c.ze[r] = z; }
+                if (VEC) { vA0 += cA * n0; vA1 += cA * n1; vA2 += cA * n2; }
+                if (MODE == P_RES) { vB0 += cB * n0; vB1 += cB * n1; vB2 += cB * n2; }
+                if (MAT) {
+                    double w0 = w * n0, w1 = w * n1, w2 = w * n2;
                     Dxx += w0 * n0; Dxy += w0 * n1; Dxz += w0 * n2; Dyy += w1 * n1; Dyz += w1 * n2; Dzz += w2 * n2;
                 }
             }
-            if (mode == P_INIT || mode == P_RES || mode == P_COR) { c.vA[v0] = vA0; c.vA[v0 + 6] = vA1; c.vA[v0 + 12] = vA2; }
-            if (mode == P_RES) { c.vB[v0] = vB0; c.vB[v0 + 6] = vB1; c.vB[v0 + 12] = vB2; }
-            if (mode == P_INIT || mode == P_RES) {
+            if (VEC) { c.vA[v0] = vA0; c.vA[v0 + 6] = vA1; c.vA[v0 + 12] = vA2; }
+            if (MODE == P_RES) { c.vB[v0] = vB0; c.vB[v0 + 6] = vB1; c.vB[v0 + 12] = vB2; }
+            if (MAT) {
                 double *D = c.Dcp + (size_t)cp * 6;
                 D[0] = Dxx; D[1] = Dxy; D[2] = Dxz; D[3] = Dyy; D[4] = Dyz; D[5] = Dzz;
             }
         }
     }
-    if (mode != P_SHIFT && mode != P_COR) {
+    if (MODE == P_RES || MODE == P_AFF || MODE == P_START || MODE == P_STEP || MODE == P_DEAD) {
         Red5 r = warp_reduce5(acc.s1, acc.s2, acc.mx, acc.mx2, 0.0);
         acc.s1 = r.s1; acc.s2 = r.s2; acc.mx = r.mx; acc.mx2 = r.mx2;
     }
     __syncwarp();
     out = acc;
 }
+
 // The helpers below are single non-inlined copies (instruction-cache footprint) and take plain arguments, so that the
 // context struct never has its address taken and stays in registers.
 // out (nr) = Z' vec (x-space)
@@ -255,27 +234,22 @@ RBPE_NOINLINE void w1_Z(const double *segmat, int M, const double *sg, double *o
     __syncwarp();
 }
 RBPE_NOINLINE void w1_build_W(const double *segmat, int M, const double *Dcp, double *Wd, double *Wo) {
-    // entry idx = r * 9 + cc of a 9 x 9 block, r = (axis k, derivative d), cc = (k2, d2); a lane owns idx = lane, lane + 32,
-    // lane + 64 of EVERY knot, so the index arithmetic is done three times per call instead of once per entry
-#pragma unroll 1
-    for (int idx = threadIdx.x & 31; idx < 81; idx += 32) {
-        const int r = idx / 9, cc = idx - 9 * r;
-        const int k = r / 3, d = r - 3 * k, k2 = cc / 3, d2 = cc - 3 * k2;
-        const int e = sym6(k, k2);
-        const bool low = cc <= r, same = k == k2;
-#pragma unroll 1
-        for (int t = 1; t < M; t++) {
-            const double *sl = segmat + (t - 1) * SEGMAT, *sr = segmat + t * SEGMAT;
-            double s = 0;
-            if (low) {
-                const double *CR = sl + SEGMAT_CR, *CL = sr + SEGMAT_CL;
-                const double *Dl = Dcp + ((size_t)(t - 1) * 6 + 3) * 6 + e, *Dr = Dcp + ((size_t)t * 6) * 6 + e;
-                for (int j = 0; j < 3; j++) s += CR[j * 3 + d] * CR[j * 3 + d2] * Dl[j * 6] + CL[j * 3 + d] * CL[j * 3 + d2] * Dr[j * 6];
-                if (same) s += sl[SEGMAT_RQ + (3 + d) * 6 + 3 + d2] + sr[SEGMAT_RQ + d * 6 + d2];
-            }
-            Wd[(t - 1) * 81 + idx] = s;
-            if (t < M - 1) Wo[(t - 1) * 81 + idx] = same ? sr[SEGMAT_RQ + (3 + d) * 6 + d2] : 0.0;
+    for (int idx = threadIdx.x & 31; idx < (M - 1) * 81; idx += 32) {
+        int t = idx / 81 + 1, r = (idx % 81) / 9, cc = idx % 9;
+        double s = 0;
+        if (cc <= r) {
+            int k = r / 3, d = r % 3, k2 = cc / 3, d2 = cc % 3;
+            const double *CR = segmat + (t - 1) * SEGMAT + SEGMAT_CR, *CL = segmat + t * SEGMAT + SEGMAT_CL;
+            int e = sym6(k, k2);
+            const double *Dl = Dcp + ((size_t)(t - 1) * 6 + 3) * 6 + e, *Dr = Dcp + ((size_t)t * 6) * 6 + e;
+            for (int j = 0; j < 3; j++) s += CR[j * 3 + d] * CR[j * 3 + d2] * Dl[j * 6] + CL[j * 3 + d] * CL[j * 3 + d2] * Dr[j * 6];
+            if (k == k2) s += segmat[(t - 1) * SEGMAT + SEGMAT_RQ + (3 + d) * 6 + 3 + d2] + segmat[t * SEGMAT + SEGMAT_RQ + d * 6 + d2];
         }
+        Wd[idx] = s;
+    }
+    for (int idx = threadIdx.x & 31; idx < (M - 2) * 81; idx += 32) {
+        int t = idx / 81 + 1, r = (idx % 81) / 9, cc = idx % 9;
+        Wo[idx] = (r / 3 == cc / 3) ? segmat[t * SEGMAT + SEGMAT_RQ + (3 + r % 3) * 6 + cc % 3] : 0.0;
     }
     __syncwarp();
 }
@@ -305,9 +279,7 @@ RBPE_NOINLINE ObjMpx w1_dual(const double *segmat, int M, const double *QB, cons
     return r;
 }
 
-// returns the number of live (kept, non-constant) inequality rows; dead_viol = largest violation of a row made constant
-// by the start / goal equalities (rows on the fixed control points: checked here, never stored)
-RBPE_DEV int w1_setup(const W1 &c, double &dead_viol) {
+RBPE_DEV int w1_setup(const W1 &c) {   // returns the number of live (kept, non-constant) inequality rows
     const int lane = threadIdx.x & 31, M = c.M, N = c.N, nv = 18 * M;
     for (int v = lane; v < nv; v += 32) {
         int m = v / 18, r = v % 18, k = r / 6, i = r % 6;
@@ -342,7 +314,6 @@ RBPE_DEV int w1_setup(const W1 &c, double &dead_viol) {
     }
     __syncwarp();
     int live_rows = 0;
-    double dviol = -1e300;
     for (int slot = 0; slot < c.nslot; slot++) {
         const int cp = slot * 32 + lane;
         int kept = 0;
@@ -352,8 +323,6 @@ RBPE_DEV int w1_setup(const W1 &c, double &dead_viol) {
             const double *box = c.segbox + ((size_t)c.qa * M + m) * 6;
             const double *nm = c.nrm + (size_t)m * c.NR * 3;
             const size_t rb = (size_t)slot * c.NR * 32 + lane;
-            const int v0 = m * 18 + i;
-            const double xd0 = c.x[v0], xd1 = c.x[v0 + 6], xd2 = c.x[v0 + 12];
             for (int e = 0; e < c.NR; e++) {
                 double h;
                 if (e < c.NE) {
@@ -380,10 +349,6 @@ RBPE_DEV int w1_setup(const W1 &c, double &dead_viol) {
                     box_bounds(box, k, lb, ub);
                     h = ((e - c.NE) & 1) ? -lb : ub;
                 }
-                if (dead) {   // constant row: only its violation matters (P_DEAD of the round-1 layout)
-                    dviol = fmax(dviol, nm[e * 3] * xd0 + nm[e * 3 + 1] * xd1 + nm[e * 3 + 2] * xd2 - h);
-                    continue;
-                }
                 const size_t r = rb + (size_t)kept * 32;
                 c.he[r] = h; c.se[r] = 1; c.ze[r] = 1; c.ridx[r] = e;
                 kept++;
@@ -396,109 +361,103 @@ RBPE_DEV int w1_setup(const W1 &c, double &dead_viol) {
         if (lane == 0) c.cmax[slot] = mx;
     }
     for (int o = 16; o > 0; o >>= 1) live_rows += __shfl_xor_sync(0xffffffffu, live_rows, o);
-    dead_viol = warp_reduce5(0.0, 0.0, dviol, 0.0, 0.0).mx;
     __syncwarp();
     return live_rows;
 }
 
-
-// Phase machine around the single copy of the row loop.  Same sequence of operations as pdip_solve (rbpe_kernels.cuh).
-enum { PH_INIT = P_INIT, PH_START = P_START, PH_SHIFT = P_SHIFT, PH_RES = P_RES, PH_AFF = P_AFF, PH_COR = P_COR, PH_STEP = P_STEP, PH_DONE = 100 };
-
 RBPE_DEV int w1_solve_qp(const W1 &c, int max_iter, double tol_gap, double tol_res, double *obj_out, int *it_out, double *res_out) {
     const int lane = threadIdx.x & 31;
     Acc acc;
-    double dead_viol;
-    const int live_rows = w1_setup(c, dead_viol);
+    const int live_rows = w1_setup(c);
     int status = ST_NOT_CONVERGED, it = 0;
     double obj = 0, gap = 0, nrd = 0, nrg = 0, hn = 0;
-    int phase = PH_INIT;
-    if (dead_viol > PRESOLVE_FEAS_TOL) { status = ST_INFEASIBLE; phase = PH_DONE; }
-    if (phase != PH_DONE && c.nr == 0) {
-        double o = w1_dual(c.segmat, c.M, c.QB, c.x, c.vA, c.rdx).obj;
-        obj = warp_reduce5(o, 0.0, 0.0, 0.0, 0.0).s1;
-        status = ST_OK; phase = PH_DONE;
+    bool go = true, acceptable = false;
+    w1_pass<P_DEAD>(c, 0, 0, acc);
+    if (acc.mx > PRESOLVE_FEAS_TOL) { status = ST_INFEASIBLE; go = false; }
+    if (go && c.nr == 0) {
+        double o = 0;
+        o = w1_dual(c.segmat, c.M, c.QB, c.x, c.vA, c.rdx).obj;
+        o = warp_reduce5(o, 0.0, 0.0, 0.0, 0.0).s1;
+        obj = o; status = ST_OK; go = false;
     }
-    double sa = 0, sb = 0;          // pass scalars of the next pass
-    double sigmu = 0, al = 0, mu = 0;
-    const double mi = live_rows > 0 ? (double)live_rows : 1.0;
-#pragma unroll 1
-    while (phase != PH_DONE) {
-        w1_pass(c, phase, sa, sb, acc);
-        if (phase == PH_RES) {
-            if (al != 0.0) {
-                #pragma unroll 1
-                for (int v = lane; v < 18 * c.M; v += 32) c.x[v] += al * c.dx[v];
-                __syncwarp();
-            }
-            mu = acc.s1 / mi;
-            const double hz = acc.s2, zmax = acc.mx2;
-            nrg = fmax(acc.mx, 0.0);
-            ObjMpx om = w1_dual(c.segmat, c.M, c.QB, c.x, c.vA, c.rdx);
-            double o = om.obj, mpx = om.mpx;
-            w1_Zt(c.segmat, c.nr, c.rdx, c.sg);
-            w1_Zt(c.segmat, c.nr, c.vA, c.sg2);
-            double mr = 0, mc = 0;
+    if (go) {
+        double mh = 0;
+        #pragma unroll 1
+        for (int slot = 0; slot < c.nslot; slot++) {
+            const int cp = slot * 32 + lane;
+            if (cp >= c.ncp || w1_dead(c, cp)) continue;
+            const size_t rb = (size_t)slot * c.NR * 32 + lane;
+            const int cnt = c.cnt[slot * 32 + lane];
             #pragma unroll 1
-            for (int r = lane; r < c.nr; r += 32) { mr = fmax(mr, fabs(c.sg[r])); mc = fmax(mc, fabs(c.sg2[r])); }
-            { Red5 r = warp_reduce5(o, 0.0, mpx, mr, mc); o = r.s1; mpx = r.mx; mr = r.mx2; mc = r.mx3; }
-            obj = o; nrd = mr;
-            gap = mu;
-            if (!(mu == mu) || !(nrd == nrd)) { status = ST_NOT_CONVERGED; break; }
-            bool acceptable;
-            {   // acceptance rule of pdip_solve (rbpe_kernels.cuh): strict test, else the round-off floor of the dual residual
-                const bool gap_ok = gap <= tol_gap * fmax(1.0, fabs(obj)) && nrg <= tol_res * (1 + hn);
-                if (gap_ok && nrd <= tol_res * (1.0 + mpx)) { status = ST_OK; break; }
-                acceptable = gap_ok && nrd <= TOL_DUAL_FLOOR * (1.0 + mpx);
-                if (acceptable) { status = ST_OK; break; }
-            }
-            const double cert = (hz < -PRESOLVE_FEAS_TOL * zmax) ? mc / (-hz) : 1e300;
-            if (cert < CERT_RATIO) { status = ST_INFEASIBLE; break; }
-            w1_build_W(c.segmat, c.M, c.Dcp, c.Wd, c.Wo);
-            if (!factor_bt9v<1>(c.M - 1, c.Wd, c.Wo, c.dinv)) { status = cert < CERT_RATIO_BREAKDOWN ? ST_INFEASIBLE : ST_NOT_CONVERGED; break; }
-            #pragma unroll 1
-            for (int v = lane; v < 18 * c.M; v += 32) c.vB[v] = -c.rdx[v] + c.vB[v];
-            __syncwarp();
-            w1_solve(c, c.vB, c.dxa);
-            phase = PH_AFF; sa = 0; sb = 0;
-        } else if (phase == PH_AFF) {
-            const double aa = (acc.mx > 1.0) ? 1.0 / acc.mx : 1.0;
-            const double mua = (mu * mi + aa * acc.s1 + aa * aa * acc.s2) / mi;
-            const double sigma = (mu > 0) ? (mua / mu) * (mua / mu) * (mua / mu) : 0.0;
-            sigmu = sigma * mu;
-            phase = PH_COR; sa = sigmu; sb = 0;
-        } else if (phase == PH_COR) {
-            #pragma unroll 1
-            for (int v = lane; v < 18 * c.M; v += 32) c.vA[v] = -c.rdx[v] + c.vA[v];
-            __syncwarp();
-            w1_solve(c, c.vA, c.dx);
-            phase = PH_STEP; sa = sigmu; sb = 0;
-        } else if (phase == PH_STEP) {
-            al = (0.99 < acc.mx) ? 0.99 / acc.mx : 1.0;
-            it++;
-            if (it >= max_iter) break;
-            phase = PH_RES; sa = sigmu; sb = al;
-        } else if (phase == PH_INIT) {
-            hn = acc.mx2;
-            w1_build_W(c.segmat, c.M, c.Dcp, c.Wd, c.Wo);
-            if (!factor_bt9v<1>(c.M - 1, c.Wd, c.Wo, c.dinv)) break;
-            w1_dual(c.segmat, c.M, c.QB, c.x, c.vA, c.rdx);   // rdx = P x_p + vA
-            #pragma unroll 1
-            for (int v = lane; v < 18 * c.M; v += 32) c.rdx[v] = 2.0 * c.vA[v] - c.rdx[v];
-            __syncwarp();
-            w1_solve(c, c.rdx, c.dx);
-            #pragma unroll 1
-            for (int v = lane; v < 18 * c.M; v += 32) { c.x[v] += c.dx[v]; c.dx[v] = 0; }
-            __syncwarp();
-            phase = PH_START;
-        } else if (phase == PH_START) {
-            const double ap = acc.mx, ad = acc.mx2;
-            sa = ap >= 0 ? 1.0 + ap : 0.0; sb = ad >= 0 ? 1.0 + ad : 0.0;
-            phase = PH_SHIFT;
-        } else {   // PH_SHIFT
-            sa = 0; sb = 0; sigmu = 0; al = 0;
-            phase = (max_iter > 0) ? PH_RES : PH_DONE;
+            for (int j = 0; j < cnt; j++) mh = fmax(mh, fabs(c.he[rb + (size_t)j * 32]));
         }
+        mh = warp_reduce5(0.0, 0.0, mh, 0.0, 0.0).mx;
+        hn = mh;
+        w1_pass<P_INIT>(c, 0, 0, acc);
+        w1_build_W(c.segmat, c.M, c.Dcp, c.Wd, c.Wo);
+        if (!factor_bt9v<1>(c.M - 1, c.Wd, c.Wo, c.dinv)) go = false;
+    }
+    if (go) {
+        w1_dual(c.segmat, c.M, c.QB, c.x, c.vA, c.rdx);   // rdx = P x_p + vA
+        #pragma unroll 1
+        for (int v = lane; v < 18 * c.M; v += 32) c.rdx[v] = 2.0 * c.vA[v] - c.rdx[v];
+        __syncwarp();
+        w1_solve(c, c.rdx, c.dx);
+        #pragma unroll 1
+        for (int v = lane; v < 18 * c.M; v += 32) { c.x[v] += c.dx[v]; c.dx[v] = 0; }
+        __syncwarp();
+        w1_pass<P_START>(c, 0, 0, acc);
+        double ap = acc.mx, ad = acc.mx2;
+        w1_pass<P_SHIFT>(c, ap >= 0 ? 1.0 + ap : 0.0, ad >= 0 ? 1.0 + ad : 0.0, acc);
+    }
+    double sigmu = 0, al = 0;
+    const double mi = live_rows > 0 ? (double)live_rows : 1.0;
+    for (it = 0; go && it < max_iter; it++) {
+        w1_pass<P_RES>(c, sigmu, al, acc);
+        if (al != 0.0) {
+            #pragma unroll 1
+            for (int v = lane; v < 18 * c.M; v += 32) c.x[v] += al * c.dx[v];
+            __syncwarp();
+        }
+        double mu = acc.s1 / mi, hz = acc.s2;
+        nrg = fmax(acc.mx, 0.0);
+        ObjMpx om = w1_dual(c.segmat, c.M, c.QB, c.x, c.vA, c.rdx);
+        double o = om.obj, mpx = om.mpx;
+        w1_Zt(c.segmat, c.nr, c.rdx, c.sg);
+        w1_Zt(c.segmat, c.nr, c.vA, c.sg2);
+        double mr = 0, mc = 0;
+        #pragma unroll 1
+        for (int r = lane; r < c.nr; r += 32) { mr = fmax(mr, fabs(c.sg[r])); mc = fmax(mc, fabs(c.sg2[r])); }
+        { Red5 r = warp_reduce5(o, 0.0, mpx, mr, mc); o = r.s1; mpx = r.mx; mr = r.mx2; mc = r.mx3; }
+        obj = o; nrd = mr;
+        gap = mu;
+        if (!(mu == mu) || !(nrd == nrd)) { status = ST_NOT_CONVERGED; break; }
+        {   // acceptance rule of pdip_solve (rbpe_kernels.cuh): strict test, else the round-off floor of the dual residual
+            const bool gap_ok = gap <= tol_gap * fmax(1.0, fabs(obj)) && nrg <= tol_res * (1 + hn);
+            if (gap_ok && nrd <= tol_res * (1.0 + mpx)) { status = ST_OK; break; }
+            acceptable = gap_ok && nrd <= TOL_DUAL_FLOOR * (1.0 + mpx);
+            if (acceptable) { status = ST_OK; break; }
+        }
+        const double cert = (hz < -PRESOLVE_FEAS_TOL * acc.mx2) ? mc / (-hz) : 1e300;
+        if (cert < CERT_RATIO) { status = ST_INFEASIBLE; break; }
+        w1_build_W(c.segmat, c.M, c.Dcp, c.Wd, c.Wo);
+        if (!factor_bt9v<1>(c.M - 1, c.Wd, c.Wo, c.dinv)) { status = acceptable ? ST_OK : (cert < CERT_RATIO_BREAKDOWN ? ST_INFEASIBLE : ST_NOT_CONVERGED); break; }
+        #pragma unroll 1
+        for (int v = lane; v < 18 * c.M; v += 32) c.vB[v] = -c.rdx[v] + c.vB[v];
+        __syncwarp();
+        w1_solve(c, c.vB, c.dxa);
+        w1_pass<P_AFF>(c, 0, 0, acc);
+        double aa = (acc.mx > 1.0) ? 1.0 / acc.mx : 1.0;
+        double mua = (mu * mi + aa * acc.s1 + aa * aa * acc.s2) / mi;
+        double sigma = (mu > 0) ? (mua / mu) * (mua / mu) * (mua / mu) : 0.0;
+        sigmu = sigma * mu;
+        w1_pass<P_COR>(c, sigmu, 0, acc);
+        #pragma unroll 1
+        for (int v = lane; v < 18 * c.M; v += 32) c.vA[v] = -c.rdx[v] + c.vA[v];
+        __syncwarp();
+        w1_solve(c, c.vA, c.dx);
+        w1_pass<P_STEP>(c, sigmu, 0, acc);
+        al = (0.99 < acc.mx) ? 0.99 / acc.mx : 1.0;
     }
     // |Ax - b| for the record
     double mrp = 0;

@@ -505,3 +505,61 @@ def dump_world_text(m, path):
         for qi in range(m["N"]):
             for j in range(m["M"] + 1):
                 f.write(" ".join(repr(float(v)) for v in m["init_traj"][qi, j]) + "\n")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# mission packs: generated missions stored compactly (tests/golden/missions_*.npz, written by
+# tests/golden/make_missions.py), so that tests and bench.py get hundreds of distinct seeded missions without paying
+# ~1.5 s of Python path planning per 64-agent mission.  RSFC is not stored: it is a pure function of init_traj
+# (rsfc_from_init_traj); everything else is stored in the precision the generator produced (float64 boxes carry the
+# reference's `i += res` rounding noise, init_traj is float32 like octomap::point3d).
+# ---------------------------------------------------------------------------------------------------------------------
+PACK_FIELDS = ("N", "M", "rho", "seed", "T", "start", "goal", "radius", "init_traj", "sfc_offs", "sfc_box", "sfc_t", "downwash")
+
+
+def save_pack(missions, rhos, path):
+    N, M = missions[0]["N"], missions[0]["M"]
+    assert all(m["N"] == N and m["M"] == M for m in missions)
+    offs, boxes, tend = [], [], []
+    for m in missions:
+        o = [0]
+        for b, t in m["sfc"]:
+            boxes.append(np.asarray(b, np.float64)); tend.append(np.asarray(t, np.float64)); o.append(o[-1] + len(t))
+        offs.append(o)
+        assert not np.any(m["start"][:, 3:]) and not np.any(m["goal"][:, 3:])
+    np.savez_compressed(
+        path, N=N, M=M, rho=np.asarray(rhos, np.float64), seed=np.asarray([m["seed"] for m in missions], np.int64),
+        T=np.asarray([m["T"] for m in missions], np.float64),
+        start=np.asarray([m["start"][:, :3] for m in missions], np.float64),
+        goal=np.asarray([m["goal"][:, :3] for m in missions], np.float64),
+        radius=np.asarray([m["radius"] for m in missions], np.float64),
+        init_traj=np.asarray([m["init_traj"] for m in missions], np.float32),
+        sfc_offs=np.asarray(offs, np.int32), sfc_box=np.concatenate(boxes), sfc_t=np.concatenate(tend),
+        downwash=np.asarray([m["downwash"] for m in missions], np.float64))
+
+
+def load_pack(path, select=None):
+    """Missions of a pack as the dicts synth_mission returns (without the world / distance map). `select`: indices."""
+    z = np.load(path)
+    N, M = int(z["N"]), int(z["M"])
+    offs = z["sfc_offs"]
+    base = np.concatenate([[0], np.cumsum(offs[:, -1])])
+    box, tend = z["sfc_box"], z["sfc_t"]
+    idx = range(len(z["seed"])) if select is None else select
+    out = []
+    for c in idx:
+        start = np.zeros((N, 9)); goal = np.zeros((N, 9))
+        start[:, :3] = z["start"][c]; goal[:, :3] = z["goal"][c]
+        sfc = []
+        for qi in range(N):
+            lo, hi = base[c] + offs[c, qi], base[c] + offs[c, qi + 1]
+            sfc.append((box[lo:hi].copy(), tend[lo:hi].copy()))
+        T = z["T"][c].copy()
+        dw = float(z["downwash"][c])
+        rsfc_n, rsfc_t, ok = rsfc_from_init_traj(z["init_traj"][c], T, dw)
+        assert ok
+        out.append(dict(N=N, M=M, T=T, start=start, goal=goal, radius=z["radius"][c].copy(),
+                        max_vel=np.full((N, 3), DEFAULT_PARAM["max_vel"]), max_acc=np.full((N, 3), DEFAULT_PARAM["max_acc"]),
+                        sfc=sfc, rsfc_n=rsfc_n, rsfc_t=rsfc_t, init_traj=z["init_traj"][c].copy(), downwash=dw,
+                        seed=int(z["seed"][c]), rho=float(z["rho"][c])))
+    return out

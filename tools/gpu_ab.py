@@ -4,9 +4,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np
 from swarm_simulator_b200 import engine as E, synth
-ms = [synth.synth_mission(64, 5, 0.2, 3000 + i) for i in range(8)]
+npool = int(os.environ.get("AB_POOL", 64))
+ms = synth.load_pack(os.path.join(ROOT, "tests", "golden", "missions_cfg3.npz"), select=range(npool))
 count = int(os.environ.get("AB_COUNT", 2368))
-packed = synth.pack([ms[i % 8] for i in range(count)])
+packed = synth.pack([ms[i % npool] for i in range(count)])
 for lib in sys.argv[1:]:
     E._lib = E.load_library(os.path.join(ROOT, lib))
     eng = E.Engine()
