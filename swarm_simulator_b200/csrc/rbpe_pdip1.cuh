@@ -35,17 +35,25 @@ static const double c_QB[36] = {QROW(0), QROW(1), QROW(2), QROW(3), QROW(4), QRO
 #endif
 #undef QROW
 
+// Row state of one warp: blocks of W1_ROWBLK doubles, block (slot, j) = the j-th kept row of every lane of the slot:
+// h[32] | s[32] | z[32] | row number e[32] (int).  One running pointer per lane walks a lane's rows (constant offsets
+// 0 / 256 / 512 bytes, stride 896 bytes): the separate-array layout of round 1 cost ~40 integer instructions of 64-bit
+// address arithmetic per row and pass (ncu r2b), more than the row's floating-point work.
+constexpr int W1_ROWBLK = 3 * 32 + 16;
 __host__ __device__ inline size_t w1_smem_doubles(int M) {  // per warp
     size_t ncp = 6 * (size_t)M, nr = 9 * (size_t)(M > 1 ? M - 1 : 0);
     return al2(6 * 3 * ncp) + al2(6 * ncp) + al2((size_t)(M > 1 ? M - 1 : 1) * 81) + al2((size_t)(M > 2 ? M - 2 : 1) * 81) + al2(nr) + al2(nr > 32 ? nr : 32) + al2((6 * (size_t)M + 31) / 32);
 }
 __host__ __device__ inline size_t w1_scratch_doubles(int N, int M) {  // per warp, global arena
     size_t nslot = (6 * (size_t)M + 31) / 32, NR = (size_t)(N > 1 ? N - 1 : 0) + 6;   // + the 6 box rows of a control point
-    size_t rows = nslot * NR * 32;
-    return 3 * rows + al2((rows + 1) / 2) + al2(nslot * 16) + al2((size_t)M * NR * 3) + 8;
+    return nslot * NR * W1_ROWBLK + al2(nslot * 16) + al2((size_t)M * NR * 3) + 8;
 }
 
 #if defined(__CUDACC__) || defined(RBPE_EMU)
+
+// max(acc, v) that keeps acc when v is NaN (what fmax does for our accumulators) in DSETP + 2 SEL; fmax() itself expands to
+// ~10 instructions of NaN handling, and the row loop holds up to three of them per row
+RBPE_DEV double dmax(double acc, double v) { return (v > acc) ? v : acc; }
 
 RBPE_DEV double rcp_nr(double a) {  // 1/a to double rounding: 20-bit hardware seed + two Newton steps
 #ifdef RBPE_EMU
@@ -74,8 +82,7 @@ struct W1 {
     // (x_k <= ub, -x_k <= -lb) written as ordinary rows with unit normals, so that every pass is ONE loop (code size)
     // Presolve: an RSFC row whose maximal activity over the box of its control point stays below its right-hand side can
     // never be active (bound-based row redundancy) and is not stored; a lane keeps cnt <= NR rows, compacted.
-    double *he, *se, *ze;                                   // [slot][j][lane], j < cnt[slot][lane]
-    int *ridx;                                              // [slot][j][lane] row number e of the kept row (normal look-up)
+    double *rows;                                           // [slot][j][W1_ROWBLK]: h, s, z, e of the j-th kept row of every lane, j < cnt[slot][lane]
     int *cnt;                                               // [slot][lane]
     double *nrm;                                            // [m][e][3], sign folded in (FP64: no per-row F2F)
 };
@@ -89,9 +96,9 @@ RBPE_NOINLINE Red5 warp_reduce5(double s1, double s2, double mx, double mx2, dou
     for (int o = 16; o > 0; o >>= 1) {
         s1 += __shfl_xor_sync(0xffffffffu, s1, o);
         s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        mx2 = fmax(mx2, __shfl_xor_sync(0xffffffffu, mx2, o));
-        mx3 = fmax(mx3, __shfl_xor_sync(0xffffffffu, mx3, o));
+        mx = dmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        mx2 = dmax(mx2, __shfl_xor_sync(0xffffffffu, mx2, o));
+        mx3 = dmax(mx3, __shfl_xor_sync(0xffffffffu, mx3, o));
     }
     Red5 r;
     r.s1 = s1; r.s2 = s2; r.mx = mx; r.mx2 = mx2; r.mx3 = mx3;
@@ -132,32 +139,34 @@ RBPE_DEV void w1_pass(const W1 &c, const int mode, const double sa, const double
         double Dxx = 0, Dxy = 0, Dxz = 0, Dyy = 0, Dyz = 0, Dzz = 0;
         if (on) {
             const double *nm = c.nrm + (size_t)m * c.NR * 3;
-            const size_t rb = (size_t)slot * c.NR * 32 + lane;
+            double *pr = c.rows + (size_t)slot * c.NR * W1_ROWBLK + lane;          // h at pr[0], s at pr[32], z at pr[64]
+            const int *pe = (const int *)(c.rows + (size_t)slot * c.NR * W1_ROWBLK + 96) + lane;
             const int cnt = c.cnt[slot * 32 + lane];
-            int e_next = cnt > 0 ? c.ridx[rb] : 0;   // row number fetched one iteration ahead: one L2 round trip per row, not two
+            int e_next = cnt > 0 ? *pe : 0;   // row number fetched one iteration ahead: one L2 round trip per row, not two
 #pragma unroll 1
-            for (int j = 0; j < cnt; j++) {
-                const size_t r = rb + (size_t)j * 32;
+            for (int j = 0; j < cnt; j++, pr += W1_ROWBLK) {
                 const int e = e_next;
-                e_next = (j + 1 < cnt) ? c.ridx[r + 32] : 0;
-                const double n0 = nm[e * 3], n1 = nm[e * 3 + 1], n2 = nm[e * 3 + 2];
-                const double h = c.he[r];
-                double s = c.se[r], z = c.ze[r];
+                pe += 2 * W1_ROWBLK;
+                e_next = (j + 1 < cnt) ? *pe : 0;
+                const double *ne = nm + e * 3;
+                const double n0 = ne[0], n1 = ne[1], n2 = ne[2];
+                const double h = pr[0];
+                double s = pr[32], z = pr[64];
                 double gx = n0 * x0 + n1 * x1 + n2 * x2;
                 double cA, w;
                 if (mode <= P_SHIFT) {
                     if (mode != P_INIT) {
                         if (mode == P_START) {
                             z = gx - h; s = -z;
-                            acc.mx = fmax(acc.mx, -s); acc.mx2 = fmax(acc.mx2, -z);
+                            acc.mx = dmax(acc.mx, -s); acc.mx2 = dmax(acc.mx2, -z);
                         } else {
                             s += sa; z += sb;
                         }
-                        c.se[r] = s; c.ze[r] = z;
+                        pr[32] = s; pr[64] = z;
                         continue;
                     }
                     w = 1.0; cA = h - gx;
-                    acc.mx2 = fmax(acc.mx2, fabs(h));
+                    acc.mx2 = dmax(acc.mx2, fabs(h));
                 } else {
                     const double ga = n0 * a0 + n1 * a1 + n2 * a2, gd = n0 * d0 + n1 * d1 + n2 * d2;
                     double t = rcp_nr(s * z), rs = t * z;
@@ -171,13 +180,13 @@ RBPE_DEV void w1_pass(const W1 &c, const int mode, const double sa, const double
                             gx += sb * gd;
                             t = rcp_nr(s * z);
                             rs = t * z;
-                            c.se[r] = s; c.ze[r] = z;
+                            pr[32] = s; pr[64] = z;
                         }
                         const double rg = gx + s - h;
                         w = z * rs;
                         cA = z;
                         const double cB = -(w * rg - z);
-                        acc.s1 += s * z; acc.s2 += h * z; acc.mx = fmax(acc.mx, fabs(rg)); acc.mx2 = fmax(acc.mx2, z);
+                        acc.s1 += s * z; acc.s2 += h * z; acc.mx = dmax(acc.mx, fabs(rg)); acc.mx2 = dmax(acc.mx2, z);
                         vB0 += cB * n0; vB1 += cB * n1; vB2 += cB * n2;
                     } else {
                         const double rg = gx + s - h;
@@ -185,14 +194,14 @@ RBPE_DEV void w1_pass(const W1 &c, const int mode, const double sa, const double
                         const double rz = t * s;
                         const double dsa = -rg - ga, dza = -z - w * dsa;
                         if (mode == P_AFF) {
-                            acc.mx = fmax(acc.mx, fmax(-dsa * rs, -dza * rz));
+                            acc.mx = dmax(acc.mx, dmax(-dsa * rs, -dza * rz));
                             acc.s1 += s * dza + z * dsa; acc.s2 += dsa * dza;
                             continue;
                         }
                         const double rc = s * z + dsa * dza - sa;
                         if (mode == P_STEP) {
                             const double ds = -rg - gd, dz = (-rc - z * ds) * rs;
-                            acc.mx = fmax(acc.mx, fmax(-ds * rs, -dz * rz));
+                            acc.mx = dmax(acc.mx, dmax(-ds * rs, -dz * rz));
                             continue;
                         }
                         cA = -(z * rg - rc) * rs;   // P_COR
@@ -351,7 +360,7 @@ RBPE_DEV int w1_setup(const W1 &c, double &dead_viol) {
             const bool dead = w1_dead(c, cp);
             const double *box = c.segbox + ((size_t)c.qa * M + m) * 6;
             const double *nm = c.nrm + (size_t)m * c.NR * 3;
-            const size_t rb = (size_t)slot * c.NR * 32 + lane;
+            double *pr = c.rows + (size_t)slot * c.NR * W1_ROWBLK + lane;
             const int v0 = m * 18 + i;
             const double xd0 = c.x[v0], xd1 = c.x[v0 + 6], xd2 = c.x[v0 + 12];
             for (int e = 0; e < c.NR; e++) {
@@ -384,8 +393,8 @@ RBPE_DEV int w1_setup(const W1 &c, double &dead_viol) {
                     dviol = fmax(dviol, nm[e * 3] * xd0 + nm[e * 3 + 1] * xd1 + nm[e * 3 + 2] * xd2 - h);
                     continue;
                 }
-                const size_t r = rb + (size_t)kept * 32;
-                c.he[r] = h; c.se[r] = 1; c.ze[r] = 1; c.ridx[r] = e;
+                pr[0] = h; pr[32] = 1; pr[64] = 1; ((int *)(pr - lane + 96))[lane] = e;
+                pr += W1_ROWBLK;
                 kept++;
             }
             if (!dead) live_rows += kept;
@@ -573,9 +582,7 @@ __global__ void __launch_bounds__(W1_WARPS * 32, RBPE_W1_MINB) pdip1_kernel(Solv
     }
     {   // global arena of this warp
         double *g = S.scratch + (size_t)unit * S.scratch_stride;
-        const size_t rows = (size_t)c.nslot * c.NR * 32;
-        c.he = g; c.se = g + rows; c.ze = g + 2 * rows; g += 3 * rows;
-        c.ridx = (int *)g; g += al2((rows + 1) / 2);
+        c.rows = g; g += (size_t)c.nslot * c.NR * W1_ROWBLK;
         c.cnt = (int *)g; g += al2((size_t)c.nslot * 16);
         c.nrm = g;
     }
