@@ -25,7 +25,10 @@ constexpr int W1_WARPS = RBPE_W1_WARPS;   // QPs (warps) per CTA; 16 warps per S
 #ifndef RBPE_W1_UNROLL
 #define RBPE_W1_UNROLL 1
 #endif
-constexpr int W1_UNROLL = RBPE_W1_UNROLL;   // unroll factor of the row loop (tuning; 1 = smallest code)
+constexpr int W1_UNROLL = RBPE_W1_UNROLL;
+#ifndef RBPE_W1_PF
+#define RBPE_W1_PF 2   // software-pipeline depth of the row loop: 2 = rows and normals one iteration ahead, 1 = rows only
+#endif   // unroll factor of the row loop (tuning; 1 = smallest code)
 
 #define QROW(a) q_base_int(a, 0), q_base_int(a, 1), q_base_int(a, 2), q_base_int(a, 3), q_base_int(a, 4), q_base_int(a, 5)
 #if defined(__CUDACC__)
@@ -40,9 +43,13 @@ static const double c_QB[36] = {QROW(0), QROW(1), QROW(2), QROW(3), QROW(4), QRO
 // 0 / 256 / 512 bytes, stride 896 bytes): the separate-array layout of round 1 cost ~40 integer instructions of 64-bit
 // address arithmetic per row and pass (ncu r2b), more than the row's floating-point work.
 constexpr int W1_ROWBLK = 3 * 32 + 16;
+// Per-segment constants staged in shared memory (per warp): CL[3][3] | CR[3][3] | RQ[6][6] | qscale.  The knot-space helpers
+// (Z, Z', reduced Hessian, dual residual) read them with 32-bit shared addressing; from global memory every access cost a
+// 64-bit LEA pair (ncu r2b: build_W spent ~110 instructions per entry, mostly address arithmetic).
+constexpr int SEGC_CL = 0, SEGC_CR = 9, SEGC_RQ = 18, SEGC_QS = 54, SEGC = 56;
 __host__ __device__ inline size_t w1_smem_doubles(int M) {  // per warp
     size_t ncp = 6 * (size_t)M, nr = 9 * (size_t)(M > 1 ? M - 1 : 0);
-    return al2(6 * 3 * ncp) + al2(6 * ncp) + al2((size_t)(M > 1 ? M - 1 : 1) * 81) + al2((size_t)(M > 2 ? M - 2 : 1) * 81) + al2(nr) + al2(nr > 32 ? nr : 32) + al2((6 * (size_t)M + 31) / 32);
+    return al2(6 * 3 * ncp) + al2(6 * ncp) + al2((size_t)(M > 1 ? M - 1 : 1) * 81) + al2((size_t)(M > 2 ? M - 2 : 1) * 81) + al2(nr) + al2(nr > 32 ? nr : 32) + al2((6 * (size_t)M + 31) / 32) + (size_t)M * SEGC;
 }
 __host__ __device__ inline size_t w1_scratch_doubles(int N, int M) {  // per warp, global arena
     size_t nslot = (6 * (size_t)M + 31) / 32, NR = (size_t)(N > 1 ? N - 1 : 0) + 6;   // + the 6 box rows of a control point
@@ -71,6 +78,7 @@ RBPE_DEV double rcp_nr(double a) {  // 1/a to double rounding: 20-bit hardware s
 struct W1 {
     int N, M, NE, NR, ncp, nslot, nr, qa, sequential;
     const double *start, *goal, *radius, *segbox, *segmat;
+    const double *segc;   // shared-memory copy of the per-segment constants the iteration needs (SEGC_* below)
     const float *reln;
     const double *ctrl_src;
     // shared memory (per warp); x-space index v = m*18 + k*6 + i
@@ -142,16 +150,41 @@ RBPE_DEV void w1_pass(const W1 &c, const int mode, const double sa, const double
             double *pr = c.rows + (size_t)slot * c.NR * W1_ROWBLK + lane;          // h at pr[0], s at pr[32], z at pr[64]
             const int *pe = (const int *)(c.rows + (size_t)slot * c.NR * W1_ROWBLK + 96) + lane;
             const int cnt = c.cnt[slot * 32 + lane];
-            int e_next = cnt > 0 ? *pe : 0;   // row number fetched one iteration ahead: one L2 round trip per row, not two
+            // Software pipeline: the loads of row j + 1 (h, s, z and its normal) are issued at the top of iteration j, the row
+            // number e two iterations ahead, so that an L2 round trip (the arena is L2 resident) overlaps the arithmetic of a
+            // whole row instead of stalling every iteration (ncu r2b: long_scoreboard was 29 % of the stall slots).
+            int e1 = cnt > 0 ? pe[0] : 0;                       // e of row j + 1 (at loop entry: row 0)
+            int e2 = cnt > 1 ? pe[2 * W1_ROWBLK] : 0;           // e of row j + 2
+            pe += 4 * W1_ROWBLK;
+            double hN = 0, sN = 0, zN = 0, m0 = 0, m1 = 0, m2 = 0;
+            if (cnt > 0) {
+                hN = pr[0]; sN = pr[32]; zN = pr[64];
+                const double *ne = nm + e1 * 3;
+                m0 = ne[0]; m1 = ne[1]; m2 = ne[2];
+            }
 #pragma unroll 1
-            for (int j = 0; j < cnt; j++, pr += W1_ROWBLK) {
-                const int e = e_next;
-                pe += 2 * W1_ROWBLK;
-                e_next = (j + 1 < cnt) ? *pe : 0;
-                const double *ne = nm + e * 3;
+            for (int j = 0; j < cnt; j++, pr += W1_ROWBLK, pe += 2 * W1_ROWBLK) {
+#if RBPE_W1_PF == 2
+                const double n0 = m0, n1 = m1, n2 = m2, h = hN;
+                double s = sN, z = zN;
+                e1 = e2;
+                if (j + 1 < cnt) {
+                    hN = pr[W1_ROWBLK]; sN = pr[W1_ROWBLK + 32]; zN = pr[W1_ROWBLK + 64];
+                    const double *ne = nm + e1 * 3;
+                    m0 = ne[0]; m1 = ne[1]; m2 = ne[2];
+                    e2 = (j + 2 < cnt) ? *pe : 0;
+                }
+#else   // rows one ahead, normals in the iteration that uses them
+                const double h = hN;
+                double s = sN, z = zN;
+                const double *ne = nm + e1 * 3;
                 const double n0 = ne[0], n1 = ne[1], n2 = ne[2];
-                const double h = pr[0];
-                double s = pr[32], z = pr[64];
+                e1 = e2;
+                if (j + 1 < cnt) {
+                    hN = pr[W1_ROWBLK]; sN = pr[W1_ROWBLK + 32]; zN = pr[W1_ROWBLK + 64];
+                    e2 = (j + 2 < cnt) ? *pe : 0;
+                }
+#endif
                 double gx = n0 * x0 + n1 * x1 + n2 * x2;
                 double cA, w;
                 if (mode <= P_SHIFT) {
@@ -233,10 +266,10 @@ RBPE_DEV void w1_pass(const W1 &c, const int mode, const double sa, const double
 // The helpers below are single non-inlined copies (instruction-cache footprint) and take plain arguments, so that the
 // context struct never has its address taken and stays in registers.
 // out (nr) = Z' vec (x-space)
-RBPE_NOINLINE void w1_Zt(const double *segmat, int nr, const double *vec, double *out) {
+RBPE_NOINLINE void w1_Zt(const double *segc, int nr, const double *vec, double *out) {
     for (int r = threadIdx.x & 31; r < nr; r += 32) {
         int t = r / 9 + 1, cc = r % 9, k = cc / 3, d = cc % 3;
-        const double *CR = segmat + (t - 1) * SEGMAT + SEGMAT_CR, *CL = segmat + t * SEGMAT + SEGMAT_CL;
+        const double *CR = segc + (t - 1) * SEGC + SEGC_CR, *CL = segc + t * SEGC + SEGC_CL;
         const double *vl = vec + (t - 1) * 18 + k * 6 + 3, *vr = vec + t * 18 + k * 6;
         double s = 0;
         for (int j = 0; j < 3; j++) s += CR[j * 3 + d] * vl[j] + CL[j * 3 + d] * vr[j];
@@ -245,25 +278,25 @@ RBPE_NOINLINE void w1_Zt(const double *segmat, int nr, const double *vec, double
     __syncwarp();
 }
 // out (x-space) = Z sg
-RBPE_NOINLINE void w1_Z(const double *segmat, int M, const double *sg, double *out) {
+RBPE_NOINLINE void w1_Z(const double *segc, int M, const double *sg, double *out) {
     const int nv = 18 * M;
     for (int v = threadIdx.x & 31; v < nv; v += 32) {
         int m = v / 18, r = v % 18, k = r / 6, i = r % 6;
         double s = 0;
         if (i < 3) {
             if (m > 0) {
-                const double *C = segmat + m * SEGMAT + SEGMAT_CL + i * 3, *g = sg + (m - 1) * 9 + k * 3;
+                const double *C = segc + m * SEGC + SEGC_CL + i * 3, *g = sg + (m - 1) * 9 + k * 3;
                 s = C[0] * g[0] + C[1] * g[1] + C[2] * g[2];
             }
         } else if (m < M - 1) {
-            const double *C = segmat + m * SEGMAT + SEGMAT_CR + (i - 3) * 3, *g = sg + m * 9 + k * 3;
+            const double *C = segc + m * SEGC + SEGC_CR + (i - 3) * 3, *g = sg + m * 9 + k * 3;
             s = C[0] * g[0] + C[1] * g[1] + C[2] * g[2];
         }
         out[v] = s;
     }
     __syncwarp();
 }
-RBPE_NOINLINE void w1_build_W(const double *segmat, int M, const double *Dcp, double *Wd, double *Wo) {
+RBPE_NOINLINE void w1_build_W(const double *segc, int M, const double *Dcp, double *Wd, double *Wo) {
     // entry idx = r * 9 + cc of a 9 x 9 block, r = (axis k, derivative d), cc = (k2, d2); a lane owns idx = lane, lane + 32,
     // lane + 64 of EVERY knot, so the index arithmetic is done three times per call instead of once per entry
 #pragma unroll 1
@@ -274,36 +307,36 @@ RBPE_NOINLINE void w1_build_W(const double *segmat, int M, const double *Dcp, do
         const bool low = cc <= r, same = k == k2;
 #pragma unroll 1
         for (int t = 1; t < M; t++) {
-            const double *sl = segmat + (t - 1) * SEGMAT, *sr = segmat + t * SEGMAT;
+            const double *sl = segc + (t - 1) * SEGC, *sr = segc + t * SEGC;
             double s = 0;
             if (low) {
-                const double *CR = sl + SEGMAT_CR, *CL = sr + SEGMAT_CL;
+                const double *CR = sl + SEGC_CR, *CL = sr + SEGC_CL;
                 const double *Dl = Dcp + ((size_t)(t - 1) * 6 + 3) * 6 + e, *Dr = Dcp + ((size_t)t * 6) * 6 + e;
                 for (int j = 0; j < 3; j++) s += CR[j * 3 + d] * CR[j * 3 + d2] * Dl[j * 6] + CL[j * 3 + d] * CL[j * 3 + d2] * Dr[j * 6];
-                if (same) s += sl[SEGMAT_RQ + (3 + d) * 6 + 3 + d2] + sr[SEGMAT_RQ + d * 6 + d2];
+                if (same) s += sl[SEGC_RQ + (3 + d) * 6 + 3 + d2] + sr[SEGC_RQ + d * 6 + d2];
             }
             Wd[(t - 1) * 81 + idx] = s;
-            if (t < M - 1) Wo[(t - 1) * 81 + idx] = same ? sr[SEGMAT_RQ + (3 + d) * 6 + d2] : 0.0;
+            if (t < M - 1) Wo[(t - 1) * 81 + idx] = same ? sr[SEGC_RQ + (3 + d) * 6 + d2] : 0.0;
         }
     }
     __syncwarp();
 }
 // dxout = Z (Z'HZ)^-1 Z' r
 RBPE_DEV void w1_solve(const W1 &c, const double *r, double *dxout) {
-    w1_Zt(c.segmat, c.nr, r, c.sg);
+    w1_Zt(c.segc, c.nr, r, c.sg);
     solve_bt9v<1>(c.M - 1, c.Wd, c.Wo, c.sg, c.dinv);
-    w1_Z(c.segmat, c.M, c.sg, dxout);
+    w1_Z(c.segc, c.M, c.sg, dxout);
 }
 // rdx = 2 Q x + vA; returns the lane-partial objective and max|Px|
 struct ObjMpx { double obj, mpx; };
-RBPE_NOINLINE ObjMpx w1_dual(const double *segmat, int M, const double *QB, const double *x, const double *vA, double *rdx) {
+RBPE_NOINLINE ObjMpx w1_dual(const double *segc, int M, const double *QB, const double *x, const double *vA, double *rdx) {
     const int nv = 18 * M;
     double obj = 0, mpx = 0;
     for (int v = threadIdx.x & 31; v < nv; v += 32) {
         int m = v / 18, i = v % 6, b6 = v - i;
         double s = 0;
         for (int j = 0; j < 6; j++) s += QB[i * 6 + j] * x[b6 + j];
-        double pxv = 2.0 * segmat[m * SEGMAT + SEGMAT_QS] * s;
+        double pxv = 2.0 * segc[m * SEGC + SEGC_QS] * s;
         rdx[v] = pxv + vA[v];
         obj += 0.5 * x[v] * pxv;
         mpx = fmax(mpx, fabs(pxv));
@@ -424,7 +457,7 @@ RBPE_DEV int w1_solve_qp(const W1 &c, int max_iter, double tol_gap, double tol_r
     int phase = PH_INIT;
     if (dead_viol > PRESOLVE_FEAS_TOL) { status = ST_INFEASIBLE; phase = PH_DONE; }
     if (phase != PH_DONE && c.nr == 0) {
-        double o = w1_dual(c.segmat, c.M, c.QB, c.x, c.vA, c.rdx).obj;
+        double o = w1_dual(c.segc, c.M, c.QB, c.x, c.vA, c.rdx).obj;
         obj = warp_reduce5(o, 0.0, 0.0, 0.0, 0.0).s1;
         status = ST_OK; phase = PH_DONE;
     }
@@ -443,10 +476,10 @@ RBPE_DEV int w1_solve_qp(const W1 &c, int max_iter, double tol_gap, double tol_r
             mu = acc.s1 / mi;
             const double hz = acc.s2, zmax = acc.mx2;
             nrg = fmax(acc.mx, 0.0);
-            ObjMpx om = w1_dual(c.segmat, c.M, c.QB, c.x, c.vA, c.rdx);
+            ObjMpx om = w1_dual(c.segc, c.M, c.QB, c.x, c.vA, c.rdx);
             double o = om.obj, mpx = om.mpx;
-            w1_Zt(c.segmat, c.nr, c.rdx, c.sg);
-            w1_Zt(c.segmat, c.nr, c.vA, c.sg2);
+            w1_Zt(c.segc, c.nr, c.rdx, c.sg);
+            w1_Zt(c.segc, c.nr, c.vA, c.sg2);
             double mr = 0, mc = 0;
             #pragma unroll 1
             for (int r = lane; r < c.nr; r += 32) { mr = fmax(mr, fabs(c.sg[r])); mc = fmax(mc, fabs(c.sg2[r])); }
@@ -463,7 +496,7 @@ RBPE_DEV int w1_solve_qp(const W1 &c, int max_iter, double tol_gap, double tol_r
             }
             const double cert = (hz < -PRESOLVE_FEAS_TOL * zmax) ? mc / (-hz) : 1e300;
             if (cert < CERT_RATIO) { status = ST_INFEASIBLE; break; }
-            w1_build_W(c.segmat, c.M, c.Dcp, c.Wd, c.Wo);
+            w1_build_W(c.segc, c.M, c.Dcp, c.Wd, c.Wo);
             if (!factor_bt9v<1>(c.M - 1, c.Wd, c.Wo, c.dinv)) { status = cert < CERT_RATIO_BREAKDOWN ? ST_INFEASIBLE : ST_NOT_CONVERGED; break; }
             #pragma unroll 1
             for (int v = lane; v < 18 * c.M; v += 32) c.vB[v] = -c.rdx[v] + c.vB[v];
@@ -489,9 +522,9 @@ RBPE_DEV int w1_solve_qp(const W1 &c, int max_iter, double tol_gap, double tol_r
             phase = PH_RES; sa = sigmu; sb = al;
         } else if (phase == PH_INIT) {
             hn = acc.mx2;
-            w1_build_W(c.segmat, c.M, c.Dcp, c.Wd, c.Wo);
+            w1_build_W(c.segc, c.M, c.Dcp, c.Wd, c.Wo);
             if (!factor_bt9v<1>(c.M - 1, c.Wd, c.Wo, c.dinv)) break;
-            w1_dual(c.segmat, c.M, c.QB, c.x, c.vA, c.rdx);   // rdx = P x_p + vA
+            w1_dual(c.segc, c.M, c.QB, c.x, c.vA, c.rdx);   // rdx = P x_p + vA
             #pragma unroll 1
             for (int v = lane; v < 18 * c.M; v += 32) c.rdx[v] = 2.0 * c.vA[v] - c.rdx[v];
             __syncwarp();
@@ -578,7 +611,16 @@ __global__ void __launch_bounds__(W1_WARPS * 32, RBPE_W1_MINB) pdip1_kernel(Solv
         c.Wo = p; p += al2((size_t)(M > 2 ? M - 2 : 1) * 81);
         c.sg = p; p += al2(c.nr); c.sg2 = p; c.dinv = p; p += al2(c.nr > 32 ? c.nr : 32);   // the column exchange buffer of the 9x9 routines shares sg2 (dead by then)
         c.QB = c_QB;
-        c.cmax = (int *)p;
+        c.cmax = (int *)p; p += al2(((size_t)c.nslot + 1) / 2);
+        double *sc = p;
+        c.segc = sc;
+        #pragma unroll 1
+        for (int idx = lane; idx < M * SEGC; idx += 32) {
+            const int m = idx / SEGC, o = idx - m * SEGC;
+            const double *sm = c.segmat + (size_t)m * SEGMAT;
+            sc[idx] = o < SEGC_CR ? sm[SEGMAT_CL + o] : (o < SEGC_RQ ? sm[SEGMAT_CR + o - SEGC_CR] : (o < SEGC_QS ? sm[SEGMAT_RQ + o - SEGC_RQ] : (o == SEGC_QS ? sm[SEGMAT_QS] : 0.0)));
+        }
+        __syncwarp();
     }
     {   // global arena of this warp
         double *g = S.scratch + (size_t)unit * S.scratch_stride;
