@@ -71,8 +71,11 @@ RBPE_DEV double rcp_nr(double a) {  // 1/a to double rounding: 20-bit hardware s
 #endif
     double e = fma(-a, r, 1.0);
     r = fma(r, e, r);
+#ifndef RBPE_RCP_ONE_STEP
     e = fma(-a, r, 1.0);
-    return fma(r, e, r);
+    r = fma(r, e, r);
+#endif
+    return r;
 }
 
 struct W1 {
@@ -267,6 +270,7 @@ RBPE_DEV void w1_pass(const W1 &c, const int mode, const double sa, const double
 // context struct never has its address taken and stays in registers.
 // out (nr) = Z' vec (x-space)
 RBPE_NOINLINE void w1_Zt(const double *segc, int nr, const double *vec, double *out) {
+    #pragma unroll 1
     for (int r = threadIdx.x & 31; r < nr; r += 32) {
         int t = r / 9 + 1, cc = r % 9, k = cc / 3, d = cc % 3;
         const double *CR = segc + (t - 1) * SEGC + SEGC_CR, *CL = segc + t * SEGC + SEGC_CL;
@@ -280,6 +284,7 @@ RBPE_NOINLINE void w1_Zt(const double *segc, int nr, const double *vec, double *
 // out (x-space) = Z sg
 RBPE_NOINLINE void w1_Z(const double *segc, int M, const double *sg, double *out) {
     const int nv = 18 * M;
+    #pragma unroll 1
     for (int v = threadIdx.x & 31; v < nv; v += 32) {
         int m = v / 18, r = v % 18, k = r / 6, i = r % 6;
         double s = 0;
@@ -332,6 +337,7 @@ struct ObjMpx { double obj, mpx; };
 RBPE_NOINLINE ObjMpx w1_dual(const double *segc, int M, const double *QB, const double *x, const double *vA, double *rdx) {
     const int nv = 18 * M;
     double obj = 0, mpx = 0;
+    #pragma unroll 1
     for (int v = threadIdx.x & 31; v < nv; v += 32) {
         int m = v / 18, i = v % 6, b6 = v - i;
         double s = 0;
@@ -351,6 +357,7 @@ RBPE_NOINLINE ObjMpx w1_dual(const double *segc, int M, const double *QB, const 
 // by the start / goal equalities (rows on the fixed control points: checked here, never stored)
 RBPE_DEV int w1_setup(const W1 &c, double &dead_viol) {
     const int lane = threadIdx.x & 31, M = c.M, N = c.N, nv = 18 * M;
+    #pragma unroll 1
     for (int v = lane; v < nv; v += 32) {
         int m = v / 18, r = v % 18, k = r / 6, i = r % 6;
         double xp = 0;
@@ -366,6 +373,7 @@ RBPE_DEV int w1_setup(const W1 &c, double &dead_viol) {
     }
     // signed normals of the RSFC rows against every other agent (g = sg*n, sg = +1 if qa < qo), then the 6 unit
     // normals of the box rows
+    #pragma unroll 1
     for (int idx = lane; idx < M * c.NR; idx += 32) {
         int m = idx / c.NR, e = idx % c.NR;
         double n0, n1, n2;
@@ -385,6 +393,7 @@ RBPE_DEV int w1_setup(const W1 &c, double &dead_viol) {
     __syncwarp();
     int live_rows = 0;
     double dviol = -1e300;
+    #pragma unroll 1
     for (int slot = 0; slot < c.nslot; slot++) {
         const int cp = slot * 32 + lane;
         int kept = 0;
@@ -396,6 +405,7 @@ RBPE_DEV int w1_setup(const W1 &c, double &dead_viol) {
             double *pr = c.rows + (size_t)slot * c.NR * W1_ROWBLK + lane;
             const int v0 = m * 18 + i;
             const double xd0 = c.x[v0], xd1 = c.x[v0 + 6], xd2 = c.x[v0 + 12];
+            #pragma unroll 1
             for (int e = 0; e < c.NR; e++) {
                 double h;
                 if (e < c.NE) {
