@@ -34,16 +34,59 @@ def dense_flops_per_iter(b, M):
     return nv ** 3 / 3 + nv * nv * ne + nv * ne * ne + ne ** 3 / 3
 
 
-def structured_flops_per_iter(b, M, N):
-    """What the kernel executes: block tridiagonal Cholesky over M-1 knot blocks of 9b + row passes (6 per iteration)."""
+def structured_flops_per_iter(b, M, N, rows=None):
+    """What the kernel executes: block tridiagonal Cholesky over M-1 knot blocks of 9b + 4 row passes of ~40 flops per
+    KEPT row (rows=None counts every row of populatebyrow, an upper bound)."""
     kb = 9.0 * b
-    rows = b * (6 * M - 6) * (6 + (N - b)) + b * (b - 1) / 2 * (6 * M - 6)
-    return (M - 1) * (kb ** 3 / 3) + (M - 2) * 2 * kb ** 3 + 4 * (M - 1) * 2 * kb * kb * 2 + 6 * rows * 40
+    if rows is None:
+        rows = b * (6 * M - 6) * (6 + (N - b)) + b * (b - 1) / 2 * (6 * M - 6)
+    return (M - 1) * (kb ** 3 / 3) + (M - 2) * 2 * kb ** 3 + 4 * (M - 1) * 2 * kb * kb * 2 + 4 * rows * 40
 
 
-def make_pool(n, rank):
+WORKLOAD = ("64 agents, random forest rho=0.2, 5-segment degree-5, sequential batch_size=1 "
+            "(BASELINE configs[2]; reference Gauss-Seidel order)")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def make_pool(n, rank, pack="cfg3"):
+    """`n` distinct seeded missions for `rank` from the committed pack (tests/golden/missions_*.npz, written by
+    tests/golden/make_missions.py from swarm_simulator_b200/synth.py; seeds 1000 * config + trial)."""
     from swarm_simulator_b200 import synth
-    return [synth.synth_mission(N_AGENTS, M_SEG, RHO, 1000 * CONFIG_ID + rank * 64 + i) for i in range(n)]
+    z = np.load(os.path.join(GOLDEN, "missions_%s.npz" % pack))
+    total = len(z["seed"])
+    sel = [(rank * n + i) % total for i in range(n)]
+    return synth.load_pack(os.path.join(GOLDEN, "missions_%s.npz" % pack), select=sel)
+
+
+def kept_rows_mean(missions, ctrls):
+    """Mean number of inequality rows per agent-QP that survive the presolve (rows on fixed control points and rows the
+    bound-based redundancy test drops are never touched by the kernel): numpy restatement on the final control points."""
+    tot, nqp = 0, 0
+    for m, ctrl in zip(missions, ctrls):
+        N, M = m["N"], m["M"]
+        x = np.transpose(ctrl, (0, 2, 1))                      # [N, 6M, 3]
+        seg_of = np.repeat(np.arange(M), 6)
+        ub = np.zeros((N, 6 * M, 3)); lb = np.zeros((N, 6 * M, 3))
+        for qi, (boxes, tend) in enumerate(m["sfc"]):
+            bi = 0
+            for mm in range(M):
+                while bi < len(tend) and tend[bi] < m["T"][mm + 1]:
+                    bi += 1
+                b = boxes[min(bi, len(tend) - 1)]
+                ub[qi, mm * 6:(mm + 1) * 6] = b[3:]; lb[qi, mm * 6:(mm + 1) * 6] = b[:3]
+        live = np.ones(6 * M, bool); live[:3] = False; live[-3:] = False
+        qi_, qj_ = np.triu_indices(N, 1)
+        nrm = m["rsfc_n"][:, seg_of, :].astype(np.float64)    # [P, 6M, 3] (ri == m for these missions: one RSFC entry per segment)
+        for qa in range(N):
+            sel_lo = qi_ == qa; sel_hi = qj_ == qa
+            n = np.concatenate([nrm[sel_lo], -nrm[sel_hi]])   # qa < qo: +n, qa > qo: -n
+            other = np.concatenate([qj_[sel_lo], qi_[sel_hi]])
+            h = -(m["radius"][qa] + m["radius"][other])[:, None] + (n * x[other]).sum(-1)
+            amax = np.maximum(n * ub[qa][None], n * lb[qa][None]).sum(-1)
+            keep = ~(amax < h - 1e-9 * np.maximum(1.0, np.abs(h)))
+            tot += int(keep[:, live].sum()) + 6 * int(live.sum())
+            nqp += 1
+    return tot / max(nqp, 1)
 
 
 class ClockSampler:
@@ -112,11 +155,10 @@ def run_reference(args, rank, world):
     import oracle_util
     cores = os.cpu_count() or 1
     pool = make_pool(args.pool, 0)
-    reps = max(1, args.ref_missions // len(pool))
-    probs = [oracle_util.oracle_problem(m, sequential=True, batch_size=1) for m in pool] * reps
-    nqp = len(probs) * N_AGENTS
-    for _ in range(args.warmup):
-        oracle.update_many(probs[:len(pool)], nthreads=cores)
+    nmis = args.ref_missions or 16 * cores            # >= 16 missions per host thread per step (dynamic OpenMP schedule)
+    probs = [oracle_util.oracle_problem(pool[i % len(pool)], sequential=True, batch_size=1) for i in range(nmis)]
+    for _ in range(min(args.warmup, 2)):
+        oracle.update_many(probs[:max(len(pool), cores)], nthreads=cores)
     t0 = time.perf_counter()
     bad = 0
     for _ in range(args.steps):
@@ -126,14 +168,15 @@ def run_reference(args, rank, world):
     bad //= max(args.steps, 1)
     nqp = (len(probs) - bad) * N_AGENTS          # only the QPs of missions whose update() succeeds count
     val = nqp / dt
-    sample = "%d missions x %d agents per step (%d distinct, seeds %d..), oracle.update_many, OpenMP over missions" % (
-        len(probs), N_AGENTS, len(pool), 1000 * CONFIG_ID)
+    sample = "%d missions x %d agents per step (%d distinct, seeds %d..), oracle.update_many, OpenMP over missions, %d threads" % (
+        len(probs), N_AGENTS, len(pool), 1000 * CONFIG_ID, cores)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "failed_missions": bad,
-        "config": {"workload": "64 agents, random forest rho=0.2, 5-segment degree-5, sequential batch_size=1",
-                   "missions_per_step": len(probs), "agent_qps_per_step": nqp},
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "missions_per_step": len(probs), "agent_qps_per_step": nqp,
+                   "failed_missions_per_step": bad, "distinct_missions": len(pool),
+                   "sample_note": "bounded sample of the engine arm's workload (same missions, same order, same tolerances)"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                          "note": "CPU oracle (not CPLEX: proprietary, absent)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -147,13 +190,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--missions", type=int, default=0, help="missions per rank per step (0 = 48 per SM: 7104 = three pipeline chunks of 16 warp-resident QP chains per SM)")
-    ap.add_argument("--pool", type=int, default=8, help="distinct synthetic missions generated per rank (tiled to --missions)")
-    ap.add_argument("--ref-missions", type=int, default=64, help="missions per step of the CPU arm")
+    ap.add_argument("--pool", type=int, default=64, help="distinct synthetic missions per rank (from the committed pack, tiled to --missions)")
+    ap.add_argument("--ref-missions", type=int, default=0, help="missions per step of the CPU arm (0 = 16 per host thread)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--joint-missions", type=int, default=592, help="missions of the joint-batch leg (configs[1]); 0 = skip")
     ap.add_argument("--jacobi-missions", type=int, default=64, help="missions (replicated on every rank) of the Jacobi leg; 0 = skip")
     ap.add_argument("--jacobi-sweeps", type=int, default=2)
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the BASELINE configs[3] / configs[4] legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -199,7 +243,7 @@ def main():
     pool = make_pool(args.pool, rank)
     packed = pin(synth.pack([pool[i % len(pool)] for i in range(count)]))
     prob = E.PackedProblem(packed, sequential=True, batch_size=1)
-    res = E.Result(prob, want_ctrl=False, pinned=True)   # page-locked like the inputs; the reference's update() returns coefficients (msgs_traj_coef); `dummy` stays on the device
+    res = E.Result(prob, want_ctrl=True, pinned=True)    # page-locked like the inputs; coefficients (msgs_traj_coef) AND the updated `dummy` come back
     eng = E.Engine(device=local)
     h2d, d2h = prob.h2d_bytes(), res.d2h_bytes()
     nqp = count * N_AGENTS
@@ -214,8 +258,8 @@ def main():
     # ---- warm-up (e2e path: exercises H2D, all three kernels, D2H) ----
     for _ in range(args.warmup):
         r = eng.solve_many(prob, result=res)
-    # a mission whose QP is infeasible / does not converge makes update() return false in the reference as well; such
-    # missions are reported and their QPs do not count (seeded pools at 4+ ranks contain one: the CPU oracle agrees on it)
+    # a mission whose update() fails is reported (config.failed_missions_per_step) and its QPs do not count; the committed
+    # packs contain none (tests/test_feasibility_classifier.py)
     assert r.rc in (E.OK, E.INFEASIBLE, E.NOT_CONVERGED), (r.rc, eng.last_error())
     failed_missions = int((res.status != 0).sum())
     nqp_ok = (count - failed_missions) * N_AGENTS
@@ -274,8 +318,8 @@ def main():
     # CTA-per-QP kernel, block tridiagonal factorisation of 144 x 144 blocks on the FP64 tensor pipe (DMMA) ----
     joint = None
     if args.joint_missions > 0:
-        jm = [synth.synth_mission(16, M_SEG, RHO, 2000 + rank * 64 + i) for i in range(2)]
-        jp = E.PackedProblem(pin(synth.pack([jm[i % 2] for i in range(args.joint_missions)])), sequential=False, batch_size=16)
+        jm = make_pool(min(64, args.joint_missions), rank, "cfg2")
+        jp = E.PackedProblem(pin(synth.pack([jm[i % len(jm)] for i in range(args.joint_missions)])), sequential=False, batch_size=16)
         je = E.Engine(device=local)
         je.upload(jp); je.run(); je.sync()
         barrier()
@@ -289,8 +333,33 @@ def main():
                  "value": world * args.joint_missions * 16 / (ms_joint * 1e-3), "unit": UNIT, "ms_per_step": ms_joint,
                  "missions_per_gpu": args.joint_missions, "ipm_iterations_mean": float(jr.qp_iters.mean()), "failed": int((jr.status != 0).sum()),
                  "dense_tflops": dense_flops_per_iter(16, M_SEG) * it_j / (ms_joint * 1e-3) / 1e12,
+                 "distinct_missions_per_gpu": len(jm),
                  "kernel": "pdip_kernel (256 threads per QP; DMMA m8n8k4 block Cholesky, rbpe_blockla.cuh)"}
         je.close()
+
+    # ---- the other BASELINE configurations as single-GPU legs (rank 0 only; resident inputs, one warm + one timed pass):
+    # configs[3] = 256 agents, rho 0.4, sequential batches of 32; configs[4] = 1024 agents, rho 0.1 .. 0.5 (batch size
+    # unspecified in BASELINE.json: the per-agent b = 1 of the headline and the b = 32 of configs[3] are both run) ----
+    others = None
+    if not args.no_other_configs and rank == 0:
+        others = []
+        for name, pack, nm, seq, bsz in (("configs[3]: 256 agents, rho=0.4, sequential batch_size=32", "cfg4", 32, True, 32),
+                                         ("configs[4]: 1024 agents, rho=0.1..0.5, sequential batch_size=1", "cfg5", 5, True, 1),
+                                         ("configs[4]: 1024 agents, rho=0.1..0.5, sequential batch_size=32", "cfg5", 5, True, 32)):
+            try:
+                om = make_pool(nm, 0, pack)
+                op_ = E.PackedProblem(pin(synth.pack(om)), sequential=seq, batch_size=bsz)
+                oe = E.Engine(device=local)
+                oe.upload(op_); oe.run(); oe.sync()
+                oe.timer_start(); oe.run(); ms_o = oe.timer_stop()
+                orr = oe.download(op_)
+                nq = sum(m["N"] for m, st in zip(om, orr.status) if st == 0)
+                others.append({"workload": name, "missions": len(om), "value": nq / (ms_o * 1e-3), "unit": UNIT, "ms_per_step": ms_o,
+                               "failed_missions": int((orr.status != 0).sum()), "ipm_iterations_mean": float(orr.qp_iters.mean()),
+                               "dense_tflops": dense_flops_per_iter(bsz, M_SEG) * float(orr.qp_iters.sum()) / (ms_o * 1e-3) / 1e12})
+                oe.close()
+            except Exception as ex:   # a leg must never take the headline down with it
+                others.append({"workload": name, "error": repr(ex)})
 
     # ---- secondary leg: Jacobi mode (north-star's agent sharding): the SAME missions on every rank, each rank solves its
     # range of agents of every mission against the frozen table; the exchange of the solved control points is fused into the
@@ -346,8 +415,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "64 agents, random forest rho=0.2, 5-segment degree-5, sequential batch_size=1 "
-                               "(BASELINE configs[2]; reference Gauss-Seidel order)",
+        "config": {"workload": WORKLOAD,
                    "missions_per_step_per_gpu": count, "agent_qps_per_step": int(nqp_all), "failed_missions_per_step": failed_all, "distinct_missions_per_gpu": len(pool),
                    "parallelism": "missions sharded over %d GPU(s), no collective" % world, "cache": l2_note,
                    "ipm_iterations_mean": iters_mean, "tol_gap": 1e-10, "tol_res": 1e-9},
@@ -358,6 +426,8 @@ def main():
     }
     if joint:
         out["joint_batch"] = joint
+    if others:
+        out["other_configs"] = others
     if jac:
         out["jacobi_mode"] = jac
     if rank == 0:
@@ -386,30 +456,35 @@ def main():
         except Exception as ex:   # keep the fallback
             print("peak measurement skipped: %r" % (ex,), file=sys.stderr)
         f_dense = dense_flops_per_iter(1, M_SEG) * iters_total          # per rank per step
-        f_struct = structured_flops_per_iter(1, M_SEG, N_AGENTS) * iters_total
+        kept = kept_rows_mean(pool[:4], [res.ctrl[i] for i in range(4)])   # rows the kernel really walks (numpy, 4 missions)
+        f_struct = structured_flops_per_iter(1, M_SEG, N_AGENTS, rows=kept) * iters_total
         ach = f_dense / (kernel_ms * 1e-3) / 1e12
-        traffic, ncu = None, {}
-        try:   # DRAM bytes of one launch of the dominant kernel from the committed ncu --set full capture, scaled to this
-            # launch's mission count (missions are independent work items of identical shape)
-            prof = json.load(open(os.path.join(ROOT, "profiles", "r1_pdip1_ncu.json")))
-            traffic = prof["dram_bytes_per_launch"] * count / float(prof.get("missions", 2368))
-            ncu = {k: float(v["value"].replace(",", "")) for k, v in prof["metrics"].items() if k.endswith(".pct") or "pct_of_peak" in k}
-        except Exception:
-            pass
+        traffic, ncu, prof_name = None, {}, None
+        for prof_name in ("r2_pdip1_ncu.json", "r1_pdip1_ncu.json"):
+            try:   # DRAM bytes of one launch of the dominant kernel from the committed ncu --set full capture, scaled to this
+                # launch's mission count (missions are independent work items of identical shape)
+                prof = json.load(open(os.path.join(ROOT, "profiles", prof_name)))
+                traffic = prof["dram_bytes_per_launch"] * count / float(prof.get("missions", 2368))
+                ncu = {k: float(v["value"].replace(",", "")) for k, v in prof["metrics"].items() if k.endswith(".pct") or "pct_of_peak" in k}
+                break
+            except Exception:
+                continue
         out["roofline"] = {
             "bound": "tensor", "kernel": "pdip1_kernel", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",
             "frac": ach / tf32_peak, "traffic": traffic, "peak_source": tf32_src,
             "algorithmic": "dense reduced-KKT flops (SURVEY 8d: nv^3/3 + nv^2 ne + nv ne^2 + ne^3/3 = 0.995 MFLOP per iteration at "
                            "b=1, M=5) x iterations executed: %.3e per launch" % f_dense,
+            "algorithmic_bytes": h2d + d2h,
             "executed_structured_tflops": f_struct / (kernel_ms * 1e-3) / 1e12,
-            "executed_structured_note": "block tridiagonal factor / solves + 40 flops per inequality row and pass, counted over ALL rows "
-                                        "of populatebyrow; the presolve drops 60-95% of the RSFC rows, so this is an upper bound",
+            "executed_structured_note": "block tridiagonal factor / solves + 40 flops per KEPT inequality row and pass (%.0f of the "
+                                        "%d rows of populatebyrow survive the presolve on average)" % (kept, (6 * M_SEG - 6) * (N_AGENTS + 5)),
             "fp64_peak_tflops": fp64_peak,
             "executed_fraction_of_fp64_peak": (f_struct / (kernel_ms * 1e-3) / 1e12 / fp64_peak) if fp64_peak else None,
             "kernel_ms_per_launch": kernel_ms,
-            "traffic_note": "ncu dram__bytes_read+write of one launch (profiles/r1_pdip1_ncu.md, %d missions) scaled to %d missions; "
-                            "far above the %.2f GB of inputs + outputs because the per-warp row-state arena is written once per "
-                            "QP and spills from L2" % (2368, count, (h2d + d2h) / 1e9),
+            "traffic_note": "ncu dram__bytes_read+write of one launch (profiles/%s) scaled to %d missions; inputs + outputs are "
+                            "%.2f GB. The excess is working-set overflow of the 126 MB L2 (2368 mission chains in flight x (46 KB "
+                            "control-point table + ~25 KB of row state)), not re-reads by the kernel's loops; DRAM is at ~5 %% of its "
+                            "bandwidth, the kernel is instruction-issue / fetch bound (DESIGN.md section 6)" % (prof_name, count, (h2d + d2h) / 1e9),
             "ncu": {"issue_active_pct": ncu.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
                     "fp64_pipe_pct": ncu.get("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
                     "l2_hit_pct": ncu.get("lts__t_sector_hit_rate.pct")},
@@ -422,17 +497,18 @@ def main():
             import oracle
             import oracle_util
             cores = os.cpu_count() or 1
-            probs = [oracle_util.oracle_problem(m, sequential=True, batch_size=1) for m in pool]
-            oracle.update_many(probs, nthreads=cores)
+            nmis = 16 * cores
+            probs = [oracle_util.oracle_problem(pool[i % len(pool)], sequential=True, batch_size=1) for i in range(nmis)]
+            oracle.update_many(probs[:max(cores, 8)], nthreads=cores)
             t0 = time.perf_counter()
             n = 0
             while time.perf_counter() - t0 < args.cpu_seconds:
-                oracle.update_many(probs * 4, nthreads=cores)
-                n += 4 * len(probs)
+                oracle.update_many(probs, nthreads=cores)
+                n += len(probs)
             dt = time.perf_counter() - t0
             out["cpu_baseline"] = {"value": n * N_AGENTS / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                                   "sample": "%d missions (the %d distinct ones, repeated) in %.1f s, OpenMP over missions"
-                                             % (n, len(pool), dt),
+                                   "sample": "%d missions (%d distinct, %d per call = 16 per thread) in %.1f s, OpenMP over missions"
+                                             % (n, len(pool), len(probs), dt),
                                    "note": "CPU oracle (not CPLEX: proprietary, absent)"}
         sys.stdout.flush()
         os.write(result_fd, (json.dumps(out) + "\n").encode())

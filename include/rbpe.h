@@ -138,6 +138,10 @@ int rbpe_download(rbpe_handle *h, rbpe_result *r);                           /* 
 /* device pointers of the resident control-point table [count][N][3][6M] (f64) and coefficient table */
 double *rbpe_device_ctrl(rbpe_handle *h);
 double *rbpe_device_coef(rbpe_handle *h);
+int *rbpe_device_status(rbpe_handle *h);                                     /* [count] mission status words (int32) on the device */
+/* k3 alone on the current control-point table (after a collective exchange of the Jacobi mode); replaces the conversion
+ * loop of rbp_planner.hpp L167-L196 for the agents other ranks solved */
+int rbpe_convert(rbpe_handle *h);
 void *rbpe_stream(rbpe_handle *h);                                           /* cudaStream_t */
 int rbpe_sync(rbpe_handle *h);
 int rbpe_last_timing(const rbpe_handle *h, rbpe_timing *t);                  /* kernel_launches = total since creation */

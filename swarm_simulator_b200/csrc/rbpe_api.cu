@@ -782,6 +782,17 @@ extern "C" int rbpe_set_ctrl(rbpe_handle *h, const double *ctrl) {
 
 extern "C" double *rbpe_device_ctrl(rbpe_handle *h) { return h ? h->ctrl.as<double>() : nullptr; }
 extern "C" double *rbpe_device_coef(rbpe_handle *h) { return h ? h->coef.as<double>() : nullptr; }
+// Bernstein -> monomial conversion of the CURRENT control-point table (k3 alone).  Multi-rank Jacobi with the NCCL
+// exchange (dist.jacobi_solve, fused = false) calls it after the last all-gather: rbpe_run_jacobi_range converts before the
+// exchange, i.e. with the other ranks' agents still at their pre-sweep control points.
+extern "C" int rbpe_convert(rbpe_handle *h) {
+    if (!h) return RBPE_BAD_ARG;
+    if (!h->resident || !h->assembled) return fail(h, RBPE_BAD_ARG, "rbpe_convert: call rbpe_upload and rbpe_assemble first");
+    CU(cudaSetDevice(h->device));
+    return launch_convert(h);
+}
+// device address of the per-mission status words [count] (int32): ranks of a Jacobi solve all-reduce (MAX) them
+extern "C" int *rbpe_device_status(rbpe_handle *h) { return h ? h->status.as<int>() : nullptr; }
 extern "C" void *rbpe_stream(rbpe_handle *h) { return h ? (void *)h->stream : nullptr; }
 extern "C" int rbpe_sync(rbpe_handle *h) {
     if (!h) return RBPE_BAD_ARG;

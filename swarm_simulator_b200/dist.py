@@ -65,6 +65,20 @@ def engine_ctrl_tensor(eng, count, N, M, device):
     return torch.as_tensor(_DevicePtr(eng.device_ctrl_ptr(), (count, N, 3, 6 * M)), device=device)
 
 
+def engine_status_tensor(eng, count, device):
+    """torch view (no copy) of the engine's per-mission status words [count] (int32)."""
+    return torch.as_tensor(_DevicePtr(eng.device_status_ptr(), (count,), "<i4"), device=device)
+
+
+def merge_status(status, group=None):
+    """A batch that failed on one rank fails the mission on every rank: element-wise MAX of the status words
+    (0 OK < 1 infeasible < 2 not converged < 3 bad input), as RBPPlanner::update() returns false when ANY batch fails
+    (rbp_planner.hpp L158-L161).  One small all-reduce per solve."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(status, op=dist.ReduceOp.MAX, group=group)
+    return status
+
+
 def jacobi_attach_peers(eng, prob, group=None):
     """One-time set-up of the fused exchange: upload + assemble (allocates the tables), export the IPC handles of the
     two table buffers and the flag words, gather them over the process group (host side, any backend) and open the
@@ -113,12 +127,18 @@ def jacobi_solve(eng, prob, sweeps, group=None, device=None, fused=False):
     if fused:
         for _ in range(sweeps):
             eng.run_jacobi_fused(b0, b1)
-        return eng
-    table = engine_ctrl_tensor(eng, prob.count, prob.N, prob.M, device) if world > 1 else None
-    for _ in range(sweeps):
-        eng.run_jacobi_range(b0, b1)
+    else:
+        table = engine_ctrl_tensor(eng, prob.count, prob.N, prob.M, device) if world > 1 else None
+        for _ in range(sweeps):
+            eng.run_jacobi_range(b0, b1)
+            if world > 1:
+                eng.sync()                      # the engine has its own stream; the collective runs on torch's
+                exchange_ctrl(table, prob.N, bs, nbatch, group)
+                torch.cuda.current_stream().synchronize()
         if world > 1:
-            eng.sync()                      # the engine has its own stream; the collective runs on torch's
-            exchange_ctrl(table, prob.N, bs, nbatch, group)
-            torch.cuda.current_stream().synchronize()
+            eng.convert()                       # the sweep converted before the exchange: redo it on the complete table
+    if world > 1:                               # every rank reports the mission status every rank would
+        eng.sync()
+        merge_status(engine_status_tensor(eng, prob.count, device), group)
+        torch.cuda.current_stream().synchronize()
     return eng

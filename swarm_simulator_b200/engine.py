@@ -45,7 +45,7 @@ EXPORTS = ["rbpe_create", "rbpe_destroy", "rbpe_last_error", "rbpe_set_batch", "
            "rbpe_upload", "rbpe_assemble", "rbpe_run", "rbpe_run_jacobi_range", "rbpe_set_ctrl", "rbpe_download", "rbpe_device_ctrl",
            "rbpe_device_coef", "rbpe_stream", "rbpe_sync", "rbpe_last_timing", "rbpe_timer_start", "rbpe_timer_stop",
            "rbpe_corridor_rsfc", "rbpe_safety_metrics", "rbpe_peer_export", "rbpe_peer_attach", "rbpe_peer_attach_local",
-           "rbpe_run_jacobi_fused", "rbpe_peer_status", "rbpe_host_alloc", "rbpe_host_free"]
+           "rbpe_run_jacobi_fused", "rbpe_peer_status", "rbpe_host_alloc", "rbpe_host_free", "rbpe_convert", "rbpe_device_status"]
 IPC_HANDLE_BYTES = 64
 
 _lib = None
@@ -109,6 +109,11 @@ def load_library(path=None):
     L.rbpe_device_ctrl.restype = C.c_void_p
     L.rbpe_device_coef.argtypes = [C.c_void_p]
     L.rbpe_device_coef.restype = C.c_void_p
+    if path is None or hasattr(L, "rbpe_convert"):
+        L.rbpe_convert.argtypes = [C.c_void_p]
+        L.rbpe_convert.restype = C.c_int
+        L.rbpe_device_status.argtypes = [C.c_void_p]
+        L.rbpe_device_status.restype = C.c_void_p
     L.rbpe_stream.argtypes = [C.c_void_p]
     L.rbpe_stream.restype = C.c_void_p
     L.rbpe_sync.argtypes = [C.c_void_p]
@@ -371,6 +376,14 @@ class Engine:
 
     def device_coef_ptr(self):
         return self.lib.rbpe_device_coef(self.h)
+
+    def device_status_ptr(self):
+        return self.lib.rbpe_device_status(self.h)
+
+    def convert(self):
+        rc = self.lib.rbpe_convert(self.h)
+        if rc != OK:
+            raise RuntimeError("rbpe_convert failed (%d): %s" % (rc, self.last_error()))
 
     def stream_ptr(self):
         return self.lib.rbpe_stream(self.h)

@@ -19,7 +19,8 @@ def test_reference_arm_prints_one_json_line():
     assert d["metric"].startswith("agent-QPs/sec") and d["value"] > 0 and d["dtype"] == "f64"
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert d["config"]["agent_qps_per_step"] == (2 - d["failed_missions"]) * 64
+    assert d["config"]["agent_qps_per_step"] == (2 - d["config"]["failed_missions_per_step"]) * 64
+    assert d["config"]["workload"].startswith("64 agents, random forest rho=0.2")
 
 
 def test_reference_arm_is_rank0_only_under_torchrun():

@@ -50,7 +50,10 @@ def _worker(rank, world, port, q):
         for l, ctrl in _sweep_oracle(m, frozen, bs, range(b0, b1)).items():
             table[0, l * bs:l * bs + ctrl.shape[0]] = torch.from_numpy(ctrl.copy())
         D.exchange_ctrl(table, 5, bs, nbatch)
-    q.put((rank, table.numpy().copy()))
+    # mission status words: a batch that failed on one rank fails the mission everywhere
+    status = torch.tensor([0, 2 if rank == 1 else 0, 1 if rank == 0 else 0, 0], dtype=torch.int32)
+    D.merge_status(status)
+    q.put((rank, table.numpy().copy(), status.numpy().copy()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -62,7 +65,10 @@ def test_jacobi_exchange_world2():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got = dict(q.get(timeout=120) for _ in range(2))
+    recs = [q.get(timeout=120) for _ in range(2)]
+    got = {r[0]: r[1] for r in recs}
+    for r in recs:
+        assert r[2].tolist() == [0, 2, 1, 0]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
