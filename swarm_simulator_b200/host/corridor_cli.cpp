@@ -47,13 +47,14 @@ int main(int argc, char **argv) {
     if (!in) return 2;
     auto dm = std::make_shared<GridDistanceMap>(res, k0[0], k0[1], k0[2], n[0], n[1], n[2], std::move(edt));
     Corridor corridor(dm, mission, param);
-    if (!corridor.update(false, &pr)) { std::printf("update=false\n"); return 1; }
+    const bool sfc_only = kv.count("stage") && kv["stage"] == "sfc";   // host-only stage (no device): SFC without RSFC
+    if (!(sfc_only ? corridor.update_sfc(false, &pr) : corridor.update(false, &pr))) { std::printf("update=false\n"); return 1; }
     std::printf("update=true\n");
     for (int qi = 0; qi < N; qi++) {
         std::printf("SFC %d %zu\n", qi, pr.SFC[qi].size());
         for (auto &b : pr.SFC[qi]) std::printf("%.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", b.first[0], b.first[1], b.first[2], b.first[3], b.first[4], b.first[5], b.second);
     }
-    for (int qi = 0; qi < N; qi++)
+    for (int qi = 0; qi < N && !sfc_only; qi++)
         for (int qj = qi + 1; qj < N; qj++)
             for (auto &r : pr.RSFC[qi][qj]) std::printf("R %.9g %.9g %.9g %.17g\n", (double)r.first.x(), (double)r.first.y(), (double)r.first.z(), r.second);
     return 0;

@@ -57,6 +57,13 @@ public:
         makespan = planResult_ptr->T.back();
         return updateObsBox() && updateRelBox();
     }
+    // SFC stage alone (host only, no device needed): what tests/test_corridor_properties.py drives through corridor_cli
+    bool update_sfc(bool _log, SwarmPlanning::PlanResult *_planResult_ptr) {
+        log = _log;
+        planResult_ptr = _planResult_ptr;
+        makespan = planResult_ptr->T.back();
+        return updateObsBox();
+    }
 
 private:
     std::shared_ptr<DistMap> distmap_obj;
@@ -67,128 +74,141 @@ private:
     double makespan = 0;
     rbpe_handle *engine = nullptr;
 
-    bool isObstacleInBox(const std::vector<double> &box, double margin) {   // L44-L78
-        double x, y, z;
-        int count1 = 0;
-        for (double i = box[0]; i < box[3] + SP_EPSILON_FLOAT; i += param.box_xy_res) {
-            int count2 = 0;
-            for (double j = box[1]; j < box[4] + SP_EPSILON_FLOAT; j += param.box_xy_res) {
-                int count3 = 0;
-                for (double k = box[2]; k < box[5] + SP_EPSILON_FLOAT; k += param.box_z_res) {
-                    x = i + SP_EPSILON_FLOAT;
-                    if (count1 == 0 && box[0] > param.world_x_min + SP_EPSILON_FLOAT) x = box[0] - SP_EPSILON_FLOAT;
-                    y = j + SP_EPSILON_FLOAT;
-                    if (count2 == 0 && box[1] > param.world_y_min + SP_EPSILON_FLOAT) y = box[1] - SP_EPSILON_FLOAT;
-                    z = k + SP_EPSILON_FLOAT;
-                    if (count3 == 0 && box[2] > param.world_z_min + SP_EPSILON_FLOAT) z = box[2] - SP_EPSILON_FLOAT;
-                    octomap::point3d cur_point((float)x, (float)y, (float)z);
-                    float dist = distmap_obj->getDistance(cur_point);
-                    if (dist < margin - SP_EPSILON_FLOAT) return true;
-                    count3++;
-                }
-                count2++;
+    // ---- SFC construction (reference semantics: rbp_corridor.hpp L44-L243) -------------------------------------------
+    // Written in this repository's own structure; what is kept bit-faithful is the ARITHMETIC that decides the boxes:
+    //   * the sample lattice of an obstacle test: per axis, coordinates accumulate in double (v += res) from the lower face
+    //     while v < upper + 1e-6; a sample sits 1e-6 above its lattice coordinate, except the first one of an axis, which
+    //     sits 1e-6 BELOW the lower face unless that face is the world boundary (L47-L63);
+    //   * a box passes when no sample's clamped distance is below margin - 1e-6 (L64-L68) and it lies inside the world
+    //     with 1e-9 slack (L80-L87);
+    //   * greedy growth: faces are tried round-robin in the order -x,-y,-z,+x,+y,+z, one resolution step at a time, only
+    //     the newly added slab is tested; a face that fails is retired, and after every retirement the whole box is
+    //     re-tested before the next face is tried (L99-L147);
+    //   * box <-> time allocation: a box hands over to the next one at the middle of the stretch of path points that lie
+    //     in both (L195-L237); the last box ends at the makespan.
+    struct Aabb {
+        double lo[3], hi[3];
+        std::vector<double> as_sfc() const { return {lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]}; }
+    };
+    double axis_res(int a) const { return a == 2 ? param.box_z_res : param.box_xy_res; }
+    double world_lo(int a) const { return a == 0 ? param.world_x_min : (a == 1 ? param.world_y_min : param.world_z_min); }
+    double world_hi(int a) const { return a == 0 ? param.world_x_max : (a == 1 ? param.world_y_max : param.world_z_max); }
+
+    // sample coordinates of one axis of a box
+    void axis_samples(const Aabb &b, int a, std::vector<double> &out) const {
+        out.clear();
+        const bool nudge_first_down = b.lo[a] > world_lo(a) + SP_EPSILON_FLOAT;
+        for (double v = b.lo[a]; v < b.hi[a] + SP_EPSILON_FLOAT; v += axis_res(a))
+            out.push_back((out.empty() && nudge_first_down) ? b.lo[a] - SP_EPSILON_FLOAT : v + SP_EPSILON_FLOAT);
+    }
+    // true when every sample of the box keeps `margin` from the obstacles
+    bool clear_of_obstacles(const Aabb &b, double margin) {
+        axis_samples(b, 0, sx_); axis_samples(b, 1, sy_); axis_samples(b, 2, sz_);
+        for (double x : sx_)
+            for (double y : sy_)
+                for (double z : sz_)
+                    if (distmap_obj->getDistance(octomap::point3d((float)x, (float)y, (float)z)) < margin - SP_EPSILON_FLOAT) return false;
+        return true;
+    }
+    bool inside_world(const Aabb &b) const {
+        for (int a = 0; a < 3; a++)
+            if (!(b.lo[a] > world_lo(a) - SP_EPSILON && b.hi[a] < world_hi(a) + SP_EPSILON)) return false;
+        return true;
+    }
+    static bool holds(const Aabb &b, const octomap::point3d &p) {
+        for (int a = 0; a < 3; a++)
+            if (!(p(a) > b.lo[a] - SP_EPSILON && p(a) < b.hi[a] + SP_EPSILON)) return false;
+        return true;
+    }
+    // one resolution step of face f (0..2: lower faces, 3..5: upper faces): `grown` = box + slab, `slab` = the new layer only
+    void push_face(const Aabb &box, int f, Aabb &grown, Aabb &slab) const {
+        grown = box; slab = box;
+        const int a = f % 3;
+        if (f < 3) { slab.hi[a] = box.lo[a]; grown.lo[a] = box.lo[a] - axis_res(a); slab.lo[a] = grown.lo[a]; }
+        else       { slab.lo[a] = box.hi[a]; grown.hi[a] = box.hi[a] + axis_res(a); slab.hi[a] = grown.hi[a]; }
+    }
+    void grow(Aabb &box, double margin) {
+        std::vector<int> active{0, 1, 2, 3, 4, 5};   // faces still allowed to move, ring order
+        int at = -1;                                  // ring position of the face moved last
+        while (!active.empty()) {
+            Aabb grown = box, probe = box;            // after a retirement the whole box is probed once more
+            while (clear_of_obstacles(probe, margin) && inside_world(probe)) {
+                at = (at + 1 >= (int)active.size()) ? 0 : at + 1;
+                box = grown;                          // the step probed last is accepted
+                push_face(box, active[at], grown, probe);
             }
-            count1++;
-        }
-        return false;
-    }
-    bool isBoxInBoundary(const std::vector<double> &box) {   // L80-L87
-        return box[0] > param.world_x_min - SP_EPSILON && box[1] > param.world_y_min - SP_EPSILON &&
-               box[2] > param.world_z_min - SP_EPSILON && box[3] < param.world_x_max + SP_EPSILON &&
-               box[4] < param.world_y_max + SP_EPSILON && box[5] < param.world_z_max + SP_EPSILON;
-    }
-    static bool isPointInBox(const octomap::point3d &point, const std::vector<double> &box) {   // L89-L97
-        return point.x() > box[0] - SP_EPSILON && point.y() > box[1] - SP_EPSILON && point.z() > box[2] - SP_EPSILON &&
-               point.x() < box[3] + SP_EPSILON && point.y() < box[4] + SP_EPSILON && point.z() < box[5] + SP_EPSILON;
-    }
-    void expand_box(std::vector<double> &box, double margin) {   // L99-L147
-        std::vector<double> box_cand, box_update;
-        std::vector<int> axis_cand{0, 1, 2, 3, 4, 5};
-        int i = -1, axis;
-        while (!axis_cand.empty()) {
-            box_cand = box;
-            box_update = box;
-            // only the newly added slab is tested: update_box + current_box = cand_box
-            while (!isObstacleInBox(box_update, margin) && isBoxInBoundary(box_update)) {
-                i++;
-                if (i >= (int)axis_cand.size()) i = 0;
-                axis = axis_cand[i];
-                box = box_cand;
-                box_update = box_cand;
-                if (axis < 3) {
-                    box_update[axis + 3] = box_cand[axis];
-                    box_cand[axis] = box_cand[axis] - (axis == 2 ? param.box_z_res : param.box_xy_res);
-                    box_update[axis] = box_cand[axis];
-                } else {
-                    box_update[axis - 3] = box_cand[axis];
-                    box_cand[axis] = box_cand[axis] + (axis == 5 ? param.box_z_res : param.box_xy_res);
-                    box_update[axis] = box_cand[axis];
-                }
-            }
-            axis_cand.erase(axis_cand.begin() + i);
-            if (i > 0) i--;
-            else i = (int)axis_cand.size() - 1;
+            if (at < 0) at = 0;                       // seed outside the world: nothing moved yet (the reference erases begin() - 1 here)
+            active.erase(active.begin() + at);       // the face whose step failed retires
+            at = (at > 0) ? at - 1 : (int)active.size() - 1;
         }
     }
 
-    bool updateObsBox() {   // L149-L243
+    bool updateObsBox() {
         PlanResult &pr = *planResult_ptr;
         pr.SFC.assign(mission.qn, {});
         for (int qi = 0; qi < mission.qn; ++qi) {
-            std::vector<double> box_prev{0, 0, 0, 0, 0, 0};
-            for (int i = 0; i + 1 < (int)pr.initTraj[qi].size(); i++) {
-                octomap::point3d state = pr.initTraj[qi][i], state_next = pr.initTraj[qi][i + 1];
-                double x = state.x(), y = state.y(), z = state.z();
-                double x_next = state_next.x(), y_next = state_next.y(), z_next = state_next.z();
-                if (isPointInBox(octomap::point3d((float)x_next, (float)y_next, (float)z_next), box_prev)) continue;
-                std::vector<double> box;
-                box.emplace_back(std::round(std::min(x, x_next) / param.box_xy_res) * param.box_xy_res);
-                box.emplace_back(std::round(std::min(y, y_next) / param.box_xy_res) * param.box_xy_res);
-                box.emplace_back(std::round(std::min(z, z_next) / param.box_z_res) * param.box_z_res);
-                box.emplace_back(std::round(std::max(x, x_next) / param.box_xy_res) * param.box_xy_res);
-                box.emplace_back(std::round(std::max(y, y_next) / param.box_xy_res) * param.box_xy_res);
-                box.emplace_back(std::round(std::max(z, z_next) / param.box_z_res) * param.box_z_res);
-                if (isObstacleInBox(box, mission.quad_size[qi])) {
+            const auto &path = pr.initTraj[qi];
+            const int npts = (int)path.size();
+            std::vector<Aabb> boxes;
+            // 1. one box per path edge that leaves the previous box
+            for (int j = 0; j + 1 < npts; j++) {
+                if (!boxes.empty() ? holds(boxes.back(), path[j + 1]) : holds(Aabb{{0, 0, 0}, {0, 0, 0}}, path[j + 1])) continue;
+                Aabb seed;
+                for (int a = 0; a < 3; a++) {
+                    const double u = path[j](a), v = path[j + 1](a), r = axis_res(a);
+                    seed.lo[a] = std::round(std::min(u, v) / r) * r;
+                    seed.hi[a] = std::round(std::max(u, v) / r) * r;
+                }
+                if (!clear_of_obstacles(seed, mission.quad_size[qi])) {
                     std::fprintf(stderr, "Corridor: Invalid initial trajectory. Obstacle invades initial trajectory.\n");
                     return false;
                 }
-                expand_box(box, mission.quad_size[qi]);
-                pr.SFC[qi].emplace_back(std::make_pair(box, -1));
-                box_prev = box;
+                grow(seed, mission.quad_size[qi]);
+                boxes.push_back(seed);
             }
-            // box <-> time allocation through the run-length table box_log (L195-L237)
-            int box_max = (int)pr.SFC[qi].size(), path_max = (int)pr.initTraj[qi].size();
-            std::vector<double> box_log((size_t)box_max * path_max, 0.0);
-            auto BL = [&](int i, int j) -> double & { return box_log[(size_t)i * path_max + j]; };
-            for (int i = 0; i < box_max; i++)
-                for (int j = 0; j < path_max; j++)
-                    if (isPointInBox(pr.initTraj[qi][j], pr.SFC[qi][i].first)) BL(i, j) = (j == 0) ? 1 : BL(i, j - 1) + 1;
-            int box_iter = 0;
-            for (int path_iter = 0; path_iter < path_max; path_iter++) {
-                if (box_iter == box_max - 1) {
-                    if (BL(box_iter, path_iter) > 0) continue;
-                    else box_iter--;
+            const int nbox = (int)boxes.size();
+            if (nbox == 0) {
+                std::fprintf(stderr, "Corridor: agent %d has no corridor box (degenerate initial trajectory)\n", qi);
+                return false;
+            }
+            // 2. hand-over times.  in_box[i][j]: path point j lies in box i (the reference keeps run lengths in `box_log`
+            // but only ever asks whether they are positive)
+            std::vector<std::vector<char>> in_box(nbox, std::vector<char>(npts, 0));
+            for (int i = 0; i < nbox; i++)
+                for (int j = 0; j < npts; j++) in_box[i][j] = holds(boxes[i], path[j]) ? 1 : 0;
+            std::vector<double> t_end(nbox, -1.0);
+            int cur = 0;   // box being timed
+            for (int j = 0; j < npts; j++) {
+                if (cur == nbox - 1) {
+                    if (in_box[cur][j]) continue;
+                    cur--;
                 }
-                if (box_iter < 0) return false;   // the reference indexes box_log(-1, .) here (undefined behaviour)
-                if (BL(box_iter, path_iter) > 0 && BL(box_iter + 1, path_iter) > 0) {
-                    int count = 1;
-                    while (path_iter + count < path_max && BL(box_iter, path_iter + count) > 0 &&
-                           BL(box_iter + 1, path_iter + count) > 0)
-                        count++;
-                    int obs_index = path_iter + count / 2;
-                    pr.SFC[qi][box_iter].second = pr.T[obs_index];
-                    path_iter = path_iter + count / 2;
-                    box_iter++;
-                } else if (BL(box_iter, path_iter) == 0) {
-                    box_iter--;
-                    path_iter--;
-                    if (box_iter < 0 || path_iter < -1) return false;
+                if (cur < 0) {   // the reference reads box_log(-1, .) here (undefined behaviour); reported instead
+                    std::fprintf(stderr, "Corridor: box/time allocation ran off the first box (agent %d)\n", qi);
+                    return false;
+                }
+                if (in_box[cur][j] && in_box[cur + 1][j]) {
+                    int shared = 1;   // length of the stretch of points lying in both boxes
+                    while (j + shared < npts && in_box[cur][j + shared] && in_box[cur + 1][j + shared]) shared++;
+                    const int mid = j + shared / 2;
+                    t_end[cur] = pr.T[mid];
+                    j = mid;
+                    cur++;
+                } else if (!in_box[cur][j]) {   // fell out of the box: step back one box and look at this point again
+                    cur--;
+                    j--;
+                    if (cur < 0 || j < -1) {
+                        std::fprintf(stderr, "Corridor: box/time allocation ran off the first box (agent %d)\n", qi);
+                        return false;
+                    }
                 }
             }
-            pr.SFC[qi][box_max - 1].second = makespan;
+            t_end[nbox - 1] = makespan;
+            for (int i = 0; i < nbox; i++) pr.SFC[qi].emplace_back(std::make_pair(boxes[i].as_sfc(), t_end[i]));
         }
         return true;
     }
+    std::vector<double> sx_, sy_, sz_;   // scratch of clear_of_obstacles
 
     bool updateRelBox() {   // L338-L398, arithmetic on the device (bit-identical float32 semantics)
         PlanResult &pr = *planResult_ptr;
