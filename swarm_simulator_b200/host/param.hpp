@@ -21,6 +21,11 @@ public:
     double box_xy_res = 0.1, box_z_res = 0.1;
 
     bool time_scale = true;
+    // Not in the reference: which roots of the acceleration cubic the velocity check of timeScale looks at.
+    //   0 = every real root (default here: the true extrema);
+    //   2 = the reference rule, "the first two eigenvalues of the companion matrix that are real" (rbp_planner.hpp
+    //       L741-L753), with the eigenvalues taken in order of decreasing modulus -- see rbp_planner.hpp (timeScale)
+    int time_scale_roots = 0;
     double time_step = 1;
     double downwash = 2.0;  // downwash coefficient
     int iteration = 1;
@@ -44,7 +49,7 @@ public:
         d("grid/xy_res", grid_xy_res); d("grid/z_res", grid_z_res); d("grid/margin", grid_margin);
         d("ecbs/w", ecbs_w);
         d("box/xy_res", box_xy_res); d("box/z_res", box_z_res);
-        b("plan/time_scale", time_scale); d("plan/time_step", time_step); d("plan/downwash", downwash);
+        b("plan/time_scale", time_scale); i("plan/time_scale_roots", time_scale_roots); d("plan/time_step", time_step); d("plan/downwash", downwash);
         i("plan/n", n); i("plan/phi", phi);
         b("plan/sequential", sequential); i("plan/batch_size", batch_size); i("plan/batch_iter", batch_iter);
         i("plan/iteration", iteration);

@@ -10,6 +10,7 @@
 // timeScale, generateROSMsg and generateCoefCSV stay on the host (they are O(N M) arithmetic on the result).
 #pragma once
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <fstream>
@@ -68,6 +69,20 @@ public:
     double last_time_scale() const { return time_scale_used; }
     int device = 0;
 
+    // Host-only entry to the timeScale stage (L209-L266) for given monomial coefficients (coef_in[qi] column-major
+    // M(n+1) x 3, highest power first per segment): rescales coef_in and *pr exactly as update() would and returns the scale.
+    // Used by tests/test_time_scale.py (no device needed).
+    double time_scale_only(std::vector<std::vector<double>> &coef_in, SwarmPlanning::PlanResult *pr) {
+        planResult_ptr = pr;
+        M = (int)pr->T.size() - 1;
+        offset_quad = M * (n + 1);
+        offset_seg = n + 1;
+        coef = coef_in;
+        timeScale();
+        coef_in = coef;
+        return time_scale_used;
+    }
+
 private:
     Mission mission;
     Param param;
@@ -100,9 +115,12 @@ private:
             }
             sfc_offs[qi + 1] = (int)sfc_t.size();
             if (param.sequential) {
-                if ((int)pr.initTraj[qi].size() < M + 1) return false;
+                // a path shorter than M + 1 points holds its last point (build_dummy L519-L528: `idx >= path_size - 1`)
+                const int npts = (int)pr.initTraj[qi].size();
+                if (npts < 1) return false;
                 for (int j = 0; j <= M; j++)
-                    for (int k = 0; k < 3; k++) init_traj[((size_t)qi * (M + 1) + j) * 3 + k] = pr.initTraj[qi][j](k);
+                    for (int k = 0; k < 3; k++)
+                        init_traj[((size_t)qi * (M + 1) + j) * 3 + k] = pr.initTraj[qi][j < npts ? j : npts - 1](k);
             }
         }
         size_t it = 0;
@@ -164,8 +182,18 @@ private:
                 cd[i][5 - j] = (i <= j) ? f * C(qi, m * offset_seg + 5 - j, k) : 0.0;
             }
     }
-    // real roots of a x^3 + b x^2 + c x + d (the reference takes eigenvalues of the companion matrix and keeps the
-    // first two that are real, L741-L753, which depends on Eigen's eigenvalue order; every real root is used here)
+    // Roots of a x^3 + b x^2 + c x + d.  The reference takes the eigenvalues of the companion matrix from
+    // Eigen::EigenSolver and keeps those of THE FIRST TWO that are real (`for j < i`, i = 2: L741-L753), so with three real
+    // roots one extremum candidate is silently dropped -- which one depends on the order in which Eigen's real Schur
+    // iteration deflates the 3 x 3 companion matrix (Eigen is absent here; that order cannot be reproduced bit for bit).
+    // Two selectable rules (Param::time_scale_roots):
+    //   0 (default)  every real root: the velocity bound is checked at all true extrema;
+    //   2            the reference rule with a DOCUMENTED order: eigenvalues by decreasing modulus (complex pairs by their
+    //                modulus, the member with positive imaginary part first), the first two inspected, real ones kept.
+    //                The shifted QR iteration converges its bottom diagonal entry to the eigenvalue of smallest modulus
+    //                first, which leaves the larger ones in the leading positions -- the closest statement of Eigen's
+    //                order that does not need Eigen.
+    // tests/test_time_scale.py measures how often, and by how much, the two rules differ.
     static std::vector<double> real_roots_cubic(double a, double b, double c, double d) {
         std::vector<double> r;
         const double PI = 3.14159265358979323846;
@@ -190,6 +218,31 @@ private:
         }
         return r;
     }
+    // extremum candidates of the velocity under the selected rule (see above)
+    std::vector<double> velocity_extrema(double a, double b, double c, double d) const {
+        std::vector<double> all = real_roots_cubic(a, b, c, d);
+        if (param.time_scale_roots != 2) return all;
+        int deg = a != 0 ? 3 : (b != 0 ? 2 : (c != 0 ? 1 : 0));
+        struct Ev { double re, im, mod; };
+        std::vector<Ev> ev;
+        for (double r : all) ev.push_back({r, 0.0, std::fabs(r)});
+        if ((int)all.size() < deg) {   // the missing eigenvalues form one complex pair: from the sum and product of the roots
+            double lead = deg == 3 ? a : b, s1 = deg == 3 ? -b / a : -c / b, prod = deg == 3 ? -d / a : d / b;
+            (void)lead;
+            double re = (deg == 3) ? (s1 - all[0]) / 2 : s1 / 2;
+            double mod2 = (deg == 3) ? (all[0] != 0 ? prod / all[0] : 0.0) : prod;
+            if (deg == 3 && all[0] == 0) mod2 = c / a;               // x (a x^2 + b x + c): pair of the quadratic factor
+            double mod = std::sqrt(std::fabs(mod2)), im2 = mod2 - re * re;
+            double im = im2 > 0 ? std::sqrt(im2) : 0.0;
+            ev.push_back({re, im, mod});
+            ev.push_back({re, -im, mod});
+        }
+        std::stable_sort(ev.begin(), ev.end(), [](const Ev &x, const Ev &y) { return x.mod > y.mod; });
+        std::vector<double> out;
+        for (size_t j = 0; j < ev.size() && j < 2; j++)
+            if (ev[j].im == 0) out.push_back(ev[j].re);
+        return out;
+    }
     double scale_to_max_vel(int qi, int k, int m, const double cd[4][6]) {
         const double dt = planResult_ptr->T[m + 1] - planResult_ptr->T[m], rate = 1.1;
         double vel_max = 0, t_max = 0;
@@ -200,7 +253,7 @@ private:
         if (lead < 3) {
             double co[4] = {0, 0, 0, 0};
             for (int j = lead; j < 4; j++) co[j] = cd[2][j];
-            ts = real_roots_cubic(co[0], co[1], co[2], co[3]);
+            ts = velocity_extrema(co[0], co[1], co[2], co[3]);
         }
         ts.push_back(0);
         ts.push_back(dt);
