@@ -335,6 +335,7 @@ static int fill_solve_args(rbpe_handle *h, SolveArgs &S, int mode, int grid) {
     for (int p = 0; p < RBPE_MAX_PEERS; p++) { S.peer_ctrl[p] = nullptr; S.peer_flags[p] = nullptr; }
     S.scratch_stride = scratch_doubles(h->N, h->M, h->bs);
     S.smem_bytes = (unsigned)smem_for(h, S.scratch_stride);
+    S.panel_bytes = 0;
     CU(h->scratch.reserve(S.scratch_stride * 8 * (size_t)grid));
     S.scratch = h->scratch.as<double>();
     return RBPE_OK;
@@ -369,6 +370,16 @@ static int launch_pdip_prepared(rbpe_handle *h, SolveArgs &S, long units, cudaSt
     } else {
         S.scratch_stride = scratch_doubles(h->N, h->M, h->bs);
         S.smem_bytes = (unsigned)smem_for(h, S.scratch_stride);
+        S.panel_bytes = 0;
+        // TMA-staged panel of the block factorisation, in front of the arena: on by default where it measured faster (blocks of
+        // order > 144, i.e. b >= 17: +6.5 % at b = 32; -4 % at b <= 16 where it costs the second CTA per SM its shared memory);
+        // RBPE_TMA=1 / 0 forces it on / off
+        const char *tma_env = getenv("RBPE_TMA");
+        const bool use_tma = tma_env ? atoi(tma_env) != 0 : kp_of(h->bs) > 144;
+        if (h->bs > 1 && use_tma) {
+            size_t pb = bla_panel_doubles((int)kp_of(h->bs)) * 8;
+            if (S.smem_bytes + pb <= h->smem_optin - 20 * 1024) { S.panel_bytes = (unsigned)pb; S.smem_bytes += (unsigned)pb; }
+        }
         CU(h->scratch.reserve(S.scratch_stride * 8 * (size_t)slots));
         S.scratch = h->scratch.as<double>() + (size_t)slot0 * S.scratch_stride;
         // joint batches use the full CTA (CTA-wide DMMA factorisation); one-agent batches through this kernel keep the knob

@@ -43,6 +43,70 @@ RBPE_DEV void dmma884(double &d0, double &d1, double a, double b) {
 #endif
 }
 
+// ---- TMA staging of the shared operand of a block column ------------------------------------------------------------
+// Every 8-row strip of a block column multiplies its own earlier columns with the SAME 32 rows of L (the rows of the
+// block column's diagonal block): that panel is copied once per block column into shared memory by the bulk-copy engine
+// (cp.async.bulk global -> shared, completion on an mbarrier; SASS UBLKCP) and all warps feed their DMMAs from there.
+// Row r of the panel lands at r * (klen + 4) doubles: the stride is 4 mod 16 doubles, so the 8 x 4 doubles a DMMA B operand
+// load touches fall into distinct banks within each half warp.
+constexpr int BLA_PANEL_PAD = 4;
+__host__ __device__ inline size_t bla_panel_doubles(int kp) { return kp > 9 ? (size_t)BLA_W * (kp + BLA_PANEL_PAD) : 0; }
+
+#if defined(__CUDACC__) && !defined(RBPE_EMU)
+RBPE_DEV unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+RBPE_DEV void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+RBPE_DEV void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+RBPE_DEV void tma_bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// returns false after ~1 s without completion (a lost copy must not hang the device)
+RBPE_DEV bool mbar_wait(unsigned long long *bar, unsigned parity) {
+    const long long t0 = clock64();
+    unsigned done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (!done && clock64() - t0 > 2000000000LL) return false;
+    }
+    return true;
+}
+#endif
+
+// Stage rows [r0, r0 + nrows) x columns [0, klen) of the row-major matrix Mx (leading dimension ld) into `panel`
+// (row stride klen + BLA_PANEL_PAD).  All threads of the CTA call; on return the panel is readable by all of them.
+// `bar` / `phase`: the CTA's mbarrier and its running parity (shared memory).  Generic-proxy stores to the source rows
+// (the previous block column's step 3) are ordered before the async-proxy reads by the fence + barrier below.
+RBPE_DEV bool stage_panel(double *panel, const double *Mx, int ld, int r0, int nrows, int klen, unsigned long long *bar, unsigned *phase) {
+    const int tid = threadIdx.x;
+    const int ps = klen + BLA_PANEL_PAD;
+#if defined(__CUDACC__) && !defined(RBPE_EMU)
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __syncthreads();
+    const unsigned par = *phase;
+    if (tid < 32) {
+        if (tid == 0) mbar_expect_tx(bar, (unsigned)(nrows * klen * 8));
+        __syncwarp();
+        if (tid < nrows) tma_bulk_g2s(panel + (size_t)tid * ps, Mx + (size_t)(r0 + tid) * ld, (unsigned)(klen * 8), bar);
+    }
+    const bool ok = mbar_wait(bar, par);
+    __syncthreads();
+    if (tid == 0) *phase = par ^ 1u;
+    return ok;
+#else
+    __syncthreads();
+    for (int i = tid; i < nrows * klen; i += blockDim.x) panel[(size_t)(i / klen) * ps + i % klen] = Mx[(size_t)(r0 + i / klen) * ld + i % klen];
+    __syncthreads();
+    (void)bar; (void)phase;
+    return true;
+#endif
+}
+
 // acc[jt] (8 x 8 tiles jt < ntj of the strip rows A0.., columns = rows B0 + 8 jt.. of Bm) += A0[.][0..klen) * Bm[.][0..klen)'
 // tiles with jt > jt_max are skipped (upper triangle).  Warp-uniform arguments.
 RBPE_DEV void strip_mma(double (&acc)[4][2], const double *A0, const double *B0, int ld, int ldb, int klen, int ntj, int jt_max) {
@@ -139,34 +203,102 @@ RBPE_NOINLINE bool chol32_warp(double *Db, int ld, int wJ, double *X) {
     return ok;
 }
 
+// CTA-wide version of chol32_warp: same right-looking elimination, same products, hence the same L and X bit for bit,
+// but the rank-1 update of a column step is spread over ALL threads of the CTA (one element per thread and 32 x 32 / nt
+// sub-steps) with one block barrier per column, instead of 32 dependent FMAs per lane of a single warp.  A lone warp runs
+// its dependent chain at ~0.1 instructions per cycle: chol32_warp took ~96 k cycles per call and was 25-41 % of the whole
+// joint-batch kernel (tools/gpu_joint.py with -DRBPE_PROFILE, r2); this version needs ~32 barriers.
+// As (trailing matrix, then L unscaled by column) and Rs (right-hand side of L X = I) live in shared memory with a
+// leading dimension of 33 (column reads are conflict free).  All threads of the CTA must call; returns false on a
+// non-positive pivot.
+RBPE_NOINLINE bool chol32_cta(double *Db, int ld, int wJ, double *X) {
+    RBPE_STATIC_SMEM(double, As, 32 * 33);
+    RBPE_STATIC_SMEM(double, Rs, 32 * 33);
+    RBPE_STATIC_SMEM(double, invs, 32);
+    const int tid = threadIdx.x, nt = blockDim.x, c = tid & 31, w0 = tid >> 5, nw = nt >> 5;
+    bool ok = true;
+    for (int r = w0; r < 32; r += nw) {
+        As[r * 33 + c] = (r < wJ && c <= r) ? Db[(size_t)r * ld + c] : ((r == c) ? 1.0 : 0.0);
+        Rs[r * 33 + c] = (r == c) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int j = 0; j < wJ; j++) {
+        double piv = As[j * 33 + j];
+        if (!(piv > 0)) { ok = false; piv = 1.0; }
+        const double inv = rsqrt(piv);
+        if (tid == 0) invs[j] = inv;
+        // column j of L is As[.][j] * inv, row j of X is Rs[j][.] * inv; neither is written during this step
+        const double lc = As[c * 33 + j] * inv, xj = Rs[j * 33 + c] * inv;
+        if (c > j) {
+            for (int r = w0; r < 32; r += nw)
+                if (r > j) As[r * 33 + c] = As[r * 33 + c] - (As[r * 33 + j] * inv) * lc;
+        } else {
+            for (int r = w0; r < 32; r += nw)
+                if (r > j) Rs[r * 33 + c] = Rs[r * 33 + c] - (As[r * 33 + j] * inv) * xj;
+        }
+        __syncthreads();
+    }
+    for (int r = w0; r < 32; r += nw) {
+        if (r < wJ) {
+            if (c <= r) Db[(size_t)r * ld + c] = As[r * 33 + c] * invs[c];
+            X[r * BLA_W + c] = (c <= r) ? Rs[r * 33 + c] * invs[r] : 0.0;
+        } else {
+            X[r * BLA_W + c] = (r == c) ? 1.0 : 0.0;
+        }
+    }
+    __syncthreads();
+    return ok;
+}
+
 // Factor the tall matrix [D; O] (see the header).  Pm = L_{t,t-1} of the previous knot (kp x kp) or null.
 // Linv receives the inverses of the 32 x 32 diagonal blocks of L ([bla_ninv][32*32], row-major, lower).
 // `flag`: one double of shared / global scratch for the verdict of warp 0.  All threads of the CTA must call.
-RBPE_NOINLINE bool chol_tall(int kp, double *D, double *O, const double *Pm, double *Linv, double *flag) {
+RBPE_NOINLINE bool chol_tall(int kp, double *D, double *O, const double *Pm, double *Linv, double *flag, double *panel = nullptr) {
     const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, nw = nt >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
     const int ntile = kp >> 3;
     PROF_DECL;
-    if (tid == 0) *flag = 0.0;
+    RBPE_STATIC_SMEM(unsigned long long, tma_bar, 1);
+    RBPE_STATIC_SMEM(unsigned, tma_phase, 1);
+    if (tid == 0) {
+        *flag = 0.0;
+#if defined(__CUDACC__) && !defined(RBPE_EMU)
+        if (panel) { mbar_init(tma_bar, 1); tma_phase[0] = 0; }
+#endif
+    }
+    if (panel) __syncthreads();
     for (int j0 = 0; j0 < kp; j0 += BLA_W) {
         const int wJ = (kp - j0 < BLA_W) ? kp - j0 : BLA_W, ntJ = wJ >> 3;
         double *X = Linv + (size_t)(j0 / BLA_W) * BLA_W * BLA_W;
+        // the 32 rows of L every strip of this block column multiplies with: staged once, by TMA, into shared memory
+        const double *Bp = D + (size_t)j0 * kp;
+        int ldb = kp;
+        if (panel && j0 > 0) {
+            if (!stage_panel(panel, D, kp, j0, wJ, j0, tma_bar, tma_phase) && tid == 0) *flag = 1.0;
+            Bp = panel; ldb = j0 + BLA_PANEL_PAD;
+        }
         // ---- 1. left-looking update of the block column: C -= L[., 0..j0) L[J, 0..j0)'  (+ the previous knot's block).
         // 1a: the strips of the diagonal block (all warps), barrier; 1b: the remaining strips by warps 1.., overlapped
         // with 2: warp 0 factors and inverts the diagonal block (a serial 32-step chain).
         const int nsD = (kp - j0) >> 3, nsO = O ? ntile : 0;
         const bool upd = (j0 > 0 || Pm);
+        // Two ways to do the 32 x 32 diagonal block, chosen by size (same-box A/B, tools/gpu_joint.py):
+        //   small blocks (kp <= 64: the launch default b = 4) -- the CTA-wide chol32_cta, then all warps do the strips below
+        //     (+13..22 % throughput, single-mission latency 102 -> 86 ms: little strip work exists to hide a serial warp);
+        //   large blocks (b >= 16) -- warp 0 runs the serial chol32_warp while warps 1.. update the strips below it
+        //     (the CTA-wide version was 4 % slower there: with two CTAs per SM the idle warps of one CTA are filled by the other).
+        const bool cta_diag = kp <= 64 || nw < 2;
         for (int pass = 0; pass < 2; pass++) {
-            const bool solo = nw < 2;   // a one-warp CTA (tuning knob) cannot overlap: everything in pass 0
-            const int s_begin = pass == 0 ? 0 : ntJ, s_end = (pass == 0 && !solo) ? ntJ : nsD + nsO;
-            const int w = pass == 0 ? warp : warp - 1, wn = pass == 0 ? nw : nw - 1;
-            if (upd && w >= 0 && !(solo && pass == 1))
+            const int s_begin = pass == 0 ? 0 : ntJ, s_end = pass == 0 ? ntJ : nsD + nsO;
+            const int w = (pass == 0 || cta_diag) ? warp : warp - 1, wn = (pass == 0 || cta_diag) ? nw : nw - 1;
+            if (upd && w >= 0)
                 for (int s = s_begin + w; s < s_end; s += wn) {
                     const bool isO = s >= nsD;
                     const int i0 = isO ? (s - nsD) * 8 : j0 + s * 8;
                     double *C0 = (isO ? O : D) + (size_t)i0 * kp;
                     const int jt_max = isO ? 3 : (i0 - j0) >> 3;
                     double acc[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
-                    if (j0 > 0) strip_mma(acc, C0, D + (size_t)j0 * kp, kp, kp, j0, ntJ, jt_max);
+                    if (j0 > 0) strip_mma(acc, C0, Bp, kp, ldb, j0, ntJ, jt_max);
                     if (!isO && Pm) strip_mma(acc, Pm + (size_t)i0 * kp, Pm + (size_t)j0 * kp, kp, kp, kp, ntJ, jt_max);
 #pragma unroll
                     for (int jt = 0; jt < 4; jt++)
@@ -179,9 +311,12 @@ RBPE_NOINLINE bool chol_tall(int kp, double *D, double *O, const double *Pm, dou
             if (pass == 0) {
                 if (upd) __syncthreads();
                 PROF(6);
-                // ---- 2. diagonal block: factor + invert, one warp ----
-                if (warp == 0) {
-                    bool ok = chol32_warp(D + (size_t)j0 * kp + j0, kp, wJ, X);
+                // ---- 2. diagonal block: factor + invert ----
+                if (cta_diag) {
+                    const bool ok = chol32_cta(D + (size_t)j0 * kp + j0, kp, wJ, X);
+                    if (!ok && tid == 0) *flag = 1.0;
+                } else if (warp == 0) {
+                    const bool ok = chol32_warp(D + (size_t)j0 * kp + j0, kp, wJ, X);
                     if (!ok && lane == 0) *flag = 1.0;
                 }
             }
@@ -258,12 +393,12 @@ RBPE_NOINLINE bool chol_tall(int kp, double *D, double *O, const double *Pm, dou
 }
 
 // block tridiagonal Cholesky: Dall (nblk diagonal blocks, lower), Oall (nblk-1 blocks (t+1, t)), ld = kp
-RBPE_DEV bool factor_bt_blk(int nblk, int kp, double *Dall, double *Oall, double *Linv, double *flag) {
+RBPE_DEV bool factor_bt_blk(int nblk, int kp, double *Dall, double *Oall, double *Linv, double *flag, double *panel = nullptr) {
     const size_t kk = (size_t)kp * kp, li = (size_t)bla_ninv(kp) * BLA_W * BLA_W;
     bool ok = true;
     for (int t = 0; t < nblk; t++)
         ok = chol_tall(kp, Dall + t * kk, (t < nblk - 1) ? Oall + t * kk : nullptr, (t > 0) ? Oall + (t - 1) * kk : nullptr,
-                       Linv + t * li, flag) && ok;
+                       Linv + t * li, flag, panel) && ok;
     return ok;
 }
 

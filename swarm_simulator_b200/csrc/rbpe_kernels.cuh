@@ -311,6 +311,7 @@ struct QP {
     double *sg, *sg2;
     double *dinv;        // [max(nr, 32)] column exchange buffer of the 9 x 9 routines (one-agent batches)
     double *Wd, *Wo;     // reduced Hessian Z'HZ: (M-1) diagonal blocks, (M-2) blocks (t+1,t), each kp x kp (9nb used)
+    double *panel;       // joint batches: shared-memory panel the factorisation stages with TMA (rbpe_blockla.cuh), or null
     double *Linv, *wk, *yk;   // joint batches: inverted 32 x 32 diagonal blocks of the factor, solve work vectors (rbpe_blockla.cuh)
     double *Dcp;         // [M*nb*6][6]  sum_rows w g g' restricted to one control point (3x3 symmetric over axes)
     double *Dint;        // [nrint][6]   -w n n' of a row between two batch agents
@@ -689,7 +690,7 @@ RBPE_NOINLINE bool kkt_factor(const QP &q) {
         __syncthreads();
         return q.red[60] == 0.0;
     }
-    return factor_bt_blk(q.M - 1, q.kp, q.Wd, q.Wo, q.Linv, q.red + 60);
+    return factor_bt_blk(q.M - 1, q.kp, q.Wd, q.Wo, q.Linv, q.red + 60, q.panel);
 }
 
 // dxout (nv) = Z (Z'HZ)^-1 Z' r   with r (nv) in x-space; uses q.sg
@@ -1024,7 +1025,11 @@ __global__ void __launch_bounds__(CTA_THREADS, RBPE_PDIP_MINB) pdip_kernel(Solve
                 int live_cp = 6 * M - 6;
                 q.mi = q.nb * live_cp * (6 + q.NE) + q.nb * (q.nb - 1) / 2 * live_cp;
             }
-            layout(q, smem, S.smem_bytes, gs);
+            {   // the front of the dynamic shared memory is the TMA panel of the factorisation (joint batches only)
+                const size_t pb = (q.nb > 1 && S.panel_bytes >= bla_panel_doubles(q.kp) * 8) ? bla_panel_doubles(q.kp) * 8 : 0;
+                q.panel = pb ? (double *)smem : nullptr;
+                layout(q, smem + pb, S.smem_bytes - pb, gs);
+            }
             if (threadIdx.x < 36) q.QB[threadIdx.x] = q_base_entry(threadIdx.x / 6, threadIdx.x % 6);
             __syncthreads();
             int rec = (S.mode == 0 ? iter * S.nbatch : S.rec_offset) + l;

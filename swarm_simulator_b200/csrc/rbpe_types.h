@@ -76,6 +76,7 @@ struct SolveArgs {
     double *scratch;        // per-CTA global scratch
     size_t scratch_stride;  // doubles per CTA
     unsigned smem_bytes;    // dynamic shared memory given to the kernel
+    unsigned panel_bytes;   // leading part of it reserved for the TMA-staged factor panel (joint batches; 0 = no staging)
 };
 
 struct ConvertArgs {

@@ -48,6 +48,7 @@ extern "C" int emu_solve_many(const rbpe_problem *p, int count, int mode, rbpe_r
     S.nrec = nrec; S.status = status.data();
     S.scratch_stride = scratch_doubles(N, M, bs);
     S.smem_bytes = (unsigned)smem_bytes;
+    S.panel_bytes = 0;
     // same kernel selection as rbpe_api.cu: one-agent batches -> warp-per-QP kernel, else CTA-per-QP kernel
     const bool warp_kernel = (bs == 1) && threads != 64;   // threads == 64 forces the CTA kernel (A/B in tests)
     const int wpc = 2;
@@ -61,10 +62,11 @@ extern "C" int emu_solve_many(const rbpe_problem *p, int count, int mode, rbpe_r
             emu::launch([&] { pdip1_kernel(S); }, (unsigned)grid, wpc * 32, S.smem_bytes);
         } else {
             S.scratch_stride = scratch_doubles(N, M, bs);
-            S.smem_bytes = (unsigned)smem_bytes;
+            S.panel_bytes = bs > 1 ? (unsigned)(bla_panel_doubles((int)kp_of(bs)) * 8) : 0;   // same carve-out as rbpe_api.cu
+            S.smem_bytes = (unsigned)smem_bytes + S.panel_bytes;
             std::vector<double> scratch(S.scratch_stride * units);
             S.scratch = scratch.data();
-            emu::launch([&] { pdip_kernel(S); }, (unsigned)units, threads, smem_bytes);
+            emu::launch([&] { pdip_kernel(S); }, (unsigned)units, threads, S.smem_bytes);
         }
     };
     if (nbatch > 0) {

@@ -262,3 +262,25 @@ def test_pipelined_call_equals_plain_call(monkeypatch):
         assert np.array_equal(a.coef, b.coef) and np.array_equal(a.ctrl, b.ctrl)
         assert np.array_equal(a.qp_iters, b.qp_iters) and np.array_equal(a.qp_obj, b.qp_obj)
         assert np.array_equal(a.status, b.status)
+
+
+def test_tma_staged_factor_panel_changes_nothing(eng):
+    """The joint-batch factorisation can stage the shared 32-row panel of a block column with TMA (cp.async.bulk +
+    mbarrier, rbpe_blockla.cuh) or read it from L2: same DMMA products in the same order, so identical bits; and both
+    equal the oracle (configs[1]: one joint batch of 16, and a batch of 32 where the staging is on by default)."""
+    import os
+    import feas_util as fu
+    for pack, seq, bs, pick in (("cfg2", False, 16, 3), ("cfg4", True, 32, 0)):
+        m = fu.missions(pack)[pick]
+        prob = E.PackedProblem(synth.pack([m]), sequential=seq, batch_size=bs, batch_iter=2 if seq else -1)
+        out = {}
+        for flag in ("1", "0"):
+            os.environ["RBPE_TMA"] = flag
+            out[flag] = eng.solve_many(prob)
+        os.environ.pop("RBPE_TMA", None)
+        assert out["1"].rc == out["0"].rc == 0
+        assert np.array_equal(out["1"].ctrl, out["0"].ctrl) and np.array_equal(out["1"].qp_iters, out["0"].qp_iters)
+        if bs == 16:
+            ro = oracle_util.oracle_problem(m, sequential=seq, batch_size=bs).update()
+            assert np.array_equal(out["1"].qp_iters[0][:1], ro["batch_iters"][:1])
+            assert np.abs(out["1"].ctrl[0] - ro["ctrl"]).max() < CTRL_TOL

@@ -29,7 +29,8 @@ def main():
     for ci, (N, M, rho, seq, bs, seed, count) in enumerate(CASES):
         if only and str(ci) not in only.split(","):
             continue
-        m = synth.synth_mission(N, M, rho, seed)
+        pack = {4: "cfg1", 16: "cfg2", 64: "cfg3", 256: "cfg4"}[N]
+        m = synth.load_pack(os.path.join(ROOT, "tests", "golden", "missions_%s.npz" % pack), select=[seed % 1000])[0]
         prob1 = E.PackedProblem(synth.pack([m]), sequential=seq, batch_size=bs)
         t = time.time(); r = eng.solve_many(prob1); dt1 = time.time() - t
         err = float("nan"); same = None; dto = 0.0
