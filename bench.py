@@ -197,6 +197,7 @@ def main():
     ap.add_argument("--joint-missions", type=int, default=592, help="missions of the joint-batch leg (configs[1]); 0 = skip")
     ap.add_argument("--jacobi-missions", type=int, default=64, help="missions (replicated on every rank) of the Jacobi leg; 0 = skip")
     ap.add_argument("--jacobi-sweeps", type=int, default=2)
+    ap.add_argument("--jacobi-missions-large", type=int, default=1184, help="missions of the throughput-bound Jacobi leg; 0 = skip")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the BASELINE configs[3] / configs[4] legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -367,25 +368,26 @@ def main():
     jac = None
     if args.jacobi_missions > 0:
         from swarm_simulator_b200 import dist as D
-        jpool = make_pool(min(args.pool, 4), 0)
+        jpool = make_pool(min(args.pool, 64), 0)
         jprob = E.PackedProblem(pin(synth.pack([jpool[i % len(jpool)] for i in range(args.jacobi_missions)])),
                                 sequential=True, batch_size=1, iteration=args.jacobi_sweeps)
         dev = torch.device("cuda", local)
 
-        def jacobi_leg(fused):
+        def jacobi_leg(fused, jprob_=None, resident=False):
+            jp_ = jprob_ or jprob
             jeng = E.Engine(device=local)
             if fused:
-                D.jacobi_attach_peers(jeng, jprob)                            # one-time exchange of IPC handles (host side)
-            D.jacobi_solve(jeng, jprob, args.jacobi_sweeps, device=dev, fused=fused)   # warm-up (also allocates)
+                D.jacobi_attach_peers(jeng, jp_)                            # one-time exchange of IPC handles (host side)
+            D.jacobi_solve(jeng, jp_, args.jacobi_sweeps, device=dev, fused=fused)   # warm-up (also allocates, uploads)
             jeng.sync()
             l0 = jeng.timing()["kernel_launches"]
             barrier()
             jeng.timer_start()                               # CUDA events on the engine's stream; every phase in between
             for _ in range(args.steps):                      # (H2D, sweeps, exchange) is stream- or host-synchronised
-                D.jacobi_solve(jeng, jprob, args.jacobi_sweeps, device=dev, fused=fused)
+                D.jacobi_solve(jeng, jp_, args.jacobi_sweeps, device=dev, fused=fused, upload=not resident)
             ms_j = max_over_ranks(jeng.timer_stop() / args.steps)
             barrier()
-            jr = jeng.download(jprob)
+            jr = jeng.download(jp_)
             if fused:
                 jeng.peer_status()
             out = (ms_j, int(jeng.timing()["kernel_launches"] - l0), int((jr.status != 0).sum()))
@@ -410,6 +412,25 @@ def main():
             ms_ag, _, _ = jacobi_leg(fused=False)
             jac["allgather_baseline"] = {"value": args.jacobi_missions * N_AGENTS * args.jacobi_sweeps / (ms_ag * 1e-3),
                                          "ms_per_step": ms_ag, "collective": "1 NCCL all-gather of control points per sweep"}
+        # the same leg with the inputs resident (no H2D inside): what remains is assembly + sweeps + exchange
+        try:
+            ms_r, _, _ = jacobi_leg(fused=fused_ok, resident=True)
+            jac["resident"] = {"value": args.jacobi_missions * N_AGENTS * args.jacobi_sweeps / (ms_r * 1e-3), "ms_per_step": ms_r}
+        except RuntimeError as ex:
+            print("resident Jacobi leg skipped: %s" % ex, file=sys.stderr)
+        # ... and a batch large enough to be throughput bound on 8 GPUs (the 64-mission leg is bound by the latency of one
+        # QP: 4096 QPs are less than two waves of one GPU's 2368 resident warps)
+        if args.jacobi_missions_large > 0:
+            try:
+                lpool = make_pool(min(args.pool, 64), 0)
+                lprob = E.PackedProblem(pin(synth.pack([lpool[i % len(lpool)] for i in range(args.jacobi_missions_large)])),
+                                        sequential=True, batch_size=1, iteration=args.jacobi_sweeps)
+                ms_l, _, lfail = jacobi_leg(fused=fused_ok, jprob_=lprob, resident=True)
+                jac["large_batch"] = {"missions": args.jacobi_missions_large, "ms_per_step": ms_l, "failed": lfail,
+                                      "value": args.jacobi_missions_large * N_AGENTS * args.jacobi_sweeps / (ms_l * 1e-3),
+                                      "note": "inputs resident; same missions on every rank, agents sharded"}
+            except RuntimeError as ex:
+                print("large Jacobi leg skipped: %s" % ex, file=sys.stderr)
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

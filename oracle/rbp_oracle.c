@@ -690,6 +690,38 @@ static int presolve_dead_rows(const nsp_t *K, double *h, unsigned char *dead, in
                 ub[i] = mid + PRESOLVE_FEAS_TOL; lb[i] = mid - PRESOLVE_FEAS_TOL;
             }
         }
+        /* The same rule for the two control points that C0 continuity identifies (control point 5 of segment m = control
+         * point 0 of segment m + 1, RP L390-L399): consecutive corridor boxes that only share a face pin the knot to that
+         * face -- a fixed variable to CPLEX's presolve.  The binding faces of the INTERSECTION of the two boxes are moved
+         * 1e-6 apart (worlds/map32.bt of the reference's smoke loop produces such a pair). */
+        {
+            int *varof = (int *)malloc(sizeof(int) * nv);
+            for (int v = 0; v < nv; v++) varof[K->seg[v] * K->n + K->loc[v]] = v;
+            double *ub0 = (double *)malloc(sizeof(double) * nv), *lb0 = (double *)malloc(sizeof(double) * nv);
+            memcpy(ub0, ub, sizeof(double) * nv); memcpy(lb0, lb, sizeof(double) * nv);
+            for (int m = 0; m + 1 < K->M; m++)
+                for (int ak = 0; ak < 3 * K->nb; ak++) {
+                    int va = varof[m * K->n + ak * 6 + 5], vb = varof[(m + 1) * K->n + ak * 6];
+                    if (ub0[va] >= 1e300 || ub0[vb] >= 1e300 || lb0[va] <= -1e300 || lb0[vb] <= -1e300) continue;
+                    double lo = lb0[va] > lb0[vb] ? lb0[va] : lb0[vb], hi = ub0[va] < ub0[vb] ? ub0[va] : ub0[vb], wdt = hi - lo;
+                    if (wdt < 2 * PRESOLVE_FEAS_TOL && wdt > -2 * PRESOLVE_FEAS_TOL) {
+                        double mid = 0.5 * (hi + lo);
+                        int vv[2] = {va, vb};
+                        for (int t = 0; t < 2; t++) {
+                            if (ub[vv[t]] < mid + PRESOLVE_FEAS_TOL) ub[vv[t]] = mid + PRESOLVE_FEAS_TOL;
+                            if (lb[vv[t]] > mid - PRESOLVE_FEAS_TOL) lb[vv[t]] = mid - PRESOLVE_FEAS_TOL;
+                        }
+                    }
+                }
+            free(varof); free(ub0); free(lb0);
+            for (int r = 0; r < q->n_box_rows && r < q->mi; r++)   /* loosened bounds back into the rows */
+                if (!dead[r] && q->g_ptr[r + 1] - q->g_ptr[r] == 1) {
+                    int c = q->g_idx[q->g_ptr[r]];
+                    double g = q->g_val[q->g_ptr[r]];
+                    if (g > 0 && ub[c] < 1e300 && h[r] / g < ub[c]) h[r] = g * ub[c];
+                    if (g < 0 && lb[c] > -1e300 && h[r] / g > lb[c]) h[r] = g * lb[c];
+                }
+        }
         for (int r = q->n_box_rows; r < q->mi; r++) {          /* the RSFC rows (RP L636-L684) */
             if (dead[r] || q->g_ptr[r + 1] == q->g_ptr[r]) continue;
             double amax = 0;

@@ -55,6 +55,7 @@ struct rbpe_handle {
     int max_iter = 100;
     double tol_gap = 1e-10, tol_res = 1e-9;
     size_t smem_budget = 0, smem_optin = 0;
+    size_t pdip_dyn_cap = 0;   // largest dynamic shared memory pdip_kernel can be launched with (opt-in limit minus its static part)
     int threads = 128;
     int threads_forced = 0;   // RBPE_THREADS / rbpe_config.reserved[0] given: applies to joint batches too
     int force_cta = 0;   // RBPE_KERNEL=cta: never use the warp-per-QP kernel (A/B testing)
@@ -170,7 +171,13 @@ extern "C" int rbpe_create(const rbpe_config *cfg, rbpe_handle **out) {
     for (int i = 0; i < 7; i++) cudaEventCreate(&h->ev[i]);
     cudaEventCreate(&h->tev[0]);
     cudaEventCreate(&h->tev[1]);
-    cudaFuncSetAttribute(pdip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin - 20 * 1024);
+    {
+        cudaFuncAttributes fa;
+        size_t st = 36 * 1024;
+        if (cudaFuncGetAttributes(&fa, pdip_kernel) == cudaSuccess) st = fa.sharedSizeBytes;
+        h->pdip_dyn_cap = (h->smem_optin - st - 1024) & ~(size_t)15;
+        cudaFuncSetAttribute(pdip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->pdip_dyn_cap);
+    }
     cudaFuncSetAttribute(pdip1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
     *out = h;
     return RBPE_OK;
@@ -303,9 +310,15 @@ extern "C" int rbpe_assemble(rbpe_handle *h) {
     return RBPE_OK;
 }
 
-static size_t smem_for(const rbpe_handle *h, size_t scratch_d) {
+// Dynamic shared memory of the CTA-per-QP kernel: the first `budget` bytes of a CTA's scratch live in shared memory, the
+// rest in the L2-resident arena (layout() in rbpe_kernels.cuh takes the small hot arrays first).  Throughput regime (more
+// CTAs than SMs): the configured budget (default 48 KB -> two CTAs per SM).  Latency regime (a handful of missions: at most
+// one CTA per SM anyway): everything the SM has, so that vectors, reduced Hessian and factor stay on chip.
+static size_t smem_for(const rbpe_handle *h, size_t scratch_d, long units = -1) {
     size_t need = scratch_d * 8 + 1024;
-    size_t s = need < h->smem_budget ? need : h->smem_budget;
+    size_t budget = h->smem_budget;
+    if (units >= 0 && units <= h->sm_count && !getenv("RBPE_SMEM_KB")) budget = h->pdip_dyn_cap;
+    size_t s = need < budget ? need : budget;
     return (s + 15) & ~(size_t)15;
 }
 
@@ -369,7 +382,7 @@ static int launch_pdip_prepared(rbpe_handle *h, SolveArgs &S, long units, cudaSt
         pdip1_kernel<<<(unsigned)grid, wpc * 32, S.smem_bytes, st>>>(S);
     } else {
         S.scratch_stride = scratch_doubles(h->N, h->M, h->bs);
-        S.smem_bytes = (unsigned)smem_for(h, S.scratch_stride);
+        S.smem_bytes = (unsigned)smem_for(h, S.scratch_stride, units);
         S.panel_bytes = 0;
         // TMA-staged panel of the block factorisation, in front of the arena: on by default where it measured faster (blocks of
         // order > 144, i.e. b >= 17: +6.5 % at b = 32; -4 % at b <= 16 where it costs the second CTA per SM its shared memory);
@@ -378,7 +391,12 @@ static int launch_pdip_prepared(rbpe_handle *h, SolveArgs &S, long units, cudaSt
         const bool use_tma = tma_env ? atoi(tma_env) != 0 : kp_of(h->bs) > 144;
         if (h->bs > 1 && use_tma) {
             size_t pb = bla_panel_doubles((int)kp_of(h->bs)) * 8;
-            if (S.smem_bytes + pb <= h->smem_optin - 20 * 1024) { S.panel_bytes = (unsigned)pb; S.smem_bytes += (unsigned)pb; }
+            const size_t cap = h->pdip_dyn_cap;
+            if (pb + 16 * 1024 <= cap) {   // the arena keeps at least 16 KB; in the latency regime it shrinks to make room
+                if (S.smem_bytes + pb > cap) S.smem_bytes = (unsigned)((cap - pb) & ~(size_t)15);
+                S.panel_bytes = (unsigned)pb;
+                S.smem_bytes += (unsigned)pb;
+            }
         }
         CU(h->scratch.reserve(S.scratch_stride * 8 * (size_t)slots));
         S.scratch = h->scratch.as<double>() + (size_t)slot0 * S.scratch_stride;

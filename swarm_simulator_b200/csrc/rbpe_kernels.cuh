@@ -721,6 +721,25 @@ RBPE_DEV void box_bounds(const double *box, int k, double &lb, double &ub) {
     }
 }
 
+// Bounds of control point i of segment m (box = the segment's box, its neighbours' boxes at box -+ 6): the segment's own
+// box, and for the two control points that C0 continuity identifies with a control point of the neighbouring segment
+// (i = 5 with the next segment's i = 0) the same tolerance rule applied to the INTERSECTION of the two boxes: consecutive
+// corridor boxes that only share a face (worlds/map32.bt of the reference's smoke loop has one) pin the knot to that face,
+// which CPLEX's presolve turns into a fixed variable; here the two binding faces are moved 1e-6 apart.
+RBPE_DEV void cp_bounds(const double *box, int M, int m, int i, int k, double &lb, double &ub) {
+    box_bounds(box, k, lb, ub);
+    const double *ob = (i == 5 && m + 1 < M) ? box + 6 : ((i == 0 && m > 0) ? box - 6 : nullptr);
+    if (!ob) return;
+    double olb, oub;
+    box_bounds(ob, k, olb, oub);
+    const double lo = lb > olb ? lb : olb, hi = ub < oub ? ub : oub, wdt = hi - lo;
+    if (wdt < 2 * PRESOLVE_FEAS_TOL && wdt > -2 * PRESOLVE_FEAS_TOL) {
+        const double mid = 0.5 * (hi + lo);
+        if (ub < mid + PRESOLVE_FEAS_TOL) ub = mid + PRESOLVE_FEAS_TOL;
+        if (lb > mid - PRESOLVE_FEAS_TOL) lb = mid - PRESOLVE_FEAS_TOL;
+    }
+}
+
 // rows of populatebyrow for the batch starting at agent q0 (h, normals; s = z = 1 until the start point is known);
 // x <- particular solution x_p (fixed control points from the start / goal states, zero elsewhere)
 RBPE_DEV void setup_rows(const QP &q) {
@@ -730,7 +749,7 @@ RBPE_DEV void setup_rows(const QP &q) {
         const double *box = q.segbox + ((size_t)(q.q0 + a) * M + m) * 6;
         {
             double lb, ub;
-            box_bounds(box, k, lb, ub);
+            cp_bounds(box, M, m, i, k, lb, ub);
             q.ub[v] = ub;
             q.lbn[v] = -lb;
         }
@@ -768,7 +787,7 @@ RBPE_DEV void setup_rows(const QP &q) {
             double gg[3] = {(double)f0, (double)f1, (double)f2}, amax = 0;
             for (int k = 0; k < 3; k++) {
                 double lb, ub;
-                box_bounds(box, k, lb, ub);
+                cp_bounds(box, M, m, i, k, lb, ub);
                 double a1 = gg[k] * ub, b1 = gg[k] * lb;
                 amax += (a1 > b1) ? a1 : b1;
             }
@@ -792,10 +811,10 @@ RBPE_DEV void setup_rows(const QP &q) {
             for (int k = 0; k < 3; k++) {
                 double g = (double)nf[k], lb, ub;
                 if (g == 0) continue;
-                box_bounds(bl, k, lb, ub);
+                cp_bounds(bl, M, m, j % 6, k, lb, ub);
                 double a1 = g * ub, b1 = g * lb;
                 amax += (a1 > b1) ? a1 : b1;
-                box_bounds(bh, k, lb, ub);
+                cp_bounds(bh, M, m, j % 6, k, lb, ub);
                 a1 = -g * ub; b1 = -g * lb;
                 amax += (a1 > b1) ? a1 : b1;
             }

@@ -420,7 +420,7 @@ RBPE_DEV int w1_setup(const W1 &c, double &dead_viol) {
                         double amax = 0;
                         for (int k = 0; k < 3; k++) {
                             double lb, ub;
-                            box_bounds(box, k, lb, ub);
+                            cp_bounds(box, M, m, i, k, lb, ub);
                             double g = nm[e * 3 + k], a = g * ub, b = g * lb;
                             amax += (a > b) ? a : b;
                         }
@@ -429,7 +429,7 @@ RBPE_DEV int w1_setup(const W1 &c, double &dead_viol) {
                 } else {   // x_k <= ub ; -x_k <= -lb (L626-L635)
                     int k = (e - c.NE) >> 1;
                     double lb, ub;
-                    box_bounds(box, k, lb, ub);
+                    cp_bounds(box, M, m, i, k, lb, ub);
                     h = ((e - c.NE) & 1) ? -lb : ub;
                 }
                 if (dead) {   // constant row: only its violation matters (P_DEAD of the round-1 layout)

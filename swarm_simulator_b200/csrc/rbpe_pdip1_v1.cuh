@@ -337,7 +337,7 @@ RBPE_DEV int w1_setup(const W1 &c) {   // returns the number of live (kept, non-
                         double amax = 0;
                         for (int k = 0; k < 3; k++) {
                             double lb, ub;
-                            box_bounds(box, k, lb, ub);
+                            cp_bounds(box, M, m, i, k, lb, ub);
                             double g = nm[e * 3 + k], a = g * ub, b = g * lb;
                             amax += (a > b) ? a : b;
                         }
@@ -346,7 +346,7 @@ RBPE_DEV int w1_setup(const W1 &c) {   // returns the number of live (kept, non-
                 } else {   // x_k <= ub ; -x_k <= -lb (L626-L635)
                     int k = (e - c.NE) >> 1;
                     double lb, ub;
-                    box_bounds(box, k, lb, ub);
+                    cp_bounds(box, M, m, i, k, lb, ub);
                     h = ((e - c.NE) & 1) ? -lb : ub;
                 }
                 const size_t r = rb + (size_t)kept * 32;

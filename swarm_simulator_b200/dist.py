@@ -113,8 +113,10 @@ def jacobi_attach_peers(eng, prob, group=None):
         raise err
 
 
-def jacobi_solve(eng, prob, sweeps, group=None, device=None, fused=False):
+def jacobi_solve(eng, prob, sweeps, group=None, device=None, fused=False, upload=True):
     """Jacobi mode on the ranks of `group`: inputs replicated, batches sharded.
+    upload=False: the inputs of `prob` are already resident on the device (a previous call uploaded them); only the
+    assembly kernel runs again (it resets `dummy` to the initial trajectory).
     fused=False: one NCCL all-gather of the solved control points per sweep (`exchange_ctrl`).
     fused=True (after `jacobi_attach_peers`): the sweep kernel's epilogue stores the solved control points into every
     rank's next table over NVLink peer memory and raises a flag there; no collective call, no host synchronisation."""
@@ -122,7 +124,8 @@ def jacobi_solve(eng, prob, sweeps, group=None, device=None, fused=False):
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     bs, nbatch = prob.effective_batching()
     b0, b1 = batch_range(nbatch, world, rank)
-    eng.upload(prob)
+    if upload:
+        eng.upload(prob)
     eng.assemble()
     if fused:
         for _ in range(sweeps):

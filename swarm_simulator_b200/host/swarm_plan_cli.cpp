@@ -1,6 +1,6 @@
 // swarm_plan_cli.cpp -- the planner node's whole pipeline (src/swarm_traj_planner_rbp.cpp L70-L123) without ROS:
 //   world (.bt) -> clamped distance map -> ECBSPlanner -> Corridor -> RBPPlanner (the B200 engine) -> safety metrics.
-// usage: swarm_plan_cli mission.json world.bt out_dir [stage=world|ecbs|all] [key=value ...]   (keys as in param.hpp)
+// usage: swarm_plan_cli mission.json world.bt out_dir [stage=world|ecbs|sfc|all] [key=value ...]   (keys as in param.hpp)
 // stage=world / ecbs need no GPU (map statistics, initial trajectories); stage=all runs Corridor's RSFC kernel and the QP
 // engine on the device and writes the coefficient CSVs when log=true.
 #include <cstdio>
@@ -16,7 +16,7 @@ using namespace SwarmPlanning;
 
 int main(int argc, char **argv) {
     if (argc < 4) {
-        std::fprintf(stderr, "usage: %s mission.json world.bt out_dir [stage=world|ecbs|all] [key=value ...]\n", argv[0]);
+        std::fprintf(stderr, "usage: %s mission.json world.bt out_dir [stage=world|ecbs|sfc|all] [key=value ...]\n", argv[0]);
         return 2;
     }
     std::map<std::string, std::string> kv;
@@ -72,6 +72,18 @@ int main(int argc, char **argv) {
         return 0;
     }
     Corridor corridor(dm, mission, param);
+    if (stage == "sfc") {   // host only: ECBS + SFC, dumped for offline reproduction (T, initTraj, SFC; RSFC follows from initTraj)
+        if (!corridor.update_sfc(param.log, &pr)) { std::printf("corridor=false\n"); return 1; }
+        std::printf("dump %d %d\n", mission.qn, M);
+        for (auto t : pr.T) std::printf("%.17g ", t);
+        std::printf("\n");
+        for (int qi = 0; qi < mission.qn; qi++) {
+            for (auto &p : pr.initTraj[qi]) std::printf("%.9g %.9g %.9g ", (double)p.x(), (double)p.y(), (double)p.z());
+            std::printf("\n%zu\n", pr.SFC[qi].size());
+            for (auto &b : pr.SFC[qi]) std::printf("%.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", b.first[0], b.first[1], b.first[2], b.first[3], b.first[4], b.first[5], b.second);
+        }
+        return 0;
+    }
     if (!corridor.update(param.log, &pr)) { std::printf("corridor=false\n"); return 1; }
     size_t nbox = 0;
     for (auto &s : pr.SFC) nbox += s.size();

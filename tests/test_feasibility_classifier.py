@@ -92,3 +92,20 @@ def test_seeds_the_round_one_solver_gave_up_on():
         assert r["status"] == 0, (seed, bs, r["batch_status"])
         veq, vbox, vrel = fu.joint_violation(m, r["ctrl"], True)
         assert veq < 1e-7 and vbox < 2e-6 and vrel < 2e-6
+
+
+def test_smoke_loop_map_with_face_sharing_boxes():
+    """worlds/map32.bt of the reference's smoke loop (fixture tests/golden/smoke_map32.npz, M = 36, launch default b = 4):
+    two consecutive corridor boxes of one agent share only a face, so batch 14 has no interior (HiGHS: slack exactly 0).
+    CPLEX fixes such a variable in its presolve and solves; so must we (presolve rule cp_bounds / presolve_dead_rows)."""
+    import os
+    from swarm_simulator_b200 import synth
+    m = synth.load_pack(os.path.join(fu.GOLDEN, "smoke_map32.npz"))[0]
+    assert (m["N"], m["M"]) == (64, 36)
+    _, q = fu.failing_qp(m, True, 4, 14)
+    verdict, slack, _ = fc.classify(q)
+    assert verdict == fc.BORDERLINE and abs(slack) < 1e-9
+    r = oracle_util.oracle_problem(m, sequential=True, batch_size=4).update()
+    assert r["status"] == 0, r["batch_status"]
+    veq, vbox, vrel = fu.joint_violation(m, r["ctrl"], True)
+    assert veq < 1e-7 and vbox < 2e-6 and vrel < 2e-6

@@ -67,3 +67,17 @@ def test_engine_solves_the_round_one_failures(eng):
             ro = oracle_util.oracle_problem(m, sequential=True, batch_size=bs).update()
             assert ro["status"] == 0
             assert np.abs(r.ctrl[c] - ro["ctrl"]).max() < 1e-6
+
+
+def test_engine_plans_the_smoke_loop_map_with_face_sharing_boxes(eng):
+    """GPU side of test_smoke_loop_map_with_face_sharing_boxes (reference: swarm_traj_planner_rbp_test_all.cpp L93-L94)."""
+    import os
+    m = synth.load_pack(os.path.join(fu.GOLDEN, "smoke_map32.npz"))[0]
+    for bs in (4, 1):
+        r, _ = _run_engine(eng, [m], True, bs)
+        assert r.status[0] == 0, (bs, r.qp_status[0])
+        ro = oracle_util.oracle_problem(m, sequential=True, batch_size=bs).update()
+        assert ro["status"] == 0
+        assert np.abs(r.ctrl[0] - ro["ctrl"]).max() < 1e-6
+        veq, vbox, vrel = fu.joint_violation(m, r.ctrl[0], True)
+        assert veq < 1e-7 and vbox < 2e-6 and vrel < 2e-6
