@@ -131,6 +131,8 @@ RBPE_DEV void strip_mma(double (&acc)[4][2], const double *A0, const double *B0,
 // are exchanged through a shared-memory tile Ls (64 x 32, rows 32..63 zero so that the window can run past the block)
 // as warp-wide broadcast loads.  No global memory traffic inside the two loops (a store followed by __syncwarp costs a
 // full L2 round trip).  The inverse is a second pass of the same shape (lane c owns column c of L^-1).
+// (Staging the window -- 32 / 24 / 16 / 8 live entries in four groups of steps -- saves 37 % of the load + FMA pairs but was
+// 4 % slower in the same-box A/B: four unrolled bodies instead of one.)
 // Returns false on a non-positive pivot.
 RBPE_NOINLINE bool chol32_warp(double *Db, int ld, int wJ, double *X) {
     RBPE_STATIC_SMEM(double, Ls, 64 * 32 + 32);
@@ -273,7 +275,12 @@ RBPE_NOINLINE bool chol_tall(int kp, double *D, double *O, const double *Pm, dou
         // the 32 rows of L every strip of this block column multiplies with: staged once, by TMA, into shared memory
         const double *Bp = D + (size_t)j0 * kp;
         int ldb = kp;
-        if (panel && j0 > 0) {
+#if defined(__CUDACC__) && !defined(RBPE_EMU)
+        const bool d_global = __isGlobal(D);   // small blocks can live in the shared-memory part of the arena: TMA reads global only
+#else
+        const bool d_global = true;
+#endif
+        if (panel && j0 > 0 && d_global) {
             if (!stage_panel(panel, D, kp, j0, wJ, j0, tma_bar, tma_phase) && tid == 0) *flag = 1.0;
             Bp = panel; ldb = j0 + BLA_PANEL_PAD;
         }
@@ -389,7 +396,11 @@ RBPE_NOINLINE bool chol_tall(int kp, double *D, double *O, const double *Pm, dou
         __syncthreads();
         PROF(8);
     }
-    return *flag == 0.0;
+    // every thread reads the verdict BEFORE thread 0 of the next call may reset the flag (compute-sanitizer racecheck, r2:
+    // a slow thread could otherwise miss a failure and leave the CTA's control flow divergent)
+    const bool ok_all = (*flag == 0.0);
+    __syncthreads();
+    return ok_all;
 }
 
 // block tridiagonal Cholesky: Dall (nblk diagonal blocks, lower), Oall (nblk-1 blocks (t+1, t)), ld = kp
