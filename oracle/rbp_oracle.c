@@ -757,7 +757,6 @@ int oracle_solve_qp(const oracle_qp *q, const oracle_solver_opts *opts, double *
     nsp_t K;
     int status = ORACLE_NOT_CONVERGED, it = 0, n_live = mi;
     double gap = 0, obj = 0, nrd = 0, nrg = 0, hn = 0;
-    int acceptable = 0;
     if (nsp_init(&K, q)) {
         nsp_free(&K);
         if (obj_out) *obj_out = 0;
@@ -841,8 +840,7 @@ int oracle_solve_qp(const oracle_qp *q, const oracle_solver_opts *opts, double *
              * by an independent LP, CPLEX solves them).  Once complementarity and primal feasibility meet their strict
              * tolerances the iterate is therefore accepted at CPLEX's own optimality tolerance (EpOpt, default 1e-6,
              * relative to the gradient scale) instead of iterating into a numerically singular factorisation. */
-            acceptable = gap_ok && nrd <= TOL_DUAL_FLOOR * dscale;
-            if (acceptable) { status = ORACLE_OK; break; }
+            if (gap_ok && nrd <= TOL_DUAL_FLOOR * dscale) { status = ORACLE_OK; break; }
         }
         /* infeasibility certificate of the reduced problem {G Z sigma <= h - G x_p}: z >= 0, (GZ)'z ~ 0, (h - G x_p)'z < 0.
          * By LP duality the largest uniform slack of the rows is min (h - G x_p)'z / sum(z) over such z, so the row set is
@@ -860,7 +858,7 @@ int oracle_solve_qp(const oracle_qp *q, const oracle_solver_opts *opts, double *
         if (nsp_factor(&K, K.w)) {
             /* the weights of an infeasible QP diverge by orders of magnitude per iteration; if the factorisation gives up
              * before the certificate is sharp, a certificate that already excludes every |sigma| < 1e4 decides */
-            status = acceptable ? ORACLE_OK : (cert < CERT_RATIO_BREAKDOWN ? ORACLE_INFEASIBLE : ORACLE_NOT_CONVERGED);
+            status = cert < CERT_RATIO_BREAKDOWN ? ORACLE_INFEASIBLE : ORACLE_NOT_CONVERGED;
             break;
         }
         /* affine direction: rc = s.z  =>  G' coefficient -(w rg - z) */

@@ -642,36 +642,34 @@ RBPE_DEV void Z_apply(const QP &q, const double *sg, double *out) {
 // reduced Hessian Z'(2Q + G'WG)Z from the per-control-point blocks left by the last P_INIT / P_RES pass
 RBPE_DEV void build_W(const QP &q) {
     const int kb = q.kb, kp = q.kp, kk = kp * kp, M = q.M;
-    for (int idx = threadIdx.x; idx < (M - 1) * kk; idx += blockDim.x) {
-        int t = idx / kk + 1, r = (idx % kk) / kp, c = idx % kp;
-        double s = 0;
-        if (r >= kb || c >= kb) {
-            s = (r == c) ? 1.0 : 0.0;   // identity padding up to a multiple of 8
-        } else if (c <= r) {
-            int a = r / 9, k = (r % 9) / 3, d = r % 3, a2 = c / 9, k2 = (c % 9) / 3, d2 = c % 3;
-            const double *CR = q.segmat + (t - 1) * SEGMAT + SEGMAT_CR, *CL = q.segmat + t * SEGMAT + SEGMAT_CL;
-            int e = sym6(k, k2);
-            if (a == a2) {
-                const double *Dl = q.Dcp + ((size_t)((t - 1) * q.nb + a) * 6 + 3) * 6 + e;
-                const double *Dr = q.Dcp + ((size_t)(t * q.nb + a) * 6) * 6 + e;
+    // a thread owns entry (r, c) of EVERY knot's block: the index arithmetic (agent, axis, derivative of row and column, pair
+    // number) is done once per entry instead of once per entry and knot (this phase was 11 % of the joint kernel at b = 16)
+    for (int idx = threadIdx.x; idx < kk; idx += blockDim.x) {
+        const int r = idx / kp, c = idx - r * kp;
+        if (r >= kb || c >= kb || c > r) {
+            const double v = (r >= kb || c >= kb) ? ((r == c) ? 1.0 : 0.0) : 0.0;   // identity padding up to a multiple of 8; zero above the diagonal
+            for (int t = 1; t < M; t++) q.Wd[(size_t)(t - 1) * kk + idx] = v;
+        } else {
+            const int a = r / 9, k = (r % 9) / 3, d = r % 3, a2 = c / 9, k2 = (c % 9) / 3, d2 = c % 3;
+            const int e = sym6(k, k2);
+            const bool same_agent = a == a2, same_axis = same_agent && k == k2;
+            // per-control-point blocks: rows of one agent, or the rows between two batch agents (a > a2)
+            const size_t pp = same_agent ? 0 : (size_t)a2 * q.nb - (size_t)a2 * (a2 + 1) / 2 + (a - a2 - 1);
+            for (int t = 1; t < M; t++) {
+                const double *sl = q.segmat + (t - 1) * SEGMAT, *sr = q.segmat + t * SEGMAT;
+                const double *CR = sl + SEGMAT_CR, *CL = sr + SEGMAT_CL;
+                const double *Dl = same_agent ? q.Dcp + ((size_t)((t - 1) * q.nb + a) * 6 + 3) * 6 + e : q.Dint + (pp * 6 * M + (t - 1) * 6 + 3) * 6 + e;
+                const double *Dr = same_agent ? q.Dcp + ((size_t)(t * q.nb + a) * 6) * 6 + e : q.Dint + (pp * 6 * M + t * 6) * 6 + e;
+                double s = 0;
                 for (int j = 0; j < 3; j++) s += CR[j * 3 + d] * CR[j * 3 + d2] * Dl[j * 6] + CL[j * 3 + d] * CL[j * 3 + d2] * Dr[j * 6];
-                if (k == k2)
-                    s += q.segmat[(t - 1) * SEGMAT + SEGMAT_RQ + (3 + d) * 6 + 3 + d2] + q.segmat[t * SEGMAT + SEGMAT_RQ + d * 6 + d2];
-            } else {  // a > a2: rows between the two batch agents
-                size_t pp = (size_t)a2 * q.nb - (size_t)a2 * (a2 + 1) / 2 + (a - a2 - 1);
-                const double *Dl = q.Dint + (pp * 6 * M + (t - 1) * 6 + 3) * 6 + e;
-                const double *Dr = q.Dint + (pp * 6 * M + t * 6) * 6 + e;
-                for (int j = 0; j < 3; j++) s += CR[j * 3 + d] * CR[j * 3 + d2] * Dl[j * 6] + CL[j * 3 + d] * CL[j * 3 + d2] * Dr[j * 6];
+                if (same_axis) s += sl[SEGMAT_RQ + (3 + d) * 6 + 3 + d2] + sr[SEGMAT_RQ + d * 6 + d2];
+                q.Wd[(size_t)(t - 1) * kk + idx] = s;
             }
         }
-        q.Wd[idx] = s;
-    }
-    // blocks (t+1, t), t = 1..M-2: only the cost couples neighbouring knots, per (agent, axis)
-    for (int idx = threadIdx.x; idx < (M - 2) * kk; idx += blockDim.x) {
-        int t = idx / kk + 1, r = (idx % kk) / kp, c = idx % kp;
-        double s = 0;
-        if (r < kb && c < kb && r / 3 == c / 3) s = q.segmat[t * SEGMAT + SEGMAT_RQ + (3 + r % 3) * 6 + c % 3];
-        q.Wo[idx] = s;
+        // blocks (t+1, t), t = 1..M-2: only the cost couples neighbouring knots, per (agent, axis)
+        const bool coupled = r < kb && c < kb && r / 3 == c / 3;
+        for (int t = 1; t < M - 1; t++)
+            q.Wo[(size_t)(t - 1) * kk + idx] = coupled ? q.segmat[t * SEGMAT + SEGMAT_RQ + (3 + r % 3) * 6 + c % 3] : 0.0;
     }
 }
 
@@ -857,7 +855,7 @@ RBPE_DEV int pdip_solve(const QP &q_in, int max_iter, double tol_gap, double tol
     PROF(0);
     int status = ST_NOT_CONVERGED, it = 0;
     double obj = 0, gap = 0, nrd = 0, nrg = 0, hn = 0;
-    bool go = true, acceptable = false;
+    bool go = true;
     // presolve: rows on fixed control points are constants; check them and leave them out
     row_pass<P_DEAD>(q, 0, 0, acc);
     if (acc.mx > PRESOLVE_FEAS_TOL) { status = ST_INFEASIBLE; go = false; }
@@ -942,8 +940,7 @@ RBPE_DEV int pdip_solve(const QP &q_in, int max_iter, double tol_gap, double tol
             // relative to the gradient scale) instead of iterating into a numerically singular factorisation.
             const bool gap_ok = gap <= tol_gap * fmax(1.0, fabs(obj)) && nrg <= tol_res * (1 + hn);
             if (gap_ok && nrd <= tol_res * (1.0 + mpx)) { status = ST_OK; break; }
-            acceptable = gap_ok && nrd <= TOL_DUAL_FLOOR * (1.0 + mpx);
-            if (acceptable) { status = ST_OK; break; }
+            if (gap_ok && nrd <= TOL_DUAL_FLOOR * (1.0 + mpx)) { status = ST_OK; break; }
         }
         // Farkas certificate of the reduced problem.  The largest uniform slack of the rows equals min h'z / sum(z) over
         // z >= 0 with (GZ)'z = 0, so "infeasible beyond the feasibility tolerance" needs h'z < -1e-6 sum(z) (max(z) is
@@ -952,7 +949,7 @@ RBPE_DEV int pdip_solve(const QP &q_in, int max_iter, double tol_gap, double tol
         if (cert < CERT_RATIO) { status = ST_INFEASIBLE; break; }
         // ---- factor with W = z/s ----
         PROF(4);
-        if (!kkt_factor(q)) { status = acceptable ? ST_OK : (cert < CERT_RATIO_BREAKDOWN ? ST_INFEASIBLE : ST_NOT_CONVERGED); break; }
+        if (!kkt_factor(q)) { status = cert < CERT_RATIO_BREAKDOWN ? ST_INFEASIBLE : ST_NOT_CONVERGED; break; }
         PROF(2);
         // ---- affine direction ----
         for (int v = tid; v < q.nv; v += nt) q.vB[v] = -q.rdx[v] + q.vB[v];

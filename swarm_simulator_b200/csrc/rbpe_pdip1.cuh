@@ -501,12 +501,10 @@ RBPE_DEV int w1_solve_qp(const W1 &c, int max_iter, double tol_gap, double tol_r
             obj = o; nrd = mr;
             gap = mu;
             if (!(mu == mu) || !(nrd == nrd)) { status = ST_NOT_CONVERGED; break; }
-            bool acceptable;
             {   // acceptance rule of pdip_solve (rbpe_kernels.cuh): strict test, else the round-off floor of the dual residual
                 const bool gap_ok = gap <= tol_gap * fmax(1.0, fabs(obj)) && nrg <= tol_res * (1 + hn);
                 if (gap_ok && nrd <= tol_res * (1.0 + mpx)) { status = ST_OK; break; }
-                acceptable = gap_ok && nrd <= TOL_DUAL_FLOOR * (1.0 + mpx);
-                if (acceptable) { status = ST_OK; break; }
+                if (gap_ok && nrd <= TOL_DUAL_FLOOR * (1.0 + mpx)) { status = ST_OK; break; }
             }
             const double cert = (hz < -PRESOLVE_FEAS_TOL * zmax) ? mc / (-hz) : 1e300;
             if (cert < CERT_RATIO) { status = ST_INFEASIBLE; break; }

@@ -371,7 +371,7 @@ RBPE_DEV int w1_solve_qp(const W1 &c, int max_iter, double tol_gap, double tol_r
     const int live_rows = w1_setup(c);
     int status = ST_NOT_CONVERGED, it = 0;
     double obj = 0, gap = 0, nrd = 0, nrg = 0, hn = 0;
-    bool go = true, acceptable = false;
+    bool go = true;
     w1_pass<P_DEAD>(c, 0, 0, acc);
     if (acc.mx > PRESOLVE_FEAS_TOL) { status = ST_INFEASIBLE; go = false; }
     if (go && c.nr == 0) {
@@ -435,13 +435,12 @@ RBPE_DEV int w1_solve_qp(const W1 &c, int max_iter, double tol_gap, double tol_r
         {   // acceptance rule of pdip_solve (rbpe_kernels.cuh): strict test, else the round-off floor of the dual residual
             const bool gap_ok = gap <= tol_gap * fmax(1.0, fabs(obj)) && nrg <= tol_res * (1 + hn);
             if (gap_ok && nrd <= tol_res * (1.0 + mpx)) { status = ST_OK; break; }
-            acceptable = gap_ok && nrd <= TOL_DUAL_FLOOR * (1.0 + mpx);
-            if (acceptable) { status = ST_OK; break; }
+            if (gap_ok && nrd <= TOL_DUAL_FLOOR * (1.0 + mpx)) { status = ST_OK; break; }
         }
         const double cert = (hz < -PRESOLVE_FEAS_TOL * acc.mx2) ? mc / (-hz) : 1e300;
         if (cert < CERT_RATIO) { status = ST_INFEASIBLE; break; }
         w1_build_W(c.segmat, c.M, c.Dcp, c.Wd, c.Wo);
-        if (!factor_bt9v<1>(c.M - 1, c.Wd, c.Wo, c.dinv)) { status = acceptable ? ST_OK : (cert < CERT_RATIO_BREAKDOWN ? ST_INFEASIBLE : ST_NOT_CONVERGED); break; }
+        if (!factor_bt9v<1>(c.M - 1, c.Wd, c.Wo, c.dinv)) { status = cert < CERT_RATIO_BREAKDOWN ? ST_INFEASIBLE : ST_NOT_CONVERGED; break; }
         #pragma unroll 1
         for (int v = lane; v < 18 * c.M; v += 32) c.vB[v] = -c.rdx[v] + c.vB[v];
         __syncwarp();
