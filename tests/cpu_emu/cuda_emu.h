@@ -171,6 +171,12 @@ inline int __any_sync(unsigned, int pred) {
     for (int l = 0; l < 32; l++) r |= __shfl_sync(0xffffffffu, v, l);
     return r;
 }
+inline unsigned __ballot_sync(unsigned, int pred) {
+    unsigned v = pred ? 1u : 0u, r = 0;
+    for (int l = 0; l < 32; l++) r |= __shfl_sync(0xffffffffu, v, l) << l;
+    return r;
+}
+inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline int atomicCAS(int *addr, int cmp, int val) {
     int old = *addr;
     if (old == cmp) *addr = val;

@@ -12,6 +12,7 @@ from swarm_simulator_b200 import engine as E, synth
 @pytest.mark.parametrize("N,M,rho,seq,bs,smem", [
     (4, 3, 0.0, False, 4, 48 * 1024),   # BASELINE configs[0]: 4 agents, empty map, 3 segments, one joint batch
     (5, 4, 0.2, True, 2, 0),            # sequential, ragged last batch, everything in "global" scratch
+    (38, 3, 0.1, True, 4, 48 * 1024),   # 34 frozen agents per batch: the compaction of kept rows crosses a 32-row group
 ])
 def test_emulated_kernels_match_oracle(N, M, rho, seq, bs, smem):
     m = synth.synth_mission(N, M, rho, 77)
