@@ -59,6 +59,10 @@ struct rbpe_handle {
     int threads = 128;
     int threads_forced = 0;   // RBPE_THREADS / rbpe_config.reserved[0] given: applies to joint batches too
     int force_cta = 0;   // RBPE_KERNEL=cta: never use the warp-per-QP kernel (A/B testing)
+    size_t x1_dyn_cap = 0;   // same for the several-warps-per-QP latency kernel (pdip1x_kernel)
+    int lat_mode = -1;       // RBPE_LAT=0 / 1: never / always use the latency kernel where it fits (default: by work-item count)
+    int lat_warps = X1_MAXW; // RBPE_LAT_WARPS: warps per QP of the latency kernel
+    int lat_warps_forced = 0;
     int sm_count = 0;
     char err[512] = "";
     // resident problem
@@ -152,10 +156,10 @@ extern "C" int rbpe_create(const rbpe_config *cfg, rbpe_handle **out) {
         if (cfg->tol_res > 0) h->tol_res = cfg->tol_res;
         h->smem_budget = cfg->smem_budget;
         int th = cfg->reserved[0];   // CTA size of the PDIP kernel (tuning knob): 32..256, multiple of 32
-        if (th >= 32 && th <= CTA_THREADS && th % 32 == 0) { h->threads = th; h->threads_forced = 1; }
+        if (th >= 32 && th <= CTA_THREADS_MAX && th % 32 == 0) { h->threads = th; h->threads_forced = 1; }
     }
     // tuning overrides (documented in DESIGN.md): RBPE_THREADS, RBPE_SMEM_KB
-    if (const char *e = getenv("RBPE_THREADS")) { int th = atoi(e); if (th >= 32 && th <= CTA_THREADS && th % 32 == 0) { h->threads = th; h->threads_forced = 1; } }
+    if (const char *e = getenv("RBPE_THREADS")) { int th = atoi(e); if (th >= 32 && th <= CTA_THREADS_MAX && th % 32 == 0) { h->threads = th; h->threads_forced = 1; } }
     if (const char *e = getenv("RBPE_KERNEL")) h->force_cta = (strcmp(e, "cta") == 0);
     if (const char *e = getenv("RBPE_CHUNK")) { int c = atoi(e); if (c > 0) h->chunk = c; }
     if (const char *e = getenv("RBPE_SMEM_KB")) { long kb = atol(e); if (kb > 0) h->smem_budget = (size_t)kb * 1024; }
@@ -179,6 +183,17 @@ extern "C" int rbpe_create(const rbpe_config *cfg, rbpe_handle **out) {
         cudaFuncSetAttribute(pdip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->pdip_dyn_cap);
     }
     cudaFuncSetAttribute(pdip1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
+#ifndef RBPE_W1_V1
+    {
+        cudaFuncAttributes fa;
+        size_t st = 1024;
+        if (cudaFuncGetAttributes(&fa, pdip1x_kernel) == cudaSuccess) st = fa.sharedSizeBytes;
+        h->x1_dyn_cap = (h->smem_optin - st - 1024) & ~(size_t)15;
+        cudaFuncSetAttribute(pdip1x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->x1_dyn_cap);
+        if (const char *e = getenv("RBPE_LAT")) h->lat_mode = atoi(e) != 0;
+        if (const char *e = getenv("RBPE_LAT_WARPS")) { int w = atoi(e); if (w >= 1 && w <= X1_MAXW) { h->lat_warps = w; h->lat_warps_forced = 1; } }
+    }
+#endif
     *out = h;
     return RBPE_OK;
 }
@@ -364,6 +379,29 @@ static int warps_per_cta(const rbpe_handle *h) {
     return w;
 }
 
+// Warps per QP of the latency kernel (pdip1x_kernel), 0 = not used.  It is the kernel for one-agent batches when the
+// work items are too few to fill the SMs with one warp each (a handful of missions: the reference's own use), and only
+// where the row state of a QP fits in shared memory.  Up to two CTAs per SM: beyond that pdip1_kernel's one warp per QP
+// has the higher throughput.
+static int warps_per_qp(const rbpe_handle *h, long units) {
+#ifdef RBPE_W1_V1
+    return 0;
+#else
+    if (h->bs != 1 || h->force_cta || h->lat_mode == 0) return 0;
+    int nw = h->lat_warps;
+    const size_t bytes = x1_smem_doubles(h->N, h->M, nw) * 8;
+    if (bytes > h->x1_dyn_cap) return 0;
+    if (h->lat_mode == 1) return nw;
+    // measured (tools/gpu_latency.py, 64 agents, one Jacobi sweep): 8 warps per QP win up to two CTAs per SM (0.59 / 0.61 /
+    // 0.85 ms at 64 / 128 / 256 QPs against 1.17 / 1.18 / 1.19 ms of pdip1_kernel), 4 warps per QP up to four (512 QPs:
+    // 0.91 ms against 1.48 ms), beyond that one warp per QP (1 024 QPs: 2.0 ms against 1.5 ms)
+    const long per_sm = (2 * (bytes + 1024) <= 227 * 1024) ? 2 : 1;
+    if (units <= (long)h->sm_count * per_sm) return nw;
+    if (!h->lat_warps_forced && nw > 4 && units <= 2 * (long)h->sm_count * per_sm && x1_smem_doubles(h->N, h->M, 4) * 8 <= h->x1_dyn_cap) return 4;
+    return 0;
+#endif
+}
+
 // launches k2 over `units` independent work items (missions in mode 0, (mission, batch) pairs in mode 1)
 // S must have been filled by fill_solve_args (mode, ranges, record offsets already set by the caller)
 // `st`: stream to launch on (default: the engine's); `slot0` / `slots`: this launch uses work-item slots [slot0, slot0 + units)
@@ -373,7 +411,15 @@ static int launch_pdip_prepared(rbpe_handle *h, SolveArgs &S, long units, cudaSt
     S.work_items = (unsigned)units;
     if (!st) st = h->stream;
     if (slots < units) slots = units;
-    if (wpc > 0) {
+    const int xw = warps_per_qp(h, units);
+    if (xw > 0) {
+#ifndef RBPE_W1_V1
+        S.scratch_stride = 0;
+        S.smem_bytes = (unsigned)(x1_smem_doubles(h->N, h->M, xw) * 8);
+        S.scratch = h->scratch.as<double>();
+        pdip1x_kernel<<<(unsigned)units, xw * 32, S.smem_bytes, st>>>(S);
+#endif
+    } else if (wpc > 0) {
         long grid = (units + wpc - 1) / wpc;
         S.scratch_stride = w1_scratch_doubles(h->N, h->M);
         S.smem_bytes = (unsigned)(wpc * w1_smem_doubles(h->M) * 8);
@@ -401,7 +447,11 @@ static int launch_pdip_prepared(rbpe_handle *h, SolveArgs &S, long units, cudaSt
         CU(h->scratch.reserve(S.scratch_stride * 8 * (size_t)slots));
         S.scratch = h->scratch.as<double>() + (size_t)slot0 * S.scratch_stride;
         // joint batches use the full CTA (CTA-wide DMMA factorisation); one-agent batches through this kernel keep the knob
-        const int threads = (h->bs > 1 && !h->threads_forced) ? CTA_THREADS : h->threads;
+        // latency regime (at most one CTA per SM): 16 warps per CTA -- a lone CTA is bound by the dependent-issue latency of each
+        // warp (~6 cycles per instruction), so halving the per-warp share of the row passes and the CTA-wide loops pays (one
+        // 64-agent mission at b = 4: 66.9 -> 53.1 ms); with more CTAs than SMs, 8 warps and two CTAs per SM
+        const int joint_threads = (units <= h->sm_count) ? CTA_THREADS_MAX : CTA_THREADS;
+        const int threads = (h->bs > 1 && !h->threads_forced) ? joint_threads : h->threads;
         pdip_kernel<<<(unsigned)units, threads, S.smem_bytes, st>>>(S);
     }
     CU(cudaGetLastError());

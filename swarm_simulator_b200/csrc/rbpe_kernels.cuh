@@ -111,7 +111,7 @@ __host__ __device__ inline size_t scratch_doubles(int N, int M, int bs) {
     }
     size_t rint_ = (size_t)bs * (bs - 1) / 2 * 6 * M;
     size_t kp = kp_of(bs), ninv = (kp + 31) / 32;
-    size_t t = 64 + 36;
+    size_t t = 104 + 36;
     t += 14 * al2(nv) + 2 * al2(nr) + al2(nr > 32 ? nr : 32);
     t += al2((size_t)M * bs * 36) + al2(rint_ * 6);                  // Dcp, Dint
     t += al2((size_t)(M > 1 ? M - 1 : 1) * kp * kp) + al2((size_t)(M > 2 ? M - 2 : 1) * kp * kp);
@@ -172,7 +172,7 @@ __global__ void peer_wait_kernel(const unsigned long long *flags, int world, uns
 #if defined(RBPE_PROFILE) && defined(__CUDACC__)
 __device__ unsigned long long g_prof[16];
 #define PROF_DECL long long prof_t0 = clock64()
-#define PROF(slot) do { if (threadIdx.x == 0) { long long t1_ = clock64(); atomicAdd(&g_prof[slot], (unsigned long long)(t1_ - prof_t0)); prof_t0 = t1_; } } while (0)
+#define PROF(slot) do { if (threadIdx.x == 0) { long long t1_ = clock64(); atomicAdd(&g_prof[slot], (unsigned long long)(t1_ - prof_t0)); prof_t0 = t1_; } __syncwarp(); } while (0)
 #else
 #define PROF_DECL
 #define PROF(slot)
@@ -322,7 +322,7 @@ struct QP {
     double *hi, *si, *zi, *ti;
     double *si_w, *zi_w, *ti_w;  // write side of the (s, z) pair of rows between two batch agents during the fused residual pass
     float *nix, *niy, *niz;
-    double *red;  // 64 doubles
+    double *red;  // 104 doubles: 6 per warp (up to 16 warps), verdict of the factorisation at [100]
     double *QB;   // 36 doubles: Q_base
 };
 
@@ -350,7 +350,7 @@ RBPE_DEV void layout(QP &q, unsigned char *smem, size_t smem_bytes, double *gscr
     a.sm = smem;
     a.sm_left = smem_bytes;
     a.gl = gscratch;
-    q.red = a.take(64);
+    q.red = a.take(104);
     q.QB = a.take(36);
     double **vv[14] = {&q.x, &q.dxa, &q.dx, &q.rdx, &q.ub, &q.lbn, &q.sub, &q.zub, &q.slb, &q.zlb, &q.vA, &q.vB, &q.tub, &q.tlb};
     for (int i = 0; i < 14; i++) *vv[i] = a.take(q.nv);
@@ -677,7 +677,7 @@ RBPE_DEV void build_W(const QP &q) {
     }
 }
 
-// one-agent batches: warp 0 factors out of registers, verdict through q.red[60]; joint batches: CTA-wide DMMA routines
+// one-agent batches: warp 0 factors out of registers, verdict through q.red[100]; joint batches: CTA-wide DMMA routines
 RBPE_NOINLINE bool kkt_factor(const QP &q) {
     PROF_DECL;
     __syncthreads();
@@ -687,12 +687,12 @@ RBPE_NOINLINE bool kkt_factor(const QP &q) {
     if (q.kb == 9) {
         if ((threadIdx.x >> 5) == 0) {
             bool ok = factor_bt9v<0>(q.M - 1, q.Wd, q.Wo, q.dinv);
-            if (threadIdx.x == 0) q.red[60] = ok ? 0.0 : 1.0;
+            if (threadIdx.x == 0) q.red[100] = ok ? 0.0 : 1.0;
         }
         __syncthreads();
-        return q.red[60] == 0.0;
+        return q.red[100] == 0.0;
     }
-    return factor_bt_blk(q.M - 1, q.kp, q.Wd, q.Wo, q.Linv, q.red + 60, q.panel);
+    return factor_bt_blk(q.M - 1, q.kp, q.Wd, q.Wo, q.Linv, q.red + 100, q.panel);
 }
 
 // dxout (nv) = Z (Z'HZ)^-1 Z' r   with r (nv) in x-space; uses q.sg
@@ -1032,9 +1032,9 @@ RBPE_DEV int pdip_solve(const QP &q_in, int max_iter, double tol_gap, double tol
 }
 
 #ifndef RBPE_PDIP_MINB
-#define RBPE_PDIP_MINB 2
+#define RBPE_PDIP_MINB 1
 #endif
-__global__ void __launch_bounds__(CTA_THREADS, RBPE_PDIP_MINB) pdip_kernel(SolveArgs S) {
+__global__ void __launch_bounds__(CTA_THREADS_MAX, RBPE_PDIP_MINB) pdip_kernel(SolveArgs S) {
     RBPE_DYN_SMEM(smem);
     const int N = S.N, M = S.M;
     int c, l_begin, l_end;
@@ -1111,4 +1111,5 @@ __global__ void __launch_bounds__(CTA_THREADS, RBPE_PDIP_MINB) pdip_kernel(Solve
 #include "rbpe_pdip1_v1.cuh"
 #else
 #include "rbpe_pdip1.cuh"
+#include "rbpe_pdip1x.cuh"
 #endif

@@ -465,7 +465,9 @@ RBPE_DEV int w1_solve_qp(const W1 &c, int max_iter, double tol_gap, double tol_r
     const int lane = threadIdx.x & 31;
     Acc acc;
     double dead_viol;
+    PROF_DECL;
     const int live_rows = w1_setup(c, dead_viol);
+    PROF(0);
     int status = ST_NOT_CONVERGED, it = 0;
     double obj = 0, gap = 0, nrd = 0, nrg = 0, hn = 0;
     int phase = PH_INIT;
@@ -481,6 +483,7 @@ RBPE_DEV int w1_solve_qp(const W1 &c, int max_iter, double tol_gap, double tol_r
 #pragma unroll 1
     while (phase != PH_DONE) {
         w1_pass(c, phase, sa, sb, acc);
+        PROF(1);
         if (phase == PH_RES) {
             if (al != 0.0) {
                 #pragma unroll 1
@@ -500,6 +503,7 @@ RBPE_DEV int w1_solve_qp(const W1 &c, int max_iter, double tol_gap, double tol_r
             { Red5 r = warp_reduce5(o, 0.0, mpx, mr, mc); o = r.s1; mpx = r.mx; mr = r.mx2; mc = r.mx3; }
             obj = o; nrd = mr;
             gap = mu;
+            PROF(2);
             if (!(mu == mu) || !(nrd == nrd)) { status = ST_NOT_CONVERGED; break; }
             {   // acceptance rule of pdip_solve (rbpe_kernels.cuh): strict test, else the round-off floor of the dual residual
                 const bool gap_ok = gap <= tol_gap * fmax(1.0, fabs(obj)) && nrg <= tol_res * (1 + hn);
@@ -509,11 +513,14 @@ RBPE_DEV int w1_solve_qp(const W1 &c, int max_iter, double tol_gap, double tol_r
             const double cert = (hz < -PRESOLVE_FEAS_TOL * zmax) ? mc / (-hz) : 1e300;
             if (cert < CERT_RATIO) { status = ST_INFEASIBLE; break; }
             w1_build_W(c.segc, c.M, c.Dcp, c.Wd, c.Wo);
+            PROF(3);
             if (!factor_bt9v<1>(c.M - 1, c.Wd, c.Wo, c.dinv)) { status = cert < CERT_RATIO_BREAKDOWN ? ST_INFEASIBLE : ST_NOT_CONVERGED; break; }
+            PROF(4);
             #pragma unroll 1
             for (int v = lane; v < 18 * c.M; v += 32) c.vB[v] = -c.rdx[v] + c.vB[v];
             __syncwarp();
             w1_solve(c, c.vB, c.dxa);
+            PROF(5);
             phase = PH_AFF; sa = 0; sb = 0;
         } else if (phase == PH_AFF) {
             const double aa = (acc.mx > 1.0) ? 1.0 / acc.mx : 1.0;
@@ -526,6 +533,7 @@ RBPE_DEV int w1_solve_qp(const W1 &c, int max_iter, double tol_gap, double tol_r
             for (int v = lane; v < 18 * c.M; v += 32) c.vA[v] = -c.rdx[v] + c.vA[v];
             __syncwarp();
             w1_solve(c, c.vA, c.dx);
+            PROF(5);
             phase = PH_STEP; sa = sigmu; sb = 0;
         } else if (phase == PH_STEP) {
             al = (0.99 < acc.mx) ? 0.99 / acc.mx : 1.0;
@@ -544,6 +552,7 @@ RBPE_DEV int w1_solve_qp(const W1 &c, int max_iter, double tol_gap, double tol_r
             #pragma unroll 1
             for (int v = lane; v < 18 * c.M; v += 32) { c.x[v] += c.dx[v]; c.dx[v] = 0; }
             __syncwarp();
+            PROF(6);
             phase = PH_START;
         } else if (phase == PH_START) {
             const double ap = acc.mx, ad = acc.mx2;
@@ -573,6 +582,7 @@ RBPE_DEV int w1_solve_qp(const W1 &c, int max_iter, double tol_gap, double tol_r
         mrp = fmax(mrp, fabs(sm));
     }
     mrp = warp_reduce5(0.0, 0.0, mrp, 0.0, 0.0).mx;
+    PROF(7);
     if (lane == 0) {
         *obj_out = obj;
         *it_out = it;

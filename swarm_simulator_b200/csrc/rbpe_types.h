@@ -5,7 +5,8 @@
 namespace rbpe {
 
 constexpr int NCP = 6;            // n+1 control points per segment (n = 5 only: rbp_planner.hpp L328, L361)
-constexpr int CTA_THREADS = 256;  // PDIP kernel block size
+constexpr int CTA_THREADS = 256;  // PDIP kernel block size (throughput regime: two CTAs per SM)
+constexpr int CTA_THREADS_MAX = 512;  // ... in the latency regime (at most one CTA per SM): same 128-register budget per thread
 constexpr int MAX_M = 64;
 constexpr int RBPE_MAX_PEERS = 8;   // one node: up to 8 GPUs behind one NVSwitch
 

@@ -50,10 +50,18 @@ extern "C" int emu_solve_many(const rbpe_problem *p, int count, int mode, rbpe_r
     S.smem_bytes = (unsigned)smem_bytes;
     S.panel_bytes = 0;
     // same kernel selection as rbpe_api.cu: one-agent batches -> warp-per-QP kernel, else CTA-per-QP kernel
+    // threads < 0: the several-warps-per-QP latency kernel with -threads threads per QP
+    const bool lat_kernel = (bs == 1) && threads < 0;
     const bool warp_kernel = (bs == 1) && threads != 64;   // threads == 64 forces the CTA kernel (A/B in tests)
     const int wpc = 2;
     auto launch = [&](long units) {
-        if (warp_kernel) {
+        if (lat_kernel) {
+            const int nw = -threads / 32;
+            S.scratch_stride = 0;
+            S.scratch = nullptr;
+            S.smem_bytes = (unsigned)(x1_smem_doubles(N, M, nw) * 8);
+            emu::launch([&] { pdip1x_kernel(S); }, (unsigned)units, nw * 32, S.smem_bytes);
+        } else if (warp_kernel) {
             long grid = (units + wpc - 1) / wpc;
             S.scratch_stride = w1_scratch_doubles(N, M);
             S.smem_bytes = (unsigned)(wpc * w1_smem_doubles(M) * 8);

@@ -25,6 +25,34 @@ def test_emulated_kernels_match_oracle(N, M, rho, seq, bs, smem):
     assert np.abs(r.coef[0] - ro["coef"]).max() < 1e-9
 
 
+@pytest.mark.parametrize("N,M,rho,threads,mode", [
+    (5, 4, 0.2, 256, 0),      # pdip1_kernel: one warp per QP, Gauss-Seidel chain
+    (5, 4, 0.2, -128, 0),     # pdip1x_kernel (latency kernel): 4 warps per QP
+    (12, 5, 0.1, -256, 0),    # 8 warps per QP: 17 rows per control point dealt to 8 warps
+    (7, 6, 0.1, -96, 0),      # 36 control points: two lane slots; 3 warps per QP
+    (6, 3, 0.0, -256, 1),     # Jacobi sweeps: one CTA per (mission, agent)
+])
+def test_emulated_one_agent_kernels_match_oracle(N, M, rho, threads, mode):
+    """One-agent batches (plan/batch_size = 1): the warp-per-QP kernel and the several-warps-per-QP latency kernel
+    (rbpe_pdip1.cuh, rbpe_pdip1x.cuh) against the oracle -- same iteration counts, control points to rounding."""
+    m = synth.synth_mission(N, M, rho, 78)
+    prob = E.PackedProblem(synth.pack([m]), sequential=True, batch_size=1)
+    r = emu_util.emu_solve_many(prob, mode=mode, threads=threads)
+    op = oracle_util.oracle_problem(m, sequential=True, batch_size=1)
+    if mode == 1:   # every QP of the sweep against the table frozen before the sweep
+        dummy = op.dummy()
+        for l in range(N):
+            x = op.populate(dummy, l).solve()
+            assert x["status"] == 0 and x["iters"] == r.qp_iters[0][l]
+            assert np.abs(r.ctrl[0][l] - x["x"].reshape(3, 6 * M)).max() < 1e-9
+        return
+    ro = op.update()
+    assert r.rc == 0 and ro["status"] == 0
+    assert np.array_equal(r.qp_iters[0], ro["batch_iters"][:r.qp_iters.shape[1]])
+    assert np.abs(r.ctrl[0] - ro["ctrl"]).max() < 1e-9
+    assert np.abs(r.coef[0] - ro["coef"]).max() < 1e-9
+
+
 @pytest.mark.parametrize("kb,nblk,threads", [(18, 3, 64), (36, 2, 64), (45, 3, 96), (72, 2, 128), (27, 1, 32)])
 def test_emulated_block_tridiagonal_factor_and_solve(kb, nblk, threads):
     """rbpe_blockla.cuh (DMMA tile updates, warp-level 32 x 32 diagonal blocks + inverses, blocked substitution) against

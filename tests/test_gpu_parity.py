@@ -231,7 +231,7 @@ def test_fixture_batch15_matches_cplex_csv(eng, golden):
     assert np.abs(ctrl - co).max() < 1e-7
 
 
-def test_many_missions_in_one_call(eng):
+def test_many_missions_in_one_call(eng, monkeypatch):
     """A batch of independent missions in one call equals the same missions solved one by one (no cross-talk)."""
     ms = [synth.synth_mission(8, 5, 0.2, 600 + i) for i in range(5)]
     prob = E.PackedProblem(synth.pack(ms * 60), sequential=True, batch_size=1)      # 300 CTAs: more than one wave
@@ -239,8 +239,91 @@ def test_many_missions_in_one_call(eng):
     assert r.rc == E.OK
     for c in range(5, 300):
         assert np.array_equal(r.ctrl[c], r.ctrl[c % 5])                             # deterministic, bit for bit
+    # a single mission goes through the several-warps-per-QP latency kernel (rbpe_pdip1x.cuh): same algorithm and iterates,
+    # rows summed in a different order -> equal to rounding; with that kernel switched off, bit for bit
     single = eng.solve_many(E.PackedProblem(synth.pack(ms[:1]), sequential=True, batch_size=1))
-    assert np.array_equal(single.ctrl[0], r.ctrl[0])
+    assert np.array_equal(single.qp_iters[0], r.qp_iters[0])
+    assert np.abs(single.ctrl[0] - r.ctrl[0]).max() < 1e-10
+    monkeypatch.setenv("RBPE_LAT", "0")
+    e2 = E.Engine(device=0)
+    try:
+        r2 = e2.solve_many(prob)
+        single = e2.solve_many(E.PackedProblem(synth.pack(ms[:1]), sequential=True, batch_size=1))
+    finally:
+        e2.close()
+    assert np.array_equal(single.ctrl[0], r2.ctrl[0])
+    assert np.abs(r2.ctrl - r.ctrl).max() < 1e-10
+
+
+@pytest.mark.parametrize("mode", [E.MODE_GAUSS_SEIDEL, E.MODE_JACOBI])
+@pytest.mark.parametrize("count,warps", [(1, 8), (3, 4), (2, 3)])
+def test_latency_kernel_equals_warp_kernel_and_oracle(monkeypatch, mode, count, warps):
+    """One-agent batches, a handful of missions: pdip1x_kernel (several warps per QP, rows in shared memory) against
+    pdip1_kernel (RBPE_LAT=0) and, in Gauss-Seidel mode, the oracle: same statuses and iteration counts, control points to
+    rounding.  64-agent missions of the bench pack (BASELINE configs[2] shape) and a 36-control-point case (two lane slots)."""
+    import os
+    pack = synth.load_pack(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "missions_cfg3.npz"), select=range(count))
+    cases = [pack, [synth.synth_mission(7, 6, 0.1, 900 + i) for i in range(count)]]
+    for ms in cases:
+        prob = E.PackedProblem(synth.pack(ms), sequential=True, batch_size=1)
+        out = {}
+        for lat in ("1", "0"):
+            monkeypatch.setenv("RBPE_LAT", lat)
+            monkeypatch.setenv("RBPE_LAT_WARPS", str(warps))
+            e = E.Engine(device=0)
+            try:
+                out[lat] = e.solve_many(prob, mode=mode)
+            finally:
+                e.close()
+        a, b = out["1"], out["0"]
+        assert a.rc == b.rc == E.OK
+        assert np.array_equal(a.qp_status, b.qp_status) and np.array_equal(a.qp_iters, b.qp_iters)
+        assert np.abs(a.ctrl - b.ctrl).max() < 1e-9
+        assert np.abs(a.coef - b.coef).max() < 1e-9 * max(1.0, np.abs(b.coef).max())
+        if mode == E.MODE_GAUSS_SEIDEL:
+            ro = oracle_util.oracle_problem(ms[0], sequential=True, batch_size=1).update()
+            assert np.array_equal(a.qp_iters[0][:a.nrec], ro["batch_iters"][:a.nrec])
+            assert np.abs(a.ctrl[0] - ro["ctrl"]).max() < CTRL_TOL
+
+
+def test_latency_kernel_reports_infeasible_like_the_warp_kernel(monkeypatch):
+    """Inflated radii make some QPs infeasible: the latency kernel returns the same per-QP statuses as pdip1_kernel."""
+    ms = []
+    for i in range(4):
+        m = synth.synth_mission(8, 5, 0.2, 950 + i)
+        m = dict(m); m["radius"] = m["radius"] * (2.5 + i)
+        ms.append(m)
+    prob = E.PackedProblem(synth.pack(ms), sequential=True, batch_size=1)
+    out = {}
+    for lat in ("1", "0"):
+        monkeypatch.setenv("RBPE_LAT", lat)
+        e = E.Engine(device=0)
+        try:
+            out[lat] = e.solve_many(prob)
+        finally:
+            e.close()
+    assert np.array_equal(out["1"].status, out["0"].status)
+    assert np.array_equal(out["1"].qp_status, out["0"].qp_status)
+    assert (out["1"].status != 0).any()
+
+
+def test_joint_batches_with_16_warps_equal_8_warps(monkeypatch):
+    """Latency regime of the joint-batch kernel (at most one CTA per SM): 512 threads per CTA.  Same results as the 256-thread
+    launch to rounding (CTA-wide reductions add warp partials in warp order), same iteration counts."""
+    ms = [synth.synth_mission(16, 5, 0.2, 970 + i) for i in range(2)]
+    prob = E.PackedProblem(synth.pack(ms), sequential=True, batch_size=4)
+    out = {}
+    for th in ("512", "256"):
+        monkeypatch.setenv("RBPE_THREADS", th)
+        e = E.Engine(device=0)
+        try:
+            out[th] = e.solve_many(prob)
+        finally:
+            e.close()
+    a, b = out["512"], out["256"]
+    assert a.rc == b.rc == E.OK
+    assert np.array_equal(a.qp_iters, b.qp_iters)
+    assert np.abs(a.ctrl - b.ctrl).max() < 1e-9
 
 
 def test_pipelined_call_equals_plain_call(monkeypatch):
