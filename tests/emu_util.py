@@ -14,6 +14,7 @@ _SRCS = [os.path.join(_EMU_DIR, "emu_driver.cpp"), os.path.join(_EMU_DIR, "cuda_
          os.path.join(_HERE, "..", "swarm_simulator_b200", "csrc", "rbpe_kernels.cuh"),
          os.path.join(_HERE, "..", "swarm_simulator_b200", "csrc", "rbpe_blockla.cuh"),
          os.path.join(_HERE, "..", "swarm_simulator_b200", "csrc", "rbpe_pdip1.cuh"),
+         os.path.join(_HERE, "..", "swarm_simulator_b200", "csrc", "rbpe_pdip1x.cuh"),
          os.path.join(_HERE, "..", "swarm_simulator_b200", "csrc", "rbpe_types.h")]
 
 
