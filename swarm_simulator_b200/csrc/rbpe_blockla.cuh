@@ -125,6 +125,15 @@ RBPE_DEV void strip_mma(double (&acc)[4][2], const double *A0, const double *B0,
     }
 }
 
+// Static shared memory of the 32 x 32 diagonal-block routines (chol32_warp: Ls, chol32_cta: As | Rs | invs, chol32_cta_reg:
+// colb | rowb | pivs).  One pool for all three -- a call uses exactly one of them -- instead of one array per routine:
+// 17 KB instead of 34 KB of static shared memory, which the latency regime hands to the dynamic arena.
+constexpr int BLA_POOL = 2 * 32 * 33 + 32;
+RBPE_DEV double *bla_pool() {
+    RBPE_STATIC_SMEM(double, pool, BLA_POOL);
+    return pool;
+}
+
 // One warp: Cholesky of the wJ x wJ (wJ <= 32) diagonal block at Db (leading dimension ld, lower triangle) and its
 // inverse X (32 x 32, row-major; identity beyond wJ).  Compact rolled code (the kernel is instruction-fetch bound):
 // lane i owns row i of the trailing matrix in a register window that rotates by one column per step; the columns of L
@@ -135,7 +144,8 @@ RBPE_DEV void strip_mma(double (&acc)[4][2], const double *A0, const double *B0,
 // 4 % slower in the same-box A/B: four unrolled bodies instead of one.)
 // Returns false on a non-positive pivot.
 RBPE_NOINLINE bool chol32_warp(double *Db, int ld, int wJ, double *X) {
-    RBPE_STATIC_SMEM(double, Ls, 64 * 32 + 32);
+    static_assert(64 * 32 + 32 <= BLA_POOL, "pool");
+    double *Ls = bla_pool();
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     bool ok = true;
@@ -214,9 +224,7 @@ RBPE_NOINLINE bool chol32_warp(double *Db, int ld, int wJ, double *X) {
 // leading dimension of 33 (column reads are conflict free).  All threads of the CTA must call; returns false on a
 // non-positive pivot.
 RBPE_NOINLINE bool chol32_cta(double *Db, int ld, int wJ, double *X) {
-    RBPE_STATIC_SMEM(double, As, 32 * 33);
-    RBPE_STATIC_SMEM(double, Rs, 32 * 33);
-    RBPE_STATIC_SMEM(double, invs, 32);
+    double *As = bla_pool(), *Rs = As + 32 * 33, *invs = Rs + 32 * 33;
     const int tid = threadIdx.x, nt = blockDim.x, c = tid & 31, w0 = tid >> 5, nw = nt >> 5;
     bool ok = true;
     for (int r = w0; r < 32; r += nw) {
@@ -245,6 +253,88 @@ RBPE_NOINLINE bool chol32_cta(double *Db, int ld, int wJ, double *X) {
         if (r < wJ) {
             if (c <= r) Db[(size_t)r * ld + c] = As[r * 33 + c] * invs[c];
             X[r * BLA_W + c] = (c <= r) ? Rs[r * 33 + c] * invs[r] : 0.0;
+        } else {
+            X[r * BLA_W + c] = (r == c) ? 1.0 : 0.0;
+        }
+    }
+    __syncthreads();
+    return ok;
+}
+
+// Register-resident version of chol32_cta for CTAs of >= 8 warps (the joint-batch kernel's normal launch), organised for
+// the LATENCY of the 32-step pivot chain -- a lone CTA runs every warp at ~6 cycles per instruction (dependent issue), so
+// what counts is the number of instructions between two barriers:
+//   * thread (warp w, lane c) keeps its <= 4 elements A[w + nw i][c] of the trailing matrix and of the right-hand side of
+//     L X = I in registers; a column step publishes column j of A and row j of the right-hand side (64 doubles, double
+//     buffered: ONE barrier per column), every thread reads the pivot, takes its reciprocal (MUFU.RCP64H + two Newton
+//     steps) and updates its elements with two FMAs each;
+//   * square-root free inside the chain (A[r][c] -= A[r][j] A[c][j] / pivot); the factors 1 / sqrt(pivot) are applied when
+//     the results are written (one rsqrt per thread, off the chain).
+// About 40 instructions per thread and column instead of ~250 (chol32_cta re-reads and re-writes shared memory and takes a
+// square root per column): the diagonal blocks of one b = 4 factorisation went from 59 k to XX k cycles per knot.
+// Same contract as chol32_cta; results agree with it to rounding (not bit for bit).
+RBPE_DEV double bla_rcp(double a) {  // 1/a to double rounding: hardware seed + two Newton steps (no FP64 division sequence)
+#ifdef RBPE_EMU
+    double r = (double)(1.0f / (float)a);
+#else
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+#endif
+    double e = fma(-a, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-a, r, 1.0);
+    return fma(r, e, r);
+}
+RBPE_NOINLINE bool chol32_cta_reg(double *Db, int ld, int wJ, double *X) {
+    double *colb = bla_pool(), *rowb = colb + 64, *pivs = rowb + 64;
+    const int tid = threadIdx.x, nt = blockDim.x, c = tid & 31, w0 = tid >> 5, nw = nt >> 5;
+    bool ok = true;
+    double a[4], x[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int r = w0 + nw * i;
+        a[i] = (r < wJ && c <= r) ? Db[(size_t)r * ld + c] : ((r == c) ? 1.0 : 0.0);
+        x[i] = (r == c) ? 1.0 : 0.0;
+    }
+    // publish column 0 / row 0
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int r = w0 + nw * i;
+        if (c == 0 && r < 32) colb[r] = a[i];
+        if (r == 0) rowb[c] = x[i];
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int j = 0; j < wJ; j++) {
+        const double *cb = colb + (j & 1) * 32, *rb = rowb + (j & 1) * 32;
+        double piv = cb[j];
+        if (!(piv > 0)) { ok = false; piv = 1.0; }
+        if (tid == 0) pivs[j] = piv;
+        const double ipiv = bla_rcp(piv);
+        const double ac = cb[c], xr = rb[c];          // A[c][j] (c > j), right-hand side row j
+        double *cn = colb + ((j + 1) & 1) * 32, *rn = rowb + ((j + 1) & 1) * 32;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int r = w0 + nw * i;
+            if (r > j && r < 32) {
+                const double f = cb[r] * ipiv;        // A[r][j] / pivot
+                if (c > j) a[i] = fma(-f, ac, a[i]);
+                else x[i] = fma(-f, xr, x[i]);
+                if (c == j + 1) cn[r] = a[i];         // next column, as soon as it is final
+                if (r == j + 1) rn[c] = x[i];         // next row of the right-hand side
+            }
+        }
+        __syncthreads();
+    }
+    // L[r][c] = A_c[r][c] / sqrt(pivot_c) (column c as it stood at step c), X[r][c] = rhs_r[r][c] / sqrt(pivot_r)
+    const double ic = (c < wJ) ? rsqrt(pivs[c]) : 1.0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int r = w0 + nw * i;
+        if (r >= 32) continue;
+        if (r < wJ) {
+            if (c <= r) Db[(size_t)r * ld + c] = a[i] * ic;
+            X[r * BLA_W + c] = (c <= r) ? x[i] * rsqrt(pivs[r]) : 0.0;
         } else {
             X[r * BLA_W + c] = (r == c) ? 1.0 : 0.0;
         }
@@ -320,7 +410,7 @@ RBPE_NOINLINE bool chol_tall(int kp, double *D, double *O, const double *Pm, dou
                 PROF(6);
                 // ---- 2. diagonal block: factor + invert ----
                 if (cta_diag) {
-                    const bool ok = chol32_cta(D + (size_t)j0 * kp + j0, kp, wJ, X);
+                    const bool ok = (nw >= 8) ? chol32_cta_reg(D + (size_t)j0 * kp + j0, kp, wJ, X) : chol32_cta(D + (size_t)j0 * kp + j0, kp, wJ, X);
                     if (!ok && tid == 0) *flag = 1.0;
                 } else if (warp == 0) {
                     const bool ok = chol32_warp(D + (size_t)j0 * kp + j0, kp, wJ, X);

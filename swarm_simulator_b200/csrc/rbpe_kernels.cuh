@@ -352,8 +352,15 @@ RBPE_DEV void layout(QP &q, unsigned char *smem, size_t smem_bytes, double *gscr
     a.gl = gscratch;
     q.red = a.take(104);
     q.QB = a.take(36);
+    // Throughput regime (a 48 KB arena, two CTAs per SM): the vectors of the iteration and the state of the box rows first.
+    // Latency regime (the whole SM's shared memory for one CTA, rbpe_api.cu smem_for): the reduced Hessian, its factor and the
+    // inverted diagonal blocks come before the box-row state -- for b = 4, N = 64 they then all fit (the substitutions and the
+    // L21 products read them many times per iteration; from L2 every read is a ~250-cycle round trip for a lone CTA).
+    const bool hot_first = smem_bytes > 128 * 1024;
     double **vv[14] = {&q.x, &q.dxa, &q.dx, &q.rdx, &q.ub, &q.lbn, &q.sub, &q.zub, &q.slb, &q.zlb, &q.vA, &q.vB, &q.tub, &q.tlb};
-    for (int i = 0; i < 14; i++) *vv[i] = a.take(q.nv);
+    const bool box_state[14] = {false, false, false, false, true, true, true, true, true, true, false, false, true, true};
+    for (int i = 0; i < 14; i++)
+        if (!hot_first || !box_state[i]) *vv[i] = a.take(q.nv);
     q.sg = a.take(q.nr);
     q.sg2 = a.take(q.nr);
     q.dinv = a.take(q.nr > 32 ? q.nr : 32);
@@ -367,6 +374,9 @@ RBPE_DEV void layout(QP &q, unsigned char *smem, size_t smem_bytes, double *gscr
         q.wk = a.take((size_t)(q.M > 1 ? q.M - 1 : 1) * q.kp);
         q.yk = a.take((size_t)q.kp + 32);
     }
+    if (hot_first)
+        for (int i = 0; i < 14; i++)
+            if (box_state[i]) *vv[i] = a.take(q.nv);
     q.cnt_ext = (int *)a.take(((size_t)q.M * q.nb * 6 + 1) / 2);
     q.he = a.take(q.nrext); q.se = a.take(q.nrext); q.ze = a.take(q.nrext); q.te = a.take(q.nrext);
     q.nex = (float *)a.take(((size_t)q.nrext + 1) / 2);

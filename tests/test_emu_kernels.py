@@ -9,15 +9,17 @@ import oracle_util
 from swarm_simulator_b200 import engine as E, synth
 
 
-@pytest.mark.parametrize("N,M,rho,seq,bs,smem", [
-    (4, 3, 0.0, False, 4, 48 * 1024),   # BASELINE configs[0]: 4 agents, empty map, 3 segments, one joint batch
-    (5, 4, 0.2, True, 2, 0),            # sequential, ragged last batch, everything in "global" scratch
-    (38, 3, 0.1, True, 4, 48 * 1024),   # 34 frozen agents per batch: the compaction of kept rows crosses a 32-row group
+@pytest.mark.parametrize("N,M,rho,seq,bs,smem,threads", [
+    (4, 3, 0.0, False, 4, 48 * 1024, 64),   # BASELINE configs[0]: 4 agents, empty map, 3 segments, one joint batch
+    (5, 4, 0.2, True, 2, 0, 64),            # sequential, ragged last batch, everything in "global" scratch
+    (38, 3, 0.1, True, 4, 48 * 1024, 64),   # 34 frozen agents per batch: the compaction of kept rows crosses a 32-row group
+    (8, 4, 0.2, True, 4, 48 * 1024, 256),   # the launch default b = 4 with the full CTA (8 warps: register-resident diagonal blocks)
+    (8, 3, 0.1, True, 4, 96 * 1024, 512),   # latency regime: 16 warps per CTA
 ])
-def test_emulated_kernels_match_oracle(N, M, rho, seq, bs, smem):
+def test_emulated_kernels_match_oracle(N, M, rho, seq, bs, smem, threads):
     m = synth.synth_mission(N, M, rho, 77)
     prob = E.PackedProblem(synth.pack([m]), sequential=seq, batch_size=bs)
-    r = emu_util.emu_solve_many(prob, smem_bytes=smem, threads=64)
+    r = emu_util.emu_solve_many(prob, smem_bytes=smem, threads=threads)
     ro = oracle_util.oracle_problem(m, sequential=seq, batch_size=bs).update()
     assert r.rc == 0 and ro["status"] == 0
     assert np.array_equal(r.qp_iters[0], ro["batch_iters"][:r.qp_iters.shape[1]])
@@ -53,7 +55,8 @@ def test_emulated_one_agent_kernels_match_oracle(N, M, rho, threads, mode):
     assert np.abs(r.coef[0] - ro["coef"]).max() < 1e-9
 
 
-@pytest.mark.parametrize("kb,nblk,threads", [(18, 3, 64), (36, 2, 64), (45, 3, 96), (72, 2, 128), (27, 1, 32)])
+@pytest.mark.parametrize("kb,nblk,threads", [(18, 3, 64), (36, 2, 64), (45, 3, 96), (72, 2, 128), (27, 1, 32),
+                                             (36, 4, 256), (18, 3, 512), (63, 2, 384)])   # >= 8 warps: register-resident diagonal blocks
 def test_emulated_block_tridiagonal_factor_and_solve(kb, nblk, threads):
     """rbpe_blockla.cuh (DMMA tile updates, warp-level 32 x 32 diagonal blocks + inverses, blocked substitution) against
     numpy on a random SPD block tridiagonal system, for block orders that are / are not multiples of 8 and of 32."""
