@@ -285,53 +285,60 @@ RBPE_DEV double bla_rcp(double a) {  // 1/a to double rounding: hardware seed + 
     e = fma(-a, r, 1.0);
     return fma(r, e, r);
 }
+template <int RPT>   // rows per thread: 4 for 8..15 warps, 2 for 16 warps
 RBPE_NOINLINE bool chol32_cta_reg(double *Db, int ld, int wJ, double *X) {
     double *colb = bla_pool(), *rowb = colb + 64, *pivs = rowb + 64;
     const int tid = threadIdx.x, nt = blockDim.x, c = tid & 31, w0 = tid >> 5, nw = nt >> 5;
     bool ok = true;
-    double a[4], x[4];
+    double a[RPT], x[RPT];
+    int rr[RPT];            // the thread's rows; -1 = none (a row index beyond 31)
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
+    for (int i = 0; i < RPT; i++) {
         const int r = w0 + nw * i;
+        rr[i] = r < 32 ? r : -1;
         a[i] = (r < wJ && c <= r) ? Db[(size_t)r * ld + c] : ((r == c) ? 1.0 : 0.0);
         x[i] = (r == c) ? 1.0 : 0.0;
     }
     // publish column 0 / row 0
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int r = w0 + nw * i;
-        if (c == 0 && r < 32) colb[r] = a[i];
-        if (r == 0) rowb[c] = x[i];
+    for (int i = 0; i < RPT; i++) {
+        if (c == 0 && rr[i] >= 0) colb[rr[i]] = a[i];
+        if (rr[i] == 0) rowb[c] = x[i];
     }
     __syncthreads();
+    // The loop below is written for a small instruction count (every instruction of a lone CTA costs ~6 cycles): no branch per
+    // row -- a row that is not updated in this step gets the multiplier 0 -- and the column / row selection folded into two
+    // values per step (ac, xr), not two selects per element.
+    double *cb = colb, *cn = colb + 32, *rb = rowb, *rn = rowb + 32;
 #pragma unroll 1
     for (int j = 0; j < wJ; j++) {
-        const double *cb = colb + (j & 1) * 32, *rb = rowb + (j & 1) * 32;
         double piv = cb[j];
         if (!(piv > 0)) { ok = false; piv = 1.0; }
         if (tid == 0) pivs[j] = piv;
         const double ipiv = bla_rcp(piv);
-        const double ac = cb[c], xr = rb[c];          // A[c][j] (c > j), right-hand side row j
-        double *cn = colb + ((j + 1) & 1) * 32, *rn = rowb + ((j + 1) & 1) * 32;
+        const bool right = c > j;
+        const double ac = right ? cb[c] : 0.0;       // A[c][j] for the columns still being eliminated
+        const double xr = right ? 0.0 : rb[c];       // row j of the right-hand side (columns <= j)
+        const bool nextc = c == j + 1;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int r = w0 + nw * i;
-            if (r > j && r < 32) {
-                const double f = cb[r] * ipiv;        // A[r][j] / pivot
-                if (c > j) a[i] = fma(-f, ac, a[i]);
-                else x[i] = fma(-f, xr, x[i]);
-                if (c == j + 1) cn[r] = a[i];         // next column, as soon as it is final
-                if (r == j + 1) rn[c] = x[i];         // next row of the right-hand side
-            }
+        for (int i = 0; i < RPT; i++) {
+            const int r = rr[i];
+            const bool below = r > j;
+            const double f = below ? cb[r & 31] * ipiv : 0.0;   // A[r][j] / pivot
+            a[i] = fma(-f, ac, a[i]);
+            x[i] = fma(-f, xr, x[i]);
+            if (nextc && below) cn[r] = a[i];        // next column, as soon as it is final
+            if (r == j + 1) rn[c] = x[i];            // next row of the right-hand side
         }
+        { double *t = cb; cb = cn; cn = t; t = rb; rb = rn; rn = t; }
         __syncthreads();
     }
     // L[r][c] = A_c[r][c] / sqrt(pivot_c) (column c as it stood at step c), X[r][c] = rhs_r[r][c] / sqrt(pivot_r)
     const double ic = (c < wJ) ? rsqrt(pivs[c]) : 1.0;
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int r = w0 + nw * i;
-        if (r >= 32) continue;
+    for (int i = 0; i < RPT; i++) {
+        const int r = rr[i];
+        if (r < 0) continue;
         if (r < wJ) {
             if (c <= r) Db[(size_t)r * ld + c] = a[i] * ic;
             X[r * BLA_W + c] = (c <= r) ? x[i] * rsqrt(pivs[r]) : 0.0;
@@ -410,8 +417,10 @@ RBPE_NOINLINE bool chol_tall(int kp, double *D, double *O, const double *Pm, dou
                 PROF(6);
                 // ---- 2. diagonal block: factor + invert ----
                 if (cta_diag) {
-                    const bool ok = (nw >= 8) ? chol32_cta_reg(D + (size_t)j0 * kp + j0, kp, wJ, X) : chol32_cta(D + (size_t)j0 * kp + j0, kp, wJ, X);
+                    double *Dj = D + (size_t)j0 * kp + j0;
+                    const bool ok = (nw >= 16) ? chol32_cta_reg<2>(Dj, kp, wJ, X) : ((nw >= 8) ? chol32_cta_reg<4>(Dj, kp, wJ, X) : chol32_cta(Dj, kp, wJ, X));
                     if (!ok && tid == 0) *flag = 1.0;
+                    PROF(9);
                 } else if (warp == 0) {
                     const bool ok = chol32_warp(D + (size_t)j0 * kp + j0, kp, wJ, X);
                     if (!ok && lane == 0) *flag = 1.0;
