@@ -271,7 +271,8 @@ RBPE_NOINLINE bool chol32_cta(double *Db, int ld, int wJ, double *X) {
 //   * square-root free inside the chain (A[r][c] -= A[r][j] A[c][j] / pivot); the factors 1 / sqrt(pivot) are applied when
 //     the results are written (one rsqrt per thread, off the chain).
 // About 40 instructions per thread and column instead of ~250 (chol32_cta re-reads and re-writes shared memory and takes a
-// square root per column): the diagonal blocks of one b = 4 factorisation went from 59 k to XX k cycles per knot.
+// square root per column): the diagonal blocks of one b = 4 factorisation went from 59 k to 29 k cycles per knot (clock64
+// phase timers, -DRBPE_PROFILE), the column loop is 68 SASS instructions at 16 warps.
 // Same contract as chol32_cta; results agree with it to rounding (not bit for bit).
 RBPE_DEV double bla_rcp(double a) {  // 1/a to double rounding: hardware seed + two Newton steps (no FP64 division sequence)
 #ifdef RBPE_EMU
@@ -333,6 +334,8 @@ RBPE_NOINLINE bool chol32_cta_reg(double *Db, int ld, int wJ, double *X) {
         { double *t = cb; cb = cn; cn = t; t = rb; rb = rn; rn = t; }
         __syncthreads();
     }
+    // (Letting the warps whose rows are all finished skip the column step was tried: no gain -- the step is bound by its
+    // dependent chain pivot -> reciprocal -> multiplier -> update -> publish, not by issue slots.)
     // L[r][c] = A_c[r][c] / sqrt(pivot_c) (column c as it stood at step c), X[r][c] = rhs_r[r][c] / sqrt(pivot_r)
     const double ic = (c < wJ) ? rsqrt(pivs[c]) : 1.0;
 #pragma unroll
@@ -611,6 +614,95 @@ RBPE_NOINLINE void solve_bt_blk(int nblk, int kb, int kp, const double *Dall, co
                 wt[r] -= s0 + s1;
             }
             __syncthreads();
+        }
+    }
+    for (int i = tid; i < nblk * kb; i += nt) {
+        int t = i / kb, r = i % kb;
+        g[i] = w[(size_t)t * kp + r];
+    }
+    __syncthreads();
+}
+
+// ---- small joint batches (kp <= 64: b <= 7, the launch default b = 4) ------------------------------------------------
+// Same substitutions as solve_bt_blk (products with the inverted 32 x 32 diagonal blocks, same operands), organised for
+// latency: every step is ONE matrix-vector product spread over the whole CTA -- eight threads per output, each adding
+// every eighth term, three shuffle rounds -- followed by one barrier; results go to a second vector instead of being
+// copied back, so a knot costs 2 (kp <= 32) or 4 steps per direction.  A lone CTA pays ~6 cycles per instruction and warp:
+// the general routine above (warp-per-row products with 5-round butterflies, 32-term serial loops, a copy and two
+// barriers per block) took 48 k cycles per solve at b = 4 on a lone CTA, this one 32 k; with many CTAs in flight the
+// smaller instruction count gives +12..15 % throughput at b = 4.
+// out[o] = (base ? base[o] : 0) - / + sum_k A[o * so + k * sk] v[k],  o < nout, k < nin <= 64.  No barrier inside.
+RBPE_DEV void mv8(int nout, int nin, const double *A, int so, int sk, const double *v, const double *base, double *out, bool neg) {
+    const int tid = threadIdx.x, nt = blockDim.x, part = tid & 7;
+    const int nmine = (nin - part + 7) >> 3;          // terms of this thread: k = part, part + 8, ...
+    const int step = 8 * sk;
+    for (int o0 = 0; o0 < nout; o0 += nt >> 3) {   // (uniform trip count: whole warps stay in the shuffles)
+        const int o = o0 + (tid >> 3);
+        double s0 = 0, s1 = 0;
+        if (o < nout) {
+            const double *a = A + (o * so + part * sk), *vp = v + part;   // 32-bit index arithmetic, running pointers
+            int i = 0;
+#pragma unroll 1
+            for (; i + 2 <= nmine; i += 2, a += 2 * step, vp += 16) { s0 = fma(a[0], vp[0], s0); s1 = fma(a[step], vp[8], s1); }
+            if (i < nmine) s0 = fma(a[0], vp[0], s0);
+        }
+        double sm = s0 + s1;
+        sm += __shfl_xor_sync(0xffffffffu, sm, 1);
+        sm += __shfl_xor_sync(0xffffffffu, sm, 2);
+        sm += __shfl_xor_sync(0xffffffffu, sm, 4);
+        if (o < nout && part == 0) {
+            const double b = base ? base[o] : 0.0;
+            out[o] = neg ? b - sm : b + sm;
+        }
+    }
+}
+// g (nblk blocks of kb, stride kb) <- (L L')^-1 g.  w, u: nblk*kp work doubles each.  All threads of the CTA must call.
+RBPE_NOINLINE void solve_bt_small(int nblk, int kb, int kp, const double *Dall, const double *Oall, const double *Linv, double *g,
+                                  double *w, double *u) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const size_t kk = (size_t)kp * kp, li = (size_t)bla_ninv(kp) * BLA_W * BLA_W;
+    for (int i = tid; i < nblk * kp; i += nt) {
+        int t = i / kp, r = i % kp;
+        w[i] = (r < kb) ? g[t * kb + r] : 0.0;
+    }
+    __syncthreads();
+    // ---- forward: L u = g (right-hand side in w, solution in u) ----
+    for (int t = 0; t < nblk; t++) {
+        const double *L = Dall + t * kk, *Li = Linv + t * li;
+        double *wt = w + (size_t)t * kp, *ut = u + (size_t)t * kp;
+        if (t > 0) {   // w_t -= L_{t,t-1} u_{t-1}
+            mv8(kp, kp, Oall + (t - 1) * kk, kp, 1, u + (size_t)(t - 1) * kp, wt, wt, true);
+            __syncthreads();
+        }
+        for (int j0 = 0; j0 < kp; j0 += BLA_W) {
+            const int wJ = (kp - j0 < BLA_W) ? kp - j0 : BLA_W;
+            const double *X = Li + (size_t)(j0 / BLA_W) * BLA_W * BLA_W;
+            mv8(wJ, wJ, X, BLA_W, 1, wt + j0, nullptr, ut + j0, false);          // u_J = Linv_J w_J (zeros above the diagonal)
+            __syncthreads();
+            const int below = kp - j0 - wJ;
+            if (below > 0) {                                                     // w_r -= L[r][J] u_J for the rows below
+                mv8(below, wJ, L + (size_t)(j0 + wJ) * kp + j0, kp, 1, ut + j0, wt + j0 + wJ, wt + j0 + wJ, true);
+                __syncthreads();
+            }
+        }
+    }
+    // ---- backward: L' x = u (right-hand side in u, solution in w) ----
+    for (int t = nblk - 1; t >= 0; t--) {
+        const double *L = Dall + t * kk, *Li = Linv + t * li;
+        double *wt = w + (size_t)t * kp, *ut = u + (size_t)t * kp;
+        if (t < nblk - 1) {   // u_t -= L_{t+1,t}' x_{t+1}
+            mv8(kp, kp, Oall + t * kk, 1, kp, w + (size_t)(t + 1) * kp, ut, ut, true);
+            __syncthreads();
+        }
+        for (int j0 = ((kp - 1) / BLA_W) * BLA_W; j0 >= 0; j0 -= BLA_W) {
+            const int wJ = (kp - j0 < BLA_W) ? kp - j0 : BLA_W;
+            const double *X = Li + (size_t)(j0 / BLA_W) * BLA_W * BLA_W;
+            mv8(wJ, wJ, X, 1, BLA_W, ut + j0, nullptr, wt + j0, false);          // x_J = Linv_J' u_J
+            __syncthreads();
+            if (j0 > 0) {                                                        // u_r -= L[J][r]' x_J for the rows above
+                mv8(j0, wJ, L + (size_t)j0 * kp, 1, kp, wt + j0, ut, ut, true);
+                __syncthreads();
+            }
         }
     }
     for (int i = tid; i < nblk * kb; i += nt) {

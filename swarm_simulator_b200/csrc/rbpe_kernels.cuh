@@ -115,7 +115,7 @@ __host__ __device__ inline size_t scratch_doubles(int N, int M, int bs) {
     t += 14 * al2(nv) + 2 * al2(nr) + al2(nr > 32 ? nr : 32);
     t += al2((size_t)M * bs * 36) + al2(rint_ * 6);                  // Dcp, Dint
     t += al2((size_t)(M > 1 ? M - 1 : 1) * kp * kp) + al2((size_t)(M > 2 ? M - 2 : 1) * kp * kp);
-    if (bs > 1) t += al2((size_t)(M > 1 ? M - 1 : 1) * ninv * 1024) + al2((size_t)(M > 1 ? M - 1 : 1) * kp) + al2(kp + 32);   // Linv, wk, yk
+    if (bs > 1) t += al2((size_t)(M > 1 ? M - 1 : 1) * ninv * 1024) + al2((size_t)(M > 1 ? M - 1 : 1) * kp) + al2((size_t)(M > 1 ? M - 1 : 1) * kp + 32);   // Linv, wk, yk
     t += 4 * al2(rext) + 3 * al2((rext + 1) / 2) + al2(((size_t)M * bs * 6 + 1) / 2);
     t += 7 * al2(rint_) + 3 * al2((rint_ + 1) / 2);
     return t;
@@ -372,7 +372,7 @@ RBPE_DEV void layout(QP &q, unsigned char *smem, size_t smem_bytes, double *gscr
     if (q.nb > 1) {
         q.Linv = a.take((size_t)(q.M > 1 ? q.M - 1 : 1) * bla_ninv(q.kp) * BLA_W * BLA_W);
         q.wk = a.take((size_t)(q.M > 1 ? q.M - 1 : 1) * q.kp);
-        q.yk = a.take((size_t)q.kp + 32);
+        q.yk = a.take((size_t)(q.M > 1 ? q.M - 1 : 1) * q.kp + 32);
     }
     if (hot_first)
         for (int i = 0; i < 14; i++)
@@ -707,17 +707,22 @@ RBPE_NOINLINE bool kkt_factor(const QP &q) {
 
 // dxout (nv) = Z (Z'HZ)^-1 Z' r   with r (nv) in x-space; uses q.sg
 RBPE_NOINLINE void kkt_solve(const QP &q, const double *r, double *dxout) {
+    PROF_DECL;
     __syncthreads();
     Zt_apply(q, r, q.sg);
     __syncthreads();
+    PROF(10);
     if (q.kb == 9) {
         if ((threadIdx.x >> 5) == 0) solve_bt9v<0>(q.M - 1, q.Wd, q.Wo, q.sg, q.dinv);
     } else {
-        solve_bt_blk(q.M - 1, q.kb, q.kp, q.Wd, q.Wo, q.Linv, q.sg, q.wk, q.yk);
+        if (q.kp <= 2 * BLA_W) solve_bt_small(q.M - 1, q.kb, q.kp, q.Wd, q.Wo, q.Linv, q.sg, q.wk, q.yk);
+        else solve_bt_blk(q.M - 1, q.kb, q.kp, q.Wd, q.Wo, q.Linv, q.sg, q.wk, q.yk);
     }
     __syncthreads();
+    PROF(11);
     Z_apply(q, q.sg, dxout);
     __syncthreads();
+    PROF(12);
 }
 
 // Bounds of one axis of a corridor box as the solver sees them.  A box of (numerically) zero width -- an agent flying

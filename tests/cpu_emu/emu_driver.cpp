@@ -125,13 +125,14 @@ extern "C" int rbpe_set_batch(int N, int sequential, int batch_size, int batch_i
 // numpy): Dall [nblk][kp*kp] (lower triangles used), Oall [nblk-1][kp*kp], g [nblk*kb] -> in place: factor, solution.
 extern "C" int emu_block_tridiag(int nblk, int kb, double *Dall, double *Oall, double *g, int threads) {
     const int kp = bla_kp(kb);
-    std::vector<double> Linv((size_t)nblk * bla_ninv(kp) * BLA_W * BLA_W), w((size_t)nblk * kp), y(kp + 32), flag(1);
+    std::vector<double> Linv((size_t)nblk * bla_ninv(kp) * BLA_W * BLA_W), w((size_t)nblk * kp), y((size_t)nblk * kp + 32), flag(1);
     int ok = 1;
     emu::launch([&] {
         bool f = factor_bt_blk(nblk, kp, Dall, Oall, Linv.data(), flag.data());
         if (threadIdx.x == 0) ok = f ? 1 : 0;
         __syncthreads();
-        solve_bt_blk(nblk, kb, kp, Dall, Oall, Linv.data(), g, w.data(), y.data());
+        if (kp <= 2 * BLA_W) solve_bt_small(nblk, kb, kp, Dall, Oall, Linv.data(), g, w.data(), y.data());   // same rule as kkt_solve
+        else solve_bt_blk(nblk, kb, kp, Dall, Oall, Linv.data(), g, w.data(), y.data());
     }, 1, threads, 0);
     return ok;
 }
