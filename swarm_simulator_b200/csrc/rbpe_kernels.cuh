@@ -446,18 +446,20 @@ struct Acc {  // lane-local reductions of a row pass
 // out: cA, cB (coefficients of g in the two G' products), w (weight of g g' in H); s, z, t may be rewritten.
 // One division per row and iteration (t, after the step); 1/s = t z and 1/z = t s everywhere else.  The ratio tests
 // run in max form: step = 1 / max_r(-ds_r / s_r, -dz_r / z_r).
+// max that keeps the accumulator when v is NaN (what fmax does here) without fmax's NaN-handling sequence
+RBPE_DEV double rmax2(double acc, double v) { return (v > acc) ? v : acc; }
 template <int MODE>
 RBPE_DEV void row_eval(double h, double &s, double &z, double &t, double gx, double ga, double gd, double sa, double sb,
                        bool owner, double &cA, double &cB, double &w, Acc &acc) {
     cA = 0; cB = 0; w = 0;
-    if (MODE == P_DEAD) { acc.mx = fmax(acc.mx, gx - h); return; }   // constant row: violation of its right-hand side
+    if (MODE == P_DEAD) { acc.mx = rmax2(acc.mx, gx - h); return; }   // constant row: violation of its right-hand side
     if (MODE == P_INIT) { w = 1.0; cA = h - gx; return; }
     if (MODE == P_START) {  // z = Gx - h, s = -z (least-squares start)
         z = gx - h; s = -z;
-        if (owner) { acc.mx = fmax(acc.mx, -s); acc.mx2 = fmax(acc.mx2, -z); }
+        if (owner) { acc.mx = rmax2(acc.mx, -s); acc.mx2 = rmax2(acc.mx2, -z); }
         return;
     }
-    if (MODE == P_SHIFT) { s += sa; z += sb; t = 1.0 / (s * z); return; }
+    if (MODE == P_SHIFT) { s += sa; z += sb; t = bla_rcp(s * z); return; }
     double rs = t * z;
     if (MODE == P_RES && sb != 0.0) {
         // pending step of the previous iteration (sa = its sigma*mu, sb = its step length), fused into this pass:
@@ -468,7 +470,7 @@ RBPE_DEV void row_eval(double h, double &s, double &z, double &t, double gx, dou
         double ds = -rgo - gd, dz = (-rc - z * ds) * rs;
         s += sb * ds; z += sb * dz;
         gx += sb * gd;
-        t = 1.0 / (s * z);
+        t = bla_rcp(s * z);
         rs = t * z;
     }
     double rg = gx + s - h;
@@ -476,13 +478,13 @@ RBPE_DEV void row_eval(double h, double &s, double &z, double &t, double gx, dou
     if (MODE == P_RES) {
         cA = z;
         cB = -(w * rg - z);
-        if (owner) { acc.s1 += s * z; acc.s2 += h * z; acc.mx = fmax(acc.mx, fabs(rg)); acc.mx2 = fmax(acc.mx2, z); }
+        if (owner) { acc.s1 += s * z; acc.s2 += h * z; acc.mx = rmax2(acc.mx, fabs(rg)); acc.mx2 = rmax2(acc.mx2, z); }
         return;
     }
     double rz = t * s;
     double dsa = -rg - ga, dza = -z - w * dsa;
     if (MODE == P_AFF) {
-        acc.mx = fmax(acc.mx, fmax(-dsa * rs, -dza * rz));
+        acc.mx = rmax2(acc.mx, rmax2(-dsa * rs, -dza * rz));
         // sum (s + a dsa)(z + a dza) = s'z + a * s1 + a^2 * s2 for whatever step a comes out of the ratio test
         if (owner) { acc.s1 += s * dza + z * dsa; acc.s2 += dsa * dza; }
         return;
@@ -490,13 +492,19 @@ RBPE_DEV void row_eval(double h, double &s, double &z, double &t, double gx, dou
     double rc = s * z + dsa * dza - sa;  // sa = sigma * mu
     if (MODE == P_COR) { cA = -(z * rg - rc) * rs; return; }
     double ds = -rg - gd, dz = (-rc - z * ds) * rs;
-    if (MODE == P_STEP) acc.mx = fmax(acc.mx, fmax(-ds * rs, -dz * rz));
+    if (MODE == P_STEP) acc.mx = rmax2(acc.mx, rmax2(-ds * rs, -dz * rz));
 }
 
 // Control points fixed by the start / goal equalities: 0..2 of the first segment, 3..5 of the last one.
 RBPE_DEV bool cp_dead(const QP &q, int m, int i) { return (m == 0 && i < 3) || (m == q.M - 1 && i >= 3); }
 
-// All inequality rows touching control point (m, a, i) of the batch, executed by one warp.
+// All inequality rows touching control point (m, a, i) of the batch, executed by one warp: the kept rows against agents
+// outside the batch (L643-L668), the rows against the other agents of the batch (L669-L680; evaluated from both ends, owned
+// by the lower index) and the six box rows (L626-L635: x <= ub, -x <= -lb) are dealt to the lanes as ONE list, so that the
+// row algebra (row_eval) and the accumulation of G'(.) and sum w g g' exist once per pass instead of four times -- a box
+// row is an ordinary row with a unit normal.  (Round 2: the three kinds used to be three separate sections, each with its
+// own copy of row_eval, executed one after the other by the same warp: 3 x the instructions per control point, and a lone
+// CTA pays ~6 cycles per instruction; ncu r2f: the row passes were 40 % of a single b = 4 mission.)
 template <int MODE>
 RBPE_DEV void cp_task(const QP &q, int m, int a, int i, double sa, double sb, Acc &acc) {
     constexpr bool WR = (MODE == P_START || MODE == P_SHIFT || MODE == P_RES);
@@ -504,80 +512,69 @@ RBPE_DEV void cp_task(const QP &q, int m, int a, int i, double sa, double sb, Ac
     constexpr bool MAT = (MODE == P_INIT || MODE == P_RES);
     const int lane = threadIdx.x & 31;
     const int base = m * q.n, v0 = base + a * 18 + i;
-    double x0 = q.x[v0], x1 = q.x[v0 + 6], x2 = q.x[v0 + 12];
-    double a0 = q.dxa[v0], a1 = q.dxa[v0 + 6], a2 = q.dxa[v0 + 12];
-    double d0 = q.dx[v0], d1 = q.dx[v0 + 6], d2 = q.dx[v0 + 12];
+    const double x0 = q.x[v0], x1 = q.x[v0 + 6], x2 = q.x[v0 + 12];
+    const double a0 = q.dxa[v0], a1 = q.dxa[v0 + 6], a2 = q.dxa[v0 + 12];
+    const double d0 = q.dx[v0], d1 = q.dx[v0 + 6], d2 = q.dx[v0 + 12];
     double vA0 = 0, vA1 = 0, vA2 = 0, vB0 = 0, vB1 = 0, vB2 = 0;
     double Dxx = 0, Dxy = 0, Dxz = 0, Dyy = 0, Dyz = 0, Dzz = 0;
-    // rows against agents outside the batch (L643-L668)
-    {
-        const int task = (a * q.M + m) * 6 + i;
-        const size_t rb = (size_t)task * q.NE;
-        const int cnt = q.cnt_ext[task];     // kept rows only (compacted by setup_rows)
-        for (int e = lane; e < cnt; e += 32) {
-            size_t r = rb + e;
-            double n0 = q.nex[r], n1 = q.ney[r], n2 = q.nez[r];
-            double h = q.he[r], s = q.se[r], z = q.ze[r], t = q.te[r], cA, cB, w;
-            row_eval<MODE>(h, s, z, t, n0 * x0 + n1 * x1 + n2 * x2, n0 * a0 + n1 * a1 + n2 * a2,
-                           n0 * d0 + n1 * d1 + n2 * d2, sa, sb, true, cA, cB, w, acc);
-            if (WR) { q.se[r] = s; q.ze[r] = z; q.te[r] = t; }
-            if (VEC) { vA0 += cA * n0; vA1 += cA * n1; vA2 += cA * n2; vB0 += cB * n0; vB1 += cB * n1; vB2 += cB * n2; }
-            if (MAT) {
-                Dxx += w * n0 * n0; Dxy += w * n0 * n1; Dxz += w * n0 * n2;
-                Dyy += w * n1 * n1; Dyz += w * n1 * n2; Dzz += w * n2 * n2;
-            }
+    const int task = (a * q.M + m) * 6 + i;
+    const size_t rb = (size_t)task * q.NE;
+    const int cnt = q.cnt_ext[task];     // kept rows only (compacted by setup_rows)
+    const int n_int = q.nb - 1, total = cnt + n_int + 6;
+    for (int idx = lane; idx < total; idx += 32) {
+        double n0, n1, n2, h, s, z, t, gx, ga, gd;
+        double *ps, *pz, *pt;            // where the row's (s, z, t) live; written back in the passes that change them
+        bool own = true;
+        size_t rint = 0;                 // 1 + index of a row between two agents of the batch, 0 for the other kinds
+        if (idx < cnt) {                 // row against an agent outside the batch
+            const size_t r = rb + idx;
+            n0 = q.nex[r]; n1 = q.ney[r]; n2 = q.nez[r];
+            h = q.he[r]; ps = q.se + r; pz = q.ze + r; pt = q.te + r;
+            gx = n0 * x0 + n1 * x1 + n2 * x2; ga = n0 * a0 + n1 * a1 + n2 * a2; gd = n0 * d0 + n1 * d1 + n2 * d2;
+        } else if (idx < cnt + n_int) {  // row against another agent of the batch
+            int o = idx - cnt;
+            if (o >= a) o++;
+            const int lo = a < o ? a : o, hi = a < o ? o : a;
+            const size_t r = ((size_t)lo * q.nb - (size_t)lo * (lo + 1) / 2 + (hi - lo - 1)) * 6 * q.M + m * 6 + i;
+            h = q.hi[r];
+            if (h >= ROW_PRUNED) continue;
+            own = (a == lo);
+            rint = r + 1;
+            const double sg = own ? 1.0 : -1.0;
+            n0 = sg * q.nix[r]; n1 = sg * q.niy[r]; n2 = sg * q.niz[r];
+            const int vo = base + o * 18 + i;
+            gx = n0 * (x0 - q.x[vo]) + n1 * (x1 - q.x[vo + 6]) + n2 * (x2 - q.x[vo + 12]);
+            ga = n0 * (a0 - q.dxa[vo]) + n1 * (a1 - q.dxa[vo + 6]) + n2 * (a2 - q.dxa[vo + 12]);
+            gd = n0 * (d0 - q.dx[vo]) + n1 * (d1 - q.dx[vo + 6]) + n2 * (d2 - q.dx[vo + 12]);
+            // such a row is evaluated from both of its control points; in the residual pass, which also advances (s, z), the
+            // owner writes to the other half of a double buffer so that the partner still reads the old pair
+            ps = q.si + r; pz = q.zi + r; pt = q.ti + r;
+        } else {                         // box row: x_k <= ub (side 0), -x_k <= -lb (side 1)
+            const int bx = idx - cnt - n_int, k = bx >> 1, v = v0 + 6 * k;
+            const bool lower = bx & 1;
+            const double sg = lower ? -1.0 : 1.0;
+            n0 = k == 0 ? sg : 0.0; n1 = k == 1 ? sg : 0.0; n2 = k == 2 ? sg : 0.0;
+            const double xk = k == 0 ? x0 : (k == 1 ? x1 : x2), ak = k == 0 ? a0 : (k == 1 ? a1 : a2), dk = k == 0 ? d0 : (k == 1 ? d1 : d2);
+            gx = sg * xk; ga = sg * ak; gd = sg * dk;
+            h = lower ? q.lbn[v] : q.ub[v];
+            ps = (lower ? q.slb : q.sub) + v; pz = (lower ? q.zlb : q.zub) + v; pt = (lower ? q.tlb : q.tub) + v;
         }
-    }
-    // rows between two agents of the batch (L669-L680); evaluated from both ends, owned by the lower index
-    for (int o = lane; o < q.nb; o += 32) {
-        if (o == a) continue;
-        int lo = a < o ? a : o, hi = a < o ? o : a;
-        size_t r = ((size_t)lo * q.nb - (size_t)lo * (lo + 1) / 2 + (hi - lo - 1)) * 6 * q.M + m * 6 + i;
-        double sg = (a == lo) ? 1.0 : -1.0;
-        double n0 = sg * q.nix[r], n1 = sg * q.niy[r], n2 = sg * q.niz[r];
-        int vo = base + o * 18 + i;
-        double gx = n0 * (x0 - q.x[vo]) + n1 * (x1 - q.x[vo + 6]) + n2 * (x2 - q.x[vo + 12]);
-        double ga = n0 * (a0 - q.dxa[vo]) + n1 * (a1 - q.dxa[vo + 6]) + n2 * (a2 - q.dxa[vo + 12]);
-        double gd = n0 * (d0 - q.dx[vo]) + n1 * (d1 - q.dx[vo + 6]) + n2 * (d2 - q.dx[vo + 12]);
-        double h = q.hi[r], s = q.si[r], z = q.zi[r], t = q.ti[r], cA, cB, w;
-        if (h >= ROW_PRUNED) continue;
-        bool own = (a == lo);
+        s = *ps; z = *pz; t = *pt;
+        double cA, cB, w;
         row_eval<MODE>(h, s, z, t, gx, ga, gd, sa, sb, own, cA, cB, w, acc);
         if (WR && own) {
-            // such a row is evaluated from both of its control points; in the residual pass, which also advances
-            // (s, z), the owner writes to the other half of a double buffer so that the partner still reads the old pair
-            if (MODE == P_RES) { q.si_w[r] = s; q.zi_w[r] = z; q.ti_w[r] = t; }
-            else { q.si[r] = s; q.zi[r] = z; q.ti[r] = t; }
+            if (MODE == P_RES && rint) { q.si_w[rint - 1] = s; q.zi_w[rint - 1] = z; q.ti_w[rint - 1] = t; }
+            else { *ps = s; *pz = z; *pt = t; }
         }
         if (VEC) { vA0 += cA * n0; vA1 += cA * n1; vA2 += cA * n2; vB0 += cB * n0; vB1 += cB * n1; vB2 += cB * n2; }
         if (MAT) {
-            Dxx += w * n0 * n0; Dxy += w * n0 * n1; Dxz += w * n0 * n2;
-            Dyy += w * n1 * n1; Dyz += w * n1 * n2; Dzz += w * n2 * n2;
-            if (own) {  // coupling block between the two agents at this control point: -w n n'
-                double *D = q.Dint + r * 6;
-                D[0] = -w * n0 * n0; D[1] = -w * n0 * n1; D[2] = -w * n0 * n2;
-                D[3] = -w * n1 * n1; D[4] = -w * n1 * n2; D[5] = -w * n2 * n2;
+            const double w0 = w * n0, w1 = w * n1, w2 = w * n2;
+            Dxx += w0 * n0; Dxy += w0 * n1; Dxz += w0 * n2; Dyy += w1 * n1; Dyz += w1 * n2; Dzz += w2 * n2;
+            if (rint && own) {  // coupling block between the two agents at this control point: -w n n'
+                double *D = q.Dint + (rint - 1) * 6;
+                D[0] = -w0 * n0; D[1] = -w0 * n1; D[2] = -w0 * n2; D[3] = -w1 * n1; D[4] = -w1 * n2; D[5] = -w2 * n2;
             }
         }
-    }
-    // box rows (L626-L635): x <= ub, -x <= -lb
-    if (lane < 3) {
-        int v = v0 + 6 * lane;
-        double xk = lane == 0 ? x0 : (lane == 1 ? x1 : x2);
-        double ak = lane == 0 ? a0 : (lane == 1 ? a1 : a2);
-        double dk = lane == 0 ? d0 : (lane == 1 ? d1 : d2);
-        double cA, cB, w, s, z, t, tA = 0, tB = 0, tw = 0;
-        s = q.sub[v]; z = q.zub[v]; t = q.tub[v];
-        row_eval<MODE>(q.ub[v], s, z, t, xk, ak, dk, sa, sb, true, cA, cB, w, acc);
-        if (WR) { q.sub[v] = s; q.zub[v] = z; q.tub[v] = t; }
-        tA += cA; tB += cB; tw += w;
-        s = q.slb[v]; z = q.zlb[v]; t = q.tlb[v];
-        row_eval<MODE>(q.lbn[v], s, z, t, -xk, -ak, -dk, sa, sb, true, cA, cB, w, acc);
-        if (WR) { q.slb[v] = s; q.zlb[v] = z; q.tlb[v] = t; }
-        tA -= cA; tB -= cB; tw += w;
-        if (lane == 0) { vA0 += tA; vB0 += tB; Dxx += tw; }
-        if (lane == 1) { vA1 += tA; vB1 += tB; Dyy += tw; }
-        if (lane == 2) { vA2 += tA; vB2 += tB; Dzz += tw; }
     }
     if (VEC) {
         for (int o = 16; o > 0; o >>= 1) {
