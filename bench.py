@@ -199,6 +199,7 @@ def main():
     ap.add_argument("--jacobi-sweeps", type=int, default=2)
     ap.add_argument("--jacobi-missions-large", type=int, default=1184, help="missions of the throughput-bound Jacobi leg; 0 = skip")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the BASELINE configs[3] / configs[4] legs")
+    ap.add_argument("--no-latency", action="store_true", help="skip the single-mission latency leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -365,6 +366,36 @@ def main():
             except Exception as ex:   # a leg must never take the headline down with it
                 others.append({"workload": name, "error": repr(ex)})
 
+    # ---- latency leg (rank 0): the reference's own call pattern -- ONE mission per update() (swarm_traj_planner_rbp.cpp
+    # L110-L111) -- at the launch default batch_size = 4 (plan_rbp_random_forest.launch L63-L65) and at batch_size = 1, plus one
+    # Jacobi sweep of one mission (64 independent QPs: the latency of a single QP).  Kernel time (assemble + solve + convert) with
+    # inputs resident, and end to end through rbpe_solve_many with host buffers.  One-agent batches of a handful of missions run
+    # on the several-warps-per-QP latency kernel (rbpe_pdip1x.cuh), joint batches on 16-warp CTAs (rbpe_api.cu).
+    latency = None
+    if not args.no_latency and rank == 0:
+        latency = []
+        lm = make_pool(1, 0)
+        for name, bsz, mode in (("one 64-agent mission, sequential batch_size=4 (launch default)", 4, E.MODE_GAUSS_SEIDEL),
+                                ("one 64-agent mission, sequential batch_size=1", 1, E.MODE_GAUSS_SEIDEL),
+                                ("one Jacobi sweep of one 64-agent mission (64 independent QPs)", 1, E.MODE_JACOBI)):
+            try:
+                lp = E.PackedProblem(pin(synth.pack(lm)), sequential=True, batch_size=bsz)
+                le = E.Engine(device=local)
+                le.upload(lp); le.run(mode); le.sync()
+                best = 1e30
+                for _ in range(5):
+                    le.timer_start(); le.run(mode); best = min(best, le.timer_stop())
+                lr = le.download(lp)
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    lr2 = le.solve_many(lp, mode=mode)
+                ms_call = (time.perf_counter() - t0) / 3 * 1e3
+                latency.append({"workload": name, "kernel_ms": best, "call_ms_host_buffers": ms_call, "qps": int((lr.qp_status == 0).sum()),
+                                "ipm_iterations_mean": float(lr.qp_iters.mean()), "failed_missions": int((lr.status != 0).sum())})
+                le.close()
+            except Exception as ex:
+                latency.append({"workload": name, "error": repr(ex)})
+
     # ---- secondary leg: Jacobi mode (north-star's agent sharding): the SAME missions on every rank, each rank solves its
     # range of agents of every mission against the frozen table; the exchange of the solved control points is fused into the
     # sweep kernel (peer stores over NVLink), with the NCCL all-gather variant timed beside it ----
@@ -452,6 +483,8 @@ def main():
         out["joint_batch"] = joint
     if others:
         out["other_configs"] = others
+    if latency is not None:
+        out["latency"] = latency
     if jac:
         out["jacobi_mode"] = jac
     if rank == 0:
