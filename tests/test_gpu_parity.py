@@ -256,7 +256,7 @@ def test_many_missions_in_one_call(eng, monkeypatch):
 
 
 @pytest.mark.parametrize("mode", [E.MODE_GAUSS_SEIDEL, E.MODE_JACOBI])
-@pytest.mark.parametrize("count,warps", [(1, 8), (3, 4), (2, 3)])
+@pytest.mark.parametrize("count,warps", [(1, 8), (3, 4), (2, 3), (64, 8)])   # 64: every mission of the bench pack
 def test_latency_kernel_equals_warp_kernel_and_oracle(monkeypatch, mode, count, warps):
     """One-agent batches, a handful of missions: pdip1x_kernel (several warps per QP, rows in shared memory) against
     pdip1_kernel (RBPE_LAT=0) and, in Gauss-Seidel mode, the oracle: same statuses and iteration counts, control points to
@@ -278,8 +278,13 @@ def test_latency_kernel_equals_warp_kernel_and_oracle(monkeypatch, mode, count, 
         a, b = out["1"], out["0"]
         assert a.rc == b.rc == E.OK
         assert np.array_equal(a.qp_status, b.qp_status) and np.array_equal(a.qp_iters, b.qp_iters)
-        assert np.abs(a.ctrl - b.ctrl).max() < 1e-9
-        assert np.abs(a.coef - b.coef).max() < 1e-9 * max(1.0, np.abs(b.coef).max())
+        # rows are summed in a different order -> rounding-level differences; a QP that is accepted at the round-off floor of
+        # its dual residual (nearly degenerate: 1 of the 4 096 of the pack, tools/gpu_diff64.py) is determined to ~1e-8 only,
+        # and both kernels sit that far from the oracle there
+        tol = 1e-9 if count < 64 else 5e-8
+        assert np.abs(a.ctrl - b.ctrl).max() < tol
+        assert np.median(np.abs(a.ctrl - b.ctrl).reshape(a.ctrl.shape[0], -1).max(1)) < 1e-10
+        assert np.abs(a.coef - b.coef).max() < tol * max(1.0, np.abs(b.coef).max())
         if mode == E.MODE_GAUSS_SEIDEL:
             ro = oracle_util.oracle_problem(ms[0], sequential=True, batch_size=1).update()
             assert np.array_equal(a.qp_iters[0][:a.nrec], ro["batch_iters"][:a.nrec])
