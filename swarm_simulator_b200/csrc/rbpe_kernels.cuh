@@ -539,6 +539,9 @@ RBPE_DEV void cp_task(const QP &q, int m, int a, int i, double sa, double sb, Ac
             h = q.hi[r];
             if (h >= ROW_PRUNED) continue;
             own = (a == lo);
+            // the start-point passes only touch a row through its owner (the partner would read (s, z, t) while the owner
+            // rewrites them and use nothing of what it read)
+            if (!own && (MODE == P_START || MODE == P_SHIFT)) continue;
             rint = r + 1;
             const double sg = own ? 1.0 : -1.0;
             n0 = sg * q.nix[r]; n1 = sg * q.niy[r]; n2 = sg * q.niz[r];
