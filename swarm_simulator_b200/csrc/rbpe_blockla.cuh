@@ -779,6 +779,77 @@ RBPE_NOINLINE bool factor_bt9v(int nblk, double *Dall, double *Oall, double *cb)
     return ok;
 }
 
+// Block tridiagonal factorisation by one warp, latency-oriented variant (written for the latency kernel, where the warp
+// is alone on its scheduler): same outputs as factor_bt9v (the INVERSE of
+// the diagonal factor block in place of D_t, L_{t+1,t} in place of O_t), organised for the LATENCY of the 9-step pivot
+// chain instead of the instruction count:
+//   * square-root free inside the chain: column j is eliminated with u = a_j / pivot (MUFU.RCP64H + two Newton steps);
+//     the factors 1 / sqrt(pivot) are applied afterwards, for all nine columns at once (one rsqrt latency per knot
+//     instead of nine in series);
+//   * the next pivot is computed by its own lane from registers and broadcast BEFORE the shared-memory exchange of the
+//     column, so the exchange overlaps the reciprocal of the next step;
+//   * three lane groups -- rows of D_t (0..8), rows of O_t (9..17), columns of the inverse (18..26) -- run the same
+//     update w[k-1] = w[k] - w[0] u[k] on one register window (8 FMAs per lane and column).
+// cb: >= 32 doubles, pv: >= 9 doubles of shared memory.
+template <int TAG>   // one private copy per kernel, as factor_bt9v
+RBPE_NOINLINE bool factor_bt9l(int nblk, double *Dall, double *Oall, double *cb, double *pv) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const bool isD = lane < 9, isO = lane >= 9 && lane < 18, isX = lane >= 18 && lane < 27;
+    const int row = isD ? lane : (isO ? lane - 9 : (isX ? lane - 18 : 0));
+    bool ok = true;
+#pragma unroll 1
+    for (int t = 0; t < nblk; t++) {
+        double *D = Dall + t * 81, *O = Oall + t * 81;
+        const bool hasO = t < nblk - 1;
+        if (t > 0) {   // D_t -= L_{t,t-1} L_{t,t-1}'
+            const double *P = Oall + (t - 1) * 81;
+            if (lane < 27) {
+                const int r = lane / 3, c0 = 3 * (lane % 3);
+                double s0 = D[r * 9 + c0], s1 = D[r * 9 + c0 + 1], s2 = D[r * 9 + c0 + 2];
+#pragma unroll
+                for (int k = 0; k < 9; k++) {
+                    const double pk = P[r * 9 + k];
+                    s0 -= pk * P[c0 * 9 + k]; s1 -= pk * P[(c0 + 1) * 9 + k]; s2 -= pk * P[(c0 + 2) * 9 + k];
+                }
+                D[r * 9 + c0] = s0; D[r * 9 + c0 + 1] = s1; D[r * 9 + c0 + 2] = s2;
+            }
+            __syncwarp();
+        }
+        double w[9];
+#pragma unroll
+        for (int c = 0; c < 9; c++) w[c] = isD ? D[row * 9 + c] : ((isO && hasO) ? O[row * 9 + c] : ((isX && c == row) ? 1.0 : 0.0));
+        __syncwarp();   // rows are in registers: D may now be overwritten by the inverse
+        double piv = __shfl_sync(FULL, w[0], 0);
+#pragma unroll 1
+        for (int j = 0; j < 9; j++) {
+            if (!(piv > 0)) { ok = false; piv = 1.0; }
+            const double w0 = w[0];
+            const double u = w0 * bla_rcp(piv);                            // a_j / pivot
+            const double pn = __shfl_sync(FULL, w[1] - w0 * u, (j + 1) & 31);   // next pivot, from the lane that owns it
+            cb[(lane - j) & 31] = (isD && lane >= j) ? u : 0.0;           // cb[k] = u of row j + k, zero beyond the block
+            if (lane == j) pv[j] = piv;
+            if (isO && hasO) O[row * 9 + j] = w0;                         // unscaled: times 1/sqrt(pivot_j) below
+            if (isX) D[j * 9 + row] = w0;
+            __syncwarp();
+#pragma unroll
+            for (int k = 1; k < 9; k++) w[k - 1] = w[k] - w0 * cb[k];
+            w[8] = 0.0;
+            __syncwarp();
+            piv = pn;
+        }
+        if (lane < 9) pv[lane] = rsqrt(pv[lane]);
+        __syncwarp();
+#pragma unroll 1
+        for (int idx = lane; idx < 81; idx += 32) {
+            D[idx] *= pv[idx / 9];                 // row j of the inverse
+            if (hasO) O[idx] *= pv[idx % 9];       // column j of L_{t+1,t}
+        }
+        __syncwarp();
+    }
+    return ok;
+}
+
 // g <- (L L')^-1 g with Dall = inverses of the diagonal factor blocks, Oall = L_{t+1,t} (factor_bt9v)
 template <int TAG>
 RBPE_NOINLINE void solve_bt9v(int nblk, const double *Dall, const double *Oall, double *g, double *cb) {
