@@ -817,8 +817,15 @@ RBPE_NOINLINE bool factor_bt9l(int nblk, double *Dall, double *Oall, double *cb,
             __syncwarp();
         }
         double w[9];
+        {   // one set of loads through a selected pointer (three-way branches around the loads cost ~40 instructions per knot)
+            const bool ld = isD || (isO && hasO);
+            const double *src = ((isO && hasO) ? O : D) + row * 9;
 #pragma unroll
-        for (int c = 0; c < 9; c++) w[c] = isD ? D[row * 9 + c] : ((isO && hasO) ? O[row * 9 + c] : ((isX && c == row) ? 1.0 : 0.0));
+            for (int c = 0; c < 9; c++) {
+                const double v = src[c];
+                w[c] = ld ? v : ((isX && c == row) ? 1.0 : 0.0);
+            }
+        }
         __syncwarp();   // rows are in registers: D may now be overwritten by the inverse
         double piv = __shfl_sync(FULL, w[0], 0);
 #pragma unroll 1
@@ -840,10 +847,15 @@ RBPE_NOINLINE bool factor_bt9l(int nblk, double *Dall, double *Oall, double *cb,
         }
         if (lane < 9) pv[lane] = rsqrt(pv[lane]);
         __syncwarp();
-#pragma unroll 1
-        for (int idx = lane; idx < 81; idx += 32) {
-            D[idx] *= pv[idx / 9];                 // row j of the inverse
-            if (hasO) O[idx] *= pv[idx % 9];       // column j of L_{t+1,t}
+        if (lane < 27) {   // 27 lanes x 3 entries, as in the update above: no index division in a loop
+            const int r = lane / 3, c0 = 3 * (lane % 3);
+            const double sr = pv[r], s0 = pv[c0], s1 = pv[c0 + 1], s2 = pv[c0 + 2];
+            double *d = D + r * 9 + c0;
+            d[0] *= sr; d[1] *= sr; d[2] *= sr;                  // row r of the inverse
+            if (hasO) {
+                double *o = O + r * 9 + c0;
+                o[0] *= s0; o[1] *= s1; o[2] *= s2;              // columns of L_{t+1,t}
+            }
         }
         __syncwarp();
     }
