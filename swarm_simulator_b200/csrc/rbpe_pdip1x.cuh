@@ -51,14 +51,15 @@ struct X1Red { double s1, s2, mx, mx2, mx3; };
 // CTA all-reduce of (sum, sum, max, max, max) in two halves with ONE barrier (the caller's) between them:
 // x1_red_put -- warp butterfly, one shared-memory slot per warp; x1_red_get -- every thread adds the warp results in
 // warp order.  `flip` alternates between two buffers, so that no second barrier is needed before the next reduction.
+template <int MASK>   // bit i set: slot i (s1, s2, mx, mx2, mx3) is wanted; the others are not shuffled (their results are garbage)
 RBPE_NOINLINE void x1_red_put(double *scal, int flip, double s1, double s2, double mx, double mx2, double mx3) {
 #pragma unroll 1
     for (int o = 16; o > 0; o >>= 1) {
-        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-        mx = dmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        mx2 = dmax(mx2, __shfl_xor_sync(0xffffffffu, mx2, o));
-        mx3 = dmax(mx3, __shfl_xor_sync(0xffffffffu, mx3, o));
+        if (MASK & 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        if (MASK & 2) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        if (MASK & 4) mx = dmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (MASK & 8) mx2 = dmax(mx2, __shfl_xor_sync(0xffffffffu, mx2, o));
+        if (MASK & 16) mx3 = dmax(mx3, __shfl_xor_sync(0xffffffffu, mx3, o));
     }
     if ((threadIdx.x & 31) == 0) {
         double *p = scal + flip * X1_MAXW * 8 + (threadIdx.x >> 5) * 8;
@@ -78,8 +79,9 @@ RBPE_DEV X1Red x1_red_get(const double *scal, int nw, int &flip) {
         }
     return r;
 }
+template <int MASK = 31>
 RBPE_DEV X1Red x1_reduce(double *scal, int nw, int &flip, double s1, double s2, double mx, double mx2, double mx3) {
-    x1_red_put(scal, flip, s1, s2, mx, mx2, mx3);
+    x1_red_put<MASK>(scal, flip, s1, s2, mx, mx2, mx3);
     __syncthreads();
     return x1_red_get(scal, nw, flip);
 }
@@ -189,7 +191,7 @@ RBPE_DEV void x1_pass(const X1 &c, const int mode, const double sa, const double
             if (mode == P_RES) { pp[96] = vB0; pp[128] = vB1; pp[160] = vB2; }
             if (mode != P_COR) { pp[192] = Dxx; pp[224] = Dxy; pp[256] = Dxz; pp[288] = Dyy; pp[320] = Dyz; pp[352] = Dzz; }
         }
-        if (last && mode != P_COR) x1_red_put(c.scal, flip, acc.s1, acc.s2, acc.mx, acc.mx2, 0.0);   // rides on the same barrier
+        if (last && mode != P_COR) x1_red_put<15>(c.scal, flip, acc.s1, acc.s2, acc.mx, acc.mx2, 0.0);   // rides on the same barrier
         __syncthreads();
         PROF(9);
 #pragma unroll 1
@@ -212,7 +214,11 @@ RBPE_DEV void x1_pass(const X1 &c, const int mode, const double sa, const double
         PROF(10);
     }
     if (mode != P_SHIFT && mode != P_COR) {
-        X1Red r = vec ? x1_red_get(c.scal, c.nw, flip) : x1_reduce(c.scal, c.nw, flip, acc.s1, acc.s2, acc.mx, acc.mx2, 0.0);
+        // (ratio tests need the maximum only; P_AFF also the two sums; P_START two maxima)
+        X1Red r = vec ? x1_red_get(c.scal, c.nw, flip)
+                      : (mode == P_STEP ? x1_reduce<4>(c.scal, c.nw, flip, 0.0, 0.0, acc.mx, 0.0, 0.0)
+                                        : (mode == P_AFF ? x1_reduce<7>(c.scal, c.nw, flip, acc.s1, acc.s2, acc.mx, 0.0, 0.0)
+                                                         : x1_reduce<12>(c.scal, c.nw, flip, 0.0, 0.0, acc.mx, acc.mx2, 0.0)));
         acc.s1 = r.s1; acc.s2 = r.s2; acc.mx = r.mx; acc.mx2 = r.mx2;
     }
     PROF(11);
@@ -461,7 +467,7 @@ RBPE_DEV int x1_solve_qp(const X1 &c, int max_iter, double tol_gap, double tol_r
             x1_dual(c, true, o, mpx);
             __syncthreads();
             x1_Zt2(c, c.rdx, c.sg, c.vA, c.sg2, mr, mc);
-            { X1Red r = x1_reduce(c.scal, c.nw, flip, o, 0.0, mpx, mr, mc); o = r.s1; mpx = r.mx; mr = r.mx2; mc = r.mx3; }
+            { X1Red r = x1_reduce<29>(c.scal, c.nw, flip, o, 0.0, mpx, mr, mc); o = r.s1; mpx = r.mx; mr = r.mx2; mc = r.mx3; }
             obj = o; nrd = mr;
             gap = mu;
             PROF(2);
