@@ -66,16 +66,21 @@ RBPE_NOINLINE void x1_red_put(double *scal, int flip, double s1, double s2, doub
         p[0] = s1; p[1] = s2; p[2] = mx; p[3] = mx2; p[4] = mx3;
     }
 }
+template <int MASK = 31>
 RBPE_DEV X1Red x1_red_get(const double *scal, int nw, int &flip) {
     const double *b = scal + flip * X1_MAXW * 8;
     flip ^= 1;
     X1Red r;
-    r.s1 = b[0]; r.s2 = b[1]; r.mx = b[2]; r.mx2 = b[3]; r.mx3 = b[4];
+    r.s1 = (MASK & 1) ? b[0] : 0.0; r.s2 = (MASK & 2) ? b[1] : 0.0; r.mx = (MASK & 4) ? b[2] : 0.0; r.mx2 = (MASK & 8) ? b[3] : 0.0; r.mx3 = (MASK & 16) ? b[4] : 0.0;
 #pragma unroll
     for (int w = 1; w < X1_MAXW; w++)   // unrolled: the loads of all warps' slots are in flight together
         if (w < nw) {
             const double *p = b + w * 8;
-            r.s1 += p[0]; r.s2 += p[1]; r.mx = dmax(r.mx, p[2]); r.mx2 = dmax(r.mx2, p[3]); r.mx3 = dmax(r.mx3, p[4]);
+            if (MASK & 1) r.s1 += p[0];
+            if (MASK & 2) r.s2 += p[1];
+            if (MASK & 4) r.mx = dmax(r.mx, p[2]);
+            if (MASK & 8) r.mx2 = dmax(r.mx2, p[3]);
+            if (MASK & 16) r.mx3 = dmax(r.mx3, p[4]);
         }
     return r;
 }
@@ -83,7 +88,7 @@ template <int MASK = 31>
 RBPE_DEV X1Red x1_reduce(double *scal, int nw, int &flip, double s1, double s2, double mx, double mx2, double mx3) {
     x1_red_put<MASK>(scal, flip, s1, s2, mx, mx2, mx3);
     __syncthreads();
-    return x1_red_get(scal, nw, flip);
+    return x1_red_get<MASK>(scal, nw, flip);
 }
 
 RBPE_DEV bool x1_dead(const X1 &c, int cp) { int m = cp / 6, i = cp % 6; return (m == 0 && i < 3) || (m == c.M - 1 && i >= 3); }
@@ -112,7 +117,7 @@ RBPE_DEV void x1_pass(const X1 &c, const int mode, const double sa, const double
             double *pr = c.rows + (size_t)(slot * c.nw + warp) * c.cap * W1_ROWBLK + lane;
             const int *pe = (const int *)(c.rows + (size_t)(slot * c.nw + warp) * c.cap * W1_ROWBLK + 96) + lane;
             const int cnt = c.cnt[(slot * c.nw + warp) * 32 + lane];
-#pragma unroll 2
+#pragma unroll 1   // (2-3 rows per warp and pass: unrolling by 2 measured 3 % slower)
             for (int j = 0; j < cnt; j++, pr += W1_ROWBLK, pe += 2 * W1_ROWBLK) {
                 const double h = pr[0];
                 double s = pr[32], z = pr[64];
@@ -215,7 +220,7 @@ RBPE_DEV void x1_pass(const X1 &c, const int mode, const double sa, const double
     }
     if (mode != P_SHIFT && mode != P_COR) {
         // (ratio tests need the maximum only; P_AFF also the two sums; P_START two maxima)
-        X1Red r = vec ? x1_red_get(c.scal, c.nw, flip)
+        X1Red r = vec ? x1_red_get<15>(c.scal, c.nw, flip)
                       : (mode == P_STEP ? x1_reduce<4>(c.scal, c.nw, flip, 0.0, 0.0, acc.mx, 0.0, 0.0)
                                         : (mode == P_AFF ? x1_reduce<7>(c.scal, c.nw, flip, acc.s1, acc.s2, acc.mx, 0.0, 0.0)
                                                          : x1_reduce<12>(c.scal, c.nw, flip, 0.0, 0.0, acc.mx, acc.mx2, 0.0)));
