@@ -142,6 +142,9 @@ int *rbpe_device_status(rbpe_handle *h);                                     /* 
 /* k3 alone on the current control-point table (after a collective exchange of the Jacobi mode); replaces the conversion
  * loop of rbp_planner.hpp L167-L196 for the agents other ranks solved */
 int rbpe_convert(rbpe_handle *h);
+/* which solver kernel the last k2 launch used (diagnostics, tests): 0 none yet, 1 = one warp per QP (pdip1_kernel),
+ * 2 = several warps per QP (pdip1x_kernel, latency regime), 3 = one CTA per QP (pdip_kernel); *threads_per_qp = 32, 32 * warps, CTA size */
+int rbpe_last_solver(rbpe_handle *h, int *threads_per_qp);
 void *rbpe_stream(rbpe_handle *h);                                           /* cudaStream_t */
 int rbpe_sync(rbpe_handle *h);
 int rbpe_last_timing(const rbpe_handle *h, rbpe_timing *t);                  /* kernel_launches = total since creation */

@@ -63,6 +63,7 @@ struct rbpe_handle {
     int lat_mode = -1;       // RBPE_LAT=0 / 1: never / always use the latency kernel where it fits (default: by work-item count)
     int lat_warps = X1_MAXW; // RBPE_LAT_WARPS: warps per QP of the latency kernel
     int lat_warps_forced = 0;
+    int last_solver = 0, last_threads = 0;   // rbpe_last_solver
     int sm_count = 0;
     char err[512] = "";
     // resident problem
@@ -418,6 +419,7 @@ static int launch_pdip_prepared(rbpe_handle *h, SolveArgs &S, long units, cudaSt
         S.smem_bytes = (unsigned)(x1_smem_doubles(h->N, h->M, xw) * 8);
         S.scratch = h->scratch.as<double>();
         pdip1x_kernel<<<(unsigned)units, xw * 32, S.smem_bytes, st>>>(S);
+        h->last_solver = 2; h->last_threads = xw * 32;
 #endif
     } else if (wpc > 0) {
         long grid = (units + wpc - 1) / wpc;
@@ -426,6 +428,7 @@ static int launch_pdip_prepared(rbpe_handle *h, SolveArgs &S, long units, cudaSt
         CU(h->scratch.reserve(S.scratch_stride * 8 * (size_t)(slots + wpc)));
         S.scratch = h->scratch.as<double>() + (size_t)slot0 * S.scratch_stride;
         pdip1_kernel<<<(unsigned)grid, wpc * 32, S.smem_bytes, st>>>(S);
+        h->last_solver = 1; h->last_threads = 32;
     } else {
         S.scratch_stride = scratch_doubles(h->N, h->M, h->bs);
         S.smem_bytes = (unsigned)smem_for(h, S.scratch_stride, units);
@@ -453,6 +456,7 @@ static int launch_pdip_prepared(rbpe_handle *h, SolveArgs &S, long units, cudaSt
         const int joint_threads = (units <= h->sm_count) ? CTA_THREADS_MAX : CTA_THREADS;
         const int threads = (h->bs > 1 && !h->threads_forced) ? joint_threads : h->threads;
         pdip_kernel<<<(unsigned)units, threads, S.smem_bytes, st>>>(S);
+        h->last_solver = 3; h->last_threads = threads;
     }
     CU(cudaGetLastError());
     h->launches++;
@@ -872,6 +876,11 @@ extern "C" int rbpe_convert(rbpe_handle *h) {
 }
 // device address of the per-mission status words [count] (int32): ranks of a Jacobi solve all-reduce (MAX) them
 extern "C" int *rbpe_device_status(rbpe_handle *h) { return h ? h->status.as<int>() : nullptr; }
+extern "C" int rbpe_last_solver(rbpe_handle *h, int *threads_per_qp) {
+    if (!h) return 0;
+    if (threads_per_qp) *threads_per_qp = h->last_threads;
+    return h->last_solver;
+}
 extern "C" void *rbpe_stream(rbpe_handle *h) { return h ? (void *)h->stream : nullptr; }
 extern "C" int rbpe_sync(rbpe_handle *h) {
     if (!h) return RBPE_BAD_ARG;

@@ -45,7 +45,7 @@ EXPORTS = ["rbpe_create", "rbpe_destroy", "rbpe_last_error", "rbpe_set_batch", "
            "rbpe_upload", "rbpe_assemble", "rbpe_run", "rbpe_run_jacobi_range", "rbpe_set_ctrl", "rbpe_download", "rbpe_device_ctrl",
            "rbpe_device_coef", "rbpe_stream", "rbpe_sync", "rbpe_last_timing", "rbpe_timer_start", "rbpe_timer_stop",
            "rbpe_corridor_rsfc", "rbpe_safety_metrics", "rbpe_peer_export", "rbpe_peer_attach", "rbpe_peer_attach_local",
-           "rbpe_run_jacobi_fused", "rbpe_peer_status", "rbpe_host_alloc", "rbpe_host_free", "rbpe_convert", "rbpe_device_status"]
+           "rbpe_run_jacobi_fused", "rbpe_peer_status", "rbpe_host_alloc", "rbpe_host_free", "rbpe_convert", "rbpe_device_status", "rbpe_last_solver"]
 IPC_HANDLE_BYTES = 64
 
 _lib = None
@@ -114,6 +114,9 @@ def load_library(path=None):
         L.rbpe_convert.restype = C.c_int
         L.rbpe_device_status.argtypes = [C.c_void_p]
         L.rbpe_device_status.restype = C.c_void_p
+    if path is None or hasattr(L, "rbpe_last_solver"):
+        L.rbpe_last_solver.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+        L.rbpe_last_solver.restype = C.c_int
     L.rbpe_stream.argtypes = [C.c_void_p]
     L.rbpe_stream.restype = C.c_void_p
     L.rbpe_sync.argtypes = [C.c_void_p]
@@ -379,6 +382,12 @@ class Engine:
 
     def device_status_ptr(self):
         return self.lib.rbpe_device_status(self.h)
+
+    def last_solver(self):
+        """(kernel, threads per QP) of the last solver launch: 1 = pdip1_kernel, 2 = pdip1x_kernel, 3 = pdip_kernel."""
+        t = C.c_int(0)
+        k = self.lib.rbpe_last_solver(self.h, C.byref(t))
+        return k, t.value
 
     def convert(self):
         rc = self.lib.rbpe_convert(self.h)

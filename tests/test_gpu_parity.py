@@ -273,9 +273,11 @@ def test_latency_kernel_equals_warp_kernel_and_oracle(monkeypatch, mode, count, 
             e = E.Engine(device=0)
             try:
                 out[lat] = e.solve_many(prob, mode=mode)
+                out["solver" + lat] = e.last_solver()
             finally:
                 e.close()
         a, b = out["1"], out["0"]
+        assert out["solver1"] == (2, 32 * warps) and out["solver0"] == (1, 32)
         assert a.rc == b.rc == E.OK
         assert np.array_equal(a.qp_status, b.qp_status) and np.array_equal(a.qp_iters, b.qp_iters)
         # rows are summed in a different order -> rounding-level differences; a QP that is accepted at the round-off floor of
@@ -289,6 +291,28 @@ def test_latency_kernel_equals_warp_kernel_and_oracle(monkeypatch, mode, count, 
             ro = oracle_util.oracle_problem(ms[0], sequential=True, batch_size=1).update()
             assert np.array_equal(a.qp_iters[0][:a.nrec], ro["batch_iters"][:a.nrec])
             assert np.abs(a.ctrl[0] - ro["ctrl"]).max() < CTRL_TOL
+
+
+@pytest.mark.parametrize("N,M", [(150, 5), (40, 10)])
+def test_latency_kernel_at_the_edge_of_shared_memory(monkeypatch, N, M):
+    """Shapes whose row state barely fits: 150 agents (197 KB of dynamic shared memory, one CTA per SM) and 10 segments
+    (60 control points: two lane slots).  Latency kernel against the warp kernel, Gauss-Seidel chain of one mission."""
+    m = synth.synth_mission(N, M, 0.05, 4242)
+    prob = E.PackedProblem(synth.pack([m]), sequential=True, batch_size=1)
+    out = {}
+    for lat in ("1", "0"):
+        monkeypatch.setenv("RBPE_LAT", lat)
+        e = E.Engine(device=0)
+        try:
+            out[lat] = e.solve_many(prob)
+            out["solver" + lat] = e.last_solver()
+        finally:
+            e.close()
+    a, b = out["1"], out["0"]
+    assert out["solver1"] == (2, 256) and out["solver0"] == (1, 32)     # the latency kernel really ran (8 warps per QP)
+    assert a.rc == b.rc
+    assert np.array_equal(a.qp_status, b.qp_status) and np.array_equal(a.qp_iters, b.qp_iters)
+    assert np.abs(a.ctrl - b.ctrl).max() < 5e-8
 
 
 def test_latency_kernel_reports_infeasible_like_the_warp_kernel(monkeypatch):
@@ -323,6 +347,7 @@ def test_joint_batches_with_16_warps_equal_8_warps(monkeypatch):
         e = E.Engine(device=0)
         try:
             out[th] = e.solve_many(prob)
+            assert e.last_solver() == (3, int(th))
         finally:
             e.close()
     a, b = out["512"], out["256"]
