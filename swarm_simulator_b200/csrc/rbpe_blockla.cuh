@@ -807,7 +807,9 @@ RBPE_NOINLINE bool factor_bt9l(int nblk, double *Dall, double *Oall, double *cb,
             if (lane < 27) {
                 const int r = lane / 3, c0 = 3 * (lane % 3);
                 double s0 = D[r * 9 + c0], s1 = D[r * 9 + c0 + 1], s2 = D[r * 9 + c0 + 2];
-#pragma unroll
+                // rolled in the throughput kernel (TAG 1: instruction-fetch bound, text size counts more than 24 loop
+                // instructions: +1.3 %), unrolled in the latency kernel (TAG 2: a lone warp pays per instruction: 2 %)
+#pragma unroll (TAG == 1 ? 1 : 9)
                 for (int k = 0; k < 9; k++) {
                     const double pk = P[r * 9 + k];
                     s0 -= pk * P[c0 * 9 + k]; s1 -= pk * P[(c0 + 1) * 9 + k]; s2 -= pk * P[(c0 + 2) * 9 + k];
@@ -862,7 +864,9 @@ RBPE_NOINLINE bool factor_bt9l(int nblk, double *Dall, double *Oall, double *cb,
     return ok;
 }
 
-// g <- (L L')^-1 g with Dall = inverses of the diagonal factor blocks, Oall = L_{t+1,t} (factor_bt9v)
+// g <- (L L')^-1 g with Dall = inverses of the diagonal factor blocks, Oall = L_{t+1,t} (factor_bt9v / factor_bt9l).
+// (Rolling the four 9-term loops for the throughput kernel, as in factor_bt9l's update, measured -2 %: they run 16 x per
+// iteration, the rolled loop overhead outweighs the smaller text.)
 template <int TAG>
 RBPE_NOINLINE void solve_bt9v(int nblk, const double *Dall, const double *Oall, double *g, double *cb) {
     const int lane = threadIdx.x & 31;
