@@ -386,11 +386,13 @@ def main():
                 for _ in range(5):
                     le.timer_start(); le.run(mode); best = min(best, le.timer_stop())
                 lr = le.download(lp)
+                solver = le.last_solver()
                 t0 = time.perf_counter()
                 for _ in range(3):
                     lr2 = le.solve_many(lp, mode=mode)
                 ms_call = (time.perf_counter() - t0) / 3 * 1e3
                 latency.append({"workload": name, "kernel_ms": best, "call_ms_host_buffers": ms_call, "qps": int((lr.qp_status == 0).sum()),
+                                "solver": {1: "pdip1_kernel", 2: "pdip1x_kernel", 3: "pdip_kernel"}.get(solver[0], "?") + " (%d threads per QP)" % solver[1],
                                 "ipm_iterations_mean": float(lr.qp_iters.mean()), "failed_missions": int((lr.status != 0).sum())})
                 le.close()
             except Exception as ex:
