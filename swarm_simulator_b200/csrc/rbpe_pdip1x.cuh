@@ -41,7 +41,7 @@ struct X1 {
     double *part;   // [warp][X1_PART][32]
     double *scal;   // 2 x [warp][8]
     int *flag;
-    double *pv;     // [16] pivots of a 9 x 9 block (x1_factor_bt9)
+    double *pv;     // [16] pivots of a 9 x 9 block (factor_bt9l, rbpe_blockla.cuh)
     double *rows;   // [slot][warp][cap][W1_ROWBLK]: h | s | z | e of the warp's rows of every lane
     int *cnt;       // [slot][warp][32]
     double *nrm;    // [m][e][3]
