@@ -498,103 +498,119 @@ RBPE_DEV void row_eval(double h, double &s, double &z, double &t, double gx, dou
 // Control points fixed by the start / goal equalities: 0..2 of the first segment, 3..5 of the last one.
 RBPE_DEV bool cp_dead(const QP &q, int m, int i) { return (m == 0 && i < 3) || (m == q.M - 1 && i >= 3); }
 
-// All inequality rows touching control point (m, a, i) of the batch, executed by one warp: the kept rows against agents
-// outside the batch (L643-L668), the rows against the other agents of the batch (L669-L680; evaluated from both ends, owned
-// by the lower index) and the six box rows (L626-L635: x <= ub, -x <= -lb) are dealt to the lanes as ONE list, so that the
-// row algebra (row_eval) and the accumulation of G'(.) and sum w g g' exist once per pass instead of four times -- a box
-// row is an ordinary row with a unit normal.  (Round 2: the three kinds used to be three separate sections, each with its
-// own copy of row_eval, executed one after the other by the same warp: 3 x the instructions per control point, and a lone
-// CTA pays ~6 cycles per instruction; ncu r2f: the row passes were 40 % of a single b = 4 mission.)
+// All inequality rows touching control point (m, a, i) of the batch, executed by a GROUP OF FOUR LANES (eight control
+// points per warp): the kept rows against agents outside the batch (L643-L668), the rows against the other agents of
+// the batch (L669-L680; evaluated from both ends, owned by the lower index) and the six box rows (L626-L635: x <= ub,
+// -x <= -lb), each kind in its own loop so that the lanes of a warp stay on the same path; lane g of the group takes the
+// rows g, g + 4, ...; G'(.) and sum w g g' of the group are added with two shuffle rounds.
+// Round-2 history of this function (one 64-agent b = 4 mission, where the row passes were 40 % of the time, ncu r2f): one
+// WARP per control point used ~21 of its 32 lanes, paid a 5-round butterfly over 12 values and its prologue per control
+// point -- 6 control points x ~500 instructions per warp and pass at 16 warps; four lanes per control point run the same rows
+// in ~800 instructions per warp and pass.  (A lone CTA pays ~6 cycles per instruction and warp.)
+constexpr int CPG = 4;   // lanes per control point
 template <int MODE>
-RBPE_DEV void cp_task(const QP &q, int m, int a, int i, double sa, double sb, Acc &acc) {
+RBPE_DEV void cp_group(const QP &q, const bool active, int m, int a, int i, double sa, double sb, Acc &acc) {
     constexpr bool WR = (MODE == P_START || MODE == P_SHIFT || MODE == P_RES);
     constexpr bool VEC = (MODE == P_INIT || MODE == P_RES || MODE == P_COR);
     constexpr bool MAT = (MODE == P_INIT || MODE == P_RES);
-    const int lane = threadIdx.x & 31;
-    const int base = m * q.n, v0 = base + a * 18 + i;
-    const double x0 = q.x[v0], x1 = q.x[v0 + 6], x2 = q.x[v0 + 12];
-    const double a0 = q.dxa[v0], a1 = q.dxa[v0 + 6], a2 = q.dxa[v0 + 12];
-    const double d0 = q.dx[v0], d1 = q.dx[v0 + 6], d2 = q.dx[v0 + 12];
+    const int g = threadIdx.x & (CPG - 1);
     double vA0 = 0, vA1 = 0, vA2 = 0, vB0 = 0, vB1 = 0, vB2 = 0;
     double Dxx = 0, Dxy = 0, Dxz = 0, Dyy = 0, Dyz = 0, Dzz = 0;
-    const int task = (a * q.M + m) * 6 + i;
-    const size_t rb = (size_t)task * q.NE;
-    const int cnt = q.cnt_ext[task];     // kept rows only (compacted by setup_rows)
-    const int n_int = q.nb - 1, total = cnt + n_int + 6;
-    for (int idx = lane; idx < total; idx += 32) {
-        double n0, n1, n2, h, s, z, t, gx, ga, gd;
-        double *ps, *pz, *pt;            // where the row's (s, z, t) live; written back in the passes that change them
-        bool own = true;
-        size_t rint = 0;                 // 1 + index of a row between two agents of the batch, 0 for the other kinds
-        if (idx < cnt) {                 // row against an agent outside the batch
-            const size_t r = rb + idx;
-            n0 = q.nex[r]; n1 = q.ney[r]; n2 = q.nez[r];
-            h = q.he[r]; ps = q.se + r; pz = q.ze + r; pt = q.te + r;
-            gx = n0 * x0 + n1 * x1 + n2 * x2; ga = n0 * a0 + n1 * a1 + n2 * a2; gd = n0 * d0 + n1 * d1 + n2 * d2;
-        } else if (idx < cnt + n_int) {  // row against another agent of the batch
-            int o = idx - cnt;
-            if (o >= a) o++;
+    int v0 = 0;
+    if (active) {
+        const int base = m * q.n;
+        v0 = base + a * 18 + i;
+        const double x0 = q.x[v0], x1 = q.x[v0 + 6], x2 = q.x[v0 + 12];
+        const double a0 = q.dxa[v0], a1 = q.dxa[v0 + 6], a2 = q.dxa[v0 + 12];
+        const double d0 = q.dx[v0], d1 = q.dx[v0 + 6], d2 = q.dx[v0 + 12];
+        {   // rows against agents outside the batch
+            const int task = (a * q.M + m) * 6 + i;
+            const size_t rb = (size_t)task * q.NE;
+            const int cnt = q.cnt_ext[task];     // kept rows only (compacted by setup_rows)
+            for (int e = g; e < cnt; e += CPG) {
+                const size_t r = rb + e;
+                const double n0 = q.nex[r], n1 = q.ney[r], n2 = q.nez[r];
+                double h = q.he[r], s = q.se[r], z = q.ze[r], t = q.te[r], cA, cB, w;
+                row_eval<MODE>(h, s, z, t, n0 * x0 + n1 * x1 + n2 * x2, n0 * a0 + n1 * a1 + n2 * a2,
+                               n0 * d0 + n1 * d1 + n2 * d2, sa, sb, true, cA, cB, w, acc);
+                if (WR) { q.se[r] = s; q.ze[r] = z; q.te[r] = t; }
+                if (VEC) { vA0 += cA * n0; vA1 += cA * n1; vA2 += cA * n2; vB0 += cB * n0; vB1 += cB * n1; vB2 += cB * n2; }
+                if (MAT) {
+                    const double w0 = w * n0, w1 = w * n1, w2 = w * n2;
+                    Dxx += w0 * n0; Dxy += w0 * n1; Dxz += w0 * n2; Dyy += w1 * n1; Dyz += w1 * n2; Dzz += w2 * n2;
+                }
+            }
+        }
+        // rows between two agents of the batch
+        for (int oo = g; oo < q.nb - 1; oo += CPG) {
+            const int o = oo < a ? oo : oo + 1;
             const int lo = a < o ? a : o, hi = a < o ? o : a;
             const size_t r = ((size_t)lo * q.nb - (size_t)lo * (lo + 1) / 2 + (hi - lo - 1)) * 6 * q.M + m * 6 + i;
-            h = q.hi[r];
+            const double h = q.hi[r];
             if (h >= ROW_PRUNED) continue;
-            own = (a == lo);
+            const bool own = (a == lo);
             // the start-point passes only touch a row through its owner (the partner would read (s, z, t) while the owner
             // rewrites them and use nothing of what it read)
             if (!own && (MODE == P_START || MODE == P_SHIFT)) continue;
-            rint = r + 1;
             const double sg = own ? 1.0 : -1.0;
-            n0 = sg * q.nix[r]; n1 = sg * q.niy[r]; n2 = sg * q.niz[r];
+            const double n0 = sg * q.nix[r], n1 = sg * q.niy[r], n2 = sg * q.niz[r];
             const int vo = base + o * 18 + i;
-            gx = n0 * (x0 - q.x[vo]) + n1 * (x1 - q.x[vo + 6]) + n2 * (x2 - q.x[vo + 12]);
-            ga = n0 * (a0 - q.dxa[vo]) + n1 * (a1 - q.dxa[vo + 6]) + n2 * (a2 - q.dxa[vo + 12]);
-            gd = n0 * (d0 - q.dx[vo]) + n1 * (d1 - q.dx[vo + 6]) + n2 * (d2 - q.dx[vo + 12]);
-            // such a row is evaluated from both of its control points; in the residual pass, which also advances (s, z), the
-            // owner writes to the other half of a double buffer so that the partner still reads the old pair
-            ps = q.si + r; pz = q.zi + r; pt = q.ti + r;
-        } else {                         // box row: x_k <= ub (side 0), -x_k <= -lb (side 1)
-            const int bx = idx - cnt - n_int, k = bx >> 1, v = v0 + 6 * k;
-            const bool lower = bx & 1;
-            const double sg = lower ? -1.0 : 1.0;
-            n0 = k == 0 ? sg : 0.0; n1 = k == 1 ? sg : 0.0; n2 = k == 2 ? sg : 0.0;
-            const double xk = k == 0 ? x0 : (k == 1 ? x1 : x2), ak = k == 0 ? a0 : (k == 1 ? a1 : a2), dk = k == 0 ? d0 : (k == 1 ? d1 : d2);
-            gx = sg * xk; ga = sg * ak; gd = sg * dk;
-            h = lower ? q.lbn[v] : q.ub[v];
-            ps = (lower ? q.slb : q.sub) + v; pz = (lower ? q.zlb : q.zub) + v; pt = (lower ? q.tlb : q.tub) + v;
-        }
-        s = *ps; z = *pz; t = *pt;
-        double cA, cB, w;
-        row_eval<MODE>(h, s, z, t, gx, ga, gd, sa, sb, own, cA, cB, w, acc);
-        if (WR && own) {
-            if (MODE == P_RES && rint) { q.si_w[rint - 1] = s; q.zi_w[rint - 1] = z; q.ti_w[rint - 1] = t; }
-            else { *ps = s; *pz = z; *pt = t; }
-        }
-        if (VEC) { vA0 += cA * n0; vA1 += cA * n1; vA2 += cA * n2; vB0 += cB * n0; vB1 += cB * n1; vB2 += cB * n2; }
-        if (MAT) {
-            const double w0 = w * n0, w1 = w * n1, w2 = w * n2;
-            Dxx += w0 * n0; Dxy += w0 * n1; Dxz += w0 * n2; Dyy += w1 * n1; Dyz += w1 * n2; Dzz += w2 * n2;
-            if (rint && own) {  // coupling block between the two agents at this control point: -w n n'
-                double *D = q.Dint + (rint - 1) * 6;
-                D[0] = -w0 * n0; D[1] = -w0 * n1; D[2] = -w0 * n2; D[3] = -w1 * n1; D[4] = -w1 * n2; D[5] = -w2 * n2;
+            const double gx = n0 * (x0 - q.x[vo]) + n1 * (x1 - q.x[vo + 6]) + n2 * (x2 - q.x[vo + 12]);
+            const double ga = n0 * (a0 - q.dxa[vo]) + n1 * (a1 - q.dxa[vo + 6]) + n2 * (a2 - q.dxa[vo + 12]);
+            const double gd = n0 * (d0 - q.dx[vo]) + n1 * (d1 - q.dx[vo + 6]) + n2 * (d2 - q.dx[vo + 12]);
+            double s = q.si[r], z = q.zi[r], t = q.ti[r], cA, cB, w;
+            row_eval<MODE>(h, s, z, t, gx, ga, gd, sa, sb, own, cA, cB, w, acc);
+            if (WR && own) {
+                // such a row is evaluated from both of its control points; in the residual pass, which also advances
+                // (s, z), the owner writes to the other half of a double buffer so that the partner still reads the old pair
+                if (MODE == P_RES) { q.si_w[r] = s; q.zi_w[r] = z; q.ti_w[r] = t; }
+                else { q.si[r] = s; q.zi[r] = z; q.ti[r] = t; }
+            }
+            if (VEC) { vA0 += cA * n0; vA1 += cA * n1; vA2 += cA * n2; vB0 += cB * n0; vB1 += cB * n1; vB2 += cB * n2; }
+            if (MAT) {
+                const double w0 = w * n0, w1 = w * n1, w2 = w * n2;
+                Dxx += w0 * n0; Dxy += w0 * n1; Dxz += w0 * n2; Dyy += w1 * n1; Dyz += w1 * n2; Dzz += w2 * n2;
+                if (own) {  // coupling block between the two agents at this control point: -w n n'
+                    double *D = q.Dint + r * 6;
+                    D[0] = -w0 * n0; D[1] = -w0 * n1; D[2] = -w0 * n2; D[3] = -w1 * n1; D[4] = -w1 * n2; D[5] = -w2 * n2;
+                }
             }
         }
-    }
-    if (VEC) {
-        for (int o = 16; o > 0; o >>= 1) {
-            vA0 += shfl_down_t(vA0, o); vA1 += shfl_down_t(vA1, o); vA2 += shfl_down_t(vA2, o);
-            if (MODE == P_RES) { vB0 += shfl_down_t(vB0, o); vB1 += shfl_down_t(vB1, o); vB2 += shfl_down_t(vB2, o); }
+        // box rows: x_k <= ub (side 0), -x_k <= -lb (side 1)
+        for (int bx = g; bx < 6; bx += CPG) {
+            const int k = bx >> 1, v = v0 + 6 * k;
+            const bool lower = bx & 1;
+            const double sg = lower ? -1.0 : 1.0;
+            const double xk = k == 0 ? x0 : (k == 1 ? x1 : x2), ak = k == 0 ? a0 : (k == 1 ? a1 : a2), dk = k == 0 ? d0 : (k == 1 ? d1 : d2);
+            double *ps = (lower ? q.slb : q.sub) + v, *pz = (lower ? q.zlb : q.zub) + v, *pt = (lower ? q.tlb : q.tub) + v;
+            double s = *ps, z = *pz, t = *pt, cA, cB, w;
+            row_eval<MODE>(lower ? q.lbn[v] : q.ub[v], s, z, t, sg * xk, sg * ak, sg * dk, sa, sb, true, cA, cB, w, acc);
+            if (WR) { *ps = s; *pz = z; *pt = t; }
+            const double cAs = cA * sg, cBs = cB * sg;
+            if (k == 0) { vA0 += cAs; vB0 += cBs; Dxx += w; }
+            else if (k == 1) { vA1 += cAs; vB1 += cBs; Dyy += w; }
+            else { vA2 += cAs; vB2 += cBs; Dzz += w; }
         }
-        if (lane == 0) {
+    }
+    __syncwarp();
+    if (VEC) {
+#pragma unroll
+        for (int o = 1; o < CPG; o <<= 1) {
+            vA0 += __shfl_xor_sync(0xffffffffu, vA0, o); vA1 += __shfl_xor_sync(0xffffffffu, vA1, o); vA2 += __shfl_xor_sync(0xffffffffu, vA2, o);
+            if (MODE == P_RES) { vB0 += __shfl_xor_sync(0xffffffffu, vB0, o); vB1 += __shfl_xor_sync(0xffffffffu, vB1, o); vB2 += __shfl_xor_sync(0xffffffffu, vB2, o); }
+        }
+        if (active && g == 0) {
             q.vA[v0] = vA0; q.vA[v0 + 6] = vA1; q.vA[v0 + 12] = vA2;
             if (MODE == P_RES) { q.vB[v0] = vB0; q.vB[v0 + 6] = vB1; q.vB[v0 + 12] = vB2; }
         }
     }
     if (MAT) {
-        for (int o = 16; o > 0; o >>= 1) {
-            Dxx += shfl_down_t(Dxx, o); Dxy += shfl_down_t(Dxy, o); Dxz += shfl_down_t(Dxz, o);
-            Dyy += shfl_down_t(Dyy, o); Dyz += shfl_down_t(Dyz, o); Dzz += shfl_down_t(Dzz, o);
+#pragma unroll
+        for (int o = 1; o < CPG; o <<= 1) {
+            Dxx += __shfl_xor_sync(0xffffffffu, Dxx, o); Dxy += __shfl_xor_sync(0xffffffffu, Dxy, o); Dxz += __shfl_xor_sync(0xffffffffu, Dxz, o);
+            Dyy += __shfl_xor_sync(0xffffffffu, Dyy, o); Dyz += __shfl_xor_sync(0xffffffffu, Dyz, o); Dzz += __shfl_xor_sync(0xffffffffu, Dzz, o);
         }
-        if (lane == 0) {
+        if (active && g == 0) {
             double *D = q.Dcp + ((size_t)(m * q.nb + a) * 6 + i) * 6;
             D[0] = Dxx; D[1] = Dxy; D[2] = Dxz; D[3] = Dyy; D[4] = Dyz; D[5] = Dzz;
         }
@@ -606,11 +622,18 @@ RBPE_DEV void row_pass(const QP &q, double sa, double sb, Acc &out) {
     Acc acc;
     acc.s1 = 0; acc.s2 = 0; acc.mx = (MODE == P_AFF || MODE == P_STEP) ? 0.0 : -1e300; acc.mx2 = -1e300; acc.mn = 1e300;
     const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5, ntask = q.M * q.nb * 6;
-    for (int t = warp; t < ntask; t += nw) {
-        int i = t % 6, ma = t / 6, a, m;
-        if (q.nb == 1) { a = 0; m = ma; } else { a = ma % q.nb; m = ma / q.nb; }
-        if (cp_dead(q, m, i) != (MODE == P_DEAD)) continue;   // live passes skip fixed control points and vice versa
-        cp_task<MODE>(q, m, a, i, sa, sb, acc);
+    const int slot = (threadIdx.x & 31) / CPG, per = 32 / CPG;
+    for (int t0 = warp * per; t0 < ntask; t0 += nw * per) {   // eight consecutive control points per warp and round
+        const int t = t0 + slot;
+        bool active = t < ntask;
+        int i = 0, a = 0, m = 0;
+        if (active) {
+            i = t % 6;
+            const int ma = t / 6;
+            if (q.nb == 1) { a = 0; m = ma; } else { a = ma % q.nb; m = ma / q.nb; }
+            active = cp_dead(q, m, i) == (MODE == P_DEAD);   // live passes skip fixed control points and vice versa
+        }
+        cp_group<MODE>(q, active, m, a, i, sa, sb, acc);
     }
     if (MODE == P_SHIFT || MODE == P_COR || MODE == P_INIT) { __syncthreads(); return; }
     double v[6] = {acc.s1, acc.s2, acc.mx, acc.mx2, -1e300, acc.mn};
