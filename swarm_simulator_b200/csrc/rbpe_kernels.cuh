@@ -427,6 +427,13 @@ RBPE_DEV void block_reduce6(double *v, double *red) {
 }
 
 enum { P_INIT = 0, P_START, P_SHIFT, P_RES, P_AFF, P_COR, P_STEP, P_DEAD };
+// 1: no corrector pass over the rows.  The corrector's coefficient -(z rg - rc) / s with rc = s z + dsa dza - sigma mu is
+// affine in sigma mu, which is only known after the affine pass's reductions: that pass accumulates G'(part without
+// sigma mu) in vA and G'(1 / s) in vB, and the solver forms vA - sigma mu vB -- three passes per iteration instead of four.
+// 0: the separate pass (tools only, A/B).
+#ifndef RBPE_FUSE_COR
+#define RBPE_FUSE_COR 1
+#endif
 
 constexpr double PRESOLVE_FEAS_TOL = 1e-6;  // CPLEX's default feasibility tolerance, for rows made constant by the endpoints
 // Dual-residual floor of the acceptance rule (CPLEX's optimality tolerance EpOpt, default 1e-6); see pdip_solve and
@@ -487,6 +494,9 @@ RBPE_DEV void row_eval(double h, double &s, double &z, double &t, double gx, dou
         acc.mx = rmax2(acc.mx, rmax2(-dsa * rs, -dza * rz));
         // sum (s + a dsa)(z + a dza) = s'z + a * s1 + a^2 * s2 for whatever step a comes out of the ratio test
         if (owner) { acc.s1 += s * dza + z * dsa; acc.s2 += dsa * dza; }
+#if RBPE_FUSE_COR
+        cA = -(z * rg - (s * z + dsa * dza)) * rs; cB = rs;
+#endif
         return;
     }
     double rc = s * z + dsa * dza - sa;  // sa = sigma * mu
@@ -511,7 +521,8 @@ constexpr int CPG = 4;   // lanes per control point
 template <int MODE>
 RBPE_DEV void cp_group(const QP &q, const bool active, int m, int a, int i, double sa, double sb, Acc &acc) {
     constexpr bool WR = (MODE == P_START || MODE == P_SHIFT || MODE == P_RES);
-    constexpr bool VEC = (MODE == P_INIT || MODE == P_RES || MODE == P_COR);
+    constexpr bool VEC = (MODE == P_INIT || MODE == P_RES || MODE == P_COR || (RBPE_FUSE_COR && MODE == P_AFF));
+    constexpr bool VECB = (MODE == P_RES || (RBPE_FUSE_COR && MODE == P_AFF));   // the pass also produces vB
     constexpr bool MAT = (MODE == P_INIT || MODE == P_RES);
     const int g = threadIdx.x & (CPG - 1);
     double vA0 = 0, vA1 = 0, vA2 = 0, vB0 = 0, vB1 = 0, vB2 = 0;
@@ -597,11 +608,11 @@ RBPE_DEV void cp_group(const QP &q, const bool active, int m, int a, int i, doub
 #pragma unroll
         for (int o = 1; o < CPG; o <<= 1) {
             vA0 += __shfl_xor_sync(0xffffffffu, vA0, o); vA1 += __shfl_xor_sync(0xffffffffu, vA1, o); vA2 += __shfl_xor_sync(0xffffffffu, vA2, o);
-            if (MODE == P_RES) { vB0 += __shfl_xor_sync(0xffffffffu, vB0, o); vB1 += __shfl_xor_sync(0xffffffffu, vB1, o); vB2 += __shfl_xor_sync(0xffffffffu, vB2, o); }
+            if (VECB) { vB0 += __shfl_xor_sync(0xffffffffu, vB0, o); vB1 += __shfl_xor_sync(0xffffffffu, vB1, o); vB2 += __shfl_xor_sync(0xffffffffu, vB2, o); }
         }
         if (active && g == 0) {
             q.vA[v0] = vA0; q.vA[v0 + 6] = vA1; q.vA[v0 + 12] = vA2;
-            if (MODE == P_RES) { q.vB[v0] = vB0; q.vB[v0 + 6] = vB1; q.vB[v0 + 12] = vB2; }
+            if (VECB) { q.vB[v0] = vB0; q.vB[v0 + 6] = vB1; q.vB[v0 + 12] = vB2; }
         }
     }
     if (MAT) {
@@ -1033,9 +1044,13 @@ RBPE_DEV int pdip_solve(const QP &q_in, int max_iter, double tol_gap, double tol
         double sigma = (mu > 0) ? (mua / mu) * (mua / mu) * (mua / mu) : 0.0;
         sigmu = sigma * mu;
         // ---- corrector ----
+#if RBPE_FUSE_COR
+        for (int v = tid; v < q.nv; v += nt) q.vA[v] = -q.rdx[v] + (q.vA[v] - sigmu * q.vB[v]);
+#else
         row_pass<P_COR>(q, sigmu, 0, acc);
         PROF(1);
         for (int v = tid; v < q.nv; v += nt) q.vA[v] = -q.rdx[v] + q.vA[v];
+#endif
         kkt_solve(q, q.vA, q.dx);
         PROF(3);
         row_pass<P_STEP>(q, sigmu, 0, acc);

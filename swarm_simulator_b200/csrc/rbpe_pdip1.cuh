@@ -27,6 +27,11 @@ constexpr int W1_WARPS = RBPE_W1_WARPS;   // QPs (warps) per CTA; 16 warps per S
 #define RBPE_W1_UNROLL 1
 #endif
 constexpr int W1_UNROLL = RBPE_W1_UNROLL;
+#ifndef RBPE_W1_FUSE_COR
+// 1: no corrector pass over the rows -- its G' product is accumulated in two parts by the affine pass (w1_pass): +10 %
+// (same-box A/B, profiles/r2_pdip1_ab.md); 0: four passes per iteration (tools only)
+#define RBPE_W1_FUSE_COR 1
+#endif
 #ifndef RBPE_W1_PF
 #define RBPE_W1_PF 2   // software-pipeline depth of the row loop: 2 = rows and normals one iteration ahead, 1 = rows only
 #endif   // unroll factor of the row loop (tuning; 1 = smallest code)
@@ -128,7 +133,8 @@ RBPE_DEV bool w1_dead(const W1 &c, int cp) { int m = cp / 6, i = cp % 6; return 
 //   P_RES    pending step (sa = its sigma mu, sb = its length) fused in; vA = G'z, vB = G' t_aff, D = sum w g g';
 //            acc.s1 = s'z, acc.s2 = h'z, acc.mx = max |rg|, acc.mx2 = max z
 //   P_AFF    ratio test of the affine direction (max form) in acc.mx; acc.s1, acc.s2 = coefficients of mu_aff(a)
-//   P_COR    vA = G'(corrector coefficients), sa = sigma mu
+//   P_COR    vA = G'(corrector coefficients), sa = sigma mu   (RBPE_W1_FUSE_COR = 0 only; otherwise P_AFF also leaves
+//            vA = G'(coefficients without sigma mu), vB = G'(1/s), and the phase machine forms vA - sigma mu vB)
 //   P_STEP   ratio test of the final direction in acc.mx
 // Called from ONE place (w1_solve_qp's phase machine) so that a single copy of this loop exists in the kernel text.
 RBPE_DEV void w1_pass(const W1 &c, const int mode, const double sa, const double sb, Acc &out) {
@@ -233,9 +239,24 @@ RBPE_DEV void w1_pass(const W1 &c, const int mode, const double sa, const double
                         if (mode == P_AFF) {
                             acc.mx = dmax(acc.mx, dmax(-dsa * rs, -dza * rz));
                             acc.s1 += s * dza + z * dsa; acc.s2 += dsa * dza;
+#if RBPE_W1_FUSE_COR
+                            // The corrector's coefficient -(z rg - rc) / s with rc = s z + dsa dza - sigma mu is affine in
+                            // sigma mu, which is only known after this pass's reductions: vA takes the part without it, vB
+                            // the sum of g / s; the phase machine forms vA - sigma mu vB.  Saves the fourth pass over the rows.
+                            const double c1 = -(z * rg - (s * z + dsa * dza)) * rs;
+                            vA0 += c1 * n0; vA1 += c1 * n1; vA2 += c1 * n2;
+                            vB0 += rs * n0; vB1 += rs * n1; vB2 += rs * n2;
+#endif
                             continue;
                         }
                         const double rc = s * z + dsa * dza - sa;
+#if RBPE_W1_FUSE_COR
+                        {   // P_STEP
+                            const double ds = -rg - gd, dz = (-rc - z * ds) * rs;
+                            acc.mx = dmax(acc.mx, dmax(-ds * rs, -dz * rz));
+                            continue;
+                        }
+#else
                         if (mode == P_STEP) {
                             const double ds = -rg - gd, dz = (-rc - z * ds) * rs;
                             acc.mx = dmax(acc.mx, dmax(-ds * rs, -dz * rz));
@@ -244,6 +265,7 @@ RBPE_DEV void w1_pass(const W1 &c, const int mode, const double sa, const double
                         cA = -(z * rg - rc) * rs;   // P_COR
                         vA0 += cA * n0; vA1 += cA * n1; vA2 += cA * n2;
                         continue;
+#endif
                     }
                 }
                 vA0 += cA * n0; vA1 += cA * n1; vA2 += cA * n2;
@@ -252,8 +274,13 @@ RBPE_DEV void w1_pass(const W1 &c, const int mode, const double sa, const double
                     Dxx += w0 * n0; Dxy += w0 * n1; Dxz += w0 * n2; Dyy += w1 * n1; Dyz += w1 * n2; Dzz += w2 * n2;
                 }
             }
+#if RBPE_W1_FUSE_COR
+            if (mode == P_INIT || mode == P_RES || mode == P_AFF) { c.vA[v0] = vA0; c.vA[v0 + 6] = vA1; c.vA[v0 + 12] = vA2; }
+            if (mode == P_RES || mode == P_AFF) { c.vB[v0] = vB0; c.vB[v0 + 6] = vB1; c.vB[v0 + 12] = vB2; }
+#else
             if (mode == P_INIT || mode == P_RES || mode == P_COR) { c.vA[v0] = vA0; c.vA[v0 + 6] = vA1; c.vA[v0 + 12] = vA2; }
             if (mode == P_RES) { c.vB[v0] = vB0; c.vB[v0 + 6] = vB1; c.vB[v0 + 12] = vB2; }
+#endif
             if (mode == P_INIT || mode == P_RES) {
                 double *D = c.Dcp + (size_t)cp * 6;
                 D[0] = Dxx; D[1] = Dxy; D[2] = Dxz; D[3] = Dyy; D[4] = Dyz; D[5] = Dzz;
@@ -528,7 +555,17 @@ RBPE_DEV int w1_solve_qp(const W1 &c, int max_iter, double tol_gap, double tol_r
             const double mua = (mu * mi + aa * acc.s1 + aa * aa * acc.s2) / mi;
             const double sigma = (mu > 0) ? (mua / mu) * (mua / mu) * (mua / mu) : 0.0;
             sigmu = sigma * mu;
+#if RBPE_W1_FUSE_COR
+            __syncwarp();
+            #pragma unroll 1
+            for (int v = lane; v < 18 * c.M; v += 32) c.vA[v] = -c.rdx[v] + (c.vA[v] - sigmu * c.vB[v]);
+            __syncwarp();
+            w1_solve(c, c.vA, c.dx);
+            PROF(5);
+            phase = PH_STEP; sa = sigmu; sb = 0;
+#else
             phase = PH_COR; sa = sigmu; sb = 0;
+#endif
         } else if (phase == PH_COR) {
             #pragma unroll 1
             for (int v = lane; v < 18 * c.M; v += 32) c.vA[v] = -c.rdx[v] + c.vA[v];

@@ -96,11 +96,22 @@ RBPE_DEV bool x1_dead(const X1 &c, int cp) { int m = cp / 6, i = cp % 6; return 
 // One pass over the kept rows, all warps at once (modes and row algebra: w1_pass in rbpe_pdip1.cuh).  Every thread
 // returns the same reductions.  The vectors a pass produces (vA, vB, Dcp) are complete only after the CALLER's next
 // barrier; in P_COR the pass stores vA - rdx, the right-hand side the corrector solve needs.
+// RBPE_X1_FUSE_COR = 1: no corrector pass; the affine pass leaves the two parts of its G' product in vA and vB (see
+// RBPE_W1_FUSE_COR in rbpe_pdip1.cuh) and the phase machine forms (vA - sigma mu vB) - rdx.
+#ifndef RBPE_X1_FUSE_COR
+#define RBPE_X1_FUSE_COR 1
+#endif
 RBPE_DEV void x1_pass(const X1 &c, const int mode, const double sa, const double sb, int &flip, Acc &out) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x, nt = blockDim.x;
     Acc acc;
     acc.s1 = 0; acc.s2 = 0; acc.mx = (mode == P_AFF || mode == P_STEP) ? 0.0 : -1e300; acc.mx2 = -1e300; acc.mn = 1e300;
+#if RBPE_X1_FUSE_COR
+    const bool vec = (mode == P_INIT || mode == P_RES || mode == P_AFF);
+    const int P_NOD = P_AFF;    // the vector-producing pass without the 3 x 3 blocks
+#else
     const bool vec = (mode == P_INIT || mode == P_RES || mode == P_COR);
+    const int P_NOD = P_COR;
+#endif
     PROF_DECL;
 #pragma unroll 1
     for (int slot = 0; slot < c.nslot; slot++) {
@@ -167,9 +178,21 @@ RBPE_DEV void x1_pass(const X1 &c, const int mode, const double sa, const double
                         if (mode == P_AFF) {
                             acc.mx = dmax(acc.mx, dmax(-dsa * rs, -dza * rz));
                             acc.s1 += s * dza + z * dsa; acc.s2 += dsa * dza;
+#if RBPE_X1_FUSE_COR
+                            const double c1 = -(z * rg - (s * z + dsa * dza)) * rs;
+                            vA0 += c1 * n0; vA1 += c1 * n1; vA2 += c1 * n2;
+                            vB0 += rs * n0; vB1 += rs * n1; vB2 += rs * n2;
+#endif
                             continue;
                         }
                         const double rc = s * z + dsa * dza - sa;
+#if RBPE_X1_FUSE_COR
+                        {   // P_STEP
+                            const double ds = -rg - gd, dz = (-rc - z * ds) * rs;
+                            acc.mx = dmax(acc.mx, dmax(-ds * rs, -dz * rz));
+                            continue;
+                        }
+#else
                         if (mode == P_STEP) {
                             const double ds = -rg - gd, dz = (-rc - z * ds) * rs;
                             acc.mx = dmax(acc.mx, dmax(-ds * rs, -dz * rz));
@@ -178,6 +201,7 @@ RBPE_DEV void x1_pass(const X1 &c, const int mode, const double sa, const double
                         cA = -(z * rg - rc) * rs;   // P_COR
                         vA0 += cA * n0; vA1 += cA * n1; vA2 += cA * n2;
                         continue;
+#endif
                     }
                 }
                 vA0 += cA * n0; vA1 += cA * n1; vA2 += cA * n2;
@@ -193,8 +217,8 @@ RBPE_DEV void x1_pass(const X1 &c, const int mode, const double sa, const double
         {   // partial sums of this warp; added below in warp order
             double *pp = c.part + (size_t)warp * X1_PART * 32 + lane;
             pp[0] = vA0; pp[32] = vA1; pp[64] = vA2;
-            if (mode == P_RES) { pp[96] = vB0; pp[128] = vB1; pp[160] = vB2; }
-            if (mode != P_COR) { pp[192] = Dxx; pp[224] = Dxy; pp[256] = Dxz; pp[288] = Dyy; pp[320] = Dyz; pp[352] = Dzz; }
+            if (mode == P_RES || (RBPE_X1_FUSE_COR && mode == P_AFF)) { pp[96] = vB0; pp[128] = vB1; pp[160] = vB2; }
+            if (mode != P_NOD) { pp[192] = Dxx; pp[224] = Dxy; pp[256] = Dxz; pp[288] = Dyy; pp[320] = Dyz; pp[352] = Dzz; }
         }
         if (last && mode != P_COR) x1_red_put<15>(c.scal, flip, acc.s1, acc.s2, acc.mx, acc.mx2, 0.0);   // rides on the same barrier
         __syncthreads();
@@ -203,8 +227,13 @@ RBPE_DEV void x1_pass(const X1 &c, const int mode, const double sa, const double
         for (int idx = tid; idx < X1_PART * 32; idx += nt) {
             const int k = idx >> 5, l = idx & 31, cp2 = slot * 32 + l;
             if (cp2 >= c.ncp || x1_dead(c, cp2)) continue;
+#if RBPE_X1_FUSE_COR
+            if (k >= 6 && mode == P_AFF) continue;
+            if (k >= 3 && k < 6 && mode != P_RES && mode != P_AFF) continue;
+#else
             if (k >= 3 && mode == P_COR) continue;
             if (k >= 3 && k < 6 && mode != P_RES) continue;
+#endif
             const double *pp = c.part + k * 32 + l;
             double sm = pp[0];
 #pragma unroll
@@ -502,7 +531,17 @@ RBPE_DEV int x1_solve_qp(const X1 &c, int max_iter, double tol_gap, double tol_r
             const double mua = (mu * mi + aa * acc.s1 + aa * aa * acc.s2) / mi;
             const double sigma = (mu > 0) ? (mua / mu) * (mua / mu) * (mua / mu) : 0.0;
             sigmu = sigma * mu;
+#if RBPE_X1_FUSE_COR
+            __syncthreads();   // the pass's vA / vB
+#pragma unroll 1
+            for (int v = tid; v < nv; v += nt) c.vA[v] = (c.vA[v] - sigmu * c.vB[v]) - c.rdx[v];
+            __syncthreads();
+            x1_solve(c, c.vA, c.dx);
+            PROF(5);
+            phase = PH_STEP; sa = sigmu; sb = 0;
+#else
             phase = PH_COR; sa = sigmu; sb = 0;
+#endif
         } else if (phase == PH_COR) {
             __syncthreads();   // vA - rdx, stored by the pass
             x1_solve(c, c.vA, c.dx);
