@@ -35,12 +35,13 @@ def dense_flops_per_iter(b, M):
 
 
 def structured_flops_per_iter(b, M, N, rows=None):
-    """What the kernel executes: block tridiagonal Cholesky over M-1 knot blocks of 9b + 4 row passes of ~40 flops per
-    KEPT row (rows=None counts every row of populatebyrow, an upper bound)."""
+    """What the kernel executes: block tridiagonal Cholesky over M-1 knot blocks of 9b + 3 row passes of ~44 flops per
+    KEPT row (residual, affine + corrector right-hand side, final ratio test; rows=None counts every row of
+    populatebyrow, an upper bound)."""
     kb = 9.0 * b
     if rows is None:
         rows = b * (6 * M - 6) * (6 + (N - b)) + b * (b - 1) / 2 * (6 * M - 6)
-    return (M - 1) * (kb ** 3 / 3) + (M - 2) * 2 * kb ** 3 + 4 * (M - 1) * 2 * kb * kb * 2 + 4 * rows * 40
+    return (M - 1) * (kb ** 3 / 3) + (M - 2) * 2 * kb ** 3 + 4 * (M - 1) * 2 * kb * kb * 2 + 3 * rows * 44
 
 
 WORKLOAD = ("64 agents, random forest rho=0.2, 5-segment degree-5, sequential batch_size=1 "
@@ -535,7 +536,7 @@ def main():
                            "b=1, M=5) x iterations executed: %.3e per launch" % f_dense,
             "algorithmic_bytes": h2d + d2h,
             "executed_structured_tflops": f_struct / (kernel_ms * 1e-3) / 1e12,
-            "executed_structured_note": "block tridiagonal factor / solves + 40 flops per KEPT inequality row and pass (%.0f of the "
+            "executed_structured_note": "block tridiagonal factor / solves + 44 flops per KEPT inequality row and pass (3 passes per iteration) (%.0f of the "
                                         "%d rows of populatebyrow survive the presolve on average)" % (kept, (6 * M_SEG - 6) * (N_AGENTS + 5)),
             "fp64_peak_tflops": fp64_peak,
             "executed_fraction_of_fp64_peak": (f_struct / (kernel_ms * 1e-3) / 1e12 / fp64_peak) if fp64_peak else None,
