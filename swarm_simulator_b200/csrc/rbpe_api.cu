@@ -61,7 +61,11 @@ struct rbpe_handle {
     int force_cta = 0;   // RBPE_KERNEL=cta: never use the warp-per-QP kernel (A/B testing)
     size_t x1_dyn_cap = 0;   // same for the several-warps-per-QP latency kernel (pdip1x_kernel)
     int lat_mode = -1;       // RBPE_LAT=0 / 1: never / always use the latency kernel where it fits (default: by work-item count)
+#ifdef RBPE_W1_V1
+    int lat_warps = 0;       // (the round-1 layout has no latency kernel)
+#else
     int lat_warps = X1_MAXW; // RBPE_LAT_WARPS: warps per QP of the latency kernel
+#endif
     int lat_warps_forced = 0;
     int last_solver = 0, last_threads = 0;   // rbpe_last_solver
     int sm_count = 0;
