@@ -26,6 +26,28 @@ def build():
 
 
 _lib = None
+_variants = {}
+
+
+def emu_variant(tag, flags):
+    """The same kernels compiled with extra preprocessor flags (e.g. the textbook four-pass loop, -DRBPE_FUSE_COR=0 ...):
+    returns a callable with emu_solve_many's signature bound to that library."""
+    if tag not in _variants:
+        path = os.path.join(_EMU_DIR, "librbpe_emu_%s.so" % tag)
+        if (not os.path.exists(path)) or os.path.getmtime(path) < max(os.path.getmtime(s) for s in _SRCS):
+            subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-Wno-unused", "-Wno-unknown-pragmas"] + list(flags) +
+                                  ["-o", path, _SRCS[0]])
+        lib = C.CDLL(path)
+        lib.emu_solve_many.argtypes = [C.POINTER(E.RbpeProblem), C.c_int, C.c_int, C.POINTER(E.RbpeResult),
+                                       C.c_size_t, C.c_int, C.c_double, C.c_double, C.c_int]
+        lib.emu_solve_many.restype = C.c_int
+        _variants[tag] = lib
+
+    def solve(prob, mode=0, smem_bytes=48 * 1024, max_iter=0, tol_gap=0.0, tol_res=0.0, threads=256):
+        r = E.Result(prob)
+        r.rc = _variants[tag].emu_solve_many(C.byref(prob.c), prob.count, mode, C.byref(r.c), smem_bytes, max_iter, tol_gap, tol_res, threads)
+        return r
+    return solve
 
 
 def emu_solve_many(prob, mode=0, smem_bytes=48 * 1024, max_iter=0, tol_gap=0.0, tol_res=0.0, threads=256):

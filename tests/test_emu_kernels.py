@@ -55,6 +55,24 @@ def test_emulated_one_agent_kernels_match_oracle(N, M, rho, threads, mode):
     assert np.abs(r.coef[0] - ro["coef"]).max() < 1e-9
 
 
+def test_fused_corrector_equals_the_separate_corrector_pass():
+    """The kernels form the corrector's G' product from two sums of the affine pass (RBPE_FUSE_COR, RBPE_W1_FUSE_COR,
+    RBPE_X1_FUSE_COR: three passes over the rows per iteration).  Against the same kernels compiled with the textbook
+    separate corrector pass: same statuses and iteration counts, control points to rounding -- for the warp-per-QP kernel,
+    the latency kernel and a joint batch."""
+    four = emu_util.emu_variant("fourpass", ["-DRBPE_FUSE_COR=0", "-DRBPE_W1_FUSE_COR=0", "-DRBPE_X1_FUSE_COR=0"])
+    for (N, M, rho, seq, bs, threads, smem) in ((9, 5, 0.2, True, 1, 256, 48 * 1024), (9, 5, 0.2, True, 1, -128, 48 * 1024),
+                                                (8, 4, 0.2, True, 4, 256, 48 * 1024), (6, 3, 0.1, False, 6, 64, 48 * 1024)):
+        m = synth.synth_mission(N, M, rho, 79)
+        prob = E.PackedProblem(synth.pack([m]), sequential=seq, batch_size=bs)
+        a = emu_util.emu_solve_many(prob, smem_bytes=smem, threads=threads)
+        b = four(prob, smem_bytes=smem, threads=threads)
+        assert a.rc == b.rc == 0
+        assert np.array_equal(a.qp_status, b.qp_status) and np.array_equal(a.qp_iters, b.qp_iters)
+        assert np.abs(a.ctrl - b.ctrl).max() < 1e-10
+        assert np.allclose(a.qp_obj, b.qp_obj, rtol=1e-8, atol=1e-9)   # (the bar of the GPU-vs-oracle tests)
+
+
 @pytest.mark.parametrize("kb,nblk,threads", [(18, 3, 64), (36, 2, 64), (45, 3, 96), (72, 2, 128), (27, 1, 32),
                                              (36, 4, 256), (18, 3, 512), (63, 2, 384)])   # >= 8 warps: register-resident diagonal blocks
 def test_emulated_block_tridiagonal_factor_and_solve(kb, nblk, threads):
