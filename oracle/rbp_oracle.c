@@ -884,7 +884,9 @@ int oracle_solve_qp(const oracle_qp *q, const oracle_solver_opts *opts, double *
         }
         mua /= (n_live > 0 ? n_live : 1);
         double sigma = (mu > 0) ? (mua / mu) * (mua / mu) * (mua / mu) : 0;
-        /* corrector: rc = s.z + dsa.dza - sigma mu */
+        /* corrector: rc = s.z + dsa.dza - sigma mu.  (The CUDA kernels form G'tt from two sums of their affine pass,
+           G'(-(z rg - s z - dsa dza)/s) - sigma mu G'(1/s), instead of a pass of their own: same iterates up to rounding,
+           tests/test_emu_kernels.py::test_fused_corrector_equals_the_separate_corrector_pass.) */
         for (int r = 0; r < mi; r++) {
             if (dead[r]) { tt[r] = 0; continue; }
             double dsa = -rg[r] - gxa[r], dza = -z[r] - K.w[r] * dsa;
