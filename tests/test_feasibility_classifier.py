@@ -17,6 +17,7 @@ import feas_classifier as fc
 import feas_util as fu
 import oracle
 import oracle_util
+from swarm_simulator_b200 import synth
 
 CPU_CASES = [c for c in fu.CASES if not (c[0] == "cfg4" and c[2] == 32)]   # 256-agent joint batches of 32: GPU test only (70 s of CPU)
 
@@ -50,6 +51,24 @@ def test_oracle_reports_infeasible_when_highs_does(pack, sequential, bs, count, 
     fails, tally = fu.judge(st, first_bad, ms, sequential, bs, ctrl)
     assert not fails, (tally, fails[:5])
     assert sum(v for k, v in tally.items() if k.startswith("infeasible")) >= 4, tally   # the family does produce infeasible QPs
+
+
+@pytest.mark.parametrize("N,M,rho,seed0,count,sequential,bs", [
+    (4, 3, 0.0, 51000, 48, False, 4), (4, 3, 0.0, 51000, 48, True, 1),
+    (16, 5, 0.2, 41000, 12, False, 16), (16, 5, 0.2, 41000, 12, True, 4), (16, 5, 0.5, 61000, 12, True, 1),
+])
+def test_fresh_seeds_outside_the_packs(N, M, rho, seed0, count, sequential, bs):
+    """Missions generated at test time from seeds no pack contains (the packs could have been tuned to): same judge.
+    tools/robustness_sweep.py runs this at scale (9.6 k missions, no disagreement)."""
+    ms = []
+    for i in range(count):
+        m = synth.synth_mission(N, M, rho, seed0 + i)
+        m.pop("edt", None)
+        ms.append(m)
+    st, first_bad, ctrl = _run_oracle(ms, sequential, bs)
+    fails, tally = fu.judge(st, first_bad, ms, sequential, bs, ctrl)
+    assert not fails, (tally, fails[:5])
+    assert tally.get("ok", 0) == len(ms), tally
 
 
 def test_every_qp_of_sampled_missions_classified():
